@@ -1,0 +1,109 @@
+/* uniir_b200.h -- C ABI of the B200-native UniIR hot path (libuniir_b200.so).
+ *
+ * The reference (TIGER-AI-Lab/UniIR) is 100 % Python and has no FFI of its own: every
+ * device op on its hot path is a PyTorch / cuBLAS / FAISS library call.  Each entry point
+ * below therefore cites the reference call site(s) whose library call it replaces
+ * (paths relative to the reference root; "upstream CLIP" = the un-vendored openai/CLIP
+ * dependency, restated in the reference at clip_featurefusion/clip_ff.py).
+ *
+ * Conventions:
+ *   - plain `extern "C"`, no torch types; every pointer is a DEVICE pointer owned by the
+ *     caller unless a comment says "host";
+ *   - `stream` is a cudaStream_t passed as void*; the call only enqueues work on it
+ *     (no hidden synchronisation, no hidden allocation -- scratch is passed in);
+ *   - return value: 0 = ok, negative = error (UNIIR_ERR_*); `uniir_last_error()` returns
+ *     a thread-local human-readable message for the last failing call;
+ *   - row-major everywhere, leading dimensions in ELEMENTS.
+ */
+#ifndef UNIIR_B200_H_
+#define UNIIR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UNIIR_ABI_VERSION 1
+
+#define UNIIR_OK 0
+#define UNIIR_ERR_INVALID_ARG (-1)
+#define UNIIR_ERR_CUDA (-2)
+#define UNIIR_ERR_UNSUPPORTED (-3)
+
+#define UNIIR_BF16 0
+#define UNIIR_F16 1
+#define UNIIR_F32 2
+
+#define UNIIR_ACT_NONE 0
+#define UNIIR_ACT_QUICKGELU 1 /* x*sigmoid(1.702x): upstream CLIP QuickGELU */
+#define UNIIR_ACT_GELU 2      /* exact erf GELU: BLIP vit.py:39 / med.py:308 */
+
+int uniir_abi_version(void);
+const char* uniir_last_error(void);
+/* number of this library's kernel launches since process start (bench.py "gpu_launches") */
+int64_t uniir_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * GEMM with fused epilogue on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
+ *   out[M,N] (+)= epilogue( alpha * A . B^T )     A logical [M,K], B logical [N,K]
+ * a_mn / b_mn = 0: operand stored [rows, K] (K contiguous);  1: stored [K, rows].
+ * Epilogue order: *alpha, +bias[N], (aux_out := value), act, *act'(act_grad_src),
+ *                 +residual, store / accumulate / atomic-accumulate (split_k > 1).
+ * Replaces: nn.MultiheadAttention in_proj/out_proj, mlp.c_fc/c_proj, visual.conv1 (as
+ * im2col GEMM), visual.proj, text_projection (upstream CLIP; restated clip_ff.py:35-59,
+ * 148-156) and their autograd backward (dgrad = b_mn=1, wgrad = a_mn=b_mn=1).
+ * Constraints: K % 8 == 0 (16 B rows), lda/ldb % 8 == 0, N % 8 == 0, 16 B aligned bases.
+ * ---------------------------------------------------------------------------------- */
+typedef struct uniir_gemm_desc {
+  int32_t M, N, K;
+  const void* A; int64_t lda; int32_t a_mn;
+  const void* B; int64_t ldb; int32_t b_mn;
+  int32_t in_dtype;                 /* UNIIR_BF16 | UNIIR_F16 */
+  void* out; int64_t ldo; int32_t out_dtype; /* BF16 | F16 | F32 */
+  const float* bias;                /* [N] or NULL */
+  int32_t act;                      /* UNIIR_ACT_* */
+  const void* residual; int64_t ldr; int32_t res_dtype; /* added last; NULL = none */
+  void* aux_out; int64_t ld_aux;    /* optional copy of the pre-activation, in_dtype */
+  const void* act_grad_src; int64_t ld_ags; /* optional: value *= act'(src), in_dtype */
+  float alpha;
+  int32_t accumulate;               /* out += value (out_dtype must be F32) */
+  int32_t split_k;                  /* >1: split contraction, atomic fp32 accumulate */
+} uniir_gemm_desc;
+int uniir_gemm_epi(const uniir_gemm_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Dense retrieval: exact cosine top-k (FAISS "IDMap,Flat" + METRIC_INNER_PRODUCT over
+ * L2-normalised rows).  Replaces faiss.normalize_L2 + GpuIndexFlat.search:
+ * common/mbeir_retriever.py:69,76 (index build), :190,:194,:231 (search).
+ * Embeddings stay as the stored fp16 values; 1/||row|| is applied in fp32 in the epilogue.
+ * ---------------------------------------------------------------------------------- */
+/* inv[r] = 1/||x[r,:]||_2 in fp32 (0 for an all-zero row, matching normalize_L2). */
+int uniir_row_inv_norm(const void* x, int32_t dtype, int64_t rows, int32_t d, int64_t ld,
+                       float* inv, void* stream);
+/* Number of candidate-range splits the search kernel will use for (Q, N) and the scratch
+ * it needs.  Partial outputs are [Q, splits, k]. */
+int uniir_ip_topk_plan(int64_t Q, int64_t N, int32_t k, int32_t* splits, size_t* workspace_bytes);
+/* Fused fp16 GEMM + per-row top-k.  part_scores fp32 [Q, splits, k] (descending, cosine),
+ * part_idx int32 [Q, splits, k] (candidate row in [0,N), -1 padding).  k <= 64. */
+int uniir_ip_topk(const void* q, const float* q_inv, const void* c, const float* c_inv, int64_t Q,
+                  int64_t N, int32_t d, int32_t k, int32_t splits, float* part_scores,
+                  int32_t* part_idx, void* workspace, size_t workspace_bytes, void* stream);
+/* k-way merge of L sorted partial lists per query (splits of one GPU, or shards of W GPUs):
+ * in_scores/in_idx element (q, l, j) at  q*q_stride + l*l_stride + j; in_idx is int32
+ * (idx_is_64 = 0) or int64 (idx_is_64 = 1); negative idx = padding.
+ * list_offset[l] (int64, may be NULL) is added to idx (shard row offset);
+ * id_table (int64, may be NULL) maps the resulting row to the user id (add_with_ids,
+ * mbeir_retriever.py:103).  Output: fp32 [Q,k] descending + int64 [Q,k]; missing = -1 with
+ * score -3.4028235e38 (FAISS convention).  L*k <= 512.  Replaces the host-side
+ * IndexShards merge behind mbeir_retriever.py:206,231. */
+int uniir_topk_merge(const float* in_scores, const void* in_idx, int32_t idx_is_64, int64_t Q,
+                     int32_t L, int32_t k, int64_t q_stride, int64_t l_stride,
+                     const int64_t* list_offset, const int64_t* id_table, float* out_scores,
+                     int64_t* out_ids, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNIIR_B200_H_ */

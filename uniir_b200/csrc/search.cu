@@ -1,0 +1,449 @@
+// Dense retrieval: fused fp16 tcgen05 GEMM + per-row top-k (replaces FAISS GpuIndexFlat
+// inner-product search, reference common/mbeir_retriever.py:231) plus the row-norm and
+// k-way merge kernels around it.
+//
+// Work decomposition: item = (query tile of 128 rows) x (one contiguous candidate range).
+// A CTA keeps the per-row running top-k of its item; consecutive CTAs work on different
+// query tiles of the SAME candidate range, so the 148 CTAs stream the candidate matrix in
+// near lock-step and every candidate tile is fetched from HBM once and served to the other
+// CTAs from L2.  Scores never leave the SM: the epilogue reads the fp32 accumulators from
+// TMEM, scales by 1/||c|| and rejects >99.9 % of them with one max-reduce + compare against
+// the row's current k-th best; survivors are appended to a small per-row buffer that is
+// compacted (warp-cooperative bitonic sort) when it fills.
+#include <cuda_fp16.h>
+#include <float.h>
+
+#include "gemm_sm100.cuh"
+#include "host_util.cuh"
+
+namespace uniir {
+
+constexpr int kSearchBN = 256;
+constexpr int kCap = 128;      // per-row candidate buffer (entries)
+constexpr int kMaxK = 64;
+constexpr float kNegInf = -INFINITY;
+constexpr float kFaissNeg = -3.4028234663852886e38f;
+
+struct SearchParams {
+  long long Q, N;
+  int k, splits, n_qtiles, tiles_per_split, n_tiles, kb_total;
+  const float* q_inv;
+  const float* c_inv;
+  float* part_scores;
+  int* part_idx;
+  float* ws_scores;  // [grid][128][kCap]
+  int* ws_idx;
+};
+
+struct SearchSched {
+  int n_qtiles, splits, tiles_per_split, n_tiles, kb_total;
+  __device__ __forceinline__ int num_items() const { return n_qtiles * splits; }
+  __device__ __forceinline__ bool get(int item, WorkItem& w) const {
+    const int split = item / n_qtiles;
+    w.m_blk = item - split * n_qtiles;
+    w.n_begin = split * tiles_per_split;
+    w.n_end = min(n_tiles, w.n_begin + tiles_per_split);
+    w.kb_begin = 0;
+    w.kb_end = kb_total;
+    return w.n_begin < w.n_end;
+  }
+};
+
+// strict total order "a ranks before b": higher score first, lower index on ties
+__device__ __forceinline__ bool ranks_before(float ka, long long ia, float kb, long long ib) {
+  return (ka > kb) || (ka == kb && ia < ib);
+}
+
+// Bitonic sort (descending by ranks_before) of 32*R elements held as element e = r*32 + lane.
+template <int R, typename IdxT>
+__device__ __forceinline__ void warp_bitonic_desc(float (&key)[R], IdxT (&idx)[R]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k2 = 2; k2 <= 32 * R; k2 <<= 1) {
+#pragma unroll
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int jr = j >> 5;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if ((r & jr) == 0) {
+            const int r2 = r | jr;
+            const int e = r * 32 + lane;
+            const bool desc = (e & k2) == 0;
+            const bool first_wins = ranks_before(key[r], (long long)idx[r], key[r2], (long long)idx[r2]);
+            if (first_wins != desc) {
+              const float tk = key[r]; key[r] = key[r2]; key[r2] = tk;
+              const IdxT ti = idx[r]; idx[r] = idx[r2]; idx[r2] = ti;
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int e = r * 32 + lane;
+          const float ok = __shfl_xor_sync(0xffffffffu, key[r], j);
+          const IdxT oi = __shfl_xor_sync(0xffffffffu, idx[r], j);
+          const bool lower = (lane & j) == 0;
+          const bool desc = (e & k2) == 0;
+          const bool mine_first = ranks_before(key[r], (long long)idx[r], ok, (long long)oi);
+          // the lower position keeps the element that ranks first iff this run is descending
+          const bool keep_mine = (lower == desc) ? mine_first : !mine_first;
+          const bool same = (key[r] == ok) && (idx[r] == oi);
+          if (!keep_mine && !same) { key[r] = ok; idx[r] = oi; }
+        }
+      }
+    }
+  }
+}
+
+struct SearchEpilogue {
+  const SearchParams& p;
+  float* invc_s;  // [2][256] in shared memory
+  float thr;
+  int cnt;
+  int tcount;
+  __device__ SearchEpilogue(const SearchParams& p_, float* s) : p(p_), invc_s(s), thr(kNegInf), cnt(0), tcount(0) {}
+
+  __device__ __forceinline__ long long ws_base(int row) const {
+    return (static_cast<long long>(blockIdx.x) * kBM + row) * kCap;
+  }
+
+  __device__ __forceinline__ void item_begin(const WorkItem&, int) {
+    thr = kNegInf;
+    cnt = 0;
+  }
+
+  // Compact the buffers of the rows selected by `mask` (warp-uniform) to their top-k.
+  // final != 0: also emit the sorted partial result for (query row, split).
+  __device__ __forceinline__ void compact(uint32_t mask, int row, bool final, const WorkItem& w) {
+    const int lane = threadIdx.x & 31;
+    const int row0 = row - lane;
+    __syncwarp();
+    while (mask) {
+      const int L = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const long long base = ws_base(row0 + L);
+      const int cntL = __shfl_sync(0xffffffffu, cnt, L);
+      float key[4];
+      int idx[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int e = r * 32 + lane;
+        const bool ok = e < cntL;
+        key[r] = ok ? p.ws_scores[base + e] : kNegInf;
+        idx[r] = ok ? p.ws_idx[base + e] : 0x7fffffff;
+      }
+      warp_bitonic_desc<4, int>(key, idx);
+      const int keep = min(cntL, p.k);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int e = r * 32 + lane;
+        if (e < keep) {
+          p.ws_scores[base + e] = key[r];
+          p.ws_idx[base + e] = idx[r];
+        }
+      }
+      // k-th best (element k-1) becomes the new admission threshold
+      const int kr = (p.k - 1) >> 5, kl = (p.k - 1) & 31;
+      float kth = kNegInf;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float v = __shfl_sync(0xffffffffu, key[r], kl);
+        if (r == kr) kth = v;
+      }
+      if (lane == L) {
+        cnt = keep;
+        thr = (cntL >= p.k) ? kth : kNegInf;
+      }
+      if (final) {
+        const long long q = static_cast<long long>(w.m_blk) * kBM + row0 + L;
+        if (q < p.Q) {
+          const int split = w.n_begin / p.tiles_per_split;
+          const long long ob = (q * p.splits + split) * p.k;
+          const float qi = p.q_inv[q];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int e = r * 32 + lane;
+            if (e < p.k) {
+              p.part_scores[ob + e] = (e < keep) ? key[r] * qi : kFaissNeg;
+              p.part_idx[ob + e] = (e < keep) ? idx[r] : -1;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  __device__ __forceinline__ void tile(const WorkItem& w, int n_blk, uint32_t tmem_acc, int row) {
+    float* invc = invc_s + (tcount & 1) * kSearchBN;
+    ++tcount;
+    const long long col_base = static_cast<long long>(n_blk) * kSearchBN;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const long long c = col_base + row + h * kBM;
+      invc[row + h * kBM] = (c < p.N) ? p.c_inv[c] : 0.f;
+    }
+    named_bar_sync(1, kNumEpiThreads);
+    const bool tail = col_base + kSearchBN > p.N;
+    const long long wsb = ws_base(row);
+#pragma unroll 1
+    for (int c = 0; c < kSearchBN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_acc + c * 32, r);
+      tmem_ld_wait();
+      float s[32];
+      float m = kNegInf;
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 iv = *reinterpret_cast<const float4*>(invc + c * 32 + j4 * 4);
+        s[j4 * 4 + 0] = __uint_as_float(r[j4 * 4 + 0]) * iv.x;
+        s[j4 * 4 + 1] = __uint_as_float(r[j4 * 4 + 1]) * iv.y;
+        s[j4 * 4 + 2] = __uint_as_float(r[j4 * 4 + 2]) * iv.z;
+        s[j4 * 4 + 3] = __uint_as_float(r[j4 * 4 + 3]) * iv.w;
+      }
+      if (tail) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col_base + c * 32 + j >= p.N) s[j] = kNegInf;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) m = fmaxf(m, s[j]);
+      if (m > thr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (s[j] > thr) {
+            p.ws_scores[wsb + cnt] = s[j];
+            p.ws_idx[wsb + cnt] = static_cast<int>(col_base + c * 32 + j);
+            ++cnt;
+          }
+        }
+      }
+      const uint32_t need = __ballot_sync(0xffffffffu, cnt > kCap - 32);
+      if (need) compact(need, row, false, w);
+    }
+  }
+
+  __device__ __forceinline__ void item_end(const WorkItem& w, int row) {
+    compact(0xffffffffu, row, true, w);
+  }
+};
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+ip_topk_kernel(const __grid_constant__ GemmTensorMaps maps, const SearchParams p,
+               const SearchSched sched, const uint32_t idesc) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem_1024(smem_raw);
+  using SM = GemmSmem<kSearchBN>;
+  float* invc_s = reinterpret_cast<float*>(smem + SM::kRingBytes + SM::kBarBytes);
+  SearchEpilogue epi(p, invc_s);
+  gemm_body<kSearchBN, false, false>(&maps.a, &maps.b, idesc, sched, epi, smem);
+}
+
+// ---------------------------------------------------------------------------------
+// inv-norm: one warp per row
+// ---------------------------------------------------------------------------------
+__global__ void row_inv_norm_kernel(const uint16_t* __restrict__ x, int dtype, long long rows, int d,
+                                    long long ld, float* __restrict__ inv) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const uint16_t* xr = x + row * ld;
+  float acc = 0.f;
+  for (int i = lane * 8; i < d; i += 256) {
+    const uint4 u = *reinterpret_cast<const uint4*>(xr + i);
+    const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float a, b;
+      if (dtype == UNIIR_BF16) {
+        a = __uint_as_float(wv[t] << 16);
+        b = __uint_as_float(wv[t] & 0xFFFF0000u);
+      } else {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&wv[t]));
+        a = f.x; b = f.y;
+      }
+      acc = fmaf(a, a, acc);
+      acc = fmaf(b, b, acc);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) inv[row] = acc > 0.f ? 1.f / sqrtf(acc) : 0.f;
+}
+
+// ---------------------------------------------------------------------------------
+// k-way merge: one warp per query, bitonic over L*k <= 32*R entries
+// ---------------------------------------------------------------------------------
+template <int R>
+__global__ void topk_merge_kernel(const float* __restrict__ in_s, const void* __restrict__ in_i,
+                                  int idx64, long long Q, int L, int k, long long q_stride,
+                                  long long l_stride, const long long* __restrict__ list_offset,
+                                  const long long* __restrict__ id_table, float* __restrict__ out_s,
+                                  long long* __restrict__ out_i) {
+  const long long q = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (q >= Q) return;
+  const int lane = threadIdx.x & 31;
+  float key[R];
+  long long idx[R];
+  const int total = L * k;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int e = r * 32 + lane;
+    key[r] = kNegInf;
+    idx[r] = 0x7fffffffffffffffLL;
+    if (e < total) {
+      const int l = e / k, j = e - l * k;
+      const long long off = q * q_stride + l * l_stride + j;
+      const long long raw = idx64 ? static_cast<const long long*>(in_i)[off]
+                                  : static_cast<long long>(static_cast<const int*>(in_i)[off]);
+      if (raw >= 0) {
+        key[r] = in_s[off];
+        idx[r] = raw + (list_offset ? list_offset[l] : 0);
+      }
+    }
+  }
+  warp_bitonic_desc<R, long long>(key, idx);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int e = r * 32 + lane;
+    if (e < k) {
+      const bool ok = idx[r] != 0x7fffffffffffffffLL;
+      out_s[q * k + e] = ok ? key[r] : kFaissNeg;
+      out_i[q * k + e] = ok ? (id_table ? id_table[idx[r]] : idx[r]) : -1;
+    }
+  }
+}
+
+static void plan_splits(long long Q, long long N, int* splits, int* tiles_per_split, int* n_tiles,
+                        int* n_qtiles) {
+  const int sms = num_sms();
+  const int nq = static_cast<int>((Q + kBM - 1) / kBM);
+  const int nt = static_cast<int>((N + kSearchBN - 1) / kSearchBN);
+  int best_s = 1;
+  double best_cost = 1e300;
+  for (int s = 1; s <= 64 && s <= nt; ++s) {
+    const int tps = (nt + s - 1) / s;
+    if (s > 1 && tps < 8) break;
+    const long long items = 1LL * nq * s;
+    const long long waves = (items + sms - 1) / sms;
+    // time ~ waves * (tiles per item + fixed per-item cost of ~2 tile-times)
+    const double cost = static_cast<double>(waves) * (tps + 2.0);
+    if (cost < best_cost * 0.995) { best_cost = cost; best_s = s; }
+  }
+  *splits = best_s;
+  *tiles_per_split = (nt + best_s - 1) / best_s;
+  *n_tiles = nt;
+  *n_qtiles = nq;
+}
+
+}  // namespace uniir
+
+using namespace uniir;
+
+extern "C" int uniir_row_inv_norm(const void* x, int32_t dtype, int64_t rows, int32_t d, int64_t ld,
+                                  float* inv, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  UNIIR_CHECK_ARG(x && inv && rows >= 0 && d > 0, "uniir_row_inv_norm: bad args");
+  UNIIR_CHECK_ARG(d % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+                  "uniir_row_inv_norm: d, ld must be multiples of 8 and x 16B aligned");
+  UNIIR_CHECK_ARG(dtype == UNIIR_BF16 || dtype == UNIIR_F16, "uniir_row_inv_norm: dtype");
+  if (rows == 0) return UNIIR_OK;
+  const int threads = 256;
+  const long long blocks = (rows * 32 + threads - 1) / threads;
+  row_inv_norm_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+      static_cast<const uint16_t*>(x), dtype, rows, d, ld, inv);
+  count_launch();
+  UNIIR_CUDA_OK(cudaGetLastError());
+  return UNIIR_OK;
+}
+
+extern "C" int uniir_ip_topk_plan(int64_t Q, int64_t N, int32_t k, int32_t* splits,
+                                  size_t* workspace_bytes) {
+  UNIIR_CHECK_ARG(Q > 0 && N > 0 && k > 0 && k <= kMaxK && splits && workspace_bytes,
+                  "uniir_ip_topk_plan: bad args (k must be in [1,%d])", kMaxK);
+  int s, tps, nt, nq;
+  plan_splits(Q, N, &s, &tps, &nt, &nq);
+  *splits = s;
+  *workspace_bytes = static_cast<size_t>(num_sms()) * kBM * kCap * (sizeof(float) + sizeof(int));
+  return UNIIR_OK;
+}
+
+extern "C" int uniir_ip_topk(const void* q, const float* q_inv, const void* c, const float* c_inv,
+                             int64_t Q, int64_t N, int32_t d, int32_t k, int32_t splits,
+                             float* part_scores, int32_t* part_idx, void* workspace,
+                             size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  UNIIR_CHECK_ARG(q && q_inv && c && c_inv && part_scores && part_idx && workspace,
+                  "uniir_ip_topk: null pointer");
+  UNIIR_CHECK_ARG(Q > 0 && N > 0 && N < (1LL << 31) && d > 0 && d % 8 == 0,
+                  "uniir_ip_topk: bad shape Q=%lld N=%lld d=%d", (long long)Q, (long long)N, d);
+  UNIIR_CHECK_ARG(k > 0 && k <= kMaxK, "uniir_ip_topk: k must be in [1,%d]", kMaxK);
+  int s, tps, nt, nq;
+  plan_splits(Q, N, &s, &tps, &nt, &nq);
+  UNIIR_CHECK_ARG(splits == s, "uniir_ip_topk: splits=%d does not match uniir_ip_topk_plan (%d)",
+                  splits, s);
+  const int sms = num_sms();
+  const size_t need = static_cast<size_t>(sms) * kBM * kCap * (sizeof(float) + sizeof(int));
+  UNIIR_CHECK_ARG(workspace_bytes >= need, "uniir_ip_topk: workspace too small (%zu < %zu)",
+                  workspace_bytes, need);
+
+  GemmTensorMaps maps;
+  int rc = make_tmap_2d(&maps.a, q, UNIIR_F16, d, Q, d, kBK, kBM);
+  if (rc) return rc;
+  rc = make_tmap_2d(&maps.b, c, UNIIR_F16, d, N, d, kBK, kSearchBN);
+  if (rc) return rc;
+
+  SearchParams p;
+  p.Q = Q; p.N = N; p.k = k; p.splits = s; p.n_qtiles = nq; p.tiles_per_split = tps;
+  p.n_tiles = nt; p.kb_total = (d + kBK - 1) / kBK;
+  p.q_inv = q_inv; p.c_inv = c_inv;
+  p.part_scores = part_scores; p.part_idx = part_idx;
+  p.ws_scores = static_cast<float*>(workspace);
+  p.ws_idx = reinterpret_cast<int*>(p.ws_scores + static_cast<size_t>(sms) * kBM * kCap);
+  SearchSched sched{nq, s, tps, nt, p.kb_total};
+
+  using SM = GemmSmem<kSearchBN>;
+  const int smem_bytes = SM::kRingBytes + SM::kBarBytes + 2 * kSearchBN * sizeof(float) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    UNIIR_CUDA_OK(cudaFuncSetAttribute(ip_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       smem_bytes));
+    attr_set = true;
+  }
+  const long long items = 1LL * nq * s;
+  const int grid = items < sms ? static_cast<int>(items) : sms;
+  const uint32_t idesc = make_idesc_f16(false, false, false, kBM, kSearchBN);
+  ip_topk_kernel<<<grid, kNumThreads, smem_bytes, stream>>>(maps, p, sched, idesc);
+  count_launch();
+  UNIIR_CUDA_OK(cudaGetLastError());
+  return UNIIR_OK;
+}
+
+extern "C" int uniir_topk_merge(const float* in_scores, const void* in_idx, int32_t idx_is_64,
+                                int64_t Q, int32_t L, int32_t k, int64_t q_stride, int64_t l_stride,
+                                const int64_t* list_offset, const int64_t* id_table,
+                                float* out_scores, int64_t* out_ids, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  UNIIR_CHECK_ARG(in_scores && in_idx && out_scores && out_ids, "uniir_topk_merge: null pointer");
+  UNIIR_CHECK_ARG(Q >= 0 && L > 0 && k > 0 && 1LL * L * k <= 512,
+                  "uniir_topk_merge: need L*k <= 512 (L=%d k=%d)", L, k);
+  if (Q == 0) return UNIIR_OK;
+  const int total = L * k;
+  const int threads = 128;
+  const long long blocks = (Q * 32 + threads - 1) / threads;
+  const long long* lo = reinterpret_cast<const long long*>(list_offset);
+  const long long* idt = reinterpret_cast<const long long*>(id_table);
+  long long* oi = reinterpret_cast<long long*>(out_ids);
+#define UNIIR_MERGE(R_)                                                                        \
+  topk_merge_kernel<R_><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(                \
+      in_scores, in_idx, idx_is_64, Q, L, k, q_stride, l_stride, lo, idt, out_scores, oi)
+  if (total <= 64) UNIIR_MERGE(2);
+  else if (total <= 128) UNIIR_MERGE(4);
+  else if (total <= 256) UNIIR_MERGE(8);
+  else UNIIR_MERGE(16);
+#undef UNIIR_MERGE
+  count_launch();
+  UNIIR_CUDA_OK(cudaGetLastError());
+  return UNIIR_OK;
+}

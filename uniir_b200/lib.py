@@ -1,0 +1,88 @@
+"""ctypes binding of libuniir_b200.so (include/uniir_b200.h).
+
+The product path has NO fallback: if the shared library is missing or a call fails, an
+exception is raised.  Nothing here imports ``oracle``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libuniir_b200.so")
+
+BF16, F16, F32 = 0, 1, 2
+ACT_NONE, ACT_QUICKGELU, ACT_GELU = 0, 1, 2
+
+
+class UniirError(RuntimeError):
+    pass
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("A", C.c_void_p), ("lda", C.c_int64), ("a_mn", C.c_int32),
+        ("B", C.c_void_p), ("ldb", C.c_int64), ("b_mn", C.c_int32),
+        ("in_dtype", C.c_int32),
+        ("out", C.c_void_p), ("ldo", C.c_int64), ("out_dtype", C.c_int32),
+        ("bias", C.c_void_p),
+        ("act", C.c_int32),
+        ("residual", C.c_void_p), ("ldr", C.c_int64), ("res_dtype", C.c_int32),
+        ("aux_out", C.c_void_p), ("ld_aux", C.c_int64),
+        ("act_grad_src", C.c_void_p), ("ld_ags", C.c_int64),
+        ("alpha", C.c_float),
+        ("accumulate", C.c_int32),
+        ("split_k", C.c_int32),
+    ]
+
+
+_SIGS = {
+    "uniir_abi_version": (C.c_int, []),
+    "uniir_last_error": (C.c_char_p, []),
+    "uniir_launch_count": (C.c_int64, []),
+    "uniir_gemm_epi": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
+    "uniir_row_inv_norm": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int64,
+                                     C.c_void_p, C.c_void_p]),
+    "uniir_ip_topk_plan": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_int32),
+                                     C.POINTER(C.c_size_t)]),
+    "uniir_ip_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "uniir_topk_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
+                                   C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    """Names every entry point include/uniir_b200.h declares (kept in sync by a CPU test)."""
+    return sorted(_SIGS)
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise UniirError(
+                f"{LIB_PATH} is missing: build it with `python -m uniir_b200.build` "
+                "(there is no CPU or PyTorch fallback for the uniir_b200 hot path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)  # AttributeError if the ABI drifted
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().uniir_last_error()
+        raise UniirError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")
+
+
+def launch_count() -> int:
+    return int(load().uniir_launch_count())
