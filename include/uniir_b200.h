@@ -96,12 +96,94 @@ int uniir_ip_topk(const void* q, const float* q_inv, const void* c, const float*
  * list_offset[l] (int64, may be NULL) is added to idx (shard row offset);
  * id_table (int64, may be NULL) maps the resulting row to the user id (add_with_ids,
  * mbeir_retriever.py:103).  Output: fp32 [Q,k] descending + int64 [Q,k]; missing = -1 with
- * score -3.4028235e38 (FAISS convention).  L*k <= 512.  Replaces the host-side
+ * score -3.4028235e38 (FAISS convention).  k <= 64, any L.  Replaces the host-side
  * IndexShards merge behind mbeir_retriever.py:206,231. */
 int uniir_topk_merge(const float* in_scores, const void* in_idx, int32_t idx_is_64, int64_t Q,
                      int32_t L, int32_t k, int64_t q_stride, int64_t l_stride,
                      const int64_t* list_offset, const int64_t* id_table, float* out_scores,
                      int64_t* out_ids, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Row-wise kernels around the GEMMs (HBM-bound, 128-bit coalesced).
+ * ---------------------------------------------------------------------------------- */
+/* y[r,:] = LN(x[row_index ? row_index[r] : r, :]) * gamma + beta, fp32 statistics (two-pass).
+ * Replaces upstream CLIP `LayerNorm` (fp32 subclass; ln_pre/ln_1/ln_2/ln_post/ln_final,
+ * restated clip_ff.py:49,53,58,154).  y_dtype BF16 (GEMM input) or F32 (in-place ln_pre).
+ * mean/rstd [rows] optional (saved for backward). */
+int uniir_layernorm_fwd(const float* x, int64_t ldx, const int32_t* row_index, const float* gamma,
+                        const float* beta, float eps, int64_t rows, int32_t D, void* y, int64_t ldy,
+                        int32_t y_dtype, float* mean, float* rstd, void* stream);
+/* dx[src row] (+)= LN backward; dgamma/dbeta += column sums (atomic fp32). */
+int uniir_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_dtype, const float* x, int64_t ldx,
+                        const int32_t* row_index, const float* mean, const float* rstd,
+                        const float* gamma, int64_t rows, int32_t D, float* dx, int64_t lddx,
+                        int32_t dx_accumulate, float* dgamma, float* dbeta, void* stream);
+/* visual.conv1 (stride = kernel = patch, no bias; clip_ff.py:36) as im2col:
+ * img fp32 [B,3,H,W] -> bf16 [B*(H/P)^2, Kpad], k = c*P*P + py*P + px, zero padded. */
+int uniir_patch_im2col(const float* img, int32_t B, int32_t H, int32_t W, int32_t P, int32_t Kpad,
+                       void* out, void* stream);
+/* x0[b,s,:] = (s==0 ? class_embedding : patch[b,s-1,:]) + positional_embedding[s,:]
+ * (clip_ff.py:37-48).  patch bf16 [B*(S-1), D], x0 fp32 [B,S,D]. */
+int uniir_vision_embed_fwd(const void* patch, const float* cls, const float* pos, int32_t B, int32_t S,
+                           int32_t D, float* x0, void* stream);
+int uniir_vision_embed_bwd(const float* dx0, int32_t B, int32_t S, int32_t D, void* d_patch,
+                           float* d_cls, float* d_pos, void* stream);
+/* x[b,s,:] = token_embedding[ids[b,s]] + positional_embedding[s] (upstream CLIP.encode_text;
+ * clip_ff.py:149); eot_row[b] = b*S + argmax_s ids[b,s] (EOT pooling row). */
+int uniir_text_embed_fwd(const int32_t* ids, const float* tok, const float* pos, int32_t B, int32_t S,
+                         int32_t D, float* x, int32_t* eot_row, void* stream);
+int uniir_text_embed_bwd(const float* dx, const int32_t* ids, int32_t B, int32_t S, int32_t D,
+                         float* d_tok, float* d_pos, void* stream);
+/* Score fusion, clip_sf.py:61-63: out = t*txt_mask[:,None] + v*img_mask[:,None]. */
+int uniir_score_fuse_fwd(const float* t, const float* v, const int64_t* mt, const int64_t* mv, int64_t B,
+                         int32_t E, float* out, void* stream);
+int uniir_score_fuse_bwd(const float* d, const int64_t* mt, const int64_t* mv, int64_t B, int32_t E,
+                         void* dt_bf16, void* dv_bf16, void* stream);
+/* out[n] += sum_m dy[m,n]  (bias gradients; dy bf16). */
+int uniir_colsum_accum(const void* dy, int64_t M, int32_t N, int64_t ld, float* out, void* stream);
+int uniir_pad_cast_bf16(const float* src, int64_t rows, int32_t K, int32_t Kpad, void* dst, void* stream);
+int uniir_unpad_accum(const float* src, int64_t rows, int32_t K, int32_t Kpad, float* dst, void* stream);
+int uniir_cast_bf16(const float* src, int64_t n, void* dst, void* stream);
+/* Fused AdamW (torch.optim.AdamW semantics; reference clip_scorefusion/train.py:52-61 param
+ * groups, engine.py:41-45 step + zero_grad): p,g,m,v fp32 flat segments; g is multiplied by
+ * grad_scale, then zeroed; p_bf16 (optional) receives the bf16 shadow the GEMMs read. */
+int uniir_adamw_step(float* p, float* g, float* m, float* v, void* p_bf16, int64_t n, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                     float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Attention core softmax(QK^T/sqrt(64) [+causal]) V, head_dim 64, bf16, flash-style.
+ * qkv bf16 [B*S, 3*H*64] (q | k | v, head h at columns h*64 of each third -- the layout
+ * nn.MultiheadAttention.in_proj produces); out bf16 [B*S, H*64]; lse fp32 [B,H,S].
+ * Replaces the core of nn.MultiheadAttention in upstream CLIP ResidualAttentionBlock.
+ * ---------------------------------------------------------------------------------- */
+int uniir_attn_fwd(const void* qkv, int32_t B, int32_t S, int32_t H, int32_t causal, void* out, float* lse,
+                   void* stream);
+int uniir_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int32_t B,
+                   int32_t S, int32_t H, int32_t causal, float* delta_ws /* [B*H*S] */, void* dqkv,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * In-batch contrastive loss of CLIPScoreFusion (clip_sf.py:88-103,134-147), fp32.
+ *   normalize -> [host: all-gather p over ranks] -> fwd (one fused kernel: logits tiles,
+ *   online softmax, CE mean, argmax accuracy) -> bwd (dQ, d all_p, d logit_scale)
+ *   -> [host: reduce-scatter d all_p] -> normalize_bwd.
+ * ---------------------------------------------------------------------------------- */
+size_t uniir_infonce_workspace_bytes(int32_t bs, int32_t n_cols); /* zero-fill once */
+int uniir_infonce_normalize(const float* emb, const int32_t* q_idx, const int32_t* p_idx, int32_t bs,
+                            int32_t E, float* qn, float* pn, float* q_norm, float* p_norm, void* stream);
+int uniir_infonce_fwd(const float* qn, const float* all_p, int32_t bs, int32_t n_cols, int32_t E,
+                      const float* logit_scale_log, int32_t target_offset, float* loss, float* accuracy,
+                      float* lse, void* workspace, size_t workspace_bytes, void* stream);
+/* G: scratch fp32 [bs, n_cols].  grad_out: device scalar dL (NULL = 1).  d_logit_scale += . */
+int uniir_infonce_bwd(const float* qn, const float* all_p, int32_t bs, int32_t n_cols, int32_t E,
+                      const float* logit_scale_log, int32_t target_offset, const float* lse,
+                      const float* grad_out, float* G, float* d_qn, float* d_all_p,
+                      float* d_logit_scale, void* stream);
+int uniir_infonce_normalize_bwd(const int32_t* q_idx, const int32_t* p_idx, const float* qn,
+                                const float* pn, const float* q_norm, const float* p_norm,
+                                const float* d_qn, const float* d_pn, int32_t bs, int32_t E, float* d_emb,
+                                void* stream);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,8 @@ def gemm_case(M, N, K, a_mn, b_mn, dtype=torch.bfloat16, **kw):
     Af = (A.t() if a_mn else A).float()
     Bf = (B.t() if b_mn else B).float()
     ref = Af @ Bf.t()
-    out = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32, **kw)
+    o0 = torch.zeros(M, N, device=dev) if kw.get("split_k", 1) > 1 else None
+    out = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, out=o0, out_dtype=torch.float32, **kw)
     torch.cuda.synchronize()
     r, m = rel_err(out, ref)
     ok = r < 1e-3
@@ -187,6 +188,161 @@ def case_gemm_perf():
         ms2 = e0.elapsed_time(e1) / 10
         print(f"gemm perf M={M} N={N} K={K}: {ms:.3f} ms {2.0*M*N*K/ms/1e9:.1f} TF/s | cublas {ms2:.3f} ms {2.0*M*N*K/ms2/1e9:.1f} TF/s")
     return True
+
+
+if False:
+    name = sys.argv[1]
+    ok = globals()["case_" + name]()
+    print(f"CASE {name}: {'PASS' if ok else 'FAIL'}", flush=True)
+    sys.exit(0 if ok else 1)
+
+
+def case_rowops():
+    ok = True
+    F = torch.nn.functional
+    for D, rows in [(1024, 1000), (768, 333), (128, 50)]:
+        x = torch.randn(rows, D, device=dev) * 2 + 0.5
+        g = torch.randn(D, device=dev); b = torch.randn(D, device=dev)
+        y, mean, rstd = ops.layernorm_fwd(x, g, b, 1e-5, save_stats=True)
+        ref = F.layer_norm(x, (D,), g, b, 1e-5)
+        r, _ = rel_err(y, ref); print(f"ln fwd D={D} rel={r:.2e}"); ok &= r < 5e-3
+        y32 = ops.layernorm_fwd(x, g, b, 1e-5, out_dtype=torch.float32)
+        r, _ = rel_err(y32, ref); print(f"ln fwd fp32 rel={r:.2e}"); ok &= r < 1e-5
+        # backward
+        dy = torch.randn(rows, D, device=dev).bfloat16()
+        xr = x.clone().requires_grad_(True); gr = g.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
+        F.layer_norm(xr, (D,), gr, br, 1e-5).backward(dy.float())
+        dx = torch.ones(rows, D, device=dev); dg = torch.zeros(D, device=dev); db = torch.zeros(D, device=dev)
+        ops.layernorm_bwd(dy, x, mean, rstd, g, dx, dg, db)
+        r1, _ = rel_err(dx - 1, xr.grad); r2, _ = rel_err(dg, gr.grad); r3, _ = rel_err(db, br.grad)
+        print(f"ln bwd D={D} dx={r1:.2e} dgamma={r2:.2e} dbeta={r3:.2e}"); ok &= max(r1, r2, r3) < 1e-4
+    # gathered rows
+    x = torch.randn(10, 7, 128, device=dev); g = torch.randn(128, device=dev); b = torch.randn(128, device=dev)
+    idx = (torch.arange(10, device=dev) * 7 + torch.randint(0, 7, (10,), device=dev)).int()
+    y = ops.layernorm_fwd(x, g, b, 1e-5, row_index=idx, out_dtype=torch.float32)
+    r, _ = rel_err(y, F.layer_norm(x.view(70, 128)[idx.long()], (128,), g, b, 1e-5)); print(f"ln gather rel={r:.2e}"); ok &= r < 1e-5
+    # im2col + embed
+    img = torch.randn(3, 3, 56, 56, device=dev)
+    col = ops.patch_im2col(img, 14, 592)
+    ref = F.unfold(img, 14, stride=14).transpose(1, 2).reshape(3 * 16, 588)
+    r, _ = rel_err(col[:, :588], ref); z = col[:, 588:].abs().max().item(); print(f"im2col rel={r:.2e} pad={z}"); ok &= r < 5e-3 and z == 0
+    patch = torch.randn(3 * 16, 128, device=dev).bfloat16(); cls = torch.randn(128, device=dev); pos = torch.randn(17, 128, device=dev)
+    x0 = ops.vision_embed_fwd(patch, cls, pos, 3, 17, 128)
+    ref = torch.cat([cls.expand(3, 1, 128), patch.float().view(3, 16, 128)], 1) + pos
+    r, _ = rel_err(x0, ref); print(f"vision_embed rel={r:.2e}"); ok &= r < 1e-6
+    dx0 = torch.randn(3, 17, 128, device=dev); dpatch = torch.empty(48, 128, device=dev, dtype=torch.bfloat16)
+    dcls = torch.zeros(128, device=dev); dpos = torch.zeros(17, 128, device=dev)
+    ops.vision_embed_bwd(dx0, 3, 17, 128, dpatch, dcls, dpos)
+    r1, _ = rel_err(dpatch, dx0[:, 1:].reshape(48, 128)); r2, _ = rel_err(dcls, dx0[:, 0].sum(0)); r3, _ = rel_err(dpos, dx0.sum(0))
+    print(f"vision_embed bwd {r1:.2e} {r2:.2e} {r3:.2e}"); ok &= r1 < 5e-3 and r2 < 1e-6 and r3 < 1e-6
+    ids = torch.randint(1, 500, (5, 77), device=dev).int(); ids[:, 0] = 510; ids[torch.arange(5), torch.tensor([3, 10, 76, 5, 1])] = 511
+    tok = torch.randn(512, 64, device=dev); tpos = torch.randn(77, 64, device=dev)
+    x, eot = ops.text_embed_fwd(ids, tok, tpos)
+    r, _ = rel_err(x, tok[ids.long()] + tpos); e_ok = (eot.long() == torch.arange(5, device=dev) * 77 + ids.argmax(-1)).all().item()
+    print(f"text_embed rel={r:.2e} eot_ok={e_ok}"); ok &= r < 1e-6 and e_ok
+    dx = torch.randn(5, 77, 64, device=dev); dtok = torch.zeros(512, 64, device=dev); dtpos = torch.zeros(77, 64, device=dev)
+    ops.text_embed_bwd(dx, ids, dtok, dtpos)
+    ref = torch.zeros(512, 64, device=dev).index_add_(0, ids.long().flatten(), dx.view(-1, 64))
+    r1, _ = rel_err(dtok, ref); r2, _ = rel_err(dtpos, dx.sum(0)); print(f"text_embed bwd {r1:.2e} {r2:.2e}"); ok &= r1 < 1e-5 and r2 < 1e-6
+    # fuse / colsum / pad / adamw
+    t = torch.randn(9, 64, device=dev); v = torch.randn(9, 64, device=dev)
+    mt = torch.randint(0, 2, (9,), device=dev); mv = torch.randint(0, 2, (9,), device=dev)
+    f = ops.score_fuse_fwd(t, v, mt, mv); r, _ = rel_err(f, t * mt[:, None] + v * mv[:, None]); print(f"fuse rel={r:.2e}"); ok &= r < 1e-6
+    dy = torch.randn(3000, 200, device=dev).bfloat16(); cs = torch.ones(200, device=dev)
+    ops.colsum_accum(dy, cs); r, _ = rel_err(cs - 1, dy.float().sum(0)); print(f"colsum rel={r:.2e}"); ok &= r < 1e-4
+    w = torch.randn(20, 588, device=dev); wp = ops.pad_cast_bf16(w, 640); r, _ = rel_err(wp[:, :588], w); ok &= r < 5e-3 and wp[:, 588:].abs().max().item() == 0
+    acc = torch.ones(20, 588, device=dev); ops.unpad_accum(torch.randn(20, 640, device=dev), acc)
+    n = 100003
+    p = torch.randn(n, device=dev); g = torch.randn(n, device=dev); m = torch.zeros(n, device=dev); vv = torch.zeros(n, device=dev)
+    pr = p.clone().requires_grad_(True); opt = torch.optim.AdamW([pr], lr=1e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.2)
+    p16 = torch.empty(n, device=dev, dtype=torch.bfloat16)
+    for step in (1, 2, 3):
+        gg = torch.randn(n, device=dev); pr.grad = gg.clone(); opt.step()
+        g.copy_(gg); ops.adamw_step(p, g, m, vv, p16, 1e-3, (0.9, 0.98), 1e-6, 0.2, step)
+    r, mx = rel_err(p, pr.detach()); r2, _ = rel_err(p16, p); print(f"adamw rel={r:.2e} max={mx:.2e} g_zero={g.abs().max().item()} p16={r2:.2e}"); ok &= r < 1e-5 and g.abs().max().item() == 0
+    return ok
+
+
+def attn_ref(qkv, B, S, H, causal):
+    D = H * 64
+    q, k, v = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+    att = q @ k.transpose(-1, -2) * 0.125
+    if causal:
+        att = att + torch.full((S, S), float("-inf"), device=qkv.device).triu_(1)
+    p = att.softmax(-1)
+    return (p @ v).transpose(1, 2).reshape(B * S, D), torch.logsumexp(att, -1)
+
+
+def case_attn():
+    ok = True
+    for (B, S, H, causal) in [(2, 64, 1, False), (3, 257, 4, False), (5, 77, 3, True), (2, 197, 2, False), (2, 50, 2, False), (1, 130, 2, True)]:
+        qkv = (torch.randn(B * S, 3 * H * 64, device=dev) * 1.5).bfloat16().requires_grad_(False)
+        out, lse = ops.attn_fwd(qkv, B, S, H, causal)
+        qr = qkv.float().requires_grad_(True)
+        ref, rlse = attn_ref(qr, B, S, H, causal)
+        r1, _ = rel_err(out, ref); r2, m2 = rel_err(lse, rlse)
+        dout = torch.randn(B * S, H * 64, device=dev).bfloat16()
+        ref.backward(dout.float())
+        dqkv = ops.attn_bwd(qkv, out, dout, lse, B, S, H, causal)
+        D = H * 64
+        rq, _ = rel_err(dqkv[:, :D], qr.grad[:, :D]); rk, _ = rel_err(dqkv[:, D:2 * D], qr.grad[:, D:2 * D]); rv, _ = rel_err(dqkv[:, 2 * D:], qr.grad[:, 2 * D:])
+        good = r1 < 1e-2 and m2 < 1e-2 and max(rq, rk, rv) < 2e-2
+        print(f"attn B={B} S={S} H={H} causal={causal}: out={r1:.2e} lse_max={m2:.2e} dq={rq:.2e} dk={rk:.2e} dv={rv:.2e} {'OK' if good else 'FAIL'}", flush=True)
+        ok &= good
+    # timing at model shape
+    B, S, H = 64, 257, 16
+    qkv = torch.randn(B * S, 3 * H * 64, device=dev).bfloat16()
+    out, lse = ops.attn_fwd(qkv, B, S, H, False); dout = torch.randn_like(out); dqkv = torch.empty_like(qkv)
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e2 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): ops.attn_fwd(qkv, B, S, H, False, out=out, lse=lse)
+    e1.record()
+    for _ in range(10): ops.attn_bwd(qkv, out, dout, lse, B, S, H, False, dqkv=dqkv)
+    e2.record(); torch.cuda.synchronize()
+    fl = 4.0 * B * H * S * S * 64
+    print(f"attn perf B=64 S=257 H=16: fwd {e0.elapsed_time(e1)/10:.3f} ms ({fl/(e0.elapsed_time(e1)/10)/1e9:.1f} TF/s)  bwd {e1.elapsed_time(e2)/10:.3f} ms ({2.5*fl/(e1.elapsed_time(e2)/10)/1e9:.1f} TF/s)")
+    return ok
+
+
+def case_infonce():
+    ok = True
+    F = torch.nn.functional
+    for (bs, W, E, rank) in [(4, 1, 64, 0), (100, 1, 512, 0), (64, 4, 768, 2), (512, 8, 768, 5)]:
+        n = bs * W
+        emb = torch.randn(2 * bs, E, device=dev)
+        q_idx = torch.arange(0, 2 * bs, 2, device=dev).int(); p_idx = q_idx + 1
+        ls = torch.tensor(4.6052, device=dev)
+        nce = ops.InfoNCE(bs, n, E, dev)
+        others = F.normalize(torch.randn(n, E, device=dev), dim=-1)
+        nce.all_p.copy_(others)
+        off = rank * bs
+        nce.normalize(emb, q_idx, p_idx, off)
+        for rep in range(2):  # twice: the workspace must self-reset
+            loss, acc = nce.forward(ls, off)
+        er = emb.clone().requires_grad_(True); lr_ = ls.clone().requires_grad_(True)
+        q = F.normalize(er[q_idx.long()], dim=-1); p = F.normalize(er[p_idx.long()], dim=-1)
+        allp = others.clone(); allp = torch.cat([allp[:off], p, allp[off + bs:]], 0)
+        allp_leaf = allp.detach().requires_grad_(True)
+        score = q @ allp_leaf.t() * lr_.exp()
+        tgt = off + torch.arange(bs, device=dev)
+        rl = F.cross_entropy(score, tgt); ra = (score.argmax(1) == tgt).float().mean()
+        rl.backward()
+        dls = torch.zeros((), device=dev)
+        d_qn, d_allp = nce.backward(ls, off, dls)
+        r1, _ = rel_err(d_allp, allp_leaf.grad)
+        # full chain for local rows: d_emb
+        d_emb = torch.zeros(2 * bs, E, device=dev)
+        nce.normalize_bwd(q_idx, p_idx, d_allp[off:off + bs], d_emb, off)
+        er2 = emb.clone().requires_grad_(True)
+        q2 = F.normalize(er2[q_idx.long()], dim=-1); p2 = F.normalize(er2[p_idx.long()], dim=-1)
+        allp2 = torch.cat([others[:off], p2, others[off + bs:]], 0)
+        F.cross_entropy(q2 @ allp2.t() * ls.exp(), tgt).backward()
+        r2, _ = rel_err(d_emb, er2.grad)
+        good = abs(loss.item() - rl.item()) < 1e-4 * max(1, abs(rl.item())) and abs(acc.item() - ra.item()) < 1e-6 and r1 < 1e-4 and r2 < 1e-4 and abs(dls.item() - lr_.grad.item()) < 1e-3 * max(1, abs(lr_.grad.item()))
+        print(f"infonce bs={bs} W={W} E={E}: loss {loss.item():.6f} vs {rl.item():.6f} acc {acc.item():.4f} vs {ra.item():.4f} d_allp={r1:.2e} d_emb={r2:.2e} dls {dls.item():.5f} vs {lr_.grad.item():.5f} {'OK' if good else 'FAIL'}", flush=True)
+        ok &= good
+    return ok
 
 
 if __name__ == "__main__":

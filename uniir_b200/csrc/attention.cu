@@ -1,0 +1,477 @@
+// Multi-head self-attention core for short sequences (S = 257 / 197 / 77 causal / 100),
+// head_dim 64, bf16 in / fp32 softmax + accumulate.  Replaces the softmax(QK^T/8 [+mask])V
+// inside nn.MultiheadAttention (upstream CLIP resblocks; causal mask = upstream
+// build_attention_mask) and its autograd backward.
+//
+// Flash-style: a CTA owns a 64-row query (or key) block, streams the other operand through
+// shared memory in 64-row blocks, keeps scores in registers and never writes the S x S matrix.
+// Tensor-core path is mma.sync m16n8k16 (HMMA): attention is ~4 % of the tower FLOPs and the
+// whole K/V of a head fits in one SM's shared memory, so the tcgen05/TMEM machinery (128-row
+// UMMA tiles, single-thread issue) buys nothing at S <= 257; the GEMMs that carry 96 % of the
+// FLOPs are tcgen05 (gemm_sm100.cuh).
+//   fwd     : grid (ceil(S/64), H, B)   O, LSE
+//   bwd dQ  : grid (ceil(S/64), H, B)   Q-block stationary, loops KV blocks
+//   bwd dKV : grid (ceil(S/64), H, B)   KV-block stationary, loops Q blocks
+// S is recomputed in both backward kernels (7 instead of 5 GEMM units; no atomics, no dQ
+// round trip through HBM).
+#include <cuda_bf16.h>
+
+#include "host_util.cuh"
+
+namespace uniir {
+
+constexpr int kHD = 64;          // head dim
+constexpr int kBlk = 64;         // rows per block
+constexpr int kTileBytes = kBlk * kHD * 2;  // 8 KB
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+// 64x64 bf16 tile, 128 B rows, 16 B chunks XOR-swizzled by (row & 7).
+// Rows >= valid_rows are zero-filled.  128 threads.
+__device__ __forceinline__ void load_tile(uint32_t tile, const __nv_bfloat16* g, long long ld, int row0,
+                                          int valid_rows /*absolute row limit*/) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int id = threadIdx.x + i * 128;
+    const int r = id >> 3, c = id & 7;
+    const bool ok = (row0 + r) < valid_rows;
+    const __nv_bfloat16* src = g + static_cast<long long>(ok ? row0 + r : 0) * ld + c * 8;
+    cp_async16(tile + r * 128 + ((c ^ (r & 7)) << 4), src, ok);
+  }
+}
+// A fragment (16 rows x 16 k) of a tile: rows [rbase, rbase+16), k-step kk (16 dims)
+__device__ __forceinline__ void frag_a(uint32_t tile, int rbase, int kk, uint32_t (&a)[4]) {
+  const int l = threadIdx.x & 31, mi = l >> 3;
+  const int r = rbase + (mi & 1) * 8 + (l & 7);
+  const int ch = kk * 2 + (mi >> 1);
+  ldsm_x4(tile + r * 128 + ((ch ^ (r & 7)) << 4), a[0], a[1], a[2], a[3]);
+}
+// B fragments, operand stored [n][k] (k contiguous): n-tiles j, j+1 (8 rows each), k-step kk.
+// b[0],b[1] -> n-tile j ; b[2],b[3] -> n-tile j+1
+__device__ __forceinline__ void frag_b_nk(uint32_t tile, int j, int kk, uint32_t (&b)[4]) {
+  const int l = threadIdx.x & 31, mi = l >> 3;
+  const int r = (j + (mi >> 1)) * 8 + (l & 7);
+  const int ch = kk * 2 + (mi & 1);
+  ldsm_x4(tile + r * 128 + ((ch ^ (r & 7)) << 4), b[0], b[1], b[2], b[3]);
+}
+// B fragments, operand stored [k][n] (n contiguous): k-step t (16 rows), n-tiles jd, jd+1.
+__device__ __forceinline__ void frag_b_kn(uint32_t tile, int t, int jd, uint32_t (&b)[4]) {
+  const int l = threadIdx.x & 31, mi = l >> 3;
+  const int r = t * 16 + (mi & 1) * 8 + (l & 7);
+  const int ch = jd + (mi >> 1);
+  ldsm_x4_t(tile + r * 128 + ((ch ^ (r & 7)) << 4), b[0], b[1], b[2], b[3]);
+}
+
+struct AttnParams {
+  const __nv_bfloat16* qkv;  // [B*S, 3*D]
+  __nv_bfloat16* out;        // [B*S, D]
+  float* lse;                // [B, H, S]
+  const __nv_bfloat16* dout; // [B*S, D]
+  float* delta;              // [B, H, S]
+  __nv_bfloat16* dqkv;       // [B*S, 3*D]
+  int B, S, H, D, causal;
+  float scale;               // 1/sqrt(64)
+};
+
+// ---------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
+  __shared__ __align__(128) uint8_t sm[3 * kTileBytes];
+  const uint32_t sQ = s_u32(sm), sK = sQ + kTileBytes, sV = sK + kTileBytes;
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long ld = 3LL * p.D;
+  const __nv_bfloat16* base = p.qkv + static_cast<long long>(b) * p.S * ld + h * kHD;
+  const int q0 = qb * kBlk;
+  load_tile(sQ, base, ld, q0, p.S);
+  cp_async_wait_all();
+  __syncthreads();
+  uint32_t qa[4][4];
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) frag_a(sQ, warp * 16, kk, qa[kk]);
+
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const float sc = p.scale * kLog2e;
+  const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;  // this thread's two query rows
+  const int kv_end = p.causal ? min(p.S, q0 + kBlk) : p.S;
+
+  for (int k0 = 0; k0 < kv_end; k0 += kBlk) {
+    __syncthreads();
+    load_tile(sK, base + p.D, ld, k0, p.S);
+    load_tile(sV, base + 2 * p.D, ld, k0, p.S);
+    cp_async_wait_all();
+    __syncthreads();
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        uint32_t bb[4];
+        frag_b_nk(sK, j, kk, bb);
+        mma_bf16(s[j], qa[kk], bb[0], bb[1]);
+        mma_bf16(s[j + 1], qa[kk], bb[2], bb[3]);
+      }
+    }
+    // mask + running max
+    float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = k0 + j * 8 + (lane & 3) * 2 + (e & 1);
+        const int qr = (e < 2) ? r0 : r1;
+        const bool dead = key >= p.S || (p.causal && key > qr);
+        s[j][e] = dead ? -INFINITY : s[j][e] * sc;
+      }
+      bm0 = fmaxf(bm0, fmaxf(s[j][0], s[j][1]));
+      bm1 = fmaxf(bm1, fmaxf(s[j][2], s[j][3]));
+    }
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+    const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);
+    const float base0 = (nm0 == -INFINITY) ? 0.f : nm0, base1 = (nm1 == -INFINITY) ? 0.f : nm1;
+    const float c0 = exp2f(m0 - base0), c1 = exp2f(m1 - base1);  // exp2(-inf)=0 on first block
+    m0 = nm0; m1 = nm1;
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = exp2f(s[j][0] - base0); s[j][1] = exp2f(s[j][1] - base0);
+      s[j][2] = exp2f(s[j][2] - base1); s[j][3] = exp2f(s[j][3] - base1);
+      rs0 += s[j][0] + s[j][1];
+      rs1 += s[j][2] + s[j][3];
+      o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1;
+    }
+    l0 = l0 * c0 + rs0;
+    l1 = l1 * c1 + rs1;
+    // O += P V
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16(s[2 * t][0], s[2 * t][1]);
+      pa[1] = pack_bf16(s[2 * t][2], s[2 * t][3]);
+      pa[2] = pack_bf16(s[2 * t + 1][0], s[2 * t + 1][1]);
+      pa[3] = pack_bf16(s[2 * t + 1][2], s[2 * t + 1][3]);
+#pragma unroll
+      for (int jd = 0; jd < 8; jd += 2) {
+        uint32_t bb[4];
+        frag_b_kn(sV, t, jd, bb);
+        mma_bf16(o[jd], pa, bb[0], bb[1]);
+        mma_bf16(o[jd + 1], pa, bb[2], bb[3]);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
+  __nv_bfloat16* ob = p.out + static_cast<long long>(b) * p.S * p.D + h * kHD;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = j * 8 + (lane & 3) * 2;
+    if (r0 < p.S) *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(r0) * p.D + col) = pack_bf16(o[j][0] * i0, o[j][1] * i0);
+    if (r1 < p.S) *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(r1) * p.D + col) = pack_bf16(o[j][2] * i1, o[j][3] * i1);
+  }
+  if (p.lse && (lane & 3) == 0) {
+    float* lp = p.lse + (static_cast<long long>(b) * p.H + h) * p.S;
+    // natural-log LSE of the scaled scores
+    if (r0 < p.S) lp[r0] = (m0 + log2f(l0)) / kLog2e;
+    if (r1 < p.S) lp[r1] = (m1 + log2f(l1)) / kLog2e;
+  }
+}
+
+// delta[b,h,s] = sum_d dO[b,s,h,d] * O[b,s,h,d]; one warp per (b,s,h)
+__global__ void attn_delta_kernel(const AttnParams p) {
+  const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long total = static_cast<long long>(p.B) * p.S * p.H;
+  if (w >= total) return;
+  const int lane = threadIdx.x & 31;
+  const int h = w % p.H;
+  const long long bs = w / p.H;
+  const long long off = bs * p.D + h * kHD + lane * 2;
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(p.dout + off);
+  const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162*>(p.out + off);
+  float v = __bfloat162float(a.x) * __bfloat162float(c.x) + __bfloat162float(a.y) * __bfloat162float(c.y);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) {
+    const long long b = bs / p.S, s = bs % p.S;
+    p.delta[(b * p.H + h) * p.S + s] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// backward dQ: Q-block stationary.  dQ = scale * sum_kv  [P o (dO V^T - delta)] K
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnParams p) {
+  __shared__ __align__(128) uint8_t sm[4 * kTileBytes];
+  const uint32_t sQ = s_u32(sm), sDO = sQ + kTileBytes, sK = sDO + kTileBytes, sV = sK + kTileBytes;
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long ld = 3LL * p.D;
+  const __nv_bfloat16* base = p.qkv + static_cast<long long>(b) * p.S * ld + h * kHD;
+  const __nv_bfloat16* dob = p.dout + static_cast<long long>(b) * p.S * p.D + h * kHD;
+  const int q0 = qb * kBlk;
+  load_tile(sQ, base, ld, q0, p.S);
+  load_tile(sDO, dob, p.D, q0, p.S);
+  cp_async_wait_all();
+  __syncthreads();
+  uint32_t qa[4][4], da[4][4];
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) { frag_a(sQ, warp * 16, kk, qa[kk]); frag_a(sDO, warp * 16, kk, da[kk]); }
+  const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
+  const float* lp = p.lse + (static_cast<long long>(b) * p.H + h) * p.S;
+  const float* dp = p.delta + (static_cast<long long>(b) * p.H + h) * p.S;
+  const float lse0 = (r0 < p.S) ? lp[r0] * kLog2e : 0.f, lse1 = (r1 < p.S) ? lp[r1] * kLog2e : 0.f;
+  const float dl0 = (r0 < p.S) ? dp[r0] : 0.f, dl1 = (r1 < p.S) ? dp[r1] : 0.f;
+  const float sc = p.scale * kLog2e;
+  float dq[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
+  const int kv_end = p.causal ? min(p.S, q0 + kBlk) : p.S;
+  for (int k0 = 0; k0 < kv_end; k0 += kBlk) {
+    __syncthreads();
+    load_tile(sK, base + p.D, ld, k0, p.S);
+    load_tile(sV, base + 2 * p.D, ld, k0, p.S);
+    cp_async_wait_all();
+    __syncthreads();
+    float s[8][4], dpv[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      dpv[j][0] = dpv[j][1] = dpv[j][2] = dpv[j][3] = 0.f;
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        uint32_t bb[4];
+        frag_b_nk(sK, j, kk, bb);
+        mma_bf16(s[j], qa[kk], bb[0], bb[1]);
+        mma_bf16(s[j + 1], qa[kk], bb[2], bb[3]);
+        frag_b_nk(sV, j, kk, bb);
+        mma_bf16(dpv[j], da[kk], bb[0], bb[1]);
+        mma_bf16(dpv[j + 1], da[kk], bb[2], bb[3]);
+      }
+    }
+    // dS = P o (dP - delta)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = k0 + j * 8 + (lane & 3) * 2 + (e & 1);
+        const int qr = (e < 2) ? r0 : r1;
+        const bool dead = key >= p.S || qr >= p.S || (p.causal && key > qr);
+        const float pe = dead ? 0.f : exp2f(s[j][e] * sc - ((e < 2) ? lse0 : lse1));
+        s[j][e] = pe * (dpv[j][e] - ((e < 2) ? dl0 : dl1));
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16(s[2 * t][0], s[2 * t][1]);
+      pa[1] = pack_bf16(s[2 * t][2], s[2 * t][3]);
+      pa[2] = pack_bf16(s[2 * t + 1][0], s[2 * t + 1][1]);
+      pa[3] = pack_bf16(s[2 * t + 1][2], s[2 * t + 1][3]);
+#pragma unroll
+      for (int jd = 0; jd < 8; jd += 2) {
+        uint32_t bb[4];
+        frag_b_kn(sK, t, jd, bb);
+        mma_bf16(dq[jd], pa, bb[0], bb[1]);
+        mma_bf16(dq[jd + 1], pa, bb[2], bb[3]);
+      }
+    }
+  }
+  __nv_bfloat16* ob = p.dqkv + static_cast<long long>(b) * p.S * ld + h * kHD;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = j * 8 + (lane & 3) * 2;
+    if (r0 < p.S) *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(r0) * ld + col) = pack_bf16(dq[j][0] * p.scale, dq[j][1] * p.scale);
+    if (r1 < p.S) *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(r1) * ld + col) = pack_bf16(dq[j][2] * p.scale, dq[j][3] * p.scale);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// backward dK/dV: KV-block stationary (rows of S^T are keys).
+//   S^T = K Q^T ; P^T = exp(S^T*scale - lse[q]) ; dV += P^T dO ; dP^T = V dO^T ;
+//   dS^T = P^T o (dP^T - delta[q]) ; dK += dS^T Q ;  dK *= scale
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnParams p) {
+  __shared__ __align__(128) uint8_t sm[4 * kTileBytes];
+  __shared__ float s_lse[kBlk], s_delta[kBlk];
+  const uint32_t sK = s_u32(sm), sV = sK + kTileBytes, sQ = sV + kTileBytes, sDO = sQ + kTileBytes;
+  const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long ld = 3LL * p.D;
+  const __nv_bfloat16* base = p.qkv + static_cast<long long>(b) * p.S * ld + h * kHD;
+  const __nv_bfloat16* dob = p.dout + static_cast<long long>(b) * p.S * p.D + h * kHD;
+  const int k0 = kb * kBlk;
+  load_tile(sK, base + p.D, ld, k0, p.S);
+  load_tile(sV, base + 2 * p.D, ld, k0, p.S);
+  cp_async_wait_all();
+  __syncthreads();
+  uint32_t ka[4][4], va[4][4];
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) { frag_a(sK, warp * 16, kk, ka[kk]); frag_a(sV, warp * 16, kk, va[kk]); }
+  const int key0 = k0 + warp * 16 + (lane >> 2), key1 = key0 + 8;
+  const float* lp = p.lse + (static_cast<long long>(b) * p.H + h) * p.S;
+  const float* dp = p.delta + (static_cast<long long>(b) * p.H + h) * p.S;
+  const float sc = p.scale * kLog2e;
+  float dk[8][4], dv[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f;
+    dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f;
+  }
+  const int q_begin = p.causal ? (k0 / kBlk) * kBlk : 0;  // queries before this key block see none of it
+  for (int q0 = q_begin; q0 < p.S; q0 += kBlk) {
+    __syncthreads();
+    load_tile(sQ, base, ld, q0, p.S);
+    load_tile(sDO, dob, p.D, q0, p.S);
+    if (threadIdx.x < kBlk) {
+      const int q = q0 + threadIdx.x;
+      s_lse[threadIdx.x] = (q < p.S) ? lp[q] * kLog2e : 0.f;
+      s_delta[threadIdx.x] = (q < p.S) ? dp[q] : 0.f;
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    float st[8][4], dpt[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f;
+      dpt[j][0] = dpt[j][1] = dpt[j][2] = dpt[j][3] = 0.f;
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        uint32_t bb[4];
+        frag_b_nk(sQ, j, kk, bb);
+        mma_bf16(st[j], ka[kk], bb[0], bb[1]);
+        mma_bf16(st[j + 1], ka[kk], bb[2], bb[3]);
+        frag_b_nk(sDO, j, kk, bb);
+        mma_bf16(dpt[j], va[kk], bb[0], bb[1]);
+        mma_bf16(dpt[j + 1], va[kk], bb[2], bb[3]);
+      }
+    }
+    uint32_t pt[4][4], dst[4][4];  // A fragments over 4 query k-steps
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float pe[4], de[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int ql = j * 8 + (lane & 3) * 2 + (e & 1);
+        const int q = q0 + ql;
+        const int key = (e < 2) ? key0 : key1;
+        const bool dead = key >= p.S || q >= p.S || (p.causal && key > q);
+        pe[e] = dead ? 0.f : exp2f(st[j][e] * sc - s_lse[ql]);
+        de[e] = pe[e] * (dpt[j][e] - s_delta[ql]);
+      }
+      const int t = j >> 1, hi = (j & 1) * 2;
+      pt[t][hi] = pack_bf16(pe[0], pe[1]);
+      pt[t][hi + 1] = pack_bf16(pe[2], pe[3]);
+      dst[t][hi] = pack_bf16(de[0], de[1]);
+      dst[t][hi + 1] = pack_bf16(de[2], de[3]);
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+#pragma unroll
+      for (int jd = 0; jd < 8; jd += 2) {
+        uint32_t bb[4];
+        frag_b_kn(sDO, t, jd, bb);
+        mma_bf16(dv[jd], pt[t], bb[0], bb[1]);
+        mma_bf16(dv[jd + 1], pt[t], bb[2], bb[3]);
+        frag_b_kn(sQ, t, jd, bb);
+        mma_bf16(dk[jd], dst[t], bb[0], bb[1]);
+        mma_bf16(dk[jd + 1], dst[t], bb[2], bb[3]);
+      }
+    }
+  }
+  __nv_bfloat16* ob = p.dqkv + static_cast<long long>(b) * p.S * ld + h * kHD;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = j * 8 + (lane & 3) * 2;
+    if (key0 < p.S) {
+      *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(key0) * ld + p.D + col) = pack_bf16(dk[j][0] * p.scale, dk[j][1] * p.scale);
+      *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(key0) * ld + 2 * p.D + col) = pack_bf16(dv[j][0], dv[j][1]);
+    }
+    if (key1 < p.S) {
+      *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(key1) * ld + p.D + col) = pack_bf16(dk[j][2] * p.scale, dk[j][3] * p.scale);
+      *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(key1) * ld + 2 * p.D + col) = pack_bf16(dv[j][2], dv[j][3]);
+    }
+  }
+}
+
+}  // namespace uniir
+
+using namespace uniir;
+#define ST(s) static_cast<cudaStream_t>(s)
+
+extern "C" int uniir_attn_fwd(const void* qkv, int32_t B, int32_t S, int32_t H, int32_t causal, void* out,
+                              float* lse, void* stream) {
+  UNIIR_CHECK_ARG(qkv && out && B > 0 && S > 0 && H > 0, "uniir_attn_fwd: bad args");
+  AttnParams p{};
+  p.qkv = static_cast<const __nv_bfloat16*>(qkv);
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.lse = lse;
+  p.B = B; p.S = S; p.H = H; p.D = H * kHD; p.causal = causal; p.scale = 0.125f;
+  attn_fwd_kernel<<<dim3((S + kBlk - 1) / kBlk, H, B), 128, 0, ST(stream)>>>(p);
+  count_launch();
+  UNIIR_CUDA_OK(cudaGetLastError());
+  return UNIIR_OK;
+}
+
+extern "C" int uniir_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
+                              int32_t B, int32_t S, int32_t H, int32_t causal, float* delta_ws,
+                              void* dqkv, void* stream) {
+  UNIIR_CHECK_ARG(qkv && out && dout && lse && delta_ws && dqkv && B > 0 && S > 0 && H > 0,
+                  "uniir_attn_bwd: bad args");
+  AttnParams p{};
+  p.qkv = static_cast<const __nv_bfloat16*>(qkv);
+  p.out = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(out));
+  p.dout = static_cast<const __nv_bfloat16*>(dout);
+  p.lse = const_cast<float*>(lse);
+  p.delta = delta_ws;
+  p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  p.B = B; p.S = S; p.H = H; p.D = H * kHD; p.causal = causal; p.scale = 0.125f;
+  const long long warps = 1LL * B * S * H;
+  attn_delta_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, ST(stream)>>>(p);
+  const dim3 grid((S + kBlk - 1) / kBlk, H, B);
+  attn_bwd_dq_kernel<<<grid, 128, 0, ST(stream)>>>(p);
+  attn_bwd_dkv_kernel<<<grid, 128, 0, ST(stream)>>>(p);
+  count_launch(3);
+  UNIIR_CUDA_OK(cudaGetLastError());
+  return UNIIR_OK;
+}

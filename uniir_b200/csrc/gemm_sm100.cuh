@@ -40,7 +40,7 @@ struct GemmSmem {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kRingBytes = kStages * kStageBytes;
   // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then tmem ptr
-  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 8;
+  static constexpr int kBarBytes = ((2 * kStages + 4) * 8 + 8 + 127) / 128 * 128;  // keeps what follows 128B aligned
   static constexpr int kTmemCols = 2 * BN;  // two accumulator buffers
 };
 

@@ -284,31 +284,43 @@ __global__ void topk_merge_kernel(const float* __restrict__ in_s, const void* __
   const long long q = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (q >= Q) return;
   const int lane = threadIdx.x & 31;
+  constexpr long long kNone = 0x7fffffffffffffffLL;
   float key[R];
   long long idx[R];
   const int total = L * k;
+  // Streaming merge: the first k slots hold the running best, the remaining 32R-k slots are
+  // refilled with unseen entries and the whole buffer re-sorted until the input is consumed.
+  int next = 0;      // next unseen input entry
+  int fill_from = 0; // first slot to refill
+  do {
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int e = r * 32 + lane;
-    key[r] = kNegInf;
-    idx[r] = 0x7fffffffffffffffLL;
-    if (e < total) {
-      const int l = e / k, j = e - l * k;
-      const long long off = q * q_stride + l * l_stride + j;
-      const long long raw = idx64 ? static_cast<const long long*>(in_i)[off]
-                                  : static_cast<long long>(static_cast<const int*>(in_i)[off]);
-      if (raw >= 0) {
-        key[r] = in_s[off];
-        idx[r] = raw + (list_offset ? list_offset[l] : 0);
+    for (int r = 0; r < R; ++r) {
+      const int e = r * 32 + lane;
+      if (e >= fill_from) {
+        key[r] = kNegInf;
+        idx[r] = kNone;
+        const int src = next + (e - fill_from);
+        if (src < total) {
+          const int l = src / k, j = src - l * k;
+          const long long off = q * q_stride + l * l_stride + j;
+          const long long raw = idx64 ? static_cast<const long long*>(in_i)[off]
+                                      : static_cast<long long>(static_cast<const int*>(in_i)[off]);
+          if (raw >= 0) {
+            key[r] = in_s[off];
+            idx[r] = raw + (list_offset ? list_offset[l] : 0);
+          }
+        }
       }
     }
-  }
-  warp_bitonic_desc<R, long long>(key, idx);
+    next += 32 * R - fill_from;
+    fill_from = k;
+    warp_bitonic_desc<R, long long>(key, idx);
+  } while (next < total);
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int e = r * 32 + lane;
     if (e < k) {
-      const bool ok = idx[r] != 0x7fffffffffffffffLL;
+      const bool ok = idx[r] != kNone;
       out_s[q * k + e] = ok ? key[r] : kFaissNeg;
       out_i[q * k + e] = ok ? (id_table ? id_table[idx[r]] : idx[r]) : -1;
     }
@@ -322,7 +334,7 @@ static void plan_splits(long long Q, long long N, int* splits, int* tiles_per_sp
   const int nt = static_cast<int>((N + kSearchBN - 1) / kSearchBN);
   int best_s = 1;
   double best_cost = 1e300;
-  for (int s = 1; s <= 64 && s <= nt; ++s) {
+  for (int s = 1; s <= 32 && s <= nt; ++s) {
     const int tps = (nt + s - 1) / s;
     if (s > 1 && tps < 8) break;
     const long long items = 1LL * nq * s;
@@ -426,8 +438,8 @@ extern "C" int uniir_topk_merge(const float* in_scores, const void* in_idx, int3
                                 float* out_scores, int64_t* out_ids, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   UNIIR_CHECK_ARG(in_scores && in_idx && out_scores && out_ids, "uniir_topk_merge: null pointer");
-  UNIIR_CHECK_ARG(Q >= 0 && L > 0 && k > 0 && 1LL * L * k <= 512,
-                  "uniir_topk_merge: need L*k <= 512 (L=%d k=%d)", L, k);
+  UNIIR_CHECK_ARG(Q >= 0 && L > 0 && k > 0 && k <= kMaxK,
+                  "uniir_topk_merge: need k in [1,%d] (L=%d k=%d)", kMaxK, L, k);
   if (Q == 0) return UNIIR_OK;
   const int total = L * k;
   const int threads = 128;

@@ -37,6 +37,8 @@ class GemmDesc(C.Structure):
     ]
 
 
+VP, I32, I64 = C.c_void_p, C.c_int32, C.c_int64
+
 _SIGS = {
     "uniir_abi_version": (C.c_int, []),
     "uniir_last_error": (C.c_char_p, []),
@@ -52,6 +54,28 @@ _SIGS = {
     "uniir_topk_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
                                    C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "uniir_layernorm_fwd": (C.c_int, [VP, I64, VP, VP, VP, C.c_float, I64, I32, VP, I64, I32, VP, VP, VP]),
+    "uniir_layernorm_bwd": (C.c_int, [VP, I64, I32, VP, I64, VP, VP, VP, VP, I64, I32, VP, I64, I32, VP, VP, VP]),
+    "uniir_patch_im2col": (C.c_int, [VP, I32, I32, I32, I32, I32, VP, VP]),
+    "uniir_vision_embed_fwd": (C.c_int, [VP, VP, VP, I32, I32, I32, VP, VP]),
+    "uniir_vision_embed_bwd": (C.c_int, [VP, I32, I32, I32, VP, VP, VP, VP]),
+    "uniir_text_embed_fwd": (C.c_int, [VP, VP, VP, I32, I32, I32, VP, VP, VP]),
+    "uniir_text_embed_bwd": (C.c_int, [VP, VP, I32, I32, I32, VP, VP, VP]),
+    "uniir_score_fuse_fwd": (C.c_int, [VP, VP, VP, VP, I64, I32, VP, VP]),
+    "uniir_score_fuse_bwd": (C.c_int, [VP, VP, VP, I64, I32, VP, VP, VP]),
+    "uniir_colsum_accum": (C.c_int, [VP, I64, I32, I64, VP, VP]),
+    "uniir_pad_cast_bf16": (C.c_int, [VP, I64, I32, I32, VP, VP]),
+    "uniir_unpad_accum": (C.c_int, [VP, I64, I32, I32, VP, VP]),
+    "uniir_cast_bf16": (C.c_int, [VP, I64, VP, VP]),
+    "uniir_adamw_step": (C.c_int, [VP, VP, VP, VP, VP, I64, C.c_float, C.c_float, C.c_float, C.c_float,
+                                   C.c_float, I32, C.c_float, VP]),
+    "uniir_attn_fwd": (C.c_int, [VP, I32, I32, I32, I32, VP, VP, VP]),
+    "uniir_attn_bwd": (C.c_int, [VP, VP, VP, VP, I32, I32, I32, I32, VP, VP, VP]),
+    "uniir_infonce_workspace_bytes": (C.c_size_t, [I32, I32]),
+    "uniir_infonce_normalize": (C.c_int, [VP, VP, VP, I32, I32, VP, VP, VP, VP, VP]),
+    "uniir_infonce_fwd": (C.c_int, [VP, VP, I32, I32, I32, VP, I32, VP, VP, VP, VP, C.c_size_t, VP]),
+    "uniir_infonce_bwd": (C.c_int, [VP, VP, I32, I32, I32, VP, I32, VP, VP, VP, VP, VP, VP, VP]),
+    "uniir_infonce_normalize_bwd": (C.c_int, [VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, VP, VP]),
 }
 
 _lib = None

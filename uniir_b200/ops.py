@@ -115,3 +115,215 @@ def topk_merge(scores, idx, k, list_offset=None, id_table=None):
                                       Q, Ls, k, Ls * k, k, _ptr(list_offset), _ptr(id_table),
                                       os_.data_ptr(), oi.data_ptr(), _stream()), "uniir_topk_merge")
     return os_, oi
+
+
+# ----------------------------------------------------------------------------------------
+# row-wise kernels
+# ----------------------------------------------------------------------------------------
+def layernorm_fwd(x, gamma, beta, eps, *, rows=None, ldx=None, row_index=None, out=None,
+                  out_dtype=torch.bfloat16, save_stats=False):
+    """x fp32 viewed as [rows, D] with row stride ldx (or gathered through row_index)."""
+    _require_cuda(x)
+    D = gamma.numel()
+    if rows is None:
+        rows = x.numel() // D if row_index is None else row_index.numel()
+    if ldx is None:
+        ldx = D
+    if out is None:
+        out = torch.empty(rows, D, device=x.device, dtype=out_dtype)
+    mean = rstd = None
+    if save_stats:
+        mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    L.check(L.load().uniir_layernorm_fwd(x.data_ptr(), ldx, _ptr(row_index), gamma.data_ptr(),
+                                         beta.data_ptr(), eps, rows, D, out.data_ptr(), D,
+                                         _DT[out.dtype], _ptr(mean), _ptr(rstd), _stream()),
+            "uniir_layernorm_fwd")
+    return (out, mean, rstd) if save_stats else out
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, *, rows=None, ldx=None, lddx=None,
+                  row_index=None, accumulate=True):
+    D = gamma.numel()
+    if rows is None:
+        rows = mean.numel()
+    L.check(L.load().uniir_layernorm_bwd(dy.data_ptr(), D, _DT[dy.dtype], x.data_ptr(), ldx or D,
+                                         _ptr(row_index), mean.data_ptr(), rstd.data_ptr(),
+                                         gamma.data_ptr(), rows, D, dx.data_ptr(), lddx or (ldx or D),
+                                         int(accumulate), dgamma.data_ptr(), dbeta.data_ptr(), _stream()),
+            "uniir_layernorm_bwd")
+
+
+def patch_im2col(img, P, Kpad, out=None):
+    B, C3, H, W = img.shape
+    assert C3 == 3 and img.dtype == torch.float32 and img.is_contiguous()
+    g = H // P
+    if out is None:
+        out = torch.empty(B * g * g, Kpad, device=img.device, dtype=torch.bfloat16)
+    L.check(L.load().uniir_patch_im2col(img.data_ptr(), B, H, W, P, Kpad, out.data_ptr(), _stream()),
+            "uniir_patch_im2col")
+    return out
+
+
+def vision_embed_fwd(patch, cls, pos, B, S, D, out=None):
+    if out is None:
+        out = torch.empty(B, S, D, device=patch.device, dtype=torch.float32)
+    L.check(L.load().uniir_vision_embed_fwd(patch.data_ptr(), cls.data_ptr(), pos.data_ptr(), B, S, D,
+                                            out.data_ptr(), _stream()), "uniir_vision_embed_fwd")
+    return out
+
+
+def vision_embed_bwd(dx0, B, S, D, d_patch, d_cls, d_pos):
+    L.check(L.load().uniir_vision_embed_bwd(dx0.data_ptr(), B, S, D, d_patch.data_ptr(), d_cls.data_ptr(),
+                                            d_pos.data_ptr(), _stream()), "uniir_vision_embed_bwd")
+
+
+def text_embed_fwd(ids, tok, pos, out=None):
+    B, S = ids.shape
+    D = tok.shape[1]
+    assert ids.dtype == torch.int32 and ids.is_contiguous()
+    if out is None:
+        out = torch.empty(B, S, D, device=ids.device, dtype=torch.float32)
+    eot = torch.empty(B, device=ids.device, dtype=torch.int32)
+    L.check(L.load().uniir_text_embed_fwd(ids.data_ptr(), tok.data_ptr(), pos.data_ptr(), B, S, D,
+                                          out.data_ptr(), eot.data_ptr(), _stream()), "uniir_text_embed_fwd")
+    return out, eot
+
+
+def text_embed_bwd(dx, ids, d_tok, d_pos):
+    B, S = ids.shape
+    D = d_tok.shape[1]
+    L.check(L.load().uniir_text_embed_bwd(dx.data_ptr(), ids.data_ptr(), B, S, D, d_tok.data_ptr(),
+                                          d_pos.data_ptr(), _stream()), "uniir_text_embed_bwd")
+
+
+def score_fuse_fwd(t, v, mt, mv):
+    B, E = t.shape
+    out = torch.empty(B, E, device=t.device, dtype=torch.float32)
+    L.check(L.load().uniir_score_fuse_fwd(t.data_ptr(), v.data_ptr(), mt.data_ptr(), mv.data_ptr(), B, E,
+                                          out.data_ptr(), _stream()), "uniir_score_fuse_fwd")
+    return out
+
+
+def score_fuse_bwd(d, mt, mv):
+    B, E = d.shape
+    dt = torch.empty(B, E, device=d.device, dtype=torch.bfloat16)
+    dv = torch.empty(B, E, device=d.device, dtype=torch.bfloat16)
+    L.check(L.load().uniir_score_fuse_bwd(d.data_ptr(), mt.data_ptr(), mv.data_ptr(), B, E, dt.data_ptr(),
+                                          dv.data_ptr(), _stream()), "uniir_score_fuse_bwd")
+    return dt, dv
+
+
+def colsum_accum(dy, out):
+    M, N = dy.shape
+    assert dy.dtype == torch.bfloat16 and dy.stride(1) == 1 and out.dtype == torch.float32
+    L.check(L.load().uniir_colsum_accum(dy.data_ptr(), M, N, dy.stride(0), out.data_ptr(), _stream()),
+            "uniir_colsum_accum")
+
+
+def pad_cast_bf16(src, Kpad, out=None):
+    rows, K = src.shape
+    if out is None:
+        out = torch.empty(rows, Kpad, device=src.device, dtype=torch.bfloat16)
+    L.check(L.load().uniir_pad_cast_bf16(src.data_ptr(), rows, K, Kpad, out.data_ptr(), _stream()),
+            "uniir_pad_cast_bf16")
+    return out
+
+
+def unpad_accum(src, dst):
+    rows, K = dst.shape
+    L.check(L.load().uniir_unpad_accum(src.data_ptr(), rows, K, src.shape[1], dst.data_ptr(), _stream()),
+            "uniir_unpad_accum")
+
+
+def cast_bf16(src, out=None):
+    if out is None:
+        out = torch.empty(src.shape, device=src.device, dtype=torch.bfloat16)
+    L.check(L.load().uniir_cast_bf16(src.data_ptr(), src.numel(), out.data_ptr(), _stream()), "uniir_cast_bf16")
+    return out
+
+
+def adamw_step(p, g, m, v, p16, lr, betas, eps, wd, step, grad_scale=1.0):
+    L.check(L.load().uniir_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(p16),
+                                      p.numel(), lr, betas[0], betas[1], eps, wd, step, grad_scale,
+                                      _stream()), "uniir_adamw_step")
+
+
+# ----------------------------------------------------------------------------------------
+# attention
+# ----------------------------------------------------------------------------------------
+def attn_fwd(qkv, B, S, H, causal, out=None, lse=None, need_lse=True):
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.shape == (B * S, 3 * H * 64)
+    if out is None:
+        out = torch.empty(B * S, H * 64, device=qkv.device, dtype=torch.bfloat16)
+    if lse is None and need_lse:
+        lse = torch.empty(B, H, S, device=qkv.device, dtype=torch.float32)
+    L.check(L.load().uniir_attn_fwd(qkv.data_ptr(), B, S, H, int(causal), out.data_ptr(), _ptr(lse),
+                                    _stream()), "uniir_attn_fwd")
+    return out, lse
+
+
+def attn_bwd(qkv, out, dout, lse, B, S, H, causal, dqkv=None, delta=None):
+    if dqkv is None:
+        dqkv = torch.empty_like(qkv)
+    if delta is None:
+        delta = torch.empty(B * H * S, device=qkv.device, dtype=torch.float32)
+    L.check(L.load().uniir_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), B, S, H,
+                                    int(causal), delta.data_ptr(), dqkv.data_ptr(), _stream()),
+            "uniir_attn_bwd")
+    return dqkv
+
+
+# ----------------------------------------------------------------------------------------
+# InfoNCE
+# ----------------------------------------------------------------------------------------
+class InfoNCE:
+    """Stateful helper holding the scratch of the fused loss for fixed (bs, n_cols, E)."""
+
+    def __init__(self, bs, n_cols, E, device):
+        self.bs, self.n, self.E = bs, n_cols, E
+        f = dict(device=device, dtype=torch.float32)
+        self.ws = torch.zeros(L.load().uniir_infonce_workspace_bytes(bs, n_cols), device=device, dtype=torch.uint8)
+        self.qn = torch.empty(bs, E, **f)
+        self.all_p = torch.empty(n_cols, E, **f)
+        self.q_norm = torch.empty(bs, **f)
+        self.p_norm = torch.empty(bs, **f)
+        self.lse = torch.empty(bs, **f)
+        self.loss = torch.zeros((), **f)
+        self.acc = torch.zeros((), **f)
+        self.G = torch.empty(bs, n_cols, **f)
+        self.d_qn = torch.empty(bs, E, **f)
+        self.d_all_p = torch.empty(n_cols, E, **f)
+
+    def normalize(self, emb, q_idx, p_idx, target_offset):
+        """qn <- normalize(emb[q_idx]); all_p[target_offset : +bs] <- normalize(emb[p_idx])."""
+        lib = L.load()
+        pn = self.all_p[target_offset:target_offset + self.bs]
+        L.check(lib.uniir_infonce_normalize(emb.data_ptr(), q_idx.data_ptr(), p_idx.data_ptr(), self.bs,
+                                            self.E, self.qn.data_ptr(), pn.data_ptr(),
+                                            self.q_norm.data_ptr(), self.p_norm.data_ptr(), _stream()),
+                "uniir_infonce_normalize")
+        return pn
+
+    def forward(self, logit_scale, target_offset):
+        L.check(L.load().uniir_infonce_fwd(self.qn.data_ptr(), self.all_p.data_ptr(), self.bs, self.n, self.E,
+                                           logit_scale.data_ptr(), target_offset, self.loss.data_ptr(),
+                                           self.acc.data_ptr(), self.lse.data_ptr(), self.ws.data_ptr(),
+                                           self.ws.numel(), _stream()), "uniir_infonce_fwd")
+        return self.loss, self.acc
+
+    def backward(self, logit_scale, target_offset, d_logit_scale, grad_out=None):
+        L.check(L.load().uniir_infonce_bwd(self.qn.data_ptr(), self.all_p.data_ptr(), self.bs, self.n, self.E,
+                                           logit_scale.data_ptr(), target_offset, self.lse.data_ptr(),
+                                           _ptr(grad_out), self.G.data_ptr(), self.d_qn.data_ptr(),
+                                           self.d_all_p.data_ptr(), d_logit_scale.data_ptr(), _stream()),
+                "uniir_infonce_bwd")
+        return self.d_qn, self.d_all_p
+
+    def normalize_bwd(self, q_idx, p_idx, d_pn, d_emb, target_offset):
+        pn = self.all_p[target_offset:target_offset + self.bs]
+        L.check(L.load().uniir_infonce_normalize_bwd(q_idx.data_ptr(), p_idx.data_ptr(), self.qn.data_ptr(),
+                                                     pn.data_ptr(), self.q_norm.data_ptr(),
+                                                     self.p_norm.data_ptr(), self.d_qn.data_ptr(),
+                                                     d_pn.data_ptr(), self.bs, self.E, d_emb.data_ptr(),
+                                                     _stream()), "uniir_infonce_normalize_bwd")
