@@ -190,11 +190,6 @@ def case_gemm_perf():
     return True
 
 
-if False:
-    name = sys.argv[1]
-    ok = globals()["case_" + name]()
-    print(f"CASE {name}: {'PASS' if ok else 'FAIL'}", flush=True)
-    sys.exit(0 if ok else 1)
 
 
 def case_rowops():
@@ -343,6 +338,66 @@ def case_infonce():
         print(f"infonce bs={bs} W={W} E={E}: loss {loss.item():.6f} vs {rl.item():.6f} acc {acc.item():.4f} vs {ra.item():.4f} d_allp={r1:.2e} d_emb={r2:.2e} dls {dls.item():.5f} vs {lr_.grad.item():.5f} {'OK' if good else 'FAIL'}", flush=True)
         ok &= good
     return ok
+
+
+def _make_batch(dims, bs, seed=2023, device="cpu"):
+    from uniir_b200.preprocess import synthetic_clip_tokens
+    g = torch.Generator().manual_seed(seed)
+    n = 2 * bs
+    img = torch.randn(n, 3, dims.image_size, dims.image_size, generator=g)
+    ids = synthetic_clip_tokens(n, g, dims.context, dims.vocab)
+    mt = torch.ones(n, dtype=torch.long); mv = torch.ones(n, dtype=torch.long)
+    mt[1::5] = 0; mv[2::7] = 0
+    return dict(txt_batched=ids, image_batched=img, txt_mask_batched=mt, image_mask_batched=mv,
+                index_mapping={"query": [[2 * i] for i in range(bs)], "pos_cand": [[2 * i + 1] for i in range(bs)]})
+
+
+def model_case(name, bs, mb):
+    from oracle.clip_oracle import CLIPScoreFusionOracle
+    from uniir_b200.clip_sf import CLIPScoreFusion
+    torch.manual_seed(0)
+    orc = CLIPScoreFusionOracle(name)
+    mine = CLIPScoreFusion(name, device="cuda", micro_batch=mb)
+    missing = mine.load_state_dict(orc.state_dict(), strict=True)
+    batch = _make_batch(orc.clip_model.dims, bs)
+    t0 = time.time()
+    out_o = orc(batch)
+    out_o["loss"].backward()
+    t_cpu = time.time() - t0
+    with torch.no_grad():
+        emb_o = orc.encode_multimodal_input(batch["txt_batched"], batch["image_batched"], batch["txt_mask_batched"], batch["image_mask_batched"])
+    gb = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+    emb_m = mine.encode_multimodal_input(gb["txt_batched"], gb["image_batched"], gb["txt_mask_batched"], gb["image_mask_batched"]).cpu()
+    cos = torch.nn.functional.cosine_similarity(emb_m, emb_o, dim=-1)
+    out_m = mine(gb)
+    out_m["loss"].backward()
+    torch.cuda.synchronize()
+    print(f"model {name} bs={bs} mb={mb}: emb cos min={cos.min().item():.6f} mean={cos.mean().item():.6f} | loss {out_m['loss'].item():.5f} vs {out_o['loss'].item():.5f} acc {out_m['accuracy'].item():.3f} vs {out_o['accuracy'].item():.3f} (cpu {t_cpu:.1f}s)")
+    ok = cos.min().item() > 1 - 1e-3 and abs(out_m["loss"].item() - out_o["loss"].item()) < 2e-2 * max(1.0, abs(out_o["loss"].item()))
+    worst = []
+    for (n_, p_o) in orc.named_parameters():
+        p_m = mine.get_parameter(n_)
+        if p_o.grad is None or p_m.grad is None:
+            print("  no grad for", n_, p_o.grad is None, p_m.grad is None); ok = False; continue
+        go, gm = p_o.grad.flatten().double(), p_m.grad.cpu().flatten().double()
+        c = (torch.dot(go, gm) / (go.norm() * gm.norm() + 1e-30)).item() if go.numel() > 1 else 1.0 - abs((go - gm).item()) / (abs(go.item()) + 1e-12)
+        rn = (gm.norm() / (go.norm() + 1e-30)).item()
+        worst.append((c, rn, n_))
+    worst.sort()
+    for c, rn, n_ in worst[:6]:
+        print(f"  grad cos={c:.5f} norm_ratio={rn:.4f} {n_}")
+    mc = sum(c for c, _, _ in worst) / len(worst)
+    print(f"  grads: {len(worst)} tensors, mean cos={mc:.5f}, min cos={worst[0][0]:.5f}")
+    ok &= worst[0][0] > 0.98
+    return ok
+
+
+def case_model_tiny():
+    return model_case("tiny-test", 8, 8) & model_case("tiny-test", 12, 8)
+
+
+def case_model_b32():
+    return model_case("ViT-B/32", 4, 8)
 
 
 if __name__ == "__main__":

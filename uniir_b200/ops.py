@@ -65,6 +65,24 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=None, a
     return out
 
 
+_SMS = None
+
+
+def wgrad(dy, x, out):
+    """out[N_w, K_w] += dy^T . x   (dy [T, N_w], x [T, K_w] bf16; out fp32).  Contraction over
+    tokens with both operands MN-major; splits the contraction (atomic fp32 accumulate) when
+    the output has too few tiles to fill the SMs."""
+    global _SMS
+    if _SMS is None:
+        _SMS = torch.cuda.get_device_properties(dy.device).multi_processor_count
+    Nw, Kw, T = dy.shape[1], x.shape[1], dy.shape[0]
+    tiles = ((Nw + 127) // 128) * ((Kw + 255) // 256)
+    split = 1
+    if tiles * 2 <= _SMS:
+        split = max(1, min(_SMS // tiles, (T + 63) // 64))
+    return gemm(dy, x, a_mn=True, b_mn=True, out=out, accumulate=True, split_k=split)
+
+
 def row_inv_norm(x):
     _require_cuda(x)
     assert x.dim() == 2 and x.stride(1) == 1
@@ -121,8 +139,9 @@ def topk_merge(scores, idx, k, list_offset=None, id_table=None):
 # row-wise kernels
 # ----------------------------------------------------------------------------------------
 def layernorm_fwd(x, gamma, beta, eps, *, rows=None, ldx=None, row_index=None, out=None,
-                  out_dtype=torch.bfloat16, save_stats=False):
-    """x fp32 viewed as [rows, D] with row stride ldx (or gathered through row_index)."""
+                  out_dtype=torch.bfloat16, stats=None, save_stats=False):
+    """x fp32 viewed as [rows, D] with row stride ldx (or gathered through row_index).
+    stats=(mean, rstd) preallocated fp32 [rows] to save the statistics for backward."""
     _require_cuda(x)
     D = gamma.numel()
     if rows is None:
@@ -132,7 +151,9 @@ def layernorm_fwd(x, gamma, beta, eps, *, rows=None, ldx=None, row_index=None, o
     if out is None:
         out = torch.empty(rows, D, device=x.device, dtype=out_dtype)
     mean = rstd = None
-    if save_stats:
+    if stats is not None:
+        mean, rstd = stats
+    elif save_stats:
         mean = torch.empty(rows, device=x.device, dtype=torch.float32)
         rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
     L.check(L.load().uniir_layernorm_fwd(x.data_ptr(), ldx, _ptr(row_index), gamma.data_ptr(),
