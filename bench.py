@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native UniIR hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU reference arm
+
+Default workload = BASELINE.json configs[1]: CLIP_SF ViT-L/14 in-batch contrastive training
+step, bf16, GLOBAL batch 4096 pairs (strong scaling: 4096/N pairs per GPU), synthetic
+224x224 images + 77-token text, random-init weights.  One "step" = gradient-cached forward +
+loss + backward + gradient all-reduce + AdamW over the whole global batch.
+`--workload search` = configs[4]: 190k x 5.6M x 768 fp16 top-50 (also attached to the default
+line under "extra" at N=1 unless --no-extra).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL = "ViT-L/14"
+GLOBAL_BATCH = 4096
+FLOPS_PER_PAIR = 1.052e12          # 2 items x 3 x 175.33 GFLOP (algorithmic, fwd+bwd)
+SEARCH_Q, SEARCH_N, SEARCH_D, SEARCH_K = 190_000, 5_600_000, 768, 50
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"],
+                "bf16_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampler running DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synth_batch(dims, pairs, seed, device, pinned=False):
+    """SURVEY.md 8d synthetic inputs: randn images (CLIP-normalised images are ~N(0,1)), token ids
+    [SOT, U x L, EOT, 0..], all-ones masks, query = even rows / pos_cand = odd rows."""
+    from uniir_b200.preprocess import synthetic_clip_tokens
+    n = 2 * pairs
+    g = torch.Generator().manual_seed(seed)
+    ids = synthetic_clip_tokens(n, g, dims.context, dims.vocab)
+    if device.type == "cuda" and not pinned:
+        gd = torch.Generator(device=device).manual_seed(seed)
+        img = torch.randn(n, 3, dims.image_size, dims.image_size, generator=gd, device=device)
+        ids = ids.to(device)
+        ones = torch.ones(n, dtype=torch.long, device=device)
+    else:
+        img = torch.empty(n, 3, dims.image_size, dims.image_size, pin_memory=pinned)
+        chunk = 256
+        for s in range(0, n, chunk):
+            img[s:s + chunk].normal_(generator=g)
+        ones = torch.ones(n, dtype=torch.long)
+        if pinned:
+            ids, ones = ids.pin_memory(), ones.pin_memory()
+    return dict(txt_batched=ids, image_batched=img, txt_mask_batched=ones, image_mask_batched=ones.clone(),
+                index_mapping={"query": [[2 * i] for i in range(pairs)], "pos_cand": [[2 * i + 1] for i in range(pairs)]})
+
+
+def timed(fn, steps, world):
+    """barrier + sync on both sides, CUDA events on the launch stream, max over ranks."""
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        ms = t.item()
+    return ms / steps
+
+
+# ----------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline (the oracle restatement of the reference, on host cores)
+# ----------------------------------------------------------------------------------------
+def cpu_train_reference(steps, warmup, pairs=4):
+    from oracle.clip_oracle import CLIPScoreFusionOracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(2023)
+    model = CLIPScoreFusionOracle(MODEL)
+    decay = [p for n, p in model.named_parameters() if p.ndim >= 2 and "ln" not in n and "bias" not in n]
+    nodecay = [p for n, p in model.named_parameters() if not (p.ndim >= 2 and "ln" not in n and "bias" not in n)]
+    opt = torch.optim.AdamW([{"params": decay, "weight_decay": 0.2}, {"params": nodecay, "weight_decay": 0.0}],
+                            lr=1e-5, betas=(0.9, 0.98), eps=1e-6)
+    batch = synth_batch(model.clip_model.dims, pairs, 2023, torch.device("cpu"))
+
+    def step():
+        out = model(batch)
+        out["loss"].backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": pairs / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": f"oracle CLIP_SF {MODEL} fp32, {pairs} pairs/step (of the {GLOBAL_BATCH}-pair batch), "
+                      f"fwd+bwd+AdamW, {steps} timed steps"}, dt
+
+
+def cpu_search_reference(steps, warmup, queries=1024, cands=500_000):
+    import numpy as np
+    from oracle.search_oracle import build_index, flat_ip_search
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(2023)
+    q = torch.randn(queries, SEARCH_D, generator=g).half().numpy()
+    c = torch.randn(cands, SEARCH_D, generator=g).half().numpy()
+    ids = np.arange(cands, dtype=np.int64)
+    index = build_index(c)  # create_index happens once, outside the timed search (as in the reference)
+    for _ in range(warmup):
+        flat_ip_search(q[:32], None, ids, SEARCH_K, index=index[:65536])
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        flat_ip_search(q, None, ids, SEARCH_K, index=index)
+    dt = (time.perf_counter() - t0) / steps
+    # exactly linear in N and Q: scale the sample to the 5.6M-candidate pool
+    qps = queries / (dt * SEARCH_N / cands)
+    return {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+            "sample": f"oracle fp32 search (normalise queries, matmul, topk) on a prebuilt index, {queries} queries x {cands} candidates, scaled "
+                      f"linearly to N={SEARCH_N}"}, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    if args.workload == "search":
+        cb, dt = cpu_search_reference(args.steps, args.warmup)
+        metric, unit, cfg = "queries_per_sec_top50", "queries/s", {"workload": "dense_retrieval_190k_x_5.6M_d768_fp16_top50"}
+    else:
+        cb, dt = cpu_train_reference(args.steps, args.warmup)
+        metric, unit = "contrastive_pairs_per_sec", "pairs/s"
+        cfg = {"workload": f"CLIP_SF {MODEL} in-batch contrastive training step, global batch {GLOBAL_BATCH}",
+               "global_batch": GLOBAL_BATCH}
+    print(json.dumps({"impl": "reference", "metric": metric, "value": cb["value"], "unit": unit,
+                      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+                      "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                      "data": "synthetic", "config": cfg, "cpu_baseline": cb,
+                      "e2e": {"value": cb["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ----------------------------------------------------------------------------------------
+# our arm: training step
+# ----------------------------------------------------------------------------------------
+def run_train(args, rank, world, dev, peaks):
+    from uniir_b200 import lib, ops
+    from uniir_b200.clip_sf import CLIPScoreFusion
+    from uniir_b200.engine import FlatAdamW, train_step
+
+    class Cfg:  # the two fields the reference constructor reads (clip_sf.py:28-30)
+        class model: gather_embeddings = world > 1
+        class data_config: in_batch_neg_num = 0
+
+    pairs = GLOBAL_BATCH // world
+    model = CLIPScoreFusion(MODEL, device=dev, config=Cfg, micro_batch=args.micro_batch)
+    opt = FlatAdamW(model.clip_model, lr=1e-5, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.2)
+    batch = synth_batch(model.dims, pairs, 2023 + rank, dev)
+    state = {}
+
+    def step():
+        state["loss"], state["acc"] = train_step(model, batch, opt)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    l0 = lib.launch_count()
+    ms = timed(step, args.steps, world)
+    launches = lib.launch_count() - l0
+    clocks = sampler.stop()
+    value = GLOBAL_BATCH / (ms / 1e3)
+
+    # ---- end-to-end through the public API with HOST (pinned) buffers -------------------
+    hb = {k: (torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) if torch.is_tensor(v) else v)
+          for k, v in batch.items()}
+    h2d = sum(v.numel() * v.element_size() for v in hb.values() if torch.is_tensor(v))
+
+    def e2e_step():
+        gb = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in hb.items()}
+        loss, acc = train_step(model, gb, opt)
+        state["e2e_loss"] = loss.item()  # device -> host read of the step's result
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, max(1, min(2, args.steps)), world)
+    e2e = {"value": GLOBAL_BATCH / (ms_e2e / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": h2d * world,
+           "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e}
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM), timed live with CUDA events -----
+    prof = []
+    ops.set_gemm_profiler(prof)
+    step()
+    torch.cuda.synchronize()
+    ops.set_gemm_profiler(None)
+    g_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
+    g_fl = sum(f for _, _, f in prof)
+    achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    roof = {"bound": "tensor", "kernel": "uniir::gemm_epi_kernel (tcgen05.mma kind::f16, TMA-fed, TMEM accum)",
+            "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["bf16_sustained"], "peak_src": f"{peaks['src']} sustained bf16 (kernel timed inside a long step)",
+            "launches": len(prof), "gemm_share_of_step": g_ms / ms if ms else None,
+            "traffic": _ncu_traffic("gemm"),
+            "step_algorithmic_tflops": FLOPS_PER_PAIR * GLOBAL_BATCH / world / (ms / 1e3) / 1e12}
+    out = {"metric": "contrastive_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": f"CLIP_SF {MODEL} in-batch contrastive training step (BASELINE configs[1])",
+                      "model": f"CLIP_SF {MODEL}", "global_batch": GLOBAL_BATCH, "pairs_per_gpu": pairs,
+                      "micro_batch_items": model._train_mb if hasattr(model, "_train_mb") else args.micro_batch,
+                      "seq_len": "257 vision tokens + 77 text tokens per item, 2 items per pair",
+                      "parallelism": f"dp{world}", "grad_cache": "embedding-level (1 extra forward, not credited)",
+                      "l2": "inputs+weights+activations per step >> 126 MB L2 (no flush needed)"},
+           "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof,
+           "loss": float(state["loss"].item()), "accuracy": float(state["acc"].item())}
+    del model, opt, batch, hb
+    torch.cuda.empty_cache()
+    return out
+
+
+def _ncu_traffic(key):
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(key)
+        except Exception:
+            return None
+    return None
+
+
+# ----------------------------------------------------------------------------------------
+# our arm: dense retrieval
+# ----------------------------------------------------------------------------------------
+def run_search(args, rank, world, dev, peaks, steps=None, warmup=None):
+    from uniir_b200 import lib, ops
+    from uniir_b200.retrieval import ShardedFlatIPIndex, shard_range
+    steps = steps or args.steps
+    warmup = warmup if warmup is not None else args.warmup
+    Q, N, d, k = args.search_q, args.search_n, SEARCH_D, SEARCH_K
+    lo, hi = shard_range(N, world, rank)
+    qlo, qhi = shard_range(Q, world, rank)
+    gd = torch.Generator(device=dev).manual_seed(2023 + rank)
+    cand = torch.empty(hi - lo, d, device=dev, dtype=torch.float16)
+    for s in range(0, hi - lo, 1 << 20):
+        e = min(hi - lo, s + (1 << 20))
+        cand[s:e] = torch.randn(e - s, d, generator=gd, device=dev).half()
+    q = torch.randn(qhi - qlo, d, generator=gd, device=dev).half()
+    index = ShardedFlatIPIndex(d, dev)
+    index.add_local_shard(cand, torch.arange(lo, hi, dtype=torch.int64, device=dev))
+    state = {}
+
+    def step():
+        state["out"] = index.search_sharded(q, k)
+
+    for _ in range(warmup):
+        step()
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    l0 = lib.launch_count()
+    ms = timed(step, steps, world)
+    launches = lib.launch_count() - l0
+    clocks = sampler.stop()
+    value = Q / (ms / 1e3)
+    # e2e: host fp16 queries in (pinned), host (D, I) out
+    qh = q.cpu().pin_memory()
+
+    def e2e_step():
+        qd = qh.to(dev, non_blocking=True)
+        s_, i_ = index.search_sharded(qd, k)
+        state["host"] = (s_.cpu(), i_.cpu())
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, max(1, min(2, steps)), world)
+    # dominant kernel timed alone (this rank: all Q queries vs the local shard)
+    allq = torch.randn(Q, d, generator=gd, device=dev).half() if world > 1 else q
+    qi = ops.row_inv_norm(allq)
+    splits, wsb = ops.ip_topk_plan(Q, hi - lo, k)
+    ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
+    outb = (torch.empty(Q, splits, k, device=dev), torch.empty(Q, splits, k, device=dev, dtype=torch.int32))
+    ops.ip_topk_partial(allq, qi, index.local.emb, index.local.inv, k, workspace=ws, out=outb)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ops.ip_topk_partial(allq, qi, index.local.emb, index.local.inv, k, workspace=ws, out=outb)
+    e1.record()
+    torch.cuda.synchronize()
+    kms = e0.elapsed_time(e1)
+    fl = 2.0 * Q * (hi - lo) * d
+    achieved = fl / (kms * 1e-3) / 1e12
+    roof = {"bound": "tensor", "kernel": "uniir::ip_topk_kernel (fp16 tcgen05 GEMM + fused top-k epilogue)",
+            "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_burst"],
+            "peak_src": f"{peaks['src']} burst bf16/fp16 (kernel timed alone)", "kernel_ms": kms,
+            "algorithmic_flops_per_launch": fl, "traffic": _ncu_traffic("search"),
+            "min_bytes_per_launch": (hi - lo) * d * 2 + Q * d * 2 + Q * k * 8 * splits}
+    out = {"metric": "queries_per_sec_top50", "value": value, "unit": "queries/s", "n_gpus": world, "steps": steps,
+           "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f16", "data": "synthetic",
+           "config": {"workload": f"dense retrieval {Q} queries x {N} candidates, d={d} fp16, top-{k} (BASELINE configs[4])",
+                      "parallelism": f"candidate rows sharded over {world} GPU(s)", "splits_per_gpu": splits,
+                      "l2": "candidate shard (>= 1 GB) >> 126 MB L2"},
+           "clocks": clocks, "gpu_launches": launches, "roofline": roof,
+           "e2e": {"value": Q / (ms_e2e / 1e3), "unit": "queries/s", "h2d_bytes_per_step": Q * d * 2,
+                   "d2h_bytes_per_step": Q * k * 12, "ms_per_step": ms_e2e}}
+    del index, cand
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="train", choices=["train", "search"])
+    ap.add_argument("--micro-batch", type=int, default=64, help="encoder items per micro-batch")
+    ap.add_argument("--no-extra", action="store_true", help="skip the attached retrieval measurement")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--search-q", type=int, default=SEARCH_Q)
+    ap.add_argument("--search-n", type=int, default=SEARCH_N)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (our arm) needs a CUDA device: the uniir_b200 hot path has no CPU fallback")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    if args.workload == "search":
+        out = run_search(args, rank, world, dev, peaks)
+        if rank == 0 and not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"], _ = cpu_search_reference(1, 1)
+    else:
+        out = run_train(args, rank, world, dev, peaks)
+        if not args.no_extra:
+            out["extra"] = {"retrieval": run_search(args, rank, world, dev, peaks, steps=2, warmup=3)}
+        if rank == 0 and not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"], _ = cpu_train_reference(2, 1)
+            if "extra" in out:
+                out["extra"]["retrieval"]["cpu_baseline"], _ = cpu_search_reference(1, 1)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -28,17 +28,29 @@ def normalize_l2(x: np.ndarray) -> np.ndarray:
     return out
 
 
-def flat_ip_search(q16, c16, ids, k, chunk=65536, dtype=torch.float32, threads=None):
+def build_index(c16):
+    """create_index (mbeir_retriever.py:69,76): fp16 -> fp32, normalize_L2.  Returns the fp32
+    normalised matrix the Flat index stores."""
+    return torch.from_numpy(normalize_l2(np.asarray(c16, dtype=np.float32)))
+
+
+def flat_ip_search(q16, c16, ids, k, chunk=65536, dtype=torch.float32, threads=None, index=None):
     """Brute-force cosine top-k with FAISS semantics.  q16 [Q,d], c16 [N,d] (fp16 stored
-    embeddings), ids int64 [N].  Returns (scores fp32 [Q,k], ids int64 [Q,k])."""
+    embeddings), ids int64 [N].  `index` = build_index(c16) to keep the index build (candidate
+    normalisation) out of a timed search, as in the reference where it happens in create_index.
+    Returns (scores fp32 [Q,k], ids int64 [Q,k])."""
     if threads:
         torch.set_num_threads(threads)
     qn = torch.from_numpy(normalize_l2(np.asarray(q16, dtype=np.float32))).to(dtype)
-    Q, N = qn.shape[0], len(c16)
+    Q = qn.shape[0]
+    N = len(c16) if index is None else index.shape[0]
     best_s = torch.full((Q, k), float(FAISS_NEG), dtype=dtype)
     best_i = torch.full((Q, k), -1, dtype=torch.int64)
     for s in range(0, N, chunk):
-        cn = torch.from_numpy(normalize_l2(np.asarray(c16[s:s + chunk], dtype=np.float32))).to(dtype)
+        if index is None:
+            cn = torch.from_numpy(normalize_l2(np.asarray(c16[s:s + chunk], dtype=np.float32))).to(dtype)
+        else:
+            cn = index[s:s + chunk].to(dtype)
         sc = qn @ cn.t()
         kk = min(k, sc.shape[1])
         ts, ti = torch.topk(sc, kk, dim=1)

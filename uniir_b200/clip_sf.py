@@ -210,6 +210,7 @@ class CLIPScoreFusion(nn.Module):
                 raise ValueError(f"encoder batch of {n_items} items cannot be tiled by a micro-batch "
                                  "that is a multiple of 8")
         enc = self._encoder(mb, True)
+        self._train_mb = mb
         st = dict(q_idx=q_idx, p_idx=p_idx, bs=bs, n_items=n_items, rank=rank, world=world, enc=enc)
         st["txt"], st["img"] = self._prep(batch["txt_batched"], batch["image_batched"])
         st["mt"] = batch["txt_mask_batched"].to(dev, torch.int64).contiguous()

@@ -25,6 +25,15 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+_GEMM_PROF = None
+
+
+def set_gemm_profiler(sink):
+    """sink: list that receives (start_event, end_event, flops) per GEMM launch, or None."""
+    global _GEMM_PROF
+    _GEMM_PROF = sink
+
+
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=None, act=L.ACT_NONE,
          residual=None, aux_out=None, act_grad_src=None, alpha=1.0, accumulate=False, split_k=1):
     """out[M,N] (+)= epilogue(alpha * A . B^T); see include/uniir_b200.h.
@@ -61,6 +70,13 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=None, a
     d.alpha = alpha
     d.accumulate = int(accumulate)
     d.split_k = split_k
+    if _GEMM_PROF is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(L.load().uniir_gemm_epi(C.byref(d), _stream()), "uniir_gemm_epi")
+        e1.record()
+        _GEMM_PROF.append((e0, e1, 2.0 * M * N * K))
+        return out
     L.check(L.load().uniir_gemm_epi(C.byref(d), _stream()), "uniir_gemm_epi")
     return out
 
