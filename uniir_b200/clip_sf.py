@@ -72,6 +72,7 @@ class CLIPScoreFusion(nn.Module):
             self.gather_embeddings = config.model.gather_embeddings
             self.in_batch_neg_num = config.data_config.in_batch_neg_num
         self.micro_batch = micro_batch
+        self.use_cuda_graphs = True
         self._enc = {}
         self._nce = None
         self._train_state = None
@@ -175,14 +176,9 @@ class CLIPScoreFusion(nn.Module):
         enc = enc or self._encoder(mb, False)
         self._sync_weights(enc)
         for s in range(0, n, mb):
-            e = min(n, s + mb)
-            ids_c, img_c = txt[s:e], img[s:e]
-            if e - s < mb:  # pad the ragged tail; padded rows are discarded
-                pad = mb - (e - s)
-                ids_c = torch.cat([ids_c, ids_c.new_zeros(pad, ids_c.shape[1])])
-                img_c = torch.cat([img_c, img_c.new_zeros(pad, *img_c.shape[1:])])
-            t_emb, v_emb = enc.forward(ids_c, img_c, save=False)
-            emb[s:e] = ops.score_fuse_fwd(t_emb[:e - s], v_emb[:e - s], mt[s:e], mv[s:e])
+            e = min(n, s + mb)  # a ragged tail is zero-padded inside set_inputs; padded rows are dropped
+            enc.set_inputs(txt[s:e], img[s:e], mt[s:e], mv[s:e])
+            emb[s:e].copy_(enc.embed(self.use_cuda_graphs)[:e - s])
 
     def _world(self):
         if getattr(self, "gather_embeddings", False):
@@ -251,7 +247,6 @@ class CLIPScoreFusion(nn.Module):
         mb = enc.mb
         for s in range(0, st["n_items"], mb):
             e = s + mb
-            enc.forward(st["txt"][s:e], st["img"][s:e], save=True)
-            d_t, d_v = ops.score_fuse_bwd(d_emb[s:e], st["mt"][s:e], st["mv"][s:e])
-            enc.backward(d_t, d_v)
+            enc.set_inputs(st["txt"][s:e], st["img"][s:e], st["mt"][s:e], st["mv"][s:e], d_emb[s:e])
+            enc.fwdbwd(self.use_cuda_graphs)
         self._train_state = None

@@ -164,8 +164,19 @@ class CLIPEncoder:
             self.d_patch = torch.empty(mb * d.grid * d.grid, d.v_width, **bf)
             self.d_conv_pad = torch.zeros(d.v_width, d.patch_k_pad, **f32)
             self.dx0 = torch.empty(mb, d.v_tokens, d.v_width, **f32)
-        self.eot_rows = None
+        self.eot_rows = torch.zeros(mb, device=dev, dtype=torch.int32)
         self.ids = None
+        # static I/O so that forward / forward+backward can be captured into CUDA graphs
+        self.in_ids = torch.zeros(mb, d.context, device=dev, dtype=torch.int32)
+        self.in_img = torch.zeros(mb, 3, d.image_size, d.image_size, **f32)
+        self.in_mt = torch.ones(mb, device=dev, dtype=torch.int64)
+        self.in_mv = torch.ones(mb, device=dev, dtype=torch.int64)
+        self.out_emb = torch.zeros(mb, d.embed_dim, **f32)
+        if train:
+            self.in_demb = torch.zeros(mb, d.embed_dim, **f32)
+            self.d_t = torch.zeros(mb, d.embed_dim, **bf)
+            self.d_v = torch.zeros(mb, d.embed_dim, **bf)
+        self._graphs = {}
 
     def refresh_weights(self):
         d = self.d
@@ -189,8 +200,8 @@ class CLIPEncoder:
                           stats=((self.vp_m, self.vp_r) if save else None))
         ops.gemm(self.v_pool, P.w16("visual.proj"), b_mn=True, out=self.v_emb)
         # text
-        _, self.eot_rows = ops.text_embed_fwd(ids, P.w("token_embedding.weight"), P.w("positional_embedding"),
-                                              out=self.txt.x.view(mb, d.context, d.t_width))
+        ops.text_embed_fwd(ids, P.w("token_embedding.weight"), P.w("positional_embedding"),
+                           out=self.txt.x.view(mb, d.context, d.t_width), eot=self.eot_rows)
         self.ids = ids
         self.txt.forward(save)
         ops.layernorm_fwd(self.txt.x, P.w("ln_final.weight"), P.w("ln_final.bias"), LN_EPS,
@@ -226,3 +237,52 @@ class CLIPEncoder:
                           row_index=self.eot_rows, accumulate=False)
         self.txt.backward()
         ops.text_embed_bwd(self.txt.dx, self.ids, P.g("token_embedding.weight"), P.g("positional_embedding"))
+
+    # ---- CUDA-graph front-ends over the static I/O buffers ----------------------------------
+    def _body_embed(self):
+        t, v = self.forward(self.in_ids, self.in_img, save=False)
+        ops.score_fuse_fwd(t, v, self.in_mt, self.in_mv, out=self.out_emb)
+
+    def _body_fwdbwd(self):
+        self.forward(self.in_ids, self.in_img, save=True)
+        ops.score_fuse_bwd(self.in_demb, self.in_mt, self.in_mv, out=(self.d_t, self.d_v))
+        self.backward(self.d_t, self.d_v)
+
+    def _run(self, key, body, use_graph):
+        """First call runs eagerly (sets kernel attributes, warms allocators), second call
+        captures, later calls replay: ~2000 launches per micro-batch become one graph launch."""
+        if not use_graph:
+            body()
+            return
+        st = self._graphs.get(key, 0)
+        if st == 0:
+            body()
+            self._graphs[key] = 1
+        elif st == 1:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            self._graphs[key] = g
+            # NB: capture does not execute -- replay once so this call has its effect
+            g.replay()
+        else:
+            st.replay()
+
+    def set_inputs(self, ids, img, mt, mv, d_emb=None):
+        n = ids.shape[0]
+        self.in_ids[:n].copy_(ids, non_blocking=True)
+        self.in_img[:n].copy_(img, non_blocking=True)
+        self.in_mt[:n].copy_(mt, non_blocking=True)
+        self.in_mv[:n].copy_(mv, non_blocking=True)
+        if n < self.mb:
+            self.in_ids[n:].zero_(); self.in_img[n:].zero_()
+        if d_emb is not None:
+            self.in_demb.copy_(d_emb, non_blocking=True)
+
+    def embed(self, use_graph=True):
+        self._run("embed", self._body_embed, use_graph)
+        return self.out_emb
+
+    def fwdbwd(self, use_graph=True):
+        self._run("fwdbwd", self._body_fwdbwd, use_graph)

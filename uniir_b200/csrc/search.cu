@@ -210,12 +210,22 @@ struct SearchEpilogue {
 #pragma unroll
       for (int j = 0; j < 32; ++j) m = fmaxf(m, s[j]);
       if (m > thr) {
+        // rare path (~1e-4 of the scores): locate the survivors by 8-wide group so that a
+        // single hit costs 4 group tests + 8 predicated appends instead of 32
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (s[j] > thr) {
-            p.ws_scores[wsb + cnt] = s[j];
-            p.ws_idx[wsb + cnt] = static_cast<int>(col_base + c * 32 + j);
-            ++cnt;
+        for (int g = 0; g < 4; ++g) {
+          float mg = s[g * 8];
+#pragma unroll
+          for (int j = 1; j < 8; ++j) mg = fmaxf(mg, s[g * 8 + j]);
+          if (mg > thr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (s[g * 8 + j] > thr) {
+                p.ws_scores[wsb + cnt] = s[g * 8 + j];
+                p.ws_idx[wsb + cnt] = static_cast<int>(col_base + c * 32 + g * 8 + j);
+                ++cnt;
+              }
+            }
           }
         }
       }
@@ -339,8 +349,10 @@ static void plan_splits(long long Q, long long N, int* splits, int* tiles_per_sp
     if (s > 1 && tps < 8) break;
     const long long items = 1LL * nq * s;
     const long long waves = (items + sms - 1) / sms;
-    // time ~ waves * (tiles per item + fixed per-item cost of ~2 tile-times)
-    const double cost = static_cast<double>(waves) * (tps + 2.0);
+    // time ~ waves * (tiles per item + per-item fixed cost).  The fixed cost is the threshold
+    // ramp-up: ~k*ln(n/k) admissions per row before the running k-th best becomes selective,
+    // each a divergent slow-path event; measured at roughly 300 tile-times per item.
+    const double cost = static_cast<double>(waves) * (tps + 300.0);
     if (cost < best_cost * 0.995) { best_cost = cost; best_s = s; }
   }
   *splits = best_s;

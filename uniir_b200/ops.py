@@ -29,7 +29,7 @@ _GEMM_PROF = None
 
 
 def set_gemm_profiler(sink):
-    """sink: list that receives (start_event, end_event, flops) per GEMM launch, or None."""
+    """sink: list that receives one descriptor dict per GEMM launch (shape + epilogue flags), or None."""
     global _GEMM_PROF
     _GEMM_PROF = sink
 
@@ -71,12 +71,11 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=None, a
     d.accumulate = int(accumulate)
     d.split_k = split_k
     if _GEMM_PROF is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        L.check(L.load().uniir_gemm_epi(C.byref(d), _stream()), "uniir_gemm_epi")
-        e1.record()
-        _GEMM_PROF.append((e0, e1, 2.0 * M * N * K))
-        return out
+        _GEMM_PROF.append(dict(M=M, N=N, K=K, a_mn=bool(a_mn), b_mn=bool(b_mn), dtype=a.dtype,
+                               out_dtype=out.dtype, bias=bias is not None, act=act,
+                               residual=None if residual is None else residual.dtype,
+                               aux=aux_out is not None, ags=act_grad_src is not None,
+                               accumulate=bool(accumulate), split_k=split_k))
     L.check(L.load().uniir_gemm_epi(C.byref(d), _stream()), "uniir_gemm_epi")
     return out
 
@@ -215,13 +214,14 @@ def vision_embed_bwd(dx0, B, S, D, d_patch, d_cls, d_pos):
                                             d_pos.data_ptr(), _stream()), "uniir_vision_embed_bwd")
 
 
-def text_embed_fwd(ids, tok, pos, out=None):
+def text_embed_fwd(ids, tok, pos, out=None, eot=None):
     B, S = ids.shape
     D = tok.shape[1]
     assert ids.dtype == torch.int32 and ids.is_contiguous()
     if out is None:
         out = torch.empty(B, S, D, device=ids.device, dtype=torch.float32)
-    eot = torch.empty(B, device=ids.device, dtype=torch.int32)
+    if eot is None:
+        eot = torch.empty(B, device=ids.device, dtype=torch.int32)
     L.check(L.load().uniir_text_embed_fwd(ids.data_ptr(), tok.data_ptr(), pos.data_ptr(), B, S, D,
                                           out.data_ptr(), eot.data_ptr(), _stream()), "uniir_text_embed_fwd")
     return out, eot
@@ -234,18 +234,22 @@ def text_embed_bwd(dx, ids, d_tok, d_pos):
                                           d_pos.data_ptr(), _stream()), "uniir_text_embed_bwd")
 
 
-def score_fuse_fwd(t, v, mt, mv):
+def score_fuse_fwd(t, v, mt, mv, out=None):
     B, E = t.shape
-    out = torch.empty(B, E, device=t.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty(B, E, device=t.device, dtype=torch.float32)
     L.check(L.load().uniir_score_fuse_fwd(t.data_ptr(), v.data_ptr(), mt.data_ptr(), mv.data_ptr(), B, E,
                                           out.data_ptr(), _stream()), "uniir_score_fuse_fwd")
     return out
 
 
-def score_fuse_bwd(d, mt, mv):
+def score_fuse_bwd(d, mt, mv, out=None):
     B, E = d.shape
-    dt = torch.empty(B, E, device=d.device, dtype=torch.bfloat16)
-    dv = torch.empty(B, E, device=d.device, dtype=torch.bfloat16)
+    if out is None:
+        dt = torch.empty(B, E, device=d.device, dtype=torch.bfloat16)
+        dv = torch.empty(B, E, device=d.device, dtype=torch.bfloat16)
+    else:
+        dt, dv = out
     L.check(L.load().uniir_score_fuse_bwd(d.data_ptr(), mt.data_ptr(), mv.data_ptr(), B, E, dt.data_ptr(),
                                           dv.data_ptr(), _stream()), "uniir_score_fuse_bwd")
     return dt, dv
@@ -364,3 +368,33 @@ class InfoNCE:
                                                      self.p_norm.data_ptr(), self.d_qn.data_ptr(),
                                                      d_pn.data_ptr(), self.bs, self.E, d_emb.data_ptr(),
                                                      _stream()), "uniir_infonce_normalize_bwd")
+
+
+def time_gemm_config(cfg, iters=10, device="cuda"):
+    """Average duration (ms) of one launch of the GEMM described by a trace entry, timed with CUDA
+    events over `iters` back-to-back launches on fresh (L2-cold on first touch) operands."""
+    M, N, K = cfg["M"], cfg["N"], cfg["K"]
+    dt = cfg["dtype"]
+    a = torch.randn((K, M) if cfg["a_mn"] else (M, K), device=device).to(dt)
+    b = torch.randn((K, N) if cfg["b_mn"] else (N, K), device=device).to(dt)
+    out = torch.zeros(M, N, device=device, dtype=cfg["out_dtype"])
+    kw = dict(a_mn=cfg["a_mn"], b_mn=cfg["b_mn"], out=out, act=cfg["act"], accumulate=cfg["accumulate"],
+              split_k=cfg["split_k"])
+    if cfg["bias"]:
+        kw["bias"] = torch.randn(N, device=device)
+    if cfg["residual"] is not None:
+        kw["residual"] = out if cfg["residual"] == out.dtype else torch.randn(M, N, device=device).to(cfg["residual"])
+    if cfg["aux"]:
+        kw["aux_out"] = torch.empty(M, N, device=device, dtype=dt)
+    if cfg["ags"]:
+        kw["act_grad_src"] = torch.randn(M, N, device=device).to(dt)
+    for _ in range(2):
+        gemm(a, b, **kw)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        gemm(a, b, **kw)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
