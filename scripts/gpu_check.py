@@ -428,6 +428,29 @@ def case_train_graph():
     return ok
 
 
+def case_gemm_perf2():
+    """model-shape GEMMs with their real epilogues (M = 64 items x 257 tokens)"""
+    M = 16448
+    f = dict(device=dev)
+    cfgs = [
+        ("qkv fwd  bias", dict(M=M, N=3072, K=1024, a_mn=False, b_mn=False, dtype=torch.bfloat16, out_dtype=torch.bfloat16, bias=True, act=0, residual=None, aux=False, ags=False, accumulate=False, split_k=1)),
+        ("out fwd  bias+res32", dict(M=M, N=1024, K=1024, a_mn=False, b_mn=False, dtype=torch.bfloat16, out_dtype=torch.float32, bias=True, act=0, residual=torch.float32, aux=False, ags=False, accumulate=False, split_k=1)),
+        ("fc1 fwd  bias+qgelu+aux", dict(M=M, N=4096, K=1024, a_mn=False, b_mn=False, dtype=torch.bfloat16, out_dtype=torch.bfloat16, bias=True, act=1, residual=None, aux=True, ags=False, accumulate=False, split_k=1)),
+        ("fc1 fwd  bias+qgelu", dict(M=M, N=4096, K=1024, a_mn=False, b_mn=False, dtype=torch.bfloat16, out_dtype=torch.bfloat16, bias=True, act=1, residual=None, aux=False, ags=False, accumulate=False, split_k=1)),
+        ("fc2 fwd  bias+res32", dict(M=M, N=1024, K=4096, a_mn=False, b_mn=False, dtype=torch.bfloat16, out_dtype=torch.float32, bias=True, act=0, residual=torch.float32, aux=False, ags=False, accumulate=False, split_k=1)),
+        ("fc2 dgrad qgelu'", dict(M=M, N=4096, K=1024, a_mn=False, b_mn=True, dtype=torch.bfloat16, out_dtype=torch.bfloat16, bias=False, act=1, residual=None, aux=False, ags=True, accumulate=False, split_k=1)),
+        ("fc1 dgrad", dict(M=M, N=1024, K=4096, a_mn=False, b_mn=True, dtype=torch.bfloat16, out_dtype=torch.bfloat16, bias=False, act=0, residual=None, aux=False, ags=False, accumulate=False, split_k=1)),
+        ("fc wgrad", dict(M=4096, N=1024, K=M, a_mn=True, b_mn=True, dtype=torch.bfloat16, out_dtype=torch.float32, bias=False, act=0, residual=None, aux=False, ags=False, accumulate=True, split_k=1)),
+        ("out wgrad split", dict(M=1024, N=1024, K=M, a_mn=True, b_mn=True, dtype=torch.bfloat16, out_dtype=torch.float32, bias=False, act=0, residual=None, aux=False, ags=False, accumulate=True, split_k=4)),
+        ("txt qkv fwd", dict(M=4928, N=2304, K=768, a_mn=False, b_mn=False, dtype=torch.bfloat16, out_dtype=torch.bfloat16, bias=True, act=0, residual=None, aux=False, ags=False, accumulate=False, split_k=1)),
+        ("txt fc2 fwd", dict(M=4928, N=768, K=3072, a_mn=False, b_mn=False, dtype=torch.bfloat16, out_dtype=torch.float32, bias=True, act=0, residual=torch.float32, aux=False, ags=False, accumulate=False, split_k=1)),
+    ]
+    for name, c in cfgs:
+        ms = ops.time_gemm_config(c, iters=20)
+        print(f"{name:28s} M={c['M']:6d} N={c['N']:5d} K={c['K']:6d}: {ms*1e3:8.1f} us  {2.0*c['M']*c['N']*c['K']/ms/1e9:7.1f} TF/s", flush=True)
+    return True
+
+
 if __name__ == "__main__":
     name = sys.argv[1]
     ok = globals()["case_" + name]()

@@ -3,6 +3,7 @@
 // the contract.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "gemm_sm100.cuh"
 #include "host_util.cuh"
@@ -46,15 +47,22 @@ struct TileSched {
   }
 };
 
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sigmoid(1.702 x) = 0.5 + 0.5 tanh(0.851 x): one MUFU op instead of exp + full-precision divide
+__device__ __forceinline__ float qg_sigmoid(float x) { return fmaf(0.5f, tanh_approx(0.851f * x), 0.5f); }
 __device__ __forceinline__ float act_fwd(float x, int act) {
-  if (act == UNIIR_ACT_QUICKGELU) return x / (1.f + __expf(-1.702f * x));
+  if (act == UNIIR_ACT_QUICKGELU) return x * qg_sigmoid(x);
   if (act == UNIIR_ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
   return x;
 }
 __device__ __forceinline__ float act_bwd(float x, int act) {
   if (act == UNIIR_ACT_QUICKGELU) {
-    const float s = 1.f / (1.f + __expf(-1.702f * x));
-    return s * (1.f + 1.702f * x * (1.f - s));
+    const float s = qg_sigmoid(x);
+    return s * fmaf(1.702f * x, 1.f - s, 1.f);
   }
   if (act == UNIIR_ACT_GELU) {
     const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
@@ -95,100 +103,184 @@ __device__ __forceinline__ void store8_16b(void* p, int dtype, const float (&f)[
   *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+constexpr int kGemmNE = 8;  // epilogue warps of the plain GEMM kernel
+
 template <int BN>
 struct GemmEpilogue {
   const GemmEpiParams& p;
-  __device__ explicit GemmEpilogue(const GemmEpiParams& p_) : p(p_) {}
+  float* stage_base;  // kGemmNE x 4 KB warp-private staging tiles in shared memory
+  __device__ GemmEpilogue(const GemmEpiParams& p_, float* st) : p(p_), stage_base(st) {}
   __device__ __forceinline__ void item_begin(const WorkItem&, int) {}
   __device__ __forceinline__ void item_end(const WorkItem&, int) {}
 
-  __device__ __forceinline__ void tile(const WorkItem& w, int n_blk, uint32_t tmem_acc, int row) {
-    const long long grow = static_cast<long long>(w.m_blk) * kBM + row;
-    const bool row_ok = grow < p.M;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_acc + c * 32, r);
-      tmem_ld_wait();
-      const int gcol0 = n_blk * BN + c * 32;
-      if (!row_ok || gcol0 >= p.N) continue;
+  // Epilogue inputs of one unit (8 consecutive output columns of one row), fetched early so
+  // that their global-load latency overlaps the TMEM->smem transposition of the chunk.
+  struct UnitIn {
+    uint4 a, b;  // fp32 residual / accumulate target (a,b = 8 floats)  OR  a = 16-bit residual, b = ags
+  };
+  __device__ __forceinline__ bool f32_side_input() const {
+    return (p.residual && p.res_dtype == UNIIR_F32) || (!p.residual && p.accumulate && !p.atomic);
+  }
+  __device__ __forceinline__ void prefetch(UnitIn& u, long long grow, int col) const {
+    if (grow >= p.M || col >= p.N) return;
+    if (f32_side_input()) {
+      const float* rp = p.residual ? static_cast<const float*>(p.residual) + grow * p.ldr + col
+                                   : static_cast<const float*>(p.out) + grow * p.ldo + col;
+      u.a = *reinterpret_cast<const uint4*>(rp);
+      u.b = *reinterpret_cast<const uint4*>(rp + 4);
+    } else {
+      if (p.residual)
+        u.a = *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.residual) + grow * p.ldr + col);
+      if (p.ags)
+        u.b = *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.ags) + grow * p.ld_ags + col);
+    }
+  }
+  __device__ __forceinline__ static void unpack8(const uint4& u, int dtype, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int col = gcol0 + g * 8;
-        if (col >= p.N) break;
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) * p.alpha;
-        if (p.bias) {
-          const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
-          const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
-          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-        }
-        if (p.aux_out)
-          store8_16b(static_cast<uint16_t*>(p.aux_out) + grow * p.ld_aux + col, p.in_dtype, v);
-        if (p.act != UNIIR_ACT_NONE && !p.ags) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = act_fwd(v[j], p.act);
-        }
-        if (p.ags) {
-          float s[8];
-          load8_16b(static_cast<const uint16_t*>(p.ags) + grow * p.ld_ags + col, p.in_dtype, s);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] *= act_bwd(s[j], p.act);
-        }
-        if (p.residual) {
-          if (p.res_dtype == UNIIR_F32) {
-            const float* rp = static_cast<const float*>(p.residual) + grow * p.ldr + col;
-            const float4 a = *reinterpret_cast<const float4*>(rp);
-            const float4 b = *reinterpret_cast<const float4*>(rp + 4);
-            v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
-            v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
-          } else {
-            float s[8];
-            load8_16b(static_cast<const uint16_t*>(p.residual) + grow * p.ldr + col, p.res_dtype, s);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += s[j];
-          }
-        }
-        if (p.out_dtype == UNIIR_F32) {
-          float* op = static_cast<float*>(p.out) + grow * p.ldo + col;
-          if (p.atomic) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) atomicAdd(op + j, v[j]);
-          } else {
-            if (p.accumulate) {
-              const float4 a = *reinterpret_cast<const float4*>(op);
-              const float4 b = *reinterpret_cast<const float4*>(op + 4);
-              v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
-              v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
-            }
-            *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(op + 4) = make_float4(v[4], v[5], v[6], v[7]);
-          }
-        } else {
-          store8_16b(static_cast<uint16_t*>(p.out) + grow * p.ldo + col, p.out_dtype, v);
-        }
+    for (int i = 0; i < 4; ++i) {
+      if (dtype == UNIIR_BF16) {
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+      } else {
+        const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
       }
     }
+  }
+
+  // scale / bias / (aux copy) / act / act-grad / residual / accumulate, then store
+  __device__ __forceinline__ void unit(float (&v)[8], const UnitIn& in, long long grow, int col) {
+    if (grow >= p.M || col >= p.N) return;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= p.alpha;
+    if (p.bias) {
+      const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
+      const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    }
+    if (p.aux_out)
+      store8_16b(static_cast<uint16_t*>(p.aux_out) + grow * p.ld_aux + col, p.in_dtype, v);
+    if (p.act != UNIIR_ACT_NONE && !p.ags) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = act_fwd(v[j], p.act);
+    }
+    const bool f32side = f32_side_input();
+    if (p.ags) {
+      float s[8];
+      if (f32side)  // rare combination: the prefetch slots hold the fp32 side input
+        unpack8(*reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.ags) + grow * p.ld_ags + col), p.in_dtype, s);
+      else
+        unpack8(in.b, p.in_dtype, s);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= act_bwd(s[j], p.act);
+    }
+    if (p.residual) {
+      if (p.res_dtype == UNIIR_F32) {
+        v[0] += __uint_as_float(in.a.x); v[1] += __uint_as_float(in.a.y);
+        v[2] += __uint_as_float(in.a.z); v[3] += __uint_as_float(in.a.w);
+        v[4] += __uint_as_float(in.b.x); v[5] += __uint_as_float(in.b.y);
+        v[6] += __uint_as_float(in.b.z); v[7] += __uint_as_float(in.b.w);
+      } else {
+        float s[8];
+        unpack8(in.a, p.res_dtype, s);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += s[j];
+      }
+    }
+    if (p.out_dtype == UNIIR_F32) {
+      float* op = static_cast<float*>(p.out) + grow * p.ldo + col;
+      if (p.atomic) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(op + j, v[j]);
+      } else {
+        if (p.accumulate && !p.residual) {
+          v[0] += __uint_as_float(in.a.x); v[1] += __uint_as_float(in.a.y);
+          v[2] += __uint_as_float(in.a.z); v[3] += __uint_as_float(in.a.w);
+          v[4] += __uint_as_float(in.b.x); v[5] += __uint_as_float(in.b.y);
+          v[6] += __uint_as_float(in.b.z); v[7] += __uint_as_float(in.b.w);
+        } else if (p.accumulate) {
+          const float4 a = *reinterpret_cast<const float4*>(op);
+          const float4 b = *reinterpret_cast<const float4*>(op + 4);
+          v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+          v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+        }
+        *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(op + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    } else {
+      store8_16b(static_cast<uint16_t*>(p.out) + grow * p.ldo + col, p.out_dtype, v);
+    }
+  }
+
+  // One 32-row x 32-column accumulator chunk.  TMEM hands each lane one ROW (32 columns);
+  // issuing global I/O in that shape touches 32 cache lines per instruction.  The chunk is
+  // therefore transposed through a 4 KB warp-private staging tile (16 B chunks XOR-swizzled
+  // by row, conflict-free both ways) so that 4 adjacent lanes cover one row's 32 columns and
+  // every global load/store instruction covers 8 rows x one contiguous segment.
+  __device__ __forceinline__ void chunk(uint32_t tmem_addr, float* stage, long long grow0, int gcol0) {
+    const int lane = threadIdx.x & 31;
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(tmem_addr, r);
+    // side inputs (residual / act-grad source / accumulate target) are requested while the TMEM
+    // load is in flight, in the coalesced (row = u/4, 8-column group = u%4) mapping
+    UnitIn in[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int u = i * 32 + lane;
+      prefetch(in[i], grow0 + (u >> 2), gcol0 + (u & 3) * 8);
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      *reinterpret_cast<uint4*>(stage + lane * 32 + ((c ^ (lane & 7)) << 2)) =
+          make_uint4(r[c * 4], r[c * 4 + 1], r[c * 4 + 2], r[c * 4 + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int u = i * 32 + lane, row = u >> 2, g = u & 3;
+      const float4 lo = *reinterpret_cast<const float4*>(stage + row * 32 + (((2 * g) ^ (row & 7)) << 2));
+      const float4 hi = *reinterpret_cast<const float4*>(stage + row * 32 + (((2 * g + 1) ^ (row & 7)) << 2));
+      float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+      unit(v, in[i], grow0 + row, gcol0 + g * 8);
+    }
+    __syncwarp();
+  }
+
+  // This warp owns columns [col_half*W, (col_half+1)*W) of the tile, W = BN / (NE/4); the two
+  // epilogue warps that share an SMSP overlap each other's TMEM / global-load latencies.
+  __device__ __forceinline__ void tile(const WorkItem& w, int n_blk, uint32_t tmem_acc, int row,
+                                       int col_half) {
+    constexpr int W = BN / (kGemmNE / 4);
+    constexpr int NC = W / 32;
+    const int lane = threadIdx.x & 31;
+    const long long grow0 = static_cast<long long>(w.m_blk) * kBM + (row - lane);
+    float* stage = stage_base + ((threadIdx.x >> 5) - 2) * 1024;
+    const int c0 = col_half * W;
+#pragma unroll 1
+    for (int c = 0; c < NC; ++c)
+      chunk(tmem_acc + c0 + c * 32, stage, grow0, n_blk * BN + c0 + c * 32);
   }
 };
 
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(num_threads(kGemmNE), 1)
 gemm_epi_kernel(const __grid_constant__ GemmTensorMaps maps, const GemmEpiParams p,
                 const TileSched sched, const uint32_t idesc) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
-  GemmEpilogue<BN> epi(p);
-  gemm_body<BN, A_MN, B_MN>(&maps.a, &maps.b, idesc, sched, epi, smem);
+  using SM = GemmSmem<BN>;
+  GemmEpilogue<BN> epi(p, reinterpret_cast<float*>(smem + SM::kRingBytes + SM::kBarBytes));
+  gemm_body<BN, A_MN, B_MN, kGemmNE>(&maps.a, &maps.b, idesc, sched, epi, smem);
 }
 
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm(const GemmTensorMaps& maps, const GemmEpiParams& p, const TileSched& s,
                        bool bf16, cudaStream_t stream) {
   using SM = GemmSmem<BN>;
-  const int smem_bytes = SM::kRingBytes + SM::kBarBytes + 1024;
+  const int smem_bytes = SM::kRingBytes + SM::kBarBytes + kGemmNE * 4096 + 1024;
   auto kern = gemm_epi_kernel<BN, A_MN, B_MN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -198,7 +290,7 @@ static int launch_gemm(const GemmTensorMaps& maps, const GemmEpiParams& p, const
   const int items = s.m_blocks * s.n_blocks * s.split_k;
   const int grid = items < num_sms() ? items : num_sms();
   const uint32_t idesc = make_idesc_f16(bf16, A_MN, B_MN, kBM, BN);
-  kern<<<grid, kNumThreads, smem_bytes, stream>>>(maps, p, s, idesc);
+  kern<<<grid, num_threads(kGemmNE), smem_bytes, stream>>>(maps, p, s, idesc);
   count_launch();
   UNIIR_CUDA_OK(cudaGetLastError());
   return UNIIR_OK;
@@ -225,16 +317,19 @@ extern "C" int uniir_gemm_epi(const uniir_gemm_desc* d, void* stream_) {
                               d->act == UNIIR_ACT_NONE),
                   "uniir_gemm_epi: split_k supports only the plain accumulate epilogue");
 
-  // Tile width: 256 when it does not cost a wave, else 128.
+  // Tile width.  A 128x128 tile reads 8 KB of operands per 64-cycle UMMA = 128 B/clk, the whole
+  // shared-memory bandwidth of the SM, so 128x256 (96 B/clk) is preferred unless the problem is
+  // too narrow or 256-wide tiles would leave most of the last wave empty.
   const int m_blocks = (d->M + kBM - 1) / kBM;
   const int sms = num_sms();
   int bn = 256;
   {
     const long long t256 = 1LL * m_blocks * ((d->N + 255) / 256) * (atomic ? d->split_k : 1);
     const long long t128 = 1LL * m_blocks * ((d->N + 127) / 128) * (atomic ? d->split_k : 1);
-    const long long w256 = (t256 + sms - 1) / sms * 2;  // cost in 128-wide units
-    const long long w128 = (t128 + sms - 1) / sms;
-    if (d->N <= 128 || w128 < w256) bn = 128;
+    const double c256 = static_cast<double>((t256 + sms - 1) / sms) * 1.0;
+    const double c128 = static_cast<double>((t128 + sms - 1) / sms) * 0.65;
+    if (d->N <= 128 || c128 < c256) bn = 128;
+    if (const char* e = getenv("UNIIR_GEMM_BN")) { const int v = atoi(e); if (v == 128 || (v == 256 && d->N > 128)) bn = v; }
   }
 
   GemmTensorMaps maps;

@@ -25,8 +25,9 @@ namespace uniir {
 constexpr int kBM = 128;   // UMMA M (cta_group::1)
 constexpr int kBK = 64;    // 64 x 2B = one 128B swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kNumThreads = 192;
-constexpr int kNumEpiThreads = 128;
+// threads = 2 control warps (TMA, MMA) + NE epilogue warps (4: one per TMEM lane quarter;
+// 8: two per quarter, each taking half of the tile's columns)
+constexpr int num_threads(int ne) { return 64 + 32 * ne; }
 
 struct WorkItem {
   int m_blk, n_begin, n_end, kb_begin, kb_end;
@@ -52,11 +53,12 @@ struct GemmTensorMaps {
 // The kernel body.  `Sched` : bool get(int item, WorkItem&) const;  int num_items() const
 //                   `Epi`   : see gemm.cu / search.cu.  Runs on the 128 epilogue threads:
 //       void item_begin(const WorkItem&, int row_in_tile)
-//       void tile(const WorkItem&, int n_blk, uint32_t tmem_acc /*lane-adjusted*/, int row_in_tile)
+//       void tile(const WorkItem&, int n_blk, uint32_t tmem_acc /*lane-adjusted*/, int row_in_tile,
+//                 int col_half /*0..NE/4-1: which slice of the BN columns this warp owns*/)
 //       void item_end(const WorkItem&, int row_in_tile)
 // `extra_smem` bytes after the ring/barriers are handed to Epi via its ctor.
 // ---------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN, class Sched, class Epi>
+template <int BN, bool A_MN, bool B_MN, int NE, class Sched, class Epi>
 __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensorMap* tmB,
                                           uint32_t idesc, const Sched& sched, Epi& epi,
                                           uint8_t* smem /*1024-aligned*/) {
@@ -80,7 +82,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kNumEpiThreads);
+      mbar_init(&tempty_bar[i], 32 * NE);
     }
     fence_barrier_init();
   }
@@ -168,6 +170,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
   } else {
     // ============================ epilogue ================================
     const int quarter = warp_idx & 3;  // TMEM lanes [32q, 32q+32) are visible to this warp
+    const int col_half = (warp_idx - 2) >> 2;
     const int row = quarter * 32 + lane_id();
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -178,7 +181,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
       for (int n = w.n_begin; n < w.n_end; ++n) {
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
-        epi.tile(w, n, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN, row);
+        epi.tile(w, n, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN, row, col_half);
         tc_fence_before();
         mbar_arrive(&tempty_bar[acc]);
         acc ^= 1;

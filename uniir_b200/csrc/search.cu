@@ -175,7 +175,7 @@ struct SearchEpilogue {
     __syncwarp();
   }
 
-  __device__ __forceinline__ void tile(const WorkItem& w, int n_blk, uint32_t tmem_acc, int row) {
+  __device__ __forceinline__ void tile(const WorkItem& w, int n_blk, uint32_t tmem_acc, int row, int /*col_half*/) {
     float* invc = invc_s + (tcount & 1) * kSearchBN;
     ++tcount;
     const long long col_base = static_cast<long long>(n_blk) * kSearchBN;
@@ -184,7 +184,7 @@ struct SearchEpilogue {
       const long long c = col_base + row + h * kBM;
       invc[row + h * kBM] = (c < p.N) ? p.c_inv[c] : 0.f;
     }
-    named_bar_sync(1, kNumEpiThreads);
+    named_bar_sync(1, 128);
     const bool tail = col_base + kSearchBN > p.N;
     const long long wsb = ws_base(row);
 #pragma unroll 1
@@ -239,7 +239,7 @@ struct SearchEpilogue {
   }
 };
 
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(num_threads(4), 1)
 ip_topk_kernel(const __grid_constant__ GemmTensorMaps maps, const SearchParams p,
                const SearchSched sched, const uint32_t idesc) {
   extern __shared__ uint8_t smem_raw[];
@@ -247,7 +247,7 @@ ip_topk_kernel(const __grid_constant__ GemmTensorMaps maps, const SearchParams p
   using SM = GemmSmem<kSearchBN>;
   float* invc_s = reinterpret_cast<float*>(smem + SM::kRingBytes + SM::kBarBytes);
   SearchEpilogue epi(p, invc_s);
-  gemm_body<kSearchBN, false, false>(&maps.a, &maps.b, idesc, sched, epi, smem);
+  gemm_body<kSearchBN, false, false, 4>(&maps.a, &maps.b, idesc, sched, epi, smem);
 }
 
 // ---------------------------------------------------------------------------------
@@ -438,7 +438,7 @@ extern "C" int uniir_ip_topk(const void* q, const float* q_inv, const void* c, c
   const long long items = 1LL * nq * s;
   const int grid = items < sms ? static_cast<int>(items) : sms;
   const uint32_t idesc = make_idesc_f16(false, false, false, kBM, kSearchBN);
-  ip_topk_kernel<<<grid, kNumThreads, smem_bytes, stream>>>(maps, p, sched, idesc);
+  ip_topk_kernel<<<grid, num_threads(4), smem_bytes, stream>>>(maps, p, sched, idesc);
   count_launch();
   UNIIR_CUDA_OK(cudaGetLastError());
   return UNIIR_OK;
