@@ -1,0 +1,86 @@
+"""Generate the committed golden vectors under tests/golden/ from the CPU oracle.
+
+    python scripts/make_golden.py
+
+The reference holds no golden vectors of its own; these pin OUR oracle so a
+later edit to oracle/ cannot silently change the arithmetic the CUDA path is checked against,
+and they travel to the GPU box (where /root/reference does not exist).
+  clip_tiny.npz   : tiny-test CLIP_SF weights + synthetic batch -> embeddings, loss, accuracy,
+                    gradients of 4 representative parameters
+  search_small.npz: fp16 queries/candidates/ids -> FAISS-semantics top-k (incl. N < k padding)
+  infonce.npz     : embeddings + index mapping -> loss/accuracy/d_emb for world=1 and a
+                    simulated rank 1 of world 2
+"""
+import os, sys
+import numpy as np
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle.clip_oracle import CLIPScoreFusionOracle, contrastive_loss_from_embeddings
+from oracle.search_oracle import flat_ip_search
+from uniir_b200.preprocess import synthetic_clip_tokens
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def clip_tiny():
+    torch.manual_seed(1234)
+    m = CLIPScoreFusionOracle("tiny-test")
+    d = m.clip_model.dims
+    g = torch.Generator().manual_seed(7)
+    bs = 8
+    n = 2 * bs
+    ids = synthetic_clip_tokens(n, g, d.context, d.vocab)
+    img = torch.randn(n, 3, d.image_size, d.image_size, generator=g)
+    mt = torch.ones(n, dtype=torch.long); mv = torch.ones(n, dtype=torch.long)
+    mt[3] = 0; mv[6] = 0; mt[9] = 0
+    batch = dict(txt_batched=ids, image_batched=img, txt_mask_batched=mt, image_mask_batched=mv,
+                 index_mapping={"query": [[2 * i] for i in range(bs)], "pos_cand": [[2 * i + 1] for i in range(bs)]})
+    out = m(batch)
+    out["loss"].backward()
+    with torch.no_grad():
+        emb = m.encode_multimodal_input(ids, img, mt, mv)
+    sd = {k: v.detach().numpy() for k, v in m.state_dict().items()}
+    grads = {k: m.get_parameter(k).grad.numpy() for k in
+             ["clip_model.visual.proj", "clip_model.text_projection", "clip_model.logit_scale",
+              "clip_model.visual.transformer.resblocks.0.mlp.c_fc.weight",
+              "clip_model.transformer.resblocks.1.attn.in_proj_weight", "clip_model.visual.conv1.weight"]}
+    np.savez_compressed(os.path.join(OUT, "clip_tiny.npz"), ids=ids.numpy(), img=img.numpy().astype(np.float32),
+                        mt=mt.numpy(), mv=mv.numpy(), emb=emb.numpy(), loss=out["loss"].item(), acc=out["accuracy"].item(),
+                        **{"w:" + k: v for k, v in sd.items()}, **{"g:" + k: v for k, v in grads.items()})
+
+
+def search_small():
+    rng = np.random.default_rng(11)
+    d = 64
+    c = rng.standard_normal((2500, d)).astype(np.float16)
+    c[17] = 0  # zero row: normalize_L2 leaves it, score 0
+    q = rng.standard_normal((37, d)).astype(np.float16)
+    q[5] = 0
+    ids = (rng.permutation(2500).astype(np.int64) * 10_000_000 // 7) + 3  # hash_did-like sparse ids
+    D, I = flat_ip_search(q, c, ids, 10, dtype=torch.float64)
+    D2, I2 = flat_ip_search(q, c[:6], ids[:6], 10, dtype=torch.float64)  # N < k -> -1 padding
+    np.savez_compressed(os.path.join(OUT, "search_small.npz"), q=q, c=c, ids=ids, D=D, I=I, D_small=D2, I_small=I2)
+
+
+def infonce():
+    g = torch.Generator().manual_seed(3)
+    bs, E = 6, 32
+    emb = torch.randn(2 * bs, E, generator=g, requires_grad=True)
+    im = {"query": [[2 * i] for i in range(bs)], "pos_cand": [[2 * i + 1] for i in range(bs)]}
+    scale = torch.tensor(100.0)
+    o1 = contrastive_loss_from_embeddings(emb, im, scale)
+    (g1,) = torch.autograd.grad(o1["loss"], emb)
+    other = torch.nn.functional.normalize(torch.randn(bs, E, generator=g), dim=-1)  # rank 0's p rows
+    o2 = contrastive_loss_from_embeddings(emb, im, scale, all_p_fn=lambda p: torch.cat([other, p], 0), rank=1)
+    (g2,) = torch.autograd.grad(o2["loss"], emb)
+    np.savez_compressed(os.path.join(OUT, "infonce.npz"), emb=emb.detach().numpy(), other=other.numpy(),
+                        loss1=o1["loss"].item(), acc1=o1["accuracy"].item(), g1=g1.numpy(),
+                        loss2=o2["loss"].item(), acc2=o2["accuracy"].item(), g2=g2.numpy())
+
+
+if __name__ == "__main__":
+    clip_tiny(); search_small(); infonce()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))

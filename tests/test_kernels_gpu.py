@@ -1,0 +1,160 @@
+"""GPU parity of the individual C-ABI kernels against plain fp32 CPU references (torch CPU): tcgen05
+GEMM in every operand-major mode and epilogue, LayerNorm fwd/bwd, embedding kernels, attention
+fwd/bwd, AdamW.  Tolerances are bf16-input tolerances, stated per test."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from uniir_b200 import ops
+    return ops
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (1000, 768, 1024), (333, 4096, 768), (1024, 776, 1000)])
+def test_gemm_all_operand_majors(ops, a_mn, b_mn, M, N, K):
+    if a_mn and M % 8:
+        M += 8 - M % 8
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn((K, M) if a_mn else (M, K), generator=g).bfloat16()
+    B = torch.randn((K, N) if b_mn else (N, K), generator=g).bfloat16()
+    ref = (A.t() if a_mn else A).float() @ (B.t() if b_mn else B).float().t()
+    out = ops.gemm(A.to(dev), B.to(dev), a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32)
+    assert rel(out, ref) < 1e-5  # exact products, fp32 accumulate: only summation order differs
+
+
+def test_gemm_fp16_and_split_k(ops):
+    g = torch.Generator().manual_seed(1)
+    A, B = torch.randn(512, 512, generator=g).half(), torch.randn(512, 512, generator=g).half()
+    assert rel(ops.gemm(A.to(dev), B.to(dev), out_dtype=torch.float32), A.float() @ B.float().t()) < 1e-5
+    X, dY = torch.randn(4096, 256, generator=g).bfloat16(), torch.randn(4096, 384, generator=g).bfloat16()
+    acc = torch.ones(384, 256, device=dev)
+    ops.wgrad(dY.to(dev), X.to(dev), acc)  # narrow output -> split-K atomics
+    assert rel(acc - 1, dY.float().t() @ X.float()) < 1e-4
+    acc2 = torch.ones(384, 256, device=dev)
+    ops.gemm(dY.to(dev), X.to(dev), a_mn=True, b_mn=True, out=acc2, accumulate=True)
+    assert rel(acc2 - 1, dY.float().t() @ X.float()) < 1e-5
+
+
+@pytest.mark.parametrize("dyn", [False, True])
+def test_gemm_epilogues(ops, dyn, monkeypatch):
+    from uniir_b200 import lib as L
+    if dyn:
+        monkeypatch.setenv("UNIIR_GEMM_DYN", "1")  # runtime-flag epilogue instead of the static variants
+    g = torch.Generator().manual_seed(2)
+    M, N, K = 777, 1024, 512
+    A = torch.randn(M, K, generator=g).bfloat16(); B = (torch.randn(N, K, generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, generator=g); res = torch.randn(M, N, generator=g)
+    pre = A.float() @ B.float().t() + bias
+    Ad, Bd, bd = A.to(dev), B.to(dev), bias.to(dev)
+    aux = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    out = ops.gemm(Ad, Bd, bias=bd, act=L.ACT_QUICKGELU, aux_out=aux)
+    assert rel(out, pre * torch.sigmoid(1.702 * pre)) < 5e-3 and rel(aux, pre) < 5e-3   # bf16 outputs
+    assert rel(ops.gemm(Ad, Bd, bias=bd, act=L.ACT_QUICKGELU), pre * torch.sigmoid(1.702 * pre)) < 5e-3
+    assert rel(ops.gemm(Ad, Bd, bias=bd, act=L.ACT_GELU), F.gelu(pre)) < 5e-3
+    x = res.to(dev)
+    ops.gemm(Ad, Bd, bias=bd, residual=x, out=x)                     # in-place fp32 residual stream
+    assert rel(x, pre + res) < 1e-5
+    src = torch.randn(M, N, generator=g).bfloat16()
+    Bt = B.t().contiguous()                                         # dgrad form: B stored [K, N]
+    out = ops.gemm(Ad, Bt.to(dev), b_mn=True, act=L.ACT_QUICKGELU, act_grad_src=src.to(dev), out_dtype=torch.float32)
+    s = src.float(); sg = torch.sigmoid(1.702 * s)
+    assert rel(out, (A.float() @ B.float().t()) * (sg * (1 + 1.702 * s * (1 - sg)))) < 1e-3  # tanh.approx sigmoid
+    acc = torch.randn(M, N, generator=g); accd = acc.to(dev)
+    ops.gemm(Ad, Bd, out=accd, accumulate=True, alpha=0.5)
+    assert rel(accd, acc + 0.5 * (A.float() @ B.float().t())) < 1e-5
+
+
+def test_gemm_rejects_bad_arguments(ops):
+    from uniir_b200.lib import UniirError
+    A = torch.zeros(16, 12, device=dev, dtype=torch.bfloat16)   # K=12 not a multiple of 8
+    with pytest.raises(UniirError):
+        ops.gemm(A, A)
+
+
+@pytest.mark.parametrize("D,rows", [(1024, 300), (768, 77), (128, 50), (512, 9)])
+def test_layernorm_fwd_bwd(ops, D, rows):
+    g = torch.Generator().manual_seed(D)
+    x = torch.randn(rows, D, generator=g) * 2 + 0.5
+    w, b = torch.randn(D, generator=g), torch.randn(D, generator=g)
+    y, mean, rstd = ops.layernorm_fwd(x.to(dev), w.to(dev), b.to(dev), 1e-5, out_dtype=torch.float32, save_stats=True)
+    assert rel(y, F.layer_norm(x, (D,), w, b, 1e-5)) < 1e-6
+    assert rel(ops.layernorm_fwd(x.to(dev), w.to(dev), b.to(dev), 1e-5), F.layer_norm(x, (D,), w, b, 1e-5)) < 5e-3
+    dy = torch.randn(rows, D, generator=g).bfloat16()
+    xr, wr, br = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
+    F.layer_norm(xr, (D,), wr, br, 1e-5).backward(dy.float())
+    dx = torch.ones(rows, D, device=dev); dg = torch.zeros(D, device=dev); db = torch.zeros(D, device=dev)
+    ops.layernorm_bwd(dy.to(dev), x.to(dev), mean, rstd, w.to(dev), dx, dg, db)
+    assert rel(dx - 1, xr.grad) < 1e-5 and rel(dg, wr.grad) < 1e-5 and rel(db, br.grad) < 1e-5
+
+
+def test_layernorm_gathered_rows_and_embed_kernels(ops):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(10, 7, 128, generator=g); w, b = torch.randn(128, generator=g), torch.randn(128, generator=g)
+    idx = (torch.arange(10) * 7 + torch.randint(0, 7, (10,), generator=g)).int()
+    y = ops.layernorm_fwd(x.to(dev), w.to(dev), b.to(dev), 1e-5, row_index=idx.to(dev), out_dtype=torch.float32)
+    assert rel(y, F.layer_norm(x.view(70, 128)[idx.long()], (128,), w, b, 1e-5)) < 1e-6
+    img = torch.randn(3, 3, 56, 56, generator=g)
+    col = ops.patch_im2col(img.to(dev), 14, 640)
+    assert rel(col[:, :588], F.unfold(img, 14, stride=14).transpose(1, 2).reshape(48, 588)) < 5e-3
+    assert col[:, 588:].abs().max().item() == 0
+    patch = torch.randn(48, 128, generator=g).bfloat16(); cls = torch.randn(128, generator=g); pos = torch.randn(17, 128, generator=g)
+    x0 = ops.vision_embed_fwd(patch.to(dev), cls.to(dev), pos.to(dev), 3, 17, 128)
+    assert rel(x0, torch.cat([cls.expand(3, 1, 128), patch.float().view(3, 16, 128)], 1) + pos) < 1e-6
+    ids = torch.randint(1, 500, (5, 77), generator=g).int(); ids[:, 0] = 510
+    ids[torch.arange(5), torch.tensor([3, 10, 76, 5, 1])] = 511
+    tok, tpos = torch.randn(512, 64, generator=g), torch.randn(77, 64, generator=g)
+    xt, eot = ops.text_embed_fwd(ids.to(dev), tok.to(dev), tpos.to(dev))
+    assert rel(xt, tok[ids.long()] + tpos) < 1e-6
+    assert (eot.cpu().long() == torch.arange(5) * 77 + ids.argmax(-1)).all()   # EOT pooling row = argmax(token id)
+    dxt = torch.randn(5, 77, 64, generator=g); dtok = torch.zeros(512, 64, device=dev); dpos = torch.zeros(77, 64, device=dev)
+    ops.text_embed_bwd(dxt.to(dev), ids.to(dev), dtok, dpos)
+    assert rel(dtok, torch.zeros(512, 64).index_add_(0, ids.long().flatten(), dxt.view(-1, 64))) < 1e-5
+    assert rel(dpos, dxt.sum(0)) < 1e-6
+
+
+def _attn_ref(qkv, B, S, H, causal):
+    q, k, v = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+    att = q @ k.transpose(-1, -2) * 0.125
+    if causal:
+        att = att + torch.full((S, S), float("-inf")).triu_(1)
+    return (att.softmax(-1) @ v).transpose(1, 2).reshape(B * S, H * 64), torch.logsumexp(att, -1)
+
+
+@pytest.mark.parametrize("B,S,H,causal", [(2, 64, 1, False), (3, 257, 4, False), (5, 77, 3, True), (2, 197, 2, False),
+                                           (2, 50, 2, False), (1, 130, 2, True), (2, 100, 1, False)])
+def test_attention_fwd_bwd(ops, B, S, H, causal):
+    g = torch.Generator().manual_seed(S)
+    qkv = (torch.randn(B * S, 3 * H * 64, generator=g) * 1.5).bfloat16()
+    out, lse = ops.attn_fwd(qkv.to(dev), B, S, H, causal)
+    qr = qkv.float().requires_grad_(True)
+    ref, rlse = _attn_ref(qr, B, S, H, causal)
+    assert rel(out, ref) < 6e-3 and (lse.cpu() - rlse).abs().max() < 1e-3
+    dout = torch.randn(B * S, H * 64, generator=g).bfloat16()
+    ref.backward(dout.float())
+    dqkv = ops.attn_bwd(qkv.to(dev), out, dout.to(dev), lse, B, S, H, causal)
+    assert rel(dqkv, qr.grad) < 1e-2   # bf16 P / dS operands
+
+
+def test_adamw_matches_torch(ops):
+    g = torch.Generator().manual_seed(4)
+    n = 100003
+    p = torch.randn(n, generator=g); pr = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pr], lr=1e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.2)
+    pd = p.to(dev); gd = torch.zeros(n, device=dev); m = torch.zeros(n, device=dev); v = torch.zeros(n, device=dev)
+    p16 = torch.empty(n, device=dev, dtype=torch.bfloat16)
+    for step in (1, 2, 3):
+        gg = torch.randn(n, generator=g); pr.grad = gg.clone(); opt.step()
+        gd.copy_(gg); ops.adamw_step(pd, gd, m, v, p16, 1e-3, (0.9, 0.98), 1e-6, 0.2, step)
+    assert rel(pd, pr.detach()) < 1e-6 and gd.abs().max().item() == 0 and rel(p16, pd) < 5e-3

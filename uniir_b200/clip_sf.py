@@ -19,6 +19,7 @@ import torch
 import torch.distributed as dist
 from torch import nn
 
+from . import dist_utils as du
 from . import lib as L
 from . import ops
 from .clip_towers import CLIPEncoder
@@ -219,7 +220,7 @@ class CLIPScoreFusion(nn.Module):
         off = rank * bs
         pn = nce.normalize(emb, q_idx, p_idx, off)
         if world > 1:
-            dist.all_gather_into_tensor(nce.all_p, pn.clone())
+            du.all_gather_rows(pn.clone(), out=nce.all_p)
         loss, acc = nce.forward(self.clip_model.w("logit_scale"), off)
         st["emb"] = emb
         self._train_state = st
@@ -238,8 +239,7 @@ class CLIPScoreFusion(nn.Module):
         go = None if g_loss is None else g_loss.to(torch.float32).reshape(()).contiguous()
         d_qn, d_all_p = nce.backward(P.w("logit_scale"), off, P.g("logit_scale"), grad_out=go)
         if world > 1:
-            d_pn = torch.empty(bs, E, device=self.device_, dtype=torch.float32)
-            dist.reduce_scatter_tensor(d_pn, d_all_p, op=dist.ReduceOp.SUM)
+            d_pn = du.reduce_scatter_rows(d_all_p)
         else:
             d_pn = d_all_p
         d_emb = torch.zeros(st["n_items"], E, device=self.device_, dtype=torch.float32)

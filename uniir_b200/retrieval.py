@@ -17,20 +17,14 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import dist_utils as du
 from . import lib as L
 from . import ops
+from .dist_utils import shard_range  # noqa: F401  (re-exported)
 
 
 def _dist_on():
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-
-
-def shard_range(n, world, rank):
-    """Contiguous row block of rank r: [r*ceil(n/W), min((r+1)*ceil(n/W), n)) -- the partition of
-    the reference's ContiguousDistributedSampler (common/dist_utils.py:100-109)."""
-    per = (n + world - 1) // world
-    lo = min(n, rank * per)
-    return lo, min(n, lo + per)
 
 
 class FlatIPIndex:
@@ -94,10 +88,11 @@ class FlatIPIndex:
 class ShardedFlatIPIndex:
     """Row-sharded index across the ranks of the default process group (one process per GPU)."""
 
-    def __init__(self, dim, device="cuda"):
-        self.local = FlatIPIndex(dim, device)
+    def __init__(self, dim, device="cuda", local=None):
+        # `local` is injectable so the exchange logic can be exercised on CPU (gloo) in tests
+        self.local = local if local is not None else FlatIPIndex(dim, device)
         self.dim = dim
-        self.device = self.local.device
+        self.device = torch.device(device) if local is not None else self.local.device
         self.world = dist.get_world_size() if _dist_on() else 1
         self.rank = dist.get_rank() if _dist_on() else 0
 
@@ -118,15 +113,15 @@ class ShardedFlatIPIndex:
         qmax = max(counts)
         pad = torch.zeros(qmax, self.dim, device=dev, dtype=torch.float16)
         pad[:q_local.shape[0]] = q_local
-        allq = torch.empty(W * qmax, self.dim, device=dev, dtype=torch.float16)
-        dist.all_gather_into_tensor(allq, pad)                       # the one query all-gather
+        allq = du.all_gather_rows(pad)                               # the one query all-gather
         s, i = self.local.search_device(allq, k)                     # [W*qmax, k] vs local shard
         # all-to-all: rank r receives the W partial lists of its own query slice
-        rs = torch.empty(W, qmax, k, device=dev, dtype=torch.float32)
-        ri = torch.empty(W, qmax, k, device=dev, dtype=torch.int64)
-        dist.all_to_all_single(rs.view(-1), s.view(-1))
-        dist.all_to_all_single(ri.view(-1), i.view(-1))
+        rs = du.all_to_all_rows(s.view(W, qmax, k))
+        ri = du.all_to_all_rows(i.view(W, qmax, k))
         n = q_local.shape[0]
         ps = rs[:, :n].permute(1, 0, 2).contiguous()                 # [Q_r, W, k]
         pi = ri[:, :n].permute(1, 0, 2).contiguous()
+        return self._merge(ps, pi, k)
+
+    def _merge(self, ps, pi, k):
         return ops.topk_merge(ps, pi, k)
