@@ -142,25 +142,31 @@ def test_train_step_graphs_equal_eager_and_loss_decreases():
     assert res[True][-1] < 0.2 * res[True][0]
 
 
-def test_fused_adamw_step_matches_torch_adamw_through_autograd_bridge():
-    """Same model, same batch: (a) reference-style loop loss.backward() + torch.optim.AdamW with the
-    reference param groups, (b) fused train_step.  Parameters must agree after 2 steps."""
+def test_autograd_bridge_equals_fused_path_and_trains_with_torch_adamw():
+    """(a) reference-style loop: model(batch)["loss"].backward() fills p.grad for a stock torch optimizer;
+    (b) fused path: flat gradient buffers.  Same model + batch -> same gradients (up to the summation order of
+    the split-K / LayerNorm atomics).  Then the reference-style loop must train.  (Post-Adam parameters are
+    not compared element-wise: Adam's first steps are +-lr*sign(g), so elements with |g| ~ 0 amplify
+    summation-order noise; the fused AdamW kernel itself is pinned in test_kernels_gpu.py.)"""
     from uniir_b200.clip_sf import CLIPScoreFusion
-    from uniir_b200.engine import FlatAdamW, train_step
     ma = CLIPScoreFusion("tiny-test", device="cuda", micro_batch=8, seed=3)
     mb_ = CLIPScoreFusion("tiny-test", device="cuda", micro_batch=8, seed=3)
     gb = _cuda(_batch(ma.dims, 8))
+    la = ma(gb)["loss"]; la.backward()
+    lb, _ = mb_._loss_forward(gb); mb_._loss_backward(gb, None)
+    assert abs(la.item() - lb.item()) < 1e-5 * max(1, abs(la.item()))
+    for n, pa in ma.clip_model.named_parameters():
+        ga, gbf = pa.grad.flatten().double(), mb_.clip_model.g(n).flatten().double()
+        assert (ga - gbf).norm() <= 1e-3 * (gbf.norm() + 1e-12), n
     decay = [p for n, p in ma.named_parameters() if not (p.ndim < 2 or "ln" in n or "bias" in n or "logit_scale" in n)]
     nod = [p for n, p in ma.named_parameters() if (p.ndim < 2 or "ln" in n or "bias" in n or "logit_scale" in n)]
-    opt_a = torch.optim.AdamW([{"params": decay, "weight_decay": 0.2}, {"params": nod, "weight_decay": 0.0}],
-                              lr=1e-3, betas=(0.9, 0.98), eps=1e-6)
-    opt_b = FlatAdamW(mb_.clip_model, lr=1e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.2)
-    for _ in range(2):
-        la = ma(gb)["loss"]; la.backward(); opt_a.step(); ma.zero_grad()
-        lb, _ = train_step(mb_, gb, opt_b)
-        assert abs(la.item() - lb.item()) < 1e-3 * max(1, abs(la.item()))
-    for (n, pa), (_, pb) in zip(ma.named_parameters(), mb_.named_parameters()):
-        assert torch.allclose(pa, pb, atol=2e-5, rtol=1e-4), n
+    opt = torch.optim.AdamW([{"params": decay, "weight_decay": 0.2}, {"params": nod, "weight_decay": 0.0}],
+                            lr=1e-3, betas=(0.9, 0.98), eps=1e-6)
+    losses = [la.item()]
+    for _ in range(4):
+        opt.step(); ma.zero_grad()
+        l = ma(gb)["loss"]; l.backward(); losses.append(l.item())
+    assert losses[-1] < 0.2 * losses[0], losses
 
 
 def test_infonce_kernels_match_golden():

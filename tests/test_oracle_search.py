@@ -42,7 +42,8 @@ def test_fewer_candidates_than_k_pads_like_faiss():
 def test_golden_search_vectors():
     g = np.load(os.path.join(GOLDEN, "search_small.npz"))
     D, I = flat_ip_search(g["q"], g["c"], g["ids"], 10)
-    assert (I == g["I"]).mean() > 0.995  # fp32 vs the fp64 golden: only exact ties may swap
+    nz = np.ones(len(I), bool); nz[5] = False  # all-zero query: all scores tie at 0
+    assert (I[nz] == g["I"][nz]).mean() > 0.995  # fp32 vs the fp64 golden: only exact ties may swap
     assert np.abs(D - g["D"]).max() < 2e-6
     Ds, Is = flat_ip_search(g["q"], g["c"][:6], g["ids"][:6], 10)
     assert (Is == g["I_small"]).all()
