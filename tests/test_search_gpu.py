@@ -89,3 +89,28 @@ def test_merge_kernel_streams_more_lists_than_one_buffer():
     flat_s = s.view(Q, -1).clone(); flat_s[0, :k] = -float("inf")
     ref = flat_s.sort(dim=1, descending=True).values[:, :k]
     assert torch.equal(D, ref)
+
+
+def test_create_index_and_search_index_cli_functions(tmp_path):
+    """embed .npy pair -> create_index -> search_index, same signatures/returns as the reference."""
+    from oracle.search_oracle import flat_ip_search
+    from uniir_b200 import config as cfg
+    from uniir_b200.mbeir_embedder import embed_paths, save_embeddings
+    from uniir_b200.mbeir_retriever import create_index, search_index
+    rng = np.random.default_rng(5)
+    c = rng.standard_normal((4000, 64)).astype(np.float16); q = rng.standard_normal((50, 64)).astype(np.float16)
+    ids = np.arange(4000, dtype=np.int64) + 9 * 10_000_000
+    conf = cfg.create({"uniir_dir": str(tmp_path), "experiment": {"path_suffix": "CLIP_SF/Large/Instruct/InBatch/"},
+                       "index_config": {"embed_dir_name": "embed", "index_dir_name": "index",
+                                        "faiss_config": {"idx_type": "Flat", "dim": 64, "metric": "METRIC_INNER_PRODUCT"},
+                                        "cand_pools_config": {"enable_idx": True, "cand_pools_name_to_idx": ["UNION"]}}})
+    e, i = embed_paths(str(tmp_path), "embed", conf.experiment.path_suffix, "cand_pool", "union")
+    save_embeddings(e, i, c, ids)
+    qe, qi = embed_paths(str(tmp_path), "embed", conf.experiment.path_suffix, "test", "q")
+    save_embeddings(qe, qi, q, np.arange(50))
+    create_index(conf)
+    ipath = os.path.join(str(tmp_path), "index", conf.experiment.path_suffix, "cand_pool", "mbeir_union_cand_pool.index")
+    D, I = search_index(qe, ipath, batch_size=10, num_cand_to_retrieve=10)
+    Dr, Ir = flat_ip_search(q, c, ids, 10)
+    assert D.shape == (50, 10) and D.dtype == np.float32 and I.dtype == np.int64
+    assert (I == Ir).mean() > 0.995 and np.abs(D - Dr).max() < 2e-6
