@@ -128,10 +128,17 @@ def timed(fn, steps, world):
 # ----------------------------------------------------------------------------------------
 # CPU reference arm / cpu_baseline (the oracle restatement of the reference, on host cores)
 # ----------------------------------------------------------------------------------------
+def _cpu_threads():
+    """Threads the CPU arm actually uses: all cores up to 32 (beyond that torch's intra-op pool
+    slows these batch sizes down -- measured 9x slower with 128 threads than with 8)."""
+    cores = min(os.cpu_count() or 1, 32)
+    torch.set_num_threads(cores)
+    return cores
+
+
 def cpu_train_reference(steps, warmup, pairs=4):
     from oracle.clip_oracle import CLIPScoreFusionOracle
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores = _cpu_threads()
     torch.manual_seed(2023)
     model = CLIPScoreFusionOracle(MODEL)
     decay = [p for n, p in model.named_parameters() if p.ndim >= 2 and "ln" not in n and "bias" not in n]
@@ -160,8 +167,7 @@ def cpu_train_reference(steps, warmup, pairs=4):
 def cpu_search_reference(steps, warmup, queries=1024, cands=500_000):
     import numpy as np
     from oracle.search_oracle import build_index, flat_ip_search
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores = _cpu_threads()
     g = torch.Generator().manual_seed(2023)
     q = torch.randn(queries, SEARCH_D, generator=g).half().numpy()
     c = torch.randn(cands, SEARCH_D, generator=g).half().numpy()
@@ -224,9 +230,9 @@ def run_train(args, rank, world, dev, peaks):
     torch.cuda.synchronize()
     sampler = ClockSampler(dev.index or 0)
     sampler.start()
-    l0 = lib.launch_count()
+    l0 = lib.launch_count() + ops.graph_launches()
     ms = timed(step, args.steps, world)
-    launches = lib.launch_count() - l0
+    launches = lib.launch_count() + ops.graph_launches() - l0   # direct launches + kernels replayed from CUDA graphs
     clocks = sampler.stop()
     value = GLOBAL_BATCH / (ms / 1e3)
 
@@ -422,7 +428,7 @@ def main():
         if not args.no_extra:
             out["extra"] = {"retrieval": run_search(args, rank, world, dev, peaks, steps=2, warmup=3)}
         if rank == 0 and not args.no_cpu_baseline and world == 1:
-            out["cpu_baseline"], _ = cpu_train_reference(2, 1)
+            out["cpu_baseline"], _ = cpu_train_reference(1, 1)
             if "extra" in out:
                 out["extra"]["retrieval"]["cpu_baseline"], _ = cpu_search_reference(1, 1)
     if rank == 0:

@@ -25,7 +25,7 @@ def test_golden_vectors_and_padding():
     assert (D[5] == 0).all()                      # zero rows score 0 like normalize_L2 (no NaN)
     assert (np.diff(D, axis=1) <= 0).all() and I.dtype == np.int64 and D.dtype == np.float32
     Ds, Is = _index(g["c"][:6], g["ids"][:6]).search(g["q"], 10)                # N < k -> FAISS -1 padding
-    assert (Is == g["I_small"]).all() and (Ds[:, 6:] < -3e38).all()
+    assert (Is[nz] == g["I_small"][nz]).all() and (Ds[:, 6:] < -3e38).all() and (Is[:, 6:] == -1).all()
 
 
 @pytest.mark.parametrize("Q,N,d,k", [(1, 1000, 64, 10), (100, 1000, 64, 10), (300, 5000, 128, 10), (130, 40, 128, 50),

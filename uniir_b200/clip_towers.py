@@ -261,13 +261,16 @@ class CLIPEncoder:
         elif st == 1:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
+            n0 = L.launch_count()
             with torch.cuda.graph(g):
                 body()
-            self._graphs[key] = g
+            self._graphs[key] = (g, L.launch_count() - n0)   # kernels captured in this graph
             # NB: capture does not execute -- replay once so this call has its effect
             g.replay()
+            ops.add_graph_launches(self._graphs[key][1])
         else:
-            st.replay()
+            st[0].replay()
+            ops.add_graph_launches(st[1])
 
     def set_inputs(self, ids, img, mt, mv, d_emb=None):
         n = ids.shape[0]

@@ -26,6 +26,17 @@ def _ptr(t):
 
 
 _GEMM_PROF = None
+_GRAPH_LAUNCHES = 0
+
+
+def graph_launches():
+    """uniir kernels executed through CUDA-graph replays (each replay re-runs the captured launches)."""
+    return _GRAPH_LAUNCHES
+
+
+def add_graph_launches(n):
+    global _GRAPH_LAUNCHES
+    _GRAPH_LAUNCHES += n
 
 
 def set_gemm_profiler(sink):
