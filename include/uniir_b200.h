@@ -113,11 +113,13 @@ int uniir_topk_merge(const float* in_scores, const void* in_idx, int32_t idx_is_
 int uniir_layernorm_fwd(const float* x, int64_t ldx, const int32_t* row_index, const float* gamma,
                         const float* beta, float eps, int64_t rows, int32_t D, void* y, int64_t ldy,
                         int32_t y_dtype, float* mean, float* rstd, void* stream);
-/* dx[src row] (+)= LN backward; dgamma/dbeta += column sums (atomic fp32). */
+/* dx[src row] (+)= LN backward; dgamma/dbeta += column sums (atomic fp32); dx_bf16 (optional,
+ * same row addressing as dx) receives a bf16 copy of the updated dx (next GEMM's operand). */
 int uniir_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_dtype, const float* x, int64_t ldx,
                         const int32_t* row_index, const float* mean, const float* rstd,
                         const float* gamma, int64_t rows, int32_t D, float* dx, int64_t lddx,
-                        int32_t dx_accumulate, float* dgamma, float* dbeta, void* stream);
+                        int32_t dx_accumulate, float* dgamma, float* dbeta, void* dx_bf16,
+                        void* stream);
 /* visual.conv1 (stride = kernel = patch, no bias; clip_ff.py:36) as im2col:
  * img fp32 [B,3,H,W] -> bf16 [B*(H/P)^2, Kpad], k = c*P*P + py*P + px, zero padded. */
 int uniir_patch_im2col(const float* img, int32_t B, int32_t H, int32_t W, int32_t P, int32_t Kpad,

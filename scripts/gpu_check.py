@@ -451,6 +451,26 @@ def case_gemm_perf2():
     return True
 
 
+def case_train_speed():
+    """L/14 step speed at a few micro-batch sizes (env MBS='64,128')"""
+    from uniir_b200.clip_sf import CLIPScoreFusion
+    from uniir_b200.engine import FlatAdamW, train_step
+    import bench
+    for mb in [int(x) for x in os.environ.get("MBS", "64,128").split(",")]:
+        m = CLIPScoreFusion("ViT-L/14", device="cuda", micro_batch=mb)
+        opt = FlatAdamW(m.clip_model, lr=1e-5)
+        pairs = 512
+        b = bench.synth_batch(m.dims, pairs, 1, torch.device("cuda"))
+        for _ in range(3): train_step(m, b, opt)
+        torch.cuda.synchronize(); t0 = time.time()
+        for _ in range(2): l, a = train_step(m, b, opt)
+        torch.cuda.synchronize(); dt = (time.time() - t0) / 2
+        print(f"L/14 mb={mb}: {pairs} pairs/step {dt*1e3:.1f} ms -> {pairs/dt:.1f} pairs/s ({pairs*1.052e12/dt/1e12:.1f} alg TFLOP/s) loss {l.item():.4f}", flush=True)
+        del m, opt, b
+        torch.cuda.empty_cache()
+    return True
+
+
 if __name__ == "__main__":
     name = sys.argv[1]
     ok = globals()["case_" + name]()

@@ -54,6 +54,7 @@ class Tower:
         self.x = torch.empty(T, D, **f32)          # residual stream
         if train:
             self.acts = [_LayerActs(T, D, mb, heads, S, dev) for _ in range(layers)]
+            self.x_out = torch.empty(T, D, **f32)      # tower output when the stream runs through acts
             self.dx = torch.empty(T, D, **f32)
             self.dxb = torch.empty(T, D, **bf)
             self.d_big = torch.empty(T, 4 * D, **bf)   # d_pre
@@ -73,37 +74,39 @@ class Tower:
     def _n(self, i, leaf):
         return f"{self.prefix}.resblocks.{i}.{leaf}"
 
-    # ---- forward over all blocks, in place on self.x --------------------------------
+    # ---- forward over all blocks.  Input: self.x.  Output: self.x ------------------------------
+    # Inference / gradient-cache phase A: the residual stream is updated in place.  Training
+    # (save=True): it flows through the saved per-block buffers (x_in -> x_mid -> next x_in), so
+    # saving the block inputs costs no extra copies.
     def forward(self, save):
-        P, x, B, S, H = self.P, self.x, self.mb, self.S, self.H
+        P, B, S, H = self.P, self.mb, self.S, self.H
+        w16, w = self.P.w16, self.P.w
         for i in range(self.nl):
+            n = lambda leaf: self._n(i, leaf)
             if save:
                 a = self.acts[i]
-                a.x_in.copy_(x)
-                h1, qkv, att, h2, pre, act = a.h1, a.qkv, a.att, a.h2, a.pre, a.act
-                ops.layernorm_fwd(x, P.w(self._n(i, "ln_1.weight")), P.w(self._n(i, "ln_1.bias")), LN_EPS,
-                                  out=h1, stats=(a.m1, a.r1))
+                x_in = self.x if i == 0 else a.x_in
+                if i == 0:
+                    a.x_in = self.x          # block 0 reads the tower input in place
+                x_mid = a.x_mid
+                x_out = self.acts[i + 1].x_in if i + 1 < self.nl else self.x_out
+                h1, qkv, att, h2, pre, act, lse = a.h1, a.qkv, a.att, a.h2, a.pre, a.act, a.lse
+                st1, st2 = (a.m1, a.r1), (a.m2, a.r2)
             else:
+                x_in = x_mid = x_out = self.x
                 h1 = h2 = self.h
-                qkv, att, pre, act = self.qkv, self.att, None, self.big
-                ops.layernorm_fwd(x, P.w(self._n(i, "ln_1.weight")), P.w(self._n(i, "ln_1.bias")), LN_EPS, out=h1)
-            ops.gemm(h1, P.w16(self._n(i, "attn.in_proj_weight")), bias=P.w(self._n(i, "attn.in_proj_bias")), out=qkv)
-            ops.attn_fwd(qkv, B, S, H, self.causal, out=att, lse=(self.acts[i].lse if save else None),
-                         need_lse=save)
-            ops.gemm(att, P.w16(self._n(i, "attn.out_proj.weight")), bias=P.w(self._n(i, "attn.out_proj.bias")),
-                     residual=x, out=x)
-            if save:
-                a.x_mid.copy_(x)
-                ops.layernorm_fwd(x, P.w(self._n(i, "ln_2.weight")), P.w(self._n(i, "ln_2.bias")), LN_EPS,
-                                  out=h2, stats=(a.m2, a.r2))
-            else:
-                ops.layernorm_fwd(x, P.w(self._n(i, "ln_2.weight")), P.w(self._n(i, "ln_2.bias")), LN_EPS, out=h2)
-            ops.gemm(h2, P.w16(self._n(i, "mlp.c_fc.weight")), bias=P.w(self._n(i, "mlp.c_fc.bias")),
-                     act=L.ACT_QUICKGELU, aux_out=pre, out=act)
-            ops.gemm(act, P.w16(self._n(i, "mlp.c_proj.weight")), bias=P.w(self._n(i, "mlp.c_proj.bias")),
-                     residual=x, out=x)
+                qkv, att, pre, act, lse = self.qkv, self.att, None, self.big, None
+                st1 = st2 = None
+            ops.layernorm_fwd(x_in, w(n("ln_1.weight")), w(n("ln_1.bias")), LN_EPS, out=h1, stats=st1)
+            ops.gemm(h1, w16(n("attn.in_proj_weight")), bias=w(n("attn.in_proj_bias")), out=qkv)
+            ops.attn_fwd(qkv, B, S, H, self.causal, out=att, lse=lse, need_lse=save)
+            ops.gemm(att, w16(n("attn.out_proj.weight")), bias=w(n("attn.out_proj.bias")), residual=x_in, out=x_mid)
+            ops.layernorm_fwd(x_mid, w(n("ln_2.weight")), w(n("ln_2.bias")), LN_EPS, out=h2, stats=st2)
+            ops.gemm(h2, w16(n("mlp.c_fc.weight")), bias=w(n("mlp.c_fc.bias")), act=L.ACT_QUICKGELU, aux_out=pre, out=act)
+            ops.gemm(act, w16(n("mlp.c_proj.weight")), bias=w(n("mlp.c_proj.bias")), residual=x_mid, out=x_out)
+        return self.x_out if save else self.x
 
-    # ---- backward: self.dx holds dL/dx_out on entry, dL/dx_in on exit ----------------
+    # ---- backward: self.dx holds dL/dx_out on entry, dL/dx_in on exit; self.dxb = bf16(self.dx)
     def backward(self):
         P, dx, dxb, B, S, H = self.P, self.dx, self.dxb, self.mb, self.S, self.H
         for i in reversed(range(self.nl)):
@@ -111,7 +114,6 @@ class Tower:
             g = lambda leaf: P.g(self._n(i, leaf))
             w16 = lambda leaf: P.w16(self._n(i, leaf))
             # ---- MLP branch: x_out = x_mid + c_proj(quickgelu(c_fc(ln_2(x_mid))))
-            ops.cast_bf16(dx, out=dxb)
             ops.wgrad(dxb, a.act, g("mlp.c_proj.weight"))
             ops.colsum_accum(dxb, g("mlp.c_proj.bias"))
             ops.gemm(dxb, w16("mlp.c_proj.weight"), b_mn=True, act=L.ACT_QUICKGELU, act_grad_src=a.pre,
@@ -120,9 +122,8 @@ class Tower:
             ops.colsum_accum(self.d_big, g("mlp.c_fc.bias"))
             ops.gemm(self.d_big, w16("mlp.c_fc.weight"), b_mn=True, out=self.d_h)
             ops.layernorm_bwd(self.d_h, a.x_mid, a.m2, a.r2, P.w(self._n(i, "ln_2.weight")), dx,
-                              g("ln_2.weight"), g("ln_2.bias"))
+                              g("ln_2.weight"), g("ln_2.bias"), dx_bf16=dxb)
             # ---- attention branch: x_mid = x_in + out_proj(attn(in_proj(ln_1(x_in))))
-            ops.cast_bf16(dx, out=dxb)
             ops.wgrad(dxb, a.att, g("attn.out_proj.weight"))
             ops.colsum_accum(dxb, g("attn.out_proj.bias"))
             ops.gemm(dxb, w16("attn.out_proj.weight"), b_mn=True, out=self.d_h)
@@ -131,7 +132,7 @@ class Tower:
             ops.colsum_accum(self.dqkv, g("attn.in_proj_bias"))
             ops.gemm(self.dqkv, w16("attn.in_proj_weight"), b_mn=True, out=self.d_h)
             ops.layernorm_bwd(self.d_h, a.x_in, a.m1, a.r1, P.w(self._n(i, "ln_1.weight")), dx,
-                              g("ln_1.weight"), g("ln_1.bias"))
+                              g("ln_1.weight"), g("ln_1.bias"), dx_bf16=dxb)
 
 
 class CLIPEncoder:
@@ -177,49 +178,71 @@ class CLIPEncoder:
             self.d_t = torch.zeros(mb, d.embed_dim, **bf)
             self.d_v = torch.zeros(mb, d.embed_dim, **bf)
         self._graphs = {}
+        self._side = None
 
     def refresh_weights(self):
         d = self.d
         ops.pad_cast_bf16(self.P.w("visual.conv1.weight").view(d.v_width, d.patch_k), d.patch_k_pad,
                           out=self.conv_w16)
 
-    # ---- forward: returns (t_emb, v_emb) fp32 [mb, E] (buffers reused per call) -----
-    def forward(self, ids, img, save):
+    # ---- the two towers are independent until score fusion: the text tower runs on a side
+    # stream (fork/join with events; captured as parallel branches of the CUDA graph) so its
+    # small GEMMs fill the SMs the vision kernels leave idle ------------------------------------
+    def _fork(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)
+        return main
+
+    def _join(self, main):
+        main.wait_stream(self._side)
+
+    def _vision_fwd(self, img, save):
         P, d, mb = self.P, self.d, self.mb
-        assert ids.shape == (mb, d.context) and img.shape == (mb, 3, d.image_size, d.image_size)
-        # vision
         ops.patch_im2col(img, d.patch, d.patch_k_pad, out=self.col)
         ops.gemm(self.col, self.conv_w16, out=self.patch)
         ops.vision_embed_fwd(self.patch, P.w("visual.class_embedding"), P.w("visual.positional_embedding"),
                              mb, d.v_tokens, d.v_width, out=self.x0)
         ops.layernorm_fwd(self.x0, P.w("visual.ln_pre.weight"), P.w("visual.ln_pre.bias"), LN_EPS,
                           out=self.vis.x, stats=((self.pre_m, self.pre_r) if save else None))
-        self.vis.forward(save)
-        ops.layernorm_fwd(self.vis.x, P.w("visual.ln_post.weight"), P.w("visual.ln_post.bias"), LN_EPS,
+        xo = self.vis.forward(save)
+        ops.layernorm_fwd(xo, P.w("visual.ln_post.weight"), P.w("visual.ln_post.bias"), LN_EPS,
                           row_index=self.cls_rows, out=self.v_pool,
                           stats=((self.vp_m, self.vp_r) if save else None))
         ops.gemm(self.v_pool, P.w16("visual.proj"), b_mn=True, out=self.v_emb)
-        # text
+
+    def _text_fwd(self, ids, save):
+        P, d, mb = self.P, self.d, self.mb
         ops.text_embed_fwd(ids, P.w("token_embedding.weight"), P.w("positional_embedding"),
                            out=self.txt.x.view(mb, d.context, d.t_width), eot=self.eot_rows)
         self.ids = ids
-        self.txt.forward(save)
-        ops.layernorm_fwd(self.txt.x, P.w("ln_final.weight"), P.w("ln_final.bias"), LN_EPS,
+        xo = self.txt.forward(save)
+        ops.layernorm_fwd(xo, P.w("ln_final.weight"), P.w("ln_final.bias"), LN_EPS,
                           row_index=self.eot_rows, out=self.t_pool,
                           stats=((self.tp_m, self.tp_r) if save else None))
         ops.gemm(self.t_pool, P.w16("text_projection"), b_mn=True, out=self.t_emb)
+
+    # ---- forward: returns (t_emb, v_emb) fp32 [mb, E] (buffers reused per call) -----
+    def forward(self, ids, img, save):
+        d, mb = self.d, self.mb
+        assert ids.shape == (mb, d.context) and img.shape == (mb, 3, d.image_size, d.image_size)
+        main = self._fork()
+        with torch.cuda.stream(self._side):
+            self._text_fwd(ids, save)
+        self._vision_fwd(img, save)
+        self._join(main)
         return self.t_emb, self.v_emb
 
-    # ---- backward from d t_emb / d v_emb (bf16 [mb, E]); accumulates into P.grad -----
-    def backward(self, d_t, d_v):
+    def _vision_bwd(self, d_v):
         P, d, mb = self.P, self.d, self.mb
-        # ---------------- vision ----------------
         ops.wgrad(self.v_pool, d_v, P.g("visual.proj"))                 # [D,E] += pool^T d_v
         ops.gemm(d_v, P.w16("visual.proj"), out=self.d_pool_v)          # d_pool = d_v @ proj^T
         self.vis.dx.zero_()
-        ops.layernorm_bwd(self.d_pool_v, self.vis.x, self.vp_m, self.vp_r, P.w("visual.ln_post.weight"),
+        self.vis.dxb.zero_()
+        ops.layernorm_bwd(self.d_pool_v, self.vis.x_out, self.vp_m, self.vp_r, P.w("visual.ln_post.weight"),
                           self.vis.dx, P.g("visual.ln_post.weight"), P.g("visual.ln_post.bias"),
-                          row_index=self.cls_rows, accumulate=False)
+                          row_index=self.cls_rows, accumulate=False, dx_bf16=self.vis.dxb)
         self.vis.backward()
         ops.layernorm_bwd(self.vis.dx, self.x0, self.pre_m, self.pre_r, P.w("visual.ln_pre.weight"),
                           self.dx0, P.g("visual.ln_pre.weight"), P.g("visual.ln_pre.bias"), accumulate=False)
@@ -228,15 +251,26 @@ class CLIPEncoder:
         self.d_conv_pad.zero_()
         ops.wgrad(self.d_patch, self.col, self.d_conv_pad)
         ops.unpad_accum(self.d_conv_pad, P.g("visual.conv1.weight").view(d.v_width, d.patch_k))
-        # ---------------- text ----------------
+
+    def _text_bwd(self, d_t):
+        P = self.P
         ops.wgrad(self.t_pool, d_t, P.g("text_projection"))
         ops.gemm(d_t, P.w16("text_projection"), out=self.d_pool_t)
         self.txt.dx.zero_()
-        ops.layernorm_bwd(self.d_pool_t, self.txt.x, self.tp_m, self.tp_r, P.w("ln_final.weight"),
+        self.txt.dxb.zero_()
+        ops.layernorm_bwd(self.d_pool_t, self.txt.x_out, self.tp_m, self.tp_r, P.w("ln_final.weight"),
                           self.txt.dx, P.g("ln_final.weight"), P.g("ln_final.bias"),
-                          row_index=self.eot_rows, accumulate=False)
+                          row_index=self.eot_rows, accumulate=False, dx_bf16=self.txt.dxb)
         self.txt.backward()
         ops.text_embed_bwd(self.txt.dx, self.ids, P.g("token_embedding.weight"), P.g("positional_embedding"))
+
+    # ---- backward from d t_emb / d v_emb (bf16 [mb, E]); accumulates into P.grad -----
+    def backward(self, d_t, d_v):
+        main = self._fork()
+        with torch.cuda.stream(self._side):
+            self._text_bwd(d_t)
+        self._vision_bwd(d_v)
+        self._join(main)
 
     # ---- CUDA-graph front-ends over the static I/O buffers ----------------------------------
     def _body_embed(self):

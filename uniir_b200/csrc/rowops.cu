@@ -105,7 +105,7 @@ __global__ void layernorm_bwd_kernel(const void* __restrict__ dy, long long lddy
                                      const float* __restrict__ gamma, int D, long long rows,
                                      int rows_per_cta, float* __restrict__ dx, long long lddx,
                                      int dx_accumulate, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta) {
+                                     float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dx16) {
   __shared__ float sh[33];
   float4 dg[VEC_PER_THREAD], db[VEC_PER_THREAD], g[VEC_PER_THREAD];
 #pragma unroll
@@ -157,6 +157,8 @@ __global__ void layernorm_bwd_kernel(const void* __restrict__ dy, long long lddy
           o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
         }
         *reinterpret_cast<float4*>(dp) = o;
+        // optional bf16 copy of the updated gradient: the next GEMMs' operand (saves a cast pass)
+        if (dx16) *reinterpret_cast<uint2*>(dx16 + src * lddx + c) = pack4_bf16(o.x, o.y, o.z, o.w);
       }
     }
   }
@@ -405,7 +407,7 @@ extern "C" int uniir_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_dtyp
                                    int64_t ldx, const int32_t* row_index, const float* mean,
                                    const float* rstd, const float* gamma, int64_t rows, int32_t D,
                                    float* dx, int64_t lddx, int32_t dx_accumulate, float* dgamma,
-                                   float* dbeta, void* stream) {
+                                   float* dbeta, void* dx_bf16, void* stream) {
   UNIIR_CHECK_ARG(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && D > 0 && D % 4 == 0 && D <= 4096,
                   "uniir_layernorm_bwd: bad args");
   if (rows == 0) return UNIIR_OK;
@@ -417,7 +419,7 @@ extern "C" int uniir_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_dtyp
   if (rpc < 1) rpc = 1;
   const unsigned grid = static_cast<unsigned>((rows + rpc - 1) / rpc);
   const int f32 = dy_dtype == UNIIR_F32;
-#define LN_BWD(V) layernorm_bwd_kernel<V><<<grid, threads, 0, ST(stream)>>>(dy, lddy, f32, x, ldx, row_index, mean, rstd, gamma, D, rows, rpc, dx, lddx, dx_accumulate, dgamma, dbeta)
+#define LN_BWD(V) layernorm_bwd_kernel<V><<<grid, threads, 0, ST(stream)>>>(dy, lddy, f32, x, ldx, row_index, mean, rstd, gamma, D, rows, rpc, dx, lddx, dx_accumulate, dgamma, dbeta, static_cast<__nv_bfloat16*>(dx_bf16))
   if (vecs <= 1) LN_BWD(1); else if (vecs <= 2) LN_BWD(2); else LN_BWD(4);
 #undef LN_BWD
   count_launch();

@@ -55,7 +55,7 @@ _SIGS = {
                                    C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "uniir_layernorm_fwd": (C.c_int, [VP, I64, VP, VP, VP, C.c_float, I64, I32, VP, I64, I32, VP, VP, VP]),
-    "uniir_layernorm_bwd": (C.c_int, [VP, I64, I32, VP, I64, VP, VP, VP, VP, I64, I32, VP, I64, I32, VP, VP, VP]),
+    "uniir_layernorm_bwd": (C.c_int, [VP, I64, I32, VP, I64, VP, VP, VP, VP, I64, I32, VP, I64, I32, VP, VP, VP, VP]),
     "uniir_patch_im2col": (C.c_int, [VP, I32, I32, I32, I32, I32, VP, VP]),
     "uniir_vision_embed_fwd": (C.c_int, [VP, VP, VP, I32, I32, I32, VP, VP]),
     "uniir_vision_embed_bwd": (C.c_int, [VP, I32, I32, I32, VP, VP, VP, VP]),

@@ -190,14 +190,15 @@ def layernorm_fwd(x, gamma, beta, eps, *, rows=None, ldx=None, row_index=None, o
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, *, rows=None, ldx=None, lddx=None,
-                  row_index=None, accumulate=True):
+                  row_index=None, accumulate=True, dx_bf16=None):
     D = gamma.numel()
     if rows is None:
         rows = mean.numel()
     L.check(L.load().uniir_layernorm_bwd(dy.data_ptr(), D, _DT[dy.dtype], x.data_ptr(), ldx or D,
                                          _ptr(row_index), mean.data_ptr(), rstd.data_ptr(),
                                          gamma.data_ptr(), rows, D, dx.data_ptr(), lddx or (ldx or D),
-                                         int(accumulate), dgamma.data_ptr(), dbeta.data_ptr(), _stream()),
+                                         int(accumulate), dgamma.data_ptr(), dbeta.data_ptr(), _ptr(dx_bf16),
+                                         _stream()),
             "uniir_layernorm_bwd")
 
 
