@@ -21,4 +21,11 @@ elif which == "search":
     for _ in range(2):
         ops.ip_topk_partial(q, qi, c, ci, k)
     torch.cuda.synchronize()
+if which == "attn":
+    B, S, H = 64, 257, 16
+    qkv = torch.randn(B * S, 3 * H * 64, device="cuda").bfloat16()
+    for _ in range(3):
+        out, lse = ops.attn_fwd(qkv, B, S, H, False)
+        ops.attn_bwd(qkv, out, torch.randn_like(out), lse, B, S, H, False)
+    torch.cuda.synchronize()
 print("done")

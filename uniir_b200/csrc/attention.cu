@@ -9,9 +9,9 @@
 // whole K/V of a head fits in one SM's shared memory, so the tcgen05/TMEM machinery (128-row
 // UMMA tiles, single-thread issue) buys nothing at S <= 257; the GEMMs that carry 96 % of the
 // FLOPs are tcgen05 (gemm_sm100.cuh).
-//   fwd     : grid (ceil(S/64), H, B)   O, LSE
-//   bwd dQ  : grid (ceil(S/64), H, B)   Q-block stationary, loops KV blocks
-//   bwd dKV : grid (ceil(S/64), H, B)   KV-block stationary, loops Q blocks
+//   fwd     : grid (H, B)   K,V resident; warps stride over 16-row query tiles        O, LSE
+//   bwd dQ  : grid (H, B)   K,V resident; per-warp Q / dO tiles
+//   bwd dKV : grid (H, B)   Q,dO,LSE,delta resident; per-warp K / V tiles
 // S is recomputed in both backward kernels (7 instead of 5 GEMM units; no atomics, no dQ
 // round trip through HBM).
 #include <cuda_bf16.h>
@@ -101,114 +101,153 @@ struct AttnParams {
   float scale;               // 1/sqrt(64)
 };
 
-// ---------------------------------------------------------------------------------
-// forward
-// ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
-  __shared__ __align__(128) uint8_t sm[3 * kTileBytes];
-  const uint32_t sQ = s_u32(sm), sK = sQ + kTileBytes, sV = sK + kTileBytes;
-  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+// =================================================================================
+// Head-resident kernels: one CTA per (batch, head).  The whole K and V (forward, dQ) or
+// Q and dO (dK/dV) of the head live in shared memory (S <= 768), loaded once; each warp
+// strides over 16-row tiles of the other operand held in a private 2 KB buffer.  The
+// streamed dimension is walked in 64-row blocks with a 16-row-granular tail, so S = 257
+// costs 17 x 272 score tiles instead of the 320 x 320 of plain 64 x 64 blocking, and
+// there is no block-wide barrier inside the loops.
+// =================================================================================
+constexpr int kAttnWarps = 6;
+constexpr int kAttnThreads = kAttnWarps * 32;
+
+// rows [0, spad) of a [S, 64] bf16 matrix -> swizzled smem (zero fill beyond S); all threads
+__device__ __forceinline__ void load_rows(uint32_t dst, const __nv_bfloat16* g, long long ld, int S, int spad) {
+  for (int id = threadIdx.x; id < spad * 8; id += blockDim.x) {
+    const int r = id >> 3, c = id & 7;
+    const bool ok = r < S;
+    cp_async16(dst + r * 128 + ((c ^ (r & 7)) << 4), g + static_cast<long long>(ok ? r : 0) * ld + c * 8, ok);
+  }
+}
+// 16 rows starting at row0 -> a warp-private swizzled tile; one warp
+__device__ __forceinline__ void load_rows16_warp(uint32_t dst, const __nv_bfloat16* g, long long ld, int row0, int S) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int id = lane + i * 32, r = id >> 3, c = id & 7;
+    const bool ok = row0 + r < S;
+    cp_async16(dst + r * 128 + ((c ^ (r & 7)) << 4), g + static_cast<long long>(ok ? row0 + r : 0) * ld + c * 8, ok);
+  }
+}
+
+__global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams p, int spad) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  const uint32_t sK = s_u32(sm), sV = sK + spad * 128, sQ0 = sV + spad * 128;
+  const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long ld = 3LL * p.D;
   const __nv_bfloat16* base = p.qkv + static_cast<long long>(b) * p.S * ld + h * kHD;
-  const int q0 = qb * kBlk;
-  load_tile(sQ, base, ld, q0, p.S);
+  load_rows(sK, base + p.D, ld, p.S, spad);
+  load_rows(sV, base + 2 * p.D, ld, p.S, spad);
   cp_async_wait_all();
   __syncthreads();
-  uint32_t qa[4][4];
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) frag_a(sQ, warp * 16, kk, qa[kk]);
-
-  float o[8][4];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
-  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const uint32_t sQ = sQ0 + warp * 2048;
   const float sc = p.scale * kLog2e;
-  const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;  // this thread's two query rows
-  const int kv_end = p.causal ? min(p.S, q0 + kBlk) : p.S;
-
-  for (int k0 = 0; k0 < kv_end; k0 += kBlk) {
-    __syncthreads();
-    load_tile(sK, base + p.D, ld, k0, p.S);
-    load_tile(sV, base + 2 * p.D, ld, k0, p.S);
-    cp_async_wait_all();
-    __syncthreads();
-    float s[8][4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-      for (int j = 0; j < 8; j += 2) {
-        uint32_t bb[4];
-        frag_b_nk(sK, j, kk, bb);
-        mma_bf16(s[j], qa[kk], bb[0], bb[1]);
-        mma_bf16(s[j + 1], qa[kk], bb[2], bb[3]);
-      }
-    }
-    // mask + running max
-    float bm0 = -INFINITY, bm1 = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int key = k0 + j * 8 + (lane & 3) * 2 + (e & 1);
-        const int qr = (e < 2) ? r0 : r1;
-        const bool dead = key >= p.S || (p.causal && key > qr);
-        s[j][e] = dead ? -INFINITY : s[j][e] * sc;
-      }
-      bm0 = fmaxf(bm0, fmaxf(s[j][0], s[j][1]));
-      bm1 = fmaxf(bm1, fmaxf(s[j][2], s[j][3]));
-    }
-    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
-    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
-    const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);
-    const float base0 = (nm0 == -INFINITY) ? 0.f : nm0, base1 = (nm1 == -INFINITY) ? 0.f : nm1;
-    const float c0 = exp2f(m0 - base0), c1 = exp2f(m1 - base1);  // exp2(-inf)=0 on first block
-    m0 = nm0; m1 = nm1;
-    float rs0 = 0.f, rs1 = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s[j][0] = exp2f(s[j][0] - base0); s[j][1] = exp2f(s[j][1] - base0);
-      s[j][2] = exp2f(s[j][2] - base1); s[j][3] = exp2f(s[j][3] - base1);
-      rs0 += s[j][0] + s[j][1];
-      rs1 += s[j][2] + s[j][3];
-      o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1;
-    }
-    l0 = l0 * c0 + rs0;
-    l1 = l1 * c1 + rs1;
-    // O += P V
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      uint32_t pa[4];
-      pa[0] = pack_bf16(s[2 * t][0], s[2 * t][1]);
-      pa[1] = pack_bf16(s[2 * t][2], s[2 * t][3]);
-      pa[2] = pack_bf16(s[2 * t + 1][0], s[2 * t + 1][1]);
-      pa[3] = pack_bf16(s[2 * t + 1][2], s[2 * t + 1][3]);
-#pragma unroll
-      for (int jd = 0; jd < 8; jd += 2) {
-        uint32_t bb[4];
-        frag_b_kn(sV, t, jd, bb);
-        mma_bf16(o[jd], pa, bb[0], bb[1]);
-        mma_bf16(o[jd + 1], pa, bb[2], bb[3]);
-      }
-    }
-  }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
   __nv_bfloat16* ob = p.out + static_cast<long long>(b) * p.S * p.D + h * kHD;
+  float* lp = p.lse ? p.lse + (static_cast<long long>(b) * p.H + h) * p.S : nullptr;
+  const int n_qt = spad >> 4;
+  for (int qt = warp; qt < n_qt; qt += kAttnWarps) {
+    const int q0 = qt * 16;
+    __syncwarp();
+    load_rows16_warp(sQ, base, ld, q0, p.S);
+    cp_async_wait_all();
+    __syncwarp();
+    uint32_t qa[4][4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int col = j * 8 + (lane & 3) * 2;
-    if (r0 < p.S) *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(r0) * p.D + col) = pack_bf16(o[j][0] * i0, o[j][1] * i0);
-    if (r1 < p.S) *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(r1) * p.D + col) = pack_bf16(o[j][2] * i1, o[j][3] * i1);
-  }
-  if (p.lse && (lane & 3) == 0) {
-    float* lp = p.lse + (static_cast<long long>(b) * p.H + h) * p.S;
-    // natural-log LSE of the scaled scores
-    if (r0 < p.S) lp[r0] = (m0 + log2f(l0)) / kLog2e;
-    if (r1 < p.S) lp[r1] = (m1 + log2f(l1)) / kLog2e;
+    for (int kk = 0; kk < 4; ++kk) frag_a(sQ, 0, kk, qa[kk]);
+    float o[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    const int r0 = q0 + (lane >> 2), r1 = r0 + 8;
+    const int kv_end = p.causal ? min(spad, q0 + 16) : spad;
+    for (int k0 = 0; k0 < kv_end; k0 += kBlk) {
+      const int nt = min(kBlk, kv_end - k0) >> 3;  // n-tiles of 8 keys in this block (even)
+      const uint32_t bK = sK + k0 * 128, bV = sV + k0 * 128;
+      float s[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          if (j < nt) {
+            uint32_t bb[4];
+            frag_b_nk(bK, j, kk, bb);
+            mma_bf16(s[j], qa[kk], bb[0], bb[1]);
+            mma_bf16(s[j + 1], qa[kk], bb[2], bb[3]);
+          }
+        }
+      }
+      // masking only where a block touches the sequence end or the causal diagonal (warp-uniform)
+      const bool need_mask = nt < 8 || k0 + kBlk > p.S || (p.causal && k0 + kBlk - 1 > q0);
+      if (need_mask) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int key = k0 + j * 8 + (lane & 3) * 2 + (e & 1);
+            const int qr = (e < 2) ? r0 : r1;
+            if (j >= nt || key >= p.S || (p.causal && key > qr)) s[j][e] = -INFINITY;
+          }
+        }
+      }
+      // running max in raw score units; the softmax scale rides in the FFMA that feeds exp2
+      float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        bm0 = fmaxf(bm0, fmaxf(s[j][0], s[j][1]));
+        bm1 = fmaxf(bm1, fmaxf(s[j][2], s[j][3]));
+      }
+      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+      const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);
+      const float base0 = (nm0 == -INFINITY) ? 0.f : nm0 * sc, base1 = (nm1 == -INFINITY) ? 0.f : nm1 * sc;
+      const float c0 = exp2f(fmaf(m0, sc, -base0)), c1 = exp2f(fmaf(m1, sc, -base1));
+      m0 = nm0; m1 = nm1;
+      float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j][0] = exp2f(fmaf(s[j][0], sc, -base0)); s[j][1] = exp2f(fmaf(s[j][1], sc, -base0));
+        s[j][2] = exp2f(fmaf(s[j][2], sc, -base1)); s[j][3] = exp2f(fmaf(s[j][3], sc, -base1));
+        rs0 += s[j][0] + s[j][1];
+        rs1 += s[j][2] + s[j][3];
+        o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1;
+      }
+      l0 = l0 * c0 + rs0;
+      l1 = l1 * c1 + rs1;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (2 * t < nt) {
+          uint32_t pa[4];
+          pa[0] = pack_bf16(s[2 * t][0], s[2 * t][1]);
+          pa[1] = pack_bf16(s[2 * t][2], s[2 * t][3]);
+          pa[2] = pack_bf16(s[2 * t + 1][0], s[2 * t + 1][1]);
+          pa[3] = pack_bf16(s[2 * t + 1][2], s[2 * t + 1][3]);
+#pragma unroll
+          for (int jd = 0; jd < 8; jd += 2) {
+            uint32_t bb[4];
+            frag_b_kn(bV, t, jd, bb);
+            mma_bf16(o[jd], pa, bb[0], bb[1]);
+            mma_bf16(o[jd + 1], pa, bb[2], bb[3]);
+          }
+        }
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = j * 8 + (lane & 3) * 2;
+      if (r0 < p.S) *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(r0) * p.D + col) = pack_bf16(o[j][0] * i0, o[j][1] * i0);
+      if (r1 < p.S) *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(r1) * p.D + col) = pack_bf16(o[j][2] * i1, o[j][3] * i1);
+    }
+    if (lp && (lane & 3) == 0) {
+      if (r0 < p.S) lp[r0] = (m0 * sc + log2f(l0)) / kLog2e;
+      if (r1 < p.S) lp[r1] = (m1 * sc + log2f(l1)) / kLog2e;
+    }
   }
 }
 
@@ -232,204 +271,235 @@ __global__ void attn_delta_kernel(const AttnParams p) {
   }
 }
 
-// ---------------------------------------------------------------------------------
-// backward dQ: Q-block stationary.  dQ = scale * sum_kv  [P o (dO V^T - delta)] K
-// ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnParams p) {
-  __shared__ __align__(128) uint8_t sm[4 * kTileBytes];
-  const uint32_t sQ = s_u32(sm), sDO = sQ + kTileBytes, sK = sDO + kTileBytes, sV = sK + kTileBytes;
-  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+// backward dQ: K, V resident; per warp 16 query rows (Q and dO tiles private).
+__global__ void __launch_bounds__(kAttnThreads, 2) attn_bwd_dq_kernel(const AttnParams p, int spad) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  const uint32_t sK = s_u32(sm), sV = sK + spad * 128, sW = sV + spad * 128;
+  const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long ld = 3LL * p.D;
   const __nv_bfloat16* base = p.qkv + static_cast<long long>(b) * p.S * ld + h * kHD;
   const __nv_bfloat16* dob = p.dout + static_cast<long long>(b) * p.S * p.D + h * kHD;
-  const int q0 = qb * kBlk;
-  load_tile(sQ, base, ld, q0, p.S);
-  load_tile(sDO, dob, p.D, q0, p.S);
+  load_rows(sK, base + p.D, ld, p.S, spad);
+  load_rows(sV, base + 2 * p.D, ld, p.S, spad);
   cp_async_wait_all();
   __syncthreads();
-  uint32_t qa[4][4], da[4][4];
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) { frag_a(sQ, warp * 16, kk, qa[kk]); frag_a(sDO, warp * 16, kk, da[kk]); }
-  const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
+  const uint32_t sQ = sW + warp * 4096, sDO = sQ + 2048;
   const float* lp = p.lse + (static_cast<long long>(b) * p.H + h) * p.S;
   const float* dp = p.delta + (static_cast<long long>(b) * p.H + h) * p.S;
-  const float lse0 = (r0 < p.S) ? lp[r0] * kLog2e : 0.f, lse1 = (r1 < p.S) ? lp[r1] * kLog2e : 0.f;
-  const float dl0 = (r0 < p.S) ? dp[r0] : 0.f, dl1 = (r1 < p.S) ? dp[r1] : 0.f;
   const float sc = p.scale * kLog2e;
-  float dq[8][4];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
-  const int kv_end = p.causal ? min(p.S, q0 + kBlk) : p.S;
-  for (int k0 = 0; k0 < kv_end; k0 += kBlk) {
-    __syncthreads();
-    load_tile(sK, base + p.D, ld, k0, p.S);
-    load_tile(sV, base + 2 * p.D, ld, k0, p.S);
-    cp_async_wait_all();
-    __syncthreads();
-    float s[8][4], dpv[8][4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-      dpv[j][0] = dpv[j][1] = dpv[j][2] = dpv[j][3] = 0.f;
-    }
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-      for (int j = 0; j < 8; j += 2) {
-        uint32_t bb[4];
-        frag_b_nk(sK, j, kk, bb);
-        mma_bf16(s[j], qa[kk], bb[0], bb[1]);
-        mma_bf16(s[j + 1], qa[kk], bb[2], bb[3]);
-        frag_b_nk(sV, j, kk, bb);
-        mma_bf16(dpv[j], da[kk], bb[0], bb[1]);
-        mma_bf16(dpv[j + 1], da[kk], bb[2], bb[3]);
-      }
-    }
-    // dS = P o (dP - delta)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int key = k0 + j * 8 + (lane & 3) * 2 + (e & 1);
-        const int qr = (e < 2) ? r0 : r1;
-        const bool dead = key >= p.S || qr >= p.S || (p.causal && key > qr);
-        const float pe = dead ? 0.f : exp2f(s[j][e] * sc - ((e < 2) ? lse0 : lse1));
-        s[j][e] = pe * (dpv[j][e] - ((e < 2) ? dl0 : dl1));
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      uint32_t pa[4];
-      pa[0] = pack_bf16(s[2 * t][0], s[2 * t][1]);
-      pa[1] = pack_bf16(s[2 * t][2], s[2 * t][3]);
-      pa[2] = pack_bf16(s[2 * t + 1][0], s[2 * t + 1][1]);
-      pa[3] = pack_bf16(s[2 * t + 1][2], s[2 * t + 1][3]);
-#pragma unroll
-      for (int jd = 0; jd < 8; jd += 2) {
-        uint32_t bb[4];
-        frag_b_kn(sK, t, jd, bb);
-        mma_bf16(dq[jd], pa, bb[0], bb[1]);
-        mma_bf16(dq[jd + 1], pa, bb[2], bb[3]);
-      }
-    }
-  }
   __nv_bfloat16* ob = p.dqkv + static_cast<long long>(b) * p.S * ld + h * kHD;
+  const int n_qt = spad >> 4;
+  for (int qt = warp; qt < n_qt; qt += kAttnWarps) {
+    const int q0 = qt * 16;
+    __syncwarp();
+    load_rows16_warp(sQ, base, ld, q0, p.S);
+    load_rows16_warp(sDO, dob, p.D, q0, p.S);
+    cp_async_wait_all();
+    __syncwarp();
+    uint32_t qa[4][4], da[4][4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int col = j * 8 + (lane & 3) * 2;
-    if (r0 < p.S) *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(r0) * ld + col) = pack_bf16(dq[j][0] * p.scale, dq[j][1] * p.scale);
-    if (r1 < p.S) *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(r1) * ld + col) = pack_bf16(dq[j][2] * p.scale, dq[j][3] * p.scale);
+    for (int kk = 0; kk < 4; ++kk) { frag_a(sQ, 0, kk, qa[kk]); frag_a(sDO, 0, kk, da[kk]); }
+    const int r0 = q0 + (lane >> 2), r1 = r0 + 8;
+    const float lse0 = (r0 < p.S) ? lp[r0] * kLog2e : 0.f, lse1 = (r1 < p.S) ? lp[r1] * kLog2e : 0.f;
+    const float dl0 = (r0 < p.S) ? dp[r0] : 0.f, dl1 = (r1 < p.S) ? dp[r1] : 0.f;
+    float dq[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
+    const int kv_end = p.causal ? min(spad, q0 + 16) : spad;
+    for (int k0 = 0; k0 < kv_end; k0 += kBlk) {
+      const int nt = min(kBlk, kv_end - k0) >> 3;
+      const uint32_t bK = sK + k0 * 128, bV = sV + k0 * 128;
+      float s[8][4], dpv[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+        dpv[j][0] = dpv[j][1] = dpv[j][2] = dpv[j][3] = 0.f;
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          if (j < nt) {
+            uint32_t bb[4];
+            frag_b_nk(bK, j, kk, bb);
+            mma_bf16(s[j], qa[kk], bb[0], bb[1]);
+            mma_bf16(s[j + 1], qa[kk], bb[2], bb[3]);
+            frag_b_nk(bV, j, kk, bb);
+            mma_bf16(dpv[j], da[kk], bb[0], bb[1]);
+            mma_bf16(dpv[j + 1], da[kk], bb[2], bb[3]);
+          }
+        }
+      }
+      const bool need_mask = nt < 8 || k0 + kBlk > p.S || q0 + 16 > p.S || (p.causal && k0 + kBlk - 1 > q0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j][0] = exp2f(fmaf(s[j][0], sc, -lse0)); s[j][1] = exp2f(fmaf(s[j][1], sc, -lse0));
+        s[j][2] = exp2f(fmaf(s[j][2], sc, -lse1)); s[j][3] = exp2f(fmaf(s[j][3], sc, -lse1));
+      }
+      if (need_mask) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int key = k0 + j * 8 + (lane & 3) * 2 + (e & 1);
+            const int qr = (e < 2) ? r0 : r1;
+            if (j >= nt || key >= p.S || qr >= p.S || (p.causal && key > qr)) s[j][e] = 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j][0] *= dpv[j][0] - dl0; s[j][1] *= dpv[j][1] - dl0;
+        s[j][2] *= dpv[j][2] - dl1; s[j][3] *= dpv[j][3] - dl1;
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (2 * t < nt) {
+          uint32_t pa[4];
+          pa[0] = pack_bf16(s[2 * t][0], s[2 * t][1]);
+          pa[1] = pack_bf16(s[2 * t][2], s[2 * t][3]);
+          pa[2] = pack_bf16(s[2 * t + 1][0], s[2 * t + 1][1]);
+          pa[3] = pack_bf16(s[2 * t + 1][2], s[2 * t + 1][3]);
+#pragma unroll
+          for (int jd = 0; jd < 8; jd += 2) {
+            uint32_t bb[4];
+            frag_b_kn(bK, t, jd, bb);
+            mma_bf16(dq[jd], pa, bb[0], bb[1]);
+            mma_bf16(dq[jd + 1], pa, bb[2], bb[3]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = j * 8 + (lane & 3) * 2;
+      if (r0 < p.S) *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(r0) * ld + col) = pack_bf16(dq[j][0] * p.scale, dq[j][1] * p.scale);
+      if (r1 < p.S) *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(r1) * ld + col) = pack_bf16(dq[j][2] * p.scale, dq[j][3] * p.scale);
+    }
   }
 }
 
-// ---------------------------------------------------------------------------------
-// backward dK/dV: KV-block stationary (rows of S^T are keys).
-//   S^T = K Q^T ; P^T = exp(S^T*scale - lse[q]) ; dV += P^T dO ; dP^T = V dO^T ;
-//   dS^T = P^T o (dP^T - delta[q]) ; dK += dS^T Q ;  dK *= scale
-// ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnParams p) {
-  __shared__ __align__(128) uint8_t sm[4 * kTileBytes];
-  __shared__ float s_lse[kBlk], s_delta[kBlk];
-  const uint32_t sK = s_u32(sm), sV = sK + kTileBytes, sQ = sV + kTileBytes, sDO = sQ + kTileBytes;
-  const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+// backward dK/dV: Q, dO, LSE, delta resident; per warp 16 keys (K and V tiles private).
+__global__ void __launch_bounds__(kAttnThreads) attn_bwd_dkv_kernel(const AttnParams p, int spad) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  const uint32_t sQ = s_u32(sm), sDO = sQ + spad * 128, sW = sDO + spad * 128;
+  float* s_lse = reinterpret_cast<float*>(sm + 2 * spad * 128 + kAttnWarps * 4096);
+  float* s_delta = s_lse + spad;
+  const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long ld = 3LL * p.D;
   const __nv_bfloat16* base = p.qkv + static_cast<long long>(b) * p.S * ld + h * kHD;
   const __nv_bfloat16* dob = p.dout + static_cast<long long>(b) * p.S * p.D + h * kHD;
-  const int k0 = kb * kBlk;
-  load_tile(sK, base + p.D, ld, k0, p.S);
-  load_tile(sV, base + 2 * p.D, ld, k0, p.S);
-  cp_async_wait_all();
-  __syncthreads();
-  uint32_t ka[4][4], va[4][4];
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) { frag_a(sK, warp * 16, kk, ka[kk]); frag_a(sV, warp * 16, kk, va[kk]); }
-  const int key0 = k0 + warp * 16 + (lane >> 2), key1 = key0 + 8;
   const float* lp = p.lse + (static_cast<long long>(b) * p.H + h) * p.S;
   const float* dp = p.delta + (static_cast<long long>(b) * p.H + h) * p.S;
+  load_rows(sQ, base, ld, p.S, spad);
+  load_rows(sDO, dob, p.D, p.S, spad);
+  for (int i = threadIdx.x; i < spad; i += blockDim.x) {
+    s_lse[i] = (i < p.S) ? lp[i] * kLog2e : 0.f;
+    s_delta[i] = (i < p.S) ? dp[i] : 0.f;
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  const uint32_t sKw = sW + warp * 4096, sVw = sKw + 2048;
   const float sc = p.scale * kLog2e;
-  float dk[8][4], dv[8][4];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f;
-    dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f;
-  }
-  const int q_begin = p.causal ? (k0 / kBlk) * kBlk : 0;  // queries before this key block see none of it
-  for (int q0 = q_begin; q0 < p.S; q0 += kBlk) {
-    __syncthreads();
-    load_tile(sQ, base, ld, q0, p.S);
-    load_tile(sDO, dob, p.D, q0, p.S);
-    if (threadIdx.x < kBlk) {
-      const int q = q0 + threadIdx.x;
-      s_lse[threadIdx.x] = (q < p.S) ? lp[q] * kLog2e : 0.f;
-      s_delta[threadIdx.x] = (q < p.S) ? dp[q] : 0.f;
-    }
-    cp_async_wait_all();
-    __syncthreads();
-    float st[8][4], dpt[8][4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f;
-      dpt[j][0] = dpt[j][1] = dpt[j][2] = dpt[j][3] = 0.f;
-    }
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-      for (int j = 0; j < 8; j += 2) {
-        uint32_t bb[4];
-        frag_b_nk(sQ, j, kk, bb);
-        mma_bf16(st[j], ka[kk], bb[0], bb[1]);
-        mma_bf16(st[j + 1], ka[kk], bb[2], bb[3]);
-        frag_b_nk(sDO, j, kk, bb);
-        mma_bf16(dpt[j], va[kk], bb[0], bb[1]);
-        mma_bf16(dpt[j + 1], va[kk], bb[2], bb[3]);
-      }
-    }
-    uint32_t pt[4][4], dst[4][4];  // A fragments over 4 query k-steps
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float pe[4], de[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int ql = j * 8 + (lane & 3) * 2 + (e & 1);
-        const int q = q0 + ql;
-        const int key = (e < 2) ? key0 : key1;
-        const bool dead = key >= p.S || q >= p.S || (p.causal && key > q);
-        pe[e] = dead ? 0.f : exp2f(st[j][e] * sc - s_lse[ql]);
-        de[e] = pe[e] * (dpt[j][e] - s_delta[ql]);
-      }
-      const int t = j >> 1, hi = (j & 1) * 2;
-      pt[t][hi] = pack_bf16(pe[0], pe[1]);
-      pt[t][hi + 1] = pack_bf16(pe[2], pe[3]);
-      dst[t][hi] = pack_bf16(de[0], de[1]);
-      dst[t][hi + 1] = pack_bf16(de[2], de[3]);
-    }
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-#pragma unroll
-      for (int jd = 0; jd < 8; jd += 2) {
-        uint32_t bb[4];
-        frag_b_kn(sDO, t, jd, bb);
-        mma_bf16(dv[jd], pt[t], bb[0], bb[1]);
-        mma_bf16(dv[jd + 1], pt[t], bb[2], bb[3]);
-        frag_b_kn(sQ, t, jd, bb);
-        mma_bf16(dk[jd], dst[t], bb[0], bb[1]);
-        mma_bf16(dk[jd + 1], dst[t], bb[2], bb[3]);
-      }
-    }
-  }
   __nv_bfloat16* ob = p.dqkv + static_cast<long long>(b) * p.S * ld + h * kHD;
+  const int n_kt = spad >> 4;
+  for (int kt = warp; kt < n_kt; kt += kAttnWarps) {
+    const int kbase = kt * 16;
+    __syncwarp();
+    load_rows16_warp(sKw, base + p.D, ld, kbase, p.S);
+    load_rows16_warp(sVw, base + 2 * p.D, ld, kbase, p.S);
+    cp_async_wait_all();
+    __syncwarp();
+    uint32_t ka[4][4], va[4][4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int col = j * 8 + (lane & 3) * 2;
-    if (key0 < p.S) {
-      *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(key0) * ld + p.D + col) = pack_bf16(dk[j][0] * p.scale, dk[j][1] * p.scale);
-      *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(key0) * ld + 2 * p.D + col) = pack_bf16(dv[j][0], dv[j][1]);
+    for (int kk = 0; kk < 4; ++kk) { frag_a(sKw, 0, kk, ka[kk]); frag_a(sVw, 0, kk, va[kk]); }
+    const int key0 = kbase + (lane >> 2), key1 = key0 + 8;
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f;
+      dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f;
     }
-    if (key1 < p.S) {
-      *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(key1) * ld + p.D + col) = pack_bf16(dk[j][2] * p.scale, dk[j][3] * p.scale);
-      *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(key1) * ld + 2 * p.D + col) = pack_bf16(dv[j][2], dv[j][3]);
+    const int q_begin = p.causal ? (kbase / kBlk) * kBlk : 0;  // earlier query blocks see none of these keys
+    for (int q0 = q_begin; q0 < spad; q0 += kBlk) {
+      const int nt = min(kBlk, spad - q0) >> 3;
+      const uint32_t bQ = sQ + q0 * 128, bDO = sDO + q0 * 128;
+      float st[8][4], dpt[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f;
+        dpt[j][0] = dpt[j][1] = dpt[j][2] = dpt[j][3] = 0.f;
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          if (j < nt) {
+            uint32_t bb[4];
+            frag_b_nk(bQ, j, kk, bb);
+            mma_bf16(st[j], ka[kk], bb[0], bb[1]);
+            mma_bf16(st[j + 1], ka[kk], bb[2], bb[3]);
+            frag_b_nk(bDO, j, kk, bb);
+            mma_bf16(dpt[j], va[kk], bb[0], bb[1]);
+            mma_bf16(dpt[j + 1], va[kk], bb[2], bb[3]);
+          }
+        }
+      }
+      const bool need_mask = nt < 8 || q0 + kBlk > p.S || kbase + 16 > p.S || (p.causal && kbase + 15 > q0);
+      uint32_t pt[4][4], dst[4][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float pe[4], de[4];
+        const int ql = min(q0 + j * 8 + (lane & 3) * 2, spad - 2);   // this thread's two query columns
+        const float2 ls = *reinterpret_cast<const float2*>(s_lse + ql);
+        const float2 dl = *reinterpret_cast<const float2*>(s_delta + ql);
+        pe[0] = exp2f(fmaf(st[j][0], sc, -ls.x)); pe[1] = exp2f(fmaf(st[j][1], sc, -ls.y));
+        pe[2] = exp2f(fmaf(st[j][2], sc, -ls.x)); pe[3] = exp2f(fmaf(st[j][3], sc, -ls.y));
+        if (need_mask) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int q = q0 + j * 8 + (lane & 3) * 2 + (e & 1);
+            const int key = (e < 2) ? key0 : key1;
+            if (j >= nt || key >= p.S || q >= p.S || (p.causal && key > q)) pe[e] = 0.f;
+          }
+        }
+        de[0] = pe[0] * (dpt[j][0] - dl.x); de[1] = pe[1] * (dpt[j][1] - dl.y);
+        de[2] = pe[2] * (dpt[j][2] - dl.x); de[3] = pe[3] * (dpt[j][3] - dl.y);
+        const int t = j >> 1, hi = (j & 1) * 2;
+        pt[t][hi] = pack_bf16(pe[0], pe[1]);
+        pt[t][hi + 1] = pack_bf16(pe[2], pe[3]);
+        dst[t][hi] = pack_bf16(de[0], de[1]);
+        dst[t][hi + 1] = pack_bf16(de[2], de[3]);
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (2 * t < nt) {
+#pragma unroll
+          for (int jd = 0; jd < 8; jd += 2) {
+            uint32_t bb[4];
+            frag_b_kn(bDO, t, jd, bb);
+            mma_bf16(dv[jd], pt[t], bb[0], bb[1]);
+            mma_bf16(dv[jd + 1], pt[t], bb[2], bb[3]);
+            frag_b_kn(bQ, t, jd, bb);
+            mma_bf16(dk[jd], dst[t], bb[0], bb[1]);
+            mma_bf16(dk[jd + 1], dst[t], bb[2], bb[3]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = j * 8 + (lane & 3) * 2;
+      if (key0 < p.S) {
+        *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(key0) * ld + p.D + col) = pack_bf16(dk[j][0] * p.scale, dk[j][1] * p.scale);
+        *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(key0) * ld + 2 * p.D + col) = pack_bf16(dv[j][0], dv[j][1]);
+      }
+      if (key1 < p.S) {
+        *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(key1) * ld + p.D + col) = pack_bf16(dk[j][2] * p.scale, dk[j][3] * p.scale);
+        *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(key1) * ld + 2 * p.D + col) = pack_bf16(dv[j][2], dv[j][3]);
+      }
     }
   }
 }
@@ -439,15 +509,33 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnParams p) {
 using namespace uniir;
 #define ST(s) static_cast<cudaStream_t>(s)
 
+static int attn_smem(int spad, bool dkv) {
+  return 2 * spad * 128 + kAttnWarps * (dkv ? 4096 : 2048) + (dkv ? 2 * spad * 4 : 0);
+}
+static int attn_set_smem() {
+  static bool done = false;
+  if (!done) {
+    const int mx = 227 * 1024;
+    UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    done = true;
+  }
+  return UNIIR_OK;
+}
+
 extern "C" int uniir_attn_fwd(const void* qkv, int32_t B, int32_t S, int32_t H, int32_t causal, void* out,
                               float* lse, void* stream) {
   UNIIR_CHECK_ARG(qkv && out && B > 0 && S > 0 && H > 0, "uniir_attn_fwd: bad args");
+  UNIIR_CHECK_ARG(S <= 768, "uniir_attn_fwd: S=%d exceeds the head-resident kernel's limit of 768", S);
+  if (int rc = attn_set_smem()) return rc;
   AttnParams p{};
   p.qkv = static_cast<const __nv_bfloat16*>(qkv);
   p.out = static_cast<__nv_bfloat16*>(out);
   p.lse = lse;
   p.B = B; p.S = S; p.H = H; p.D = H * kHD; p.causal = causal; p.scale = 0.125f;
-  attn_fwd_kernel<<<dim3((S + kBlk - 1) / kBlk, H, B), 128, 0, ST(stream)>>>(p);
+  const int spad = (S + 15) / 16 * 16;
+  attn_fwd_kernel<<<dim3(H, B), kAttnThreads, attn_smem(spad, false), ST(stream)>>>(p, spad);
   count_launch();
   UNIIR_CUDA_OK(cudaGetLastError());
   return UNIIR_OK;
@@ -458,6 +546,8 @@ extern "C" int uniir_attn_bwd(const void* qkv, const void* out, const void* dout
                               void* dqkv, void* stream) {
   UNIIR_CHECK_ARG(qkv && out && dout && lse && delta_ws && dqkv && B > 0 && S > 0 && H > 0,
                   "uniir_attn_bwd: bad args");
+  UNIIR_CHECK_ARG(S <= 768, "uniir_attn_bwd: S=%d exceeds the head-resident kernel's limit of 768", S);
+  if (int rc = attn_set_smem()) return rc;
   AttnParams p{};
   p.qkv = static_cast<const __nv_bfloat16*>(qkv);
   p.out = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(out));
@@ -466,11 +556,11 @@ extern "C" int uniir_attn_bwd(const void* qkv, const void* out, const void* dout
   p.delta = delta_ws;
   p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
   p.B = B; p.S = S; p.H = H; p.D = H * kHD; p.causal = causal; p.scale = 0.125f;
+  const int spad = (S + 15) / 16 * 16;
   const long long warps = 1LL * B * S * H;
   attn_delta_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, ST(stream)>>>(p);
-  const dim3 grid((S + kBlk - 1) / kBlk, H, B);
-  attn_bwd_dq_kernel<<<grid, 128, 0, ST(stream)>>>(p);
-  attn_bwd_dkv_kernel<<<grid, 128, 0, ST(stream)>>>(p);
+  attn_bwd_dq_kernel<<<dim3(H, B), kAttnThreads, attn_smem(spad, true), ST(stream)>>>(p, spad);
+  attn_bwd_dkv_kernel<<<dim3(H, B), kAttnThreads, attn_smem(spad, true), ST(stream)>>>(p, spad);
   count_launch(3);
   UNIIR_CUDA_OK(cudaGetLastError());
   return UNIIR_OK;
