@@ -389,14 +389,62 @@ def run_search(args, rank, world, dev, peaks, steps=None, warmup=None):
     return out
 
 
+# ----------------------------------------------------------------------------------------
+# our arm: embedding extraction (BASELINE configs[3]: CLIP_SF-L forward over candidate batches)
+# ----------------------------------------------------------------------------------------
+def run_embed(args, rank, world, dev, peaks):
+    from uniir_b200 import lib, ops
+    from uniir_b200.clip_sf import CLIPScoreFusion
+    B = 2048                                   # reference inference batch (embed.yaml:88)
+    model = CLIPScoreFusion(MODEL, device=dev, micro_batch=256)
+    model.eval()
+    b = synth_batch(model.dims, B // 2, 2023 + rank, dev)
+    b.pop("index_mapping"); b["did_list"] = list(range(B))
+    state = {}
+
+    def step():
+        state["emb"], _ = model(b, encode_mbeir_batch=True)
+        state["emb16"] = state["emb"].half()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(dev.index or 0); sampler.start()
+    l0 = lib.launch_count() + ops.graph_launches()
+    ms = timed(step, args.steps, world)
+    launches = lib.launch_count() + ops.graph_launches() - l0
+    clocks = sampler.stop()
+    hb = {k: (torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) if torch.is_tensor(v) else v) for k, v in b.items()}
+
+    def e2e_step():
+        gb = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in hb.items()}
+        emb, _ = model(gb, encode_mbeir_batch=True)
+        state["host"] = emb.half().cpu()
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, max(1, min(2, args.steps)), world)
+    items = B * world
+    alg = 175.33e9 * items / (ms / 1e3) / 1e12
+    return {"metric": "embedded_items_per_sec", "value": items / (ms / 1e3), "unit": "items/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"embedding extraction, CLIP_SF {MODEL}, batch {B}/GPU (BASELINE configs[3] shape; "
+                                   f"5.6M items = {5.6e6 / (items / (ms / 1e3)):.0f} s at this rate)", "micro_batch_items": 256},
+            "clocks": clocks, "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "achieved": alg, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                         "frac": alg / peaks["bf16_sustained"], "traffic": None,
+                         "note": "whole forward (175.33 GFLOP/item algorithmic) against measured sustained bf16"},
+            "e2e": {"value": items / (ms_e2e / 1e3), "unit": "items/s", "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in hb.values() if torch.is_tensor(v)) * world,
+                    "d2h_bytes_per_step": B * 768 * 2 * world, "ms_per_step": ms_e2e}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train", "search"])
-    ap.add_argument("--micro-batch", type=int, default=64, help="encoder items per micro-batch")
+    ap.add_argument("--workload", default="train", choices=["train", "search", "embed"])
+    ap.add_argument("--micro-batch", type=int, default=128, help="encoder items per micro-batch")
     ap.add_argument("--no-extra", action="store_true", help="skip the attached retrieval measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--search-q", type=int, default=SEARCH_Q)
@@ -419,7 +467,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
-    if args.workload == "search":
+    if args.workload == "embed":
+        out = run_embed(args, rank, world, dev, peaks)
+    elif args.workload == "search":
         out = run_search(args, rank, world, dev, peaks)
         if rank == 0 and not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"], _ = cpu_search_reference(1, 1)
