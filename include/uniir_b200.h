@@ -187,6 +187,16 @@ int uniir_infonce_normalize_bwd(const int32_t* q_idx, const int32_t* p_idx, cons
                                 const float* d_qn, const float* d_pn, int32_t bs, int32_t E, float* d_emb,
                                 void* stream);
 
+/* Hard-negative branch of the loss (clip_sf.py:105-131), forward + backward fused:
+ * logits_i = [q.p, q.n_1..q.n_m, q.p x k] * exp(logit_scale), k = min(bs-1, in_batch_neg_num).
+ * loss_sum / correct_sum (device scalars, zeroed by the caller) accumulate sum_i(-log_softmax_i[0])
+ * and sum_i[argmax_i == 0]; d_emb (zeroed by the caller, [items,E]) receives d(mean loss)/d emb;
+ * d_logit_scale += .  n_idx int32 [bs, neg_num]. */
+int uniir_hardneg_loss(const float* emb, const int32_t* q_idx, const int32_t* p_idx, const int32_t* n_idx,
+                       int32_t bs, int32_t neg_num, int32_t in_batch_neg_num, int32_t E,
+                       const float* logit_scale_log, float* loss_sum, float* correct_sum, float* d_emb,
+                       float* d_logit_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -119,9 +119,6 @@ def test_reference_api_contract():
     assert callable(m.get_tokenizer()) and callable(m.get_img_preprocess_fn())
     assert abs(m.get_logit_scale().item() - 100.0) < 1e-3
     assert all(k.startswith("clip_model.") for k in m.state_dict())
-    with pytest.raises(NotImplementedError):
-        hb = _cuda(_batch(d, 2)); hb["index_mapping"]["neg_cand_list"] = [[0], [1]]
-        m(hb)
     # masks: a text-only item equals encode_text, an image-only item equals encode_image
     bb = _cuda(_batch(d, 2))
     full = m.encode_multimodal_input(bb["txt_batched"], bb["image_batched"], 0 * bb["txt_mask_batched"] + 1, 0 * bb["image_mask_batched"])
@@ -191,3 +188,35 @@ def test_infonce_kernels_match_golden():
         nce.normalize_bwd(q_idx, p_idx, d_allp[off:off + bs], d_emb, off)
         ref = torch.from_numpy(g[g_k])
         assert ((d_emb.cpu() - ref).norm() / ref.norm()).item() < 1e-4
+
+
+def test_hard_negative_branch_matches_oracle():
+    """clip_sf.py:105-131 incl. the reference's in-batch-negative indexing (own positive repeated k times)."""
+    from types import SimpleNamespace as NS
+    from oracle.clip_oracle import CLIPScoreFusionOracle
+    from uniir_b200.clip_sf import CLIPScoreFusion
+    from uniir_b200.preprocess import synthetic_clip_tokens
+    torch.manual_seed(0)
+    cfg = NS(model=NS(gather_embeddings=False), data_config=NS(in_batch_neg_num=2))
+    orc = CLIPScoreFusionOracle("tiny-test", config=cfg)
+    mine = CLIPScoreFusion("tiny-test", device="cuda", config=cfg, micro_batch=16)
+    mine.load_state_dict(orc.state_dict(), strict=True)
+    d = orc.clip_model.dims
+    bs, neg = 4, 2
+    n = bs * (2 + neg)
+    g = torch.Generator().manual_seed(9)
+    b = dict(txt_batched=synthetic_clip_tokens(n, g, d.context, d.vocab),
+             image_batched=torch.randn(n, 3, d.image_size, d.image_size, generator=g),
+             txt_mask_batched=torch.ones(n, dtype=torch.long), image_mask_batched=torch.ones(n, dtype=torch.long),
+             index_mapping={"query": [[4 * i] for i in range(bs)], "pos_cand": [[4 * i + 1] for i in range(bs)],
+                            "neg_cand_list": [[4 * i + 2, 4 * i + 3] for i in range(bs)]})
+    ref = orc(b); ref["loss"].backward()
+    out = mine(_cuda(b)); out["loss"].backward()
+    assert abs(out["loss"].item() - ref["loss"].item()) < LOSS_RTOL * max(1.0, abs(ref["loss"].item()))
+    assert abs(out["accuracy"].item() - ref["accuracy"].item()) < 1e-6
+    worst = 1.0
+    for n_, p_o in orc.named_parameters():
+        a, c = p_o.grad.flatten().double(), mine.get_parameter(n_).grad.cpu().flatten().double()
+        if a.numel() > 1:
+            worst = min(worst, (torch.dot(a, c) / (a.norm() * c.norm() + 1e-30)).item())
+    assert worst > 0.99, worst

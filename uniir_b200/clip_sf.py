@@ -126,9 +126,6 @@ class CLIPScoreFusion(nn.Module):
         return embeddings, id_list
 
     def compute_inbatch_contrastive_loss(self, batch):
-        if "neg_cand_list" in batch["index_mapping"]:
-            raise NotImplementedError("hard-negative branch (clip_sf.py:105-131) is not built yet "
-                                      "(SURVEY.md 8f item 4)")
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             params = [self.clip_model.get_parameter(n) for n, *_ in self.clip_model._specs]
             loss, acc = _ContrastiveLossFn.apply(self, batch, *params)
@@ -214,6 +211,16 @@ class CLIPScoreFusion(nn.Module):
         st["mv"] = batch["image_mask_batched"].to(dev, torch.int64).contiguous()
         emb = torch.empty(n_items, E, device=dev, dtype=torch.float32)
         self._embed_into(emb, st["txt"], st["img"], st["mt"], st["mv"], enc=enc)
+        if "neg_cand_list" in im:   # hard-negative branch (clip_sf.py:105-131): no gather, fused fwd+bwd
+            n_idx = torch.tensor(im["neg_cand_list"], dtype=torch.int32).to(dev).contiguous()
+            P = self.clip_model
+            P.ensure_grad()
+            st["hard_dls"] = torch.zeros((), device=dev, dtype=torch.float32)
+            loss, acc, st["hard_d_emb"] = ops.hardneg_loss(emb, q_idx, p_idx, n_idx, int(getattr(self, "in_batch_neg_num", 0)),
+                                                           P.w("logit_scale"), st["hard_dls"])
+            st["emb"] = emb
+            self._train_state = st
+            return loss, acc
         nce = self._nce
         if nce is None or (nce.bs, nce.n, nce.E) != (bs, bs * world, E):
             nce = self._nce = ops.InfoNCE(bs, bs * world, E, dev)
@@ -237,13 +244,14 @@ class CLIPScoreFusion(nn.Module):
         bs, rank, world, E = st["bs"], st["rank"], st["world"], self.dims.embed_dim
         off = rank * bs
         go = None if g_loss is None else g_loss.to(torch.float32).reshape(()).contiguous()
-        d_qn, d_all_p = nce.backward(P.w("logit_scale"), off, P.g("logit_scale"), grad_out=go)
-        if world > 1:
-            d_pn = du.reduce_scatter_rows(d_all_p)
+        if "hard_d_emb" in st:
+            d_emb = st["hard_d_emb"] if go is None else st["hard_d_emb"] * go
+            P.g("logit_scale").add_(st["hard_dls"] if go is None else st["hard_dls"] * go)
         else:
-            d_pn = d_all_p
-        d_emb = torch.zeros(st["n_items"], E, device=self.device_, dtype=torch.float32)
-        nce.normalize_bwd(st["q_idx"], st["p_idx"], d_pn, d_emb, off)
+            d_qn, d_all_p = nce.backward(P.w("logit_scale"), off, P.g("logit_scale"), grad_out=go)
+            d_pn = du.reduce_scatter_rows(d_all_p) if world > 1 else d_all_p
+            d_emb = torch.zeros(st["n_items"], E, device=self.device_, dtype=torch.float32)
+            nce.normalize_bwd(st["q_idx"], st["p_idx"], d_pn, d_emb, off)
         mb = enc.mb
         for s in range(0, st["n_items"], mb):
             e = s + mb

@@ -307,6 +307,105 @@ nce_sgemm_kernel(const float* __restrict__ A, long long a_rs, long long a_cs, co
   }
 }
 
+
+// ---------------------------------------------------------------------------------
+// Hard-negative branch, reference clip_sf.py:105-131.  Per query row i the logits are
+//   [ q.p , q.n_1 .. q.n_m , (q.p repeated k times) ] * exp(logit_scale)
+// (the reference's "in-batch negatives" index `p.unsqueeze(1).expand(-1,bs,-1)[mask]`,
+// whose [i,j] entry is p_i, so the k extra columns repeat the row's own positive -- restated
+// faithfully), loss = mean(-log_softmax[:,0]), accuracy = mean(argmax == 0).
+// One CTA per row: normalise q, p, n_j, form the logits, softmax, and write the gradient with
+// respect to the raw embeddings (normalisation backward included) and to logit_scale.
+// ---------------------------------------------------------------------------------
+constexpr int kMaxNeg = 32;
+
+__device__ __forceinline__ float cta_sum(float v, float* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) t += sh[i];
+  return t;
+}
+
+__global__ void __launch_bounds__(128)
+nce_hardneg_kernel(const float* __restrict__ emb, const int* __restrict__ q_idx, const int* __restrict__ p_idx,
+                   const int* __restrict__ n_idx, int bs, int neg, int k, int E,
+                   const float* __restrict__ logit_scale_log, float* __restrict__ loss_sum,
+                   float* __restrict__ correct_sum, float* __restrict__ d_emb,
+                   float* __restrict__ d_logit_scale) {
+  __shared__ float sh[8];
+  __shared__ float s_dot[kMaxNeg + 1], s_nrm[kMaxNeg + 2], s_g[kMaxNeg + 1];
+  const int i = blockIdx.x;
+  const float scale = __expf(*logit_scale_log);
+  const float* q = emb + static_cast<long long>(q_idx[i]) * E;
+  // norms of q, p, n_j and raw dots q.p, q.n_j
+  for (int j = -1; j <= neg; ++j) {  // j=-1: q ; j=0: p ; j>=1: negatives
+    const float* x = (j < 0) ? q : emb + static_cast<long long>(j == 0 ? p_idx[i] : n_idx[i * neg + j - 1]) * E;
+    float nn = 0.f, dd = 0.f;
+    for (int c = threadIdx.x; c < E; c += blockDim.x) { nn += x[c] * x[c]; dd += x[c] * q[c]; }
+    nn = cta_sum(nn, sh);
+    dd = cta_sum(dd, sh);
+    if (threadIdx.x == 0) {
+      s_nrm[j + 1] = fmaxf(sqrtf(nn), 1e-12f);
+      if (j >= 0) s_dot[j] = dd;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float qn = s_nrm[0];
+    float z[kMaxNeg + 1], mx = -INFINITY;
+    for (int j = 0; j <= neg; ++j) { z[j] = s_dot[j] / (qn * s_nrm[j + 1]) * scale; mx = fmaxf(mx, z[j]); }
+    float Z = (1.f + k) * __expf(z[0] - mx);
+    for (int j = 1; j <= neg; ++j) Z += __expf(z[j] - mx);
+    const float lse = mx + logf(Z);
+    atomicAdd(loss_sum, lse - z[0]);
+    bool best = true;
+    for (int j = 1; j <= neg; ++j) best = best && (z[0] >= z[j]);   // torch.max: first index wins ties
+    atomicAdd(correct_sum, best ? 1.f : 0.f);
+    float dls = 0.f;
+    for (int j = 0; j <= neg; ++j) {
+      const float P = __expf(z[j] - lse);
+      const float g = (j == 0) ? ((1.f + k) * P - 1.f) : P;       // dL_i/dz_j (copies folded into j=0)
+      s_g[j] = g / bs;                                             // mean over rows
+      dls += s_g[j] * z[j];
+    }
+    atomicAdd(d_logit_scale, dls);
+  }
+  __syncthreads();
+  // cos_j = <qh, xh_j>;  d qh = sum_j g_j s xh_j ; d xh_j = g_j s qh ; then normalise-backward
+  const float qn = s_nrm[0];
+  float dq_dot = 0.f;  // <qh, d qh>
+  for (int c = threadIdx.x; c < E; c += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j <= neg; ++j) {
+      const float* x = emb + static_cast<long long>(j == 0 ? p_idx[i] : n_idx[i * neg + j - 1]) * E;
+      acc += s_g[j] * scale * x[c] / s_nrm[j + 1];
+    }
+    dq_dot += acc * q[c] / qn;
+  }
+  dq_dot = cta_sum(dq_dot, sh);
+  for (int c = threadIdx.x; c < E; c += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j <= neg; ++j) {
+      const float* x = emb + static_cast<long long>(j == 0 ? p_idx[i] : n_idx[i * neg + j - 1]) * E;
+      acc += s_g[j] * scale * x[c] / s_nrm[j + 1];
+    }
+    atomicAdd(d_emb + static_cast<long long>(q_idx[i]) * E + c, (acc - (q[c] / qn) * dq_dot) / qn);
+  }
+  for (int j = 0; j <= neg; ++j) {
+    const long long row = (j == 0) ? p_idx[i] : n_idx[i * neg + j - 1];
+    const float* x = emb + row * E;
+    const float xn = s_nrm[j + 1], gs = s_g[j] * scale;
+    const float cosv = s_dot[j] / (qn * xn);   // <xh, d xh> = gs * cos
+    for (int c = threadIdx.x; c < E; c += blockDim.x)
+      atomicAdd(d_emb + row * E + c, gs * (q[c] / qn - (x[c] / xn) * cosv) / xn);
+  }
+}
+
 static int nce_carve(void* workspace, size_t bytes, int bs, int nct, int nrt, NceWs* ws) {
   char* p = static_cast<char*>(workspace);
   const size_t per = static_cast<size_t>(bs) * nct;
@@ -394,6 +493,23 @@ extern "C" int uniir_infonce_normalize_bwd(const int32_t* q_idx, const int32_t* 
                   "uniir_infonce_normalize_bwd: null pointer");
   nce_normalize_bwd_kernel<<<2 * bs, 256, 0, ST(stream)>>>(q_idx, p_idx, qn, pn, q_norm, p_norm, d_qn,
                                                             d_pn, bs, E, d_emb);
+  count_launch();
+  UNIIR_CUDA_OK(cudaGetLastError());
+  return UNIIR_OK;
+}
+
+extern "C" int uniir_hardneg_loss(const float* emb, const int32_t* q_idx, const int32_t* p_idx,
+                                  const int32_t* n_idx, int32_t bs, int32_t neg_num,
+                                  int32_t in_batch_neg_num, int32_t E, const float* logit_scale_log,
+                                  float* loss_sum, float* correct_sum, float* d_emb,
+                                  float* d_logit_scale, void* stream) {
+  UNIIR_CHECK_ARG(emb && q_idx && p_idx && n_idx && logit_scale_log && loss_sum && correct_sum && d_emb &&
+                      d_logit_scale && bs > 0 && E > 0,
+                  "uniir_hardneg_loss: bad args");
+  UNIIR_CHECK_ARG(neg_num >= 1 && neg_num <= kMaxNeg, "uniir_hardneg_loss: neg_num must be in [1,%d]", kMaxNeg);
+  const int k = in_batch_neg_num < bs - 1 ? in_batch_neg_num : bs - 1;  // clip_sf.py:110
+  nce_hardneg_kernel<<<bs, 128, 0, ST(stream)>>>(emb, q_idx, p_idx, n_idx, bs, neg_num, k < 0 ? 0 : k, E,
+                                                  logit_scale_log, loss_sum, correct_sum, d_emb, d_logit_scale);
   count_launch();
   UNIIR_CUDA_OK(cudaGetLastError());
   return UNIIR_OK;

@@ -75,6 +75,7 @@ _SIGS = {
     "uniir_infonce_normalize": (C.c_int, [VP, VP, VP, I32, I32, VP, VP, VP, VP, VP]),
     "uniir_infonce_fwd": (C.c_int, [VP, VP, I32, I32, I32, VP, I32, VP, VP, VP, VP, C.c_size_t, VP]),
     "uniir_infonce_bwd": (C.c_int, [VP, VP, I32, I32, I32, VP, I32, VP, VP, VP, VP, VP, VP, VP]),
+    "uniir_hardneg_loss": (C.c_int, [VP, VP, VP, VP, I32, I32, I32, I32, VP, VP, VP, VP, VP, VP]),
     "uniir_infonce_normalize_bwd": (C.c_int, [VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, VP, VP]),
 }
 

@@ -410,3 +410,16 @@ def time_gemm_config(cfg, iters=10, device="cuda"):
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters
+
+
+def hardneg_loss(emb, q_idx, p_idx, n_idx, in_batch_neg_num, logit_scale, d_logit_scale):
+    """Fused forward+backward of the hard-negative loss branch.  Returns (loss, acc, d_emb)."""
+    bs, neg = n_idx.shape
+    E = emb.shape[1]
+    sums = torch.zeros(2, device=emb.device, dtype=torch.float32)
+    d_emb = torch.zeros_like(emb)
+    L.check(L.load().uniir_hardneg_loss(emb.data_ptr(), q_idx.data_ptr(), p_idx.data_ptr(), n_idx.data_ptr(), bs, neg,
+                                        in_batch_neg_num, E, logit_scale.data_ptr(), sums[0:1].data_ptr(),
+                                        sums[1:2].data_ptr(), d_emb.data_ptr(), d_logit_scale.data_ptr(), _stream()),
+            "uniir_hardneg_loss")
+    return sums[0] / bs, sums[1] / bs, d_emb
