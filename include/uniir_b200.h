@@ -39,6 +39,7 @@ extern "C" {
 #define UNIIR_ACT_NONE 0
 #define UNIIR_ACT_QUICKGELU 1 /* x*sigmoid(1.702x): upstream CLIP QuickGELU */
 #define UNIIR_ACT_GELU 2      /* exact erf GELU: BLIP vit.py:39 / med.py:308 */
+#define UNIIR_ACT_TANH 3      /* BERT pooler, med.py:505-511 (forward only) */
 
 int uniir_abi_version(void);
 const char* uniir_last_error(void);
@@ -161,6 +162,13 @@ int uniir_adamw_step(float* p, float* g, float* m, float* v, void* p_bf16, int64
  * ---------------------------------------------------------------------------------- */
 int uniir_attn_fwd(const void* qkv, int32_t B, int32_t S, int32_t H, int32_t causal, void* out, float* lse,
                    void* stream);
+/* General form: separate query and key/value tensors (cross-attention: BLIP med.py:150-232 with
+ * encoder_hidden_states) and an optional per-batch valid-key count kv_len[B] (BERT padding mask,
+ * med.py:687-688: keys >= kv_len[b] get the reference's -10000 additive mask, i.e. weight 0).
+ * q rows b*Sq+s at stride ldq, k/v rows b*Skv+t at stride ldkv (head h at columns h*64), out stride ldo. */
+int uniir_attn_fwd_ex(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, int32_t B,
+                      int32_t Sq, int32_t Skv, int32_t H, int32_t causal, const int32_t* kv_len, void* out,
+                      int64_t ldo, float* lse, void* stream);
 int uniir_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int32_t B,
                    int32_t S, int32_t H, int32_t causal, float* delta_ws /* [B*H*S] */, void* dqkv,
                    void* stream);

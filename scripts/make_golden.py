@@ -80,7 +80,21 @@ def infonce():
                         loss2=o2["loss"].item(), acc2=o2["accuracy"].item(), g2=g2.numpy())
 
 
+def blip_tiny():
+    from oracle.blip_oracle import BLIP_CONFIGS, BLIPFeatureFusionOracle
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_oracle_blip import _inputs
+    torch.manual_seed(4321)
+    m = BLIPFeatureFusionOracle("tiny-test").eval()
+    d = m.dims
+    ids, att, img = _inputs(d, 6, 24, 5)
+    with torch.no_grad():
+        emb = m.encode_multimodal_input(ids, att, img)
+    np.savez_compressed(os.path.join(OUT, "blip_tiny.npz"), ids=ids.numpy(), att=att.numpy(), img=img.numpy(), emb=emb.numpy(),
+                        **{"w:" + k: v.numpy() for k, v in m.state_dict().items()})
+
+
 if __name__ == "__main__":
-    clip_tiny(); search_small(); infonce()
+    clip_tiny(); search_small(); infonce(); blip_tiny()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

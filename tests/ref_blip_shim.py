@@ -1,0 +1,67 @@
+"""Import the reference's vendored BLIP modules (backbone/vit.py, backbone/med.py) without editing them,
+by shimming the transformers-4.15 / timm / fairscale symbols they expect (SURVEY.md 8c recipe).
+Only usable where /root/reference exists (the build container); the GPU box uses the golden vectors."""
+import importlib
+import os
+import sys
+import types
+
+REF_SRC = "/root/reference/src"
+
+
+def available():
+    return os.path.isdir(os.path.join(REF_SRC, "models", "uniir_blip", "backbone"))
+
+
+def load():
+    import torch
+    import torch.nn as nn
+    import transformers  # import BEFORE stubbing
+    import transformers.modeling_utils as mu
+    import transformers.pytorch_utils as pu
+    for name in ("apply_chunking_to_forward", "prune_linear_layer"):
+        if not hasattr(mu, name):
+            setattr(mu, name, getattr(pu, name))
+    if not hasattr(mu, "find_pruneable_heads_and_indices"):
+        mu.find_pruneable_heads_and_indices = None
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    class PatchEmbed(nn.Module):
+        def __init__(self, img_size=224, patch_size=16, in_chans=3, embed_dim=768):
+            super().__init__()
+            self.num_patches = (img_size // patch_size) ** 2
+            self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+
+        def forward(self, x):
+            return self.proj(x).flatten(2).transpose(1, 2)
+
+    class DropPath(nn.Module):
+        def __init__(self, p=0.0):
+            super().__init__()
+
+        def forward(self, x):
+            return x
+
+    if "timm" not in sys.modules:
+        stub("timm"); stub("timm.models")
+        stub("timm.models.vision_transformer", PatchEmbed=PatchEmbed, _cfg=lambda **k: {})
+        stub("timm.models.registry", register_model=lambda f: f)
+        stub("timm.models.layers", trunc_normal_=nn.init.trunc_normal_, DropPath=DropPath)
+        stub("timm.models.helpers", named_apply=lambda *a, **k: None, adapt_input_conv=lambda *a, **k: None)
+        stub("timm.models.hub")
+    if "fairscale" not in sys.modules:
+        stub("fairscale"); stub("fairscale.nn"); stub("fairscale.nn.checkpoint")
+        stub("fairscale.nn.checkpoint.checkpoint_activations", checkpoint_wrapper=lambda m, **k: m)
+    if REF_SRC not in sys.path:
+        sys.path.insert(0, REF_SRC)
+    vit = importlib.import_module("models.uniir_blip.backbone.vit")
+    med = importlib.import_module("models.uniir_blip.backbone.med")
+    B = med.BertPreTrainedModel
+    B.init_weights = lambda self: self.apply(self._init_weights)
+    B.get_head_mask = lambda self, head_mask, n, *a, **k: [None] * n
+    return vit, med

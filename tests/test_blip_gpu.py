@@ -1,0 +1,91 @@
+"""GPU parity of the BLIP_FF encode path against the CPU oracle / golden vectors."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+COS_TOL = 1e-3
+
+
+def _load_oracle_weights(model, sd):
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    # everything the encode path uses must have been provided; only momentum copies / queues / temp may be missing
+    assert all(("_m." in m) or m in ("query_queue", "cand_queue", "idx_queue", "new_ptr_queue", "temp") for m in missing), missing
+
+
+def test_blip_ff_golden_and_oracle():
+    from oracle.blip_oracle import BLIPFeatureFusionOracle
+    from uniir_b200.blip_ff import BLIPFeatureFusion
+    g = np.load(os.path.join(GOLDEN, "blip_tiny.npz"))
+    sd = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w:")}
+    m = BLIPFeatureFusion(vit="tiny-test", image_size=64, embed_dim=64, queue_size=64, micro_batch=4)
+    _load_oracle_weights(m, sd)
+    txt = {"input_ids": torch.from_numpy(g["ids"]).cuda(), "attention_mask": torch.from_numpy(g["att"]).cuda()}
+    emb = m.encode_multimodal_input(txt, torch.from_numpy(g["img"]).cuda(), None, None).cpu()   # 6 items, mb 4: ragged tail
+    cos = torch.nn.functional.cosine_similarity(emb, torch.from_numpy(g["emb"]), dim=-1)
+    assert cos.min().item() > 1 - COS_TOL, cos
+    assert (emb - torch.from_numpy(g["emb"])).abs().max().item() < 3e-2
+    # fresh oracle with other weights / inputs
+    torch.manual_seed(7)
+    orc = BLIPFeatureFusionOracle("tiny-test").eval()
+    _load_oracle_weights(m, orc.state_dict())
+    from test_oracle_blip import _inputs
+    ids, att, img = _inputs(orc.dims, 5, 40, 3)
+    with torch.no_grad():
+        ref = orc.encode_multimodal_input(ids, att, img)
+    out = m.encode_multimodal_input({"input_ids": ids, "attention_mask": att}, img).cpu()
+    assert torch.nn.functional.cosine_similarity(out, ref, dim=-1).min().item() > 1 - COS_TOL
+    # the momentum encoder is an exact copy at construction / after loading both
+    assert torch.equal(m.get_parameter("visual_encoder_m.cls_token"), m.get_parameter("visual_encoder_m.cls_token"))
+
+
+def test_blip_ff_api_contract():
+    from uniir_b200.blip_ff import BLIPFeatureFusion
+    m = BLIPFeatureFusion(vit="tiny-test", image_size=64, embed_dim=64, queue_size=128)
+    d = m.dims
+    from test_oracle_blip import _inputs
+    ids, att, img = _inputs(d, 3, 16, 1)
+    b = {"txt_batched": {"input_ids": ids, "attention_mask": att}, "image_batched": img,
+         "txt_mask_batched": torch.ones(3), "image_mask_batched": torch.ones(3), "did_list": [11, 12, 13]}
+    emb, idl = m(b, encode_mbeir_batch=True)
+    assert emb.shape == (3, d.t_width) and idl == [11, 12, 13]
+    b2 = dict(b); b2.pop("did_list")
+    with pytest.raises(ValueError):
+        m(b2, encode_mbeir_batch=True)
+    with pytest.raises(NotImplementedError):
+        m(b, alpha=0.4)
+    keys = set(m.state_dict())
+    for k in ("visual_encoder.patch_embed.proj.bias", "visual_encoder_m.blocks.0.attn.qkv.weight",
+              "text_encoder.encoder.layer.0.crossattention.self.key.weight", "text_encoder.embeddings.position_ids",
+              "text_encoder_m.pooler.dense.weight", "query_queue", "cand_queue", "idx_queue", "new_ptr_queue", "temp"):
+        assert k in keys, k
+    assert m.state_dict()["idx_queue"].shape == (1, 128) and not m.get_parameter("text_encoder_m.pooler.dense.weight").requires_grad
+    bad = att.clone(); bad[0, 0] = 0
+    with pytest.raises(ValueError):
+        m.encode_multimodal_input({"input_ids": ids, "attention_mask": bad}, img)
+
+
+def test_cross_attention_kernel_vs_reference():
+    from uniir_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    B, Sq, Skv, H = 3, 100, 197, 12
+    q = torch.randn(B * Sq, H * 64, generator=g).bfloat16(); kv = torch.randn(B * Skv, 2 * H * 64, generator=g).bfloat16()
+    out = ops.attn_fwd_ex(q.cuda(), kv.cuda()[:, :H * 64], kv.cuda()[:, H * 64:], B, Sq, Skv, H).cpu().float()
+    qf = q.float().view(B, Sq, H, 64).transpose(1, 2); kf = kv[:, :H * 64].float().view(B, Skv, H, 64).transpose(1, 2)
+    vf = kv[:, H * 64:].float().view(B, Skv, H, 64).transpose(1, 2)
+    ref = ((qf @ kf.transpose(-1, -2) * 0.125).softmax(-1) @ vf).transpose(1, 2).reshape(B * Sq, H * 64)
+    assert ((out - ref).norm() / ref.norm()).item() < 6e-3
+    # key padding mask (prefix lengths)
+    S = 100
+    qkv = torch.randn(B * S, 3 * H * 64, generator=g).bfloat16()
+    lens = torch.tensor([100, 7, 55], dtype=torch.int32)
+    o = ops.attn_fwd_ex(qkv.cuda()[:, :768], qkv.cuda()[:, 768:1536], qkv.cuda()[:, 1536:], B, S, S, H, kv_len=lens.cuda()).cpu().float()
+    q3, k3, v3 = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+    mask = (torch.arange(S)[None, :] >= lens[:, None]).float()[:, None, None, :] * -10000.0
+    ref = ((q3 @ k3.transpose(-1, -2) * 0.125 + mask).softmax(-1) @ v3).transpose(1, 2).reshape(B * S, H * 64)
+    assert ((o - ref).norm() / ref.norm()).item() < 6e-3

@@ -42,9 +42,16 @@ class _LayerActs:
 class Tower:
     """A stack of upstream-CLIP ResidualAttentionBlocks: x += attn(ln_1(x)); x += mlp(ln_2(x))."""
 
+    CLIP_NAMES = dict(ln1="ln_1", qkv_w="attn.in_proj_weight", qkv_b="attn.in_proj_bias", out="attn.out_proj",
+                      ln2="ln_2", fc1="mlp.c_fc", fc2="mlp.c_proj", blocks="resblocks")
+    TIMM_NAMES = dict(ln1="norm1", qkv_w="attn.qkv.weight", qkv_b="attn.qkv.bias", out="attn.proj",
+                      ln2="norm2", fc1="mlp.fc1", fc2="mlp.fc2", blocks="blocks")
+
     def __init__(self, params: FlatParamModule, prefix, width, layers, heads, S, causal, mb, dev,
-                 train):
+                 train, names=None, act=L.ACT_QUICKGELU, eps=LN_EPS):
         self.P, self.prefix = params, prefix
+        self.nm = names or self.CLIP_NAMES
+        self.act, self.eps = act, eps
         self.D, self.nl, self.H, self.S, self.causal, self.mb = width, layers, heads, S, causal, mb
         self.T = mb * S
         self.dev = dev
@@ -72,7 +79,15 @@ class Tower:
             self.big = torch.empty(T, 4 * D, **bf)
 
     def _n(self, i, leaf):
-        return f"{self.prefix}.resblocks.{i}.{leaf}"
+        """leaf is written in upstream-CLIP terms; translated for timm-style (BLIP) towers."""
+        nm = self.nm
+        for a, b in (("ln_1", nm["ln1"]), ("ln_2", nm["ln2"]), ("attn.in_proj_weight", nm["qkv_w"]),
+                     ("attn.in_proj_bias", nm["qkv_b"]), ("attn.out_proj", nm["out"]), ("mlp.c_fc", nm["fc1"]),
+                     ("mlp.c_proj", nm["fc2"])):
+            if leaf.startswith(a):
+                leaf = b + leaf[len(a):]
+                break
+        return f"{self.prefix}.{nm['blocks']}.{i}.{leaf}"
 
     # ---- forward over all blocks.  Input: self.x.  Output: self.x ------------------------------
     # Inference / gradient-cache phase A: the residual stream is updated in place.  Training
@@ -97,12 +112,12 @@ class Tower:
                 h1 = h2 = self.h
                 qkv, att, pre, act, lse = self.qkv, self.att, None, self.big, None
                 st1 = st2 = None
-            ops.layernorm_fwd(x_in, w(n("ln_1.weight")), w(n("ln_1.bias")), LN_EPS, out=h1, stats=st1)
+            ops.layernorm_fwd(x_in, w(n("ln_1.weight")), w(n("ln_1.bias")), self.eps, out=h1, stats=st1)
             ops.gemm(h1, w16(n("attn.in_proj_weight")), bias=w(n("attn.in_proj_bias")), out=qkv)
             ops.attn_fwd(qkv, B, S, H, self.causal, out=att, lse=lse, need_lse=save)
             ops.gemm(att, w16(n("attn.out_proj.weight")), bias=w(n("attn.out_proj.bias")), residual=x_in, out=x_mid)
-            ops.layernorm_fwd(x_mid, w(n("ln_2.weight")), w(n("ln_2.bias")), LN_EPS, out=h2, stats=st2)
-            ops.gemm(h2, w16(n("mlp.c_fc.weight")), bias=w(n("mlp.c_fc.bias")), act=L.ACT_QUICKGELU, aux_out=pre, out=act)
+            ops.layernorm_fwd(x_mid, w(n("ln_2.weight")), w(n("ln_2.bias")), self.eps, out=h2, stats=st2)
+            ops.gemm(h2, w16(n("mlp.c_fc.weight")), bias=w(n("mlp.c_fc.bias")), act=self.act, aux_out=pre, out=act)
             ops.gemm(act, w16(n("mlp.c_proj.weight")), bias=w(n("mlp.c_proj.bias")), residual=x_mid, out=x_out)
         return self.x_out if save else self.x
 
@@ -116,7 +131,7 @@ class Tower:
             # ---- MLP branch: x_out = x_mid + c_proj(quickgelu(c_fc(ln_2(x_mid))))
             ops.wgrad(dxb, a.act, g("mlp.c_proj.weight"))
             ops.colsum_accum(dxb, g("mlp.c_proj.bias"))
-            ops.gemm(dxb, w16("mlp.c_proj.weight"), b_mn=True, act=L.ACT_QUICKGELU, act_grad_src=a.pre,
+            ops.gemm(dxb, w16("mlp.c_proj.weight"), b_mn=True, act=self.act, act_grad_src=a.pre,
                      out=self.d_big)
             ops.wgrad(self.d_big, a.h2, g("mlp.c_fc.weight"))
             ops.colsum_accum(self.d_big, g("mlp.c_fc.bias"))

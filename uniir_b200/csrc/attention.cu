@@ -91,7 +91,11 @@ __device__ __forceinline__ void frag_b_kn(uint32_t tile, int t, int jd, uint32_t
 }
 
 struct AttnParams {
-  const __nv_bfloat16* qkv;  // [B*S, 3*D]
+  const __nv_bfloat16* qkv;  // [B*S, 3*D]   (packed self-attention; backward kernels)
+  const __nv_bfloat16 *q, *k, *v;  // forward: q rows [B*Sq] stride ldq; k/v rows [B*Skv] stride ldkv
+  long long ldq, ldkv, ldo;
+  int Sq, Skv;
+  const int* kv_len;         // optional [B]: keys >= kv_len[b] are masked (BERT padding mask)
   __nv_bfloat16* out;        // [B*S, D]
   float* lse;                // [B, H, S]
   const __nv_bfloat16* dout; // [B*S, D]
@@ -136,21 +140,21 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
   const uint32_t sK = s_u32(sm), sV = sK + spad * 128, sQ0 = sV + spad * 128;
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long ld = 3LL * p.D;
-  const __nv_bfloat16* base = p.qkv + static_cast<long long>(b) * p.S * ld + h * kHD;
-  load_rows(sK, base + p.D, ld, p.S, spad);
-  load_rows(sV, base + 2 * p.D, ld, p.S, spad);
+  const __nv_bfloat16* qb = p.q + static_cast<long long>(b) * p.Sq * p.ldq + h * kHD;
+  const int kvl = p.kv_len ? min(p.kv_len[b], p.Skv) : p.Skv;     // valid keys of this batch row
+  load_rows(sK, p.k + static_cast<long long>(b) * p.Skv * p.ldkv + h * kHD, p.ldkv, p.Skv, spad);
+  load_rows(sV, p.v + static_cast<long long>(b) * p.Skv * p.ldkv + h * kHD, p.ldkv, p.Skv, spad);
   cp_async_wait_all();
   __syncthreads();
   const uint32_t sQ = sQ0 + warp * 2048;
   const float sc = p.scale * kLog2e;
-  __nv_bfloat16* ob = p.out + static_cast<long long>(b) * p.S * p.D + h * kHD;
-  float* lp = p.lse ? p.lse + (static_cast<long long>(b) * p.H + h) * p.S : nullptr;
-  const int n_qt = spad >> 4;
+  __nv_bfloat16* ob = p.out + static_cast<long long>(b) * p.Sq * p.ldo + h * kHD;
+  float* lp = p.lse ? p.lse + (static_cast<long long>(b) * p.H + h) * p.Sq : nullptr;
+  const int n_qt = (p.Sq + 15) >> 4;
   for (int qt = warp; qt < n_qt; qt += kAttnWarps) {
     const int q0 = qt * 16;
     __syncwarp();
-    load_rows16_warp(sQ, base, ld, q0, p.S);
+    load_rows16_warp(sQ, qb, p.ldq, q0, p.Sq);
     cp_async_wait_all();
     __syncwarp();
     uint32_t qa[4][4];
@@ -181,7 +185,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
         }
       }
       // masking only where a block touches the sequence end or the causal diagonal (warp-uniform)
-      const bool need_mask = nt < 8 || k0 + kBlk > p.S || (p.causal && k0 + kBlk - 1 > q0);
+      const bool need_mask = nt < 8 || k0 + kBlk > kvl || (p.causal && k0 + kBlk - 1 > q0);
       if (need_mask) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -189,7 +193,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
           for (int e = 0; e < 4; ++e) {
             const int key = k0 + j * 8 + (lane & 3) * 2 + (e & 1);
             const int qr = (e < 2) ? r0 : r1;
-            if (j >= nt || key >= p.S || (p.causal && key > qr)) s[j][e] = -INFINITY;
+            if (j >= nt || key >= kvl || (p.causal && key > qr)) s[j][e] = -INFINITY;
           }
         }
       }
@@ -241,12 +245,12 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int col = j * 8 + (lane & 3) * 2;
-      if (r0 < p.S) *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(r0) * p.D + col) = pack_bf16(o[j][0] * i0, o[j][1] * i0);
-      if (r1 < p.S) *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(r1) * p.D + col) = pack_bf16(o[j][2] * i1, o[j][3] * i1);
+      if (r0 < p.Sq) *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(r0) * p.ldo + col) = pack_bf16(o[j][0] * i0, o[j][1] * i0);
+      if (r1 < p.Sq) *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(r1) * p.ldo + col) = pack_bf16(o[j][2] * i1, o[j][3] * i1);
     }
     if (lp && (lane & 3) == 0) {
-      if (r0 < p.S) lp[r0] = (m0 * sc + log2f(l0)) / kLog2e;
-      if (r1 < p.S) lp[r1] = (m1 * sc + log2f(l1)) / kLog2e;
+      if (r0 < p.Sq) lp[r0] = (m0 * sc + log2f(l0)) / kLog2e;
+      if (r1 < p.Sq) lp[r1] = (m1 * sc + log2f(l1)) / kLog2e;
     }
   }
 }
@@ -524,21 +528,47 @@ static int attn_set_smem() {
   return UNIIR_OK;
 }
 
-extern "C" int uniir_attn_fwd(const void* qkv, int32_t B, int32_t S, int32_t H, int32_t causal, void* out,
-                              float* lse, void* stream) {
-  UNIIR_CHECK_ARG(qkv && out && B > 0 && S > 0 && H > 0, "uniir_attn_fwd: bad args");
-  UNIIR_CHECK_ARG(S <= 768, "uniir_attn_fwd: S=%d exceeds the head-resident kernel's limit of 768", S);
+static int attn_fwd_launch(AttnParams& p, void* stream) {
+  UNIIR_CHECK_ARG(p.Skv <= 768, "uniir_attn_fwd: Skv=%d exceeds the head-resident kernel's limit of 768", p.Skv);
   if (int rc = attn_set_smem()) return rc;
-  AttnParams p{};
-  p.qkv = static_cast<const __nv_bfloat16*>(qkv);
-  p.out = static_cast<__nv_bfloat16*>(out);
-  p.lse = lse;
-  p.B = B; p.S = S; p.H = H; p.D = H * kHD; p.causal = causal; p.scale = 0.125f;
-  const int spad = (S + 15) / 16 * 16;
-  attn_fwd_kernel<<<dim3(H, B), kAttnThreads, attn_smem(spad, false), ST(stream)>>>(p, spad);
+  const int spad = (p.Skv + 15) / 16 * 16;
+  attn_fwd_kernel<<<dim3(p.H, p.B), kAttnThreads, attn_smem(spad, false), ST(stream)>>>(p, spad);
   count_launch();
   UNIIR_CUDA_OK(cudaGetLastError());
   return UNIIR_OK;
+}
+
+extern "C" int uniir_attn_fwd(const void* qkv, int32_t B, int32_t S, int32_t H, int32_t causal, void* out,
+                              float* lse, void* stream) {
+  UNIIR_CHECK_ARG(qkv && out && B > 0 && S > 0 && H > 0, "uniir_attn_fwd: bad args");
+  AttnParams p{};
+  p.qkv = static_cast<const __nv_bfloat16*>(qkv);
+  p.D = H * kHD;
+  p.q = p.qkv; p.k = p.qkv + p.D; p.v = p.qkv + 2 * p.D;
+  p.ldq = p.ldkv = 3LL * p.D; p.ldo = p.D;
+  p.Sq = p.Skv = S;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.lse = lse;
+  p.B = B; p.S = S; p.H = H; p.causal = causal; p.scale = 0.125f;
+  return attn_fwd_launch(p, stream);
+}
+
+extern "C" int uniir_attn_fwd_ex(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                                 int32_t B, int32_t Sq, int32_t Skv, int32_t H, int32_t causal,
+                                 const int32_t* kv_len, void* out, int64_t ldo, float* lse, void* stream) {
+  UNIIR_CHECK_ARG(q && k && v && out && B > 0 && Sq > 0 && Skv > 0 && H > 0, "uniir_attn_fwd_ex: bad args");
+  UNIIR_CHECK_ARG(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 2 == 0, "uniir_attn_fwd_ex: strides must keep 16 B row alignment");
+  UNIIR_CHECK_ARG(!causal || Sq == Skv, "uniir_attn_fwd_ex: causal needs Sq == Skv");
+  AttnParams p{};
+  p.q = static_cast<const __nv_bfloat16*>(q);
+  p.k = static_cast<const __nv_bfloat16*>(k);
+  p.v = static_cast<const __nv_bfloat16*>(v);
+  p.ldq = ldq; p.ldkv = ldkv; p.ldo = ldo;
+  p.Sq = Sq; p.Skv = Skv; p.kv_len = kv_len;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.lse = lse;
+  p.B = B; p.S = Sq; p.H = H; p.D = H * kHD; p.causal = causal; p.scale = 0.125f;
+  return attn_fwd_launch(p, stream);
 }
 
 extern "C" int uniir_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse,

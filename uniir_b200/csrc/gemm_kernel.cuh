@@ -57,6 +57,7 @@ __device__ __forceinline__ float qg_sigmoid(float x) { return fmaf(0.5f, tanh_ap
 __device__ __forceinline__ float act_fwd(float x, int act) {
   if (act == UNIIR_ACT_QUICKGELU) return x * qg_sigmoid(x);
   if (act == UNIIR_ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+  if (act == UNIIR_ACT_TANH) return tanhf(x);
   return x;
 }
 __device__ __forceinline__ float act_bwd(float x, int act) {

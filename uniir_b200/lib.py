@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libuniir_b200.so")
 
 BF16, F16, F32 = 0, 1, 2
-ACT_NONE, ACT_QUICKGELU, ACT_GELU = 0, 1, 2
+ACT_NONE, ACT_QUICKGELU, ACT_GELU, ACT_TANH = 0, 1, 2, 3
 
 
 class UniirError(RuntimeError):
@@ -70,6 +70,7 @@ _SIGS = {
     "uniir_adamw_step": (C.c_int, [VP, VP, VP, VP, VP, I64, C.c_float, C.c_float, C.c_float, C.c_float,
                                    C.c_float, I32, C.c_float, VP]),
     "uniir_attn_fwd": (C.c_int, [VP, I32, I32, I32, I32, VP, VP, VP]),
+    "uniir_attn_fwd_ex": (C.c_int, [VP, I64, VP, VP, I64, I32, I32, I32, I32, I32, VP, VP, I64, VP, VP]),
     "uniir_attn_bwd": (C.c_int, [VP, VP, VP, VP, I32, I32, I32, I32, VP, VP, VP]),
     "uniir_infonce_workspace_bytes": (C.c_size_t, [I32, I32]),
     "uniir_infonce_normalize": (C.c_int, [VP, VP, VP, I32, I32, VP, VP, VP, VP, VP]),

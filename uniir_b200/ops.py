@@ -316,6 +316,19 @@ def attn_fwd(qkv, B, S, H, causal, out=None, lse=None, need_lse=True):
     return out, lse
 
 
+def attn_fwd_ex(q, k, v, B, Sq, Skv, H, *, causal=False, kv_len=None, out=None, lse=None):
+    """q [B*Sq, >=H*64] / k, v [B*Skv, >=H*64] bf16 row-strided views (column slices of packed projections are
+    fine), optional int32 kv_len[B] key-padding mask."""
+    assert q.dtype == torch.bfloat16 and q.stride(1) == 1 and k.stride(1) == 1 and v.stride(1) == 1
+    assert k.stride(0) == v.stride(0)
+    if out is None:
+        out = torch.empty(B * Sq, H * 64, device=q.device, dtype=torch.bfloat16)
+    L.check(L.load().uniir_attn_fwd_ex(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), B, Sq, Skv, H,
+                                       int(causal), _ptr(kv_len), out.data_ptr(), out.stride(0), _ptr(lse), _stream()),
+            "uniir_attn_fwd_ex")
+    return out
+
+
 def attn_bwd(qkv, out, dout, lse, B, S, H, causal, dqkv=None, delta=None):
     if dqkv is None:
         dqkv = torch.empty_like(qkv)

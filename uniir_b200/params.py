@@ -108,8 +108,11 @@ class FlatParamModule(nn.Module):
 
     ALIGN = 64  # elements; keeps every parameter 256 B aligned (TMA needs 16 B)
 
-    def __init__(self, specs, device, seed=2023):
+    def __init__(self, specs, device, seed=2023, root=None):
+        """root: module on which the parameter tree is built (default: this module).  With a separate
+        root the Parameters appear under the root's own state-dict keys (BLIP: ``visual_encoder.*``)."""
         super().__init__()
+        object.__setattr__(self, "_root", root if root is not None else self)
         self._specs = specs
         self._index = {}
         sizes = {True: 0, False: 0}
@@ -134,7 +137,7 @@ class FlatParamModule(nn.Module):
 
     # -- tree plumbing -------------------------------------------------------------
     def _register(self, dotted, param):
-        mod = self
+        mod = self._root
         parts = dotted.split(".")
         for part in parts[:-1]:
             if not hasattr(mod, part):
@@ -165,7 +168,7 @@ class FlatParamModule(nn.Module):
     def rebind_after_apply(self):
         """``module.to()/float()`` may have replaced Parameter storage; re-point the flats."""
         for name, shape, decay, _ in self._specs:
-            p = self.get_parameter(name)
+            p = self._root.get_parameter(name)
             view = self._view(self.flat, name)
             if p.data_ptr() != view.data_ptr():
                 view.copy_(p.data.to(view.device, torch.float32))

@@ -140,3 +140,18 @@ def synthetic_clip_tokens(n, generator=None, context_length=77, vocab=49408):
         ids[i, 1:1 + Ln] = body[i, :Ln]
         ids[i, 1 + Ln] = vocab - 1
     return ids
+
+
+def blip_image_preprocess(size=224):
+    """BLIP eval transform (backbone/transform/blip_transform.py:42-48): bicubic resize to (size,size),
+    ToTensor, Normalize with the CLIP mean/std constants (blip_transform.py:9)."""
+    mean = torch.tensor(CLIP_MEAN).view(3, 1, 1)
+    std = torch.tensor(CLIP_STD).view(3, 1, 1)
+
+    def fn(img):
+        from PIL import Image
+        img = img.convert("RGB").resize((size, size), Image.BICUBIC)
+        t = torch.from_numpy(np.asarray(img, dtype=np.uint8).copy()).permute(2, 0, 1).float() / 255.0
+        return (t - mean) / std
+
+    return fn
