@@ -31,6 +31,7 @@ constexpr int num_threads(int ne) { return 64 + 32 * ne; }
 
 struct WorkItem {
   int m_blk, n_begin, n_end, kb_begin, kb_end;
+  int tag, aux;  // scheduler-defined (retrieval: state slot, chunk index / last-chunk flag)
 };
 
 template <int BN>

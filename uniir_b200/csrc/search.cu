@@ -2,11 +2,17 @@
 // inner-product search, reference common/mbeir_retriever.py:231) plus the row-norm and
 // k-way merge kernels around it.
 //
-// Work decomposition: item = (query tile of 128 rows) x (one contiguous candidate range).
-// A CTA keeps the per-row running top-k of its item; consecutive CTAs work on different
-// query tiles of the SAME candidate range, so the 148 CTAs stream the candidate matrix in
-// near lock-step and every candidate tile is fetched from HBM once and served to the other
-// CTAs from L2.  Scores never leave the SM: the epilogue reads the fp32 accumulators from
+// Work decomposition: item = (query tile of 128 rows) x (one CHUNK of ~16 k candidates).
+// Items are ordered chunk-major, so at any moment all 148 CTAs work on different query tiles
+// of the SAME ~25 MB candidate chunk: it is fetched from HBM once and served to everyone else
+// from L2.  (A first version gave each CTA a whole candidate range; ncu showed 10.9 TB of DRAM
+// reads for the 190k x 5.6M problem -- CTAs drift apart after the first wave and every query
+// tile re-streamed its range from HBM.)  The per-row running top-k (threshold, count, buffer)
+// lives in global memory and is handed from the CTA that processed (tile, chunk c) to the one
+// that processes (tile, chunk c+1) through a release/acquire flag per query tile; the static
+// chunk-major order guarantees the predecessor is always scheduled earlier, so the wait cannot
+// deadlock on a persistent grid.  Small query sets additionally split the candidates into
+// independent ranges (own state, merged afterwards) to keep every SM busy.  Scores never leave the SM: the epilogue reads the fp32 accumulators from
 // TMEM, scales by 1/||c|| and rejects >99.9 % of them with one max-reduce + compare against
 // the row's current k-th best; survivors are appended to a small per-row buffer that is
 // compacted (warp-cooperative bitonic sort) when it fills.
@@ -24,30 +30,53 @@ constexpr int kMaxK = 64;
 constexpr float kNegInf = -INFINITY;
 constexpr float kFaissNeg = -3.4028234663852886e38f;
 
+constexpr int kTilesPerChunk = 64;   // 64 x 256 candidates x 1536 B = 25 MB: L2-resident per wave
+
 struct SearchParams {
   long long Q, N;
-  int k, splits, n_qtiles, tiles_per_split, n_tiles, kb_total;
+  int k, splits, n_qtiles, tiles_per_split, n_tiles, kb_total, n_chunks;
   const float* q_inv;
   const float* c_inv;
   float* part_scores;
   int* part_idx;
-  float* ws_scores;  // [grid][128][kCap]
+  float* ws_scores;  // [splits][n_qtiles*128][kCap]   per-row candidate buffers
   int* ws_idx;
+  float* g_thr;      // [splits][n_qtiles*128]         running k-th best per row
+  int* g_cnt;        // [splits][n_qtiles*128]         entries in the row buffer
+  int* done;         // [splits][n_qtiles]             chunks completed (release/acquire hand-off)
 };
 
 struct SearchSched {
-  int n_qtiles, splits, tiles_per_split, n_tiles, kb_total;
-  __device__ __forceinline__ int num_items() const { return n_qtiles * splits; }
+  int n_qtiles, splits, tiles_per_split, n_tiles, kb_total, n_chunks;
+  __device__ __forceinline__ int num_items() const { return n_chunks * splits * n_qtiles; }
   __device__ __forceinline__ bool get(int item, WorkItem& w) const {
-    const int split = item / n_qtiles;
-    w.m_blk = item - split * n_qtiles;
-    w.n_begin = split * tiles_per_split;
-    w.n_end = min(n_tiles, w.n_begin + tiles_per_split);
+    const int slots = splits * n_qtiles;
+    const int chunk = item / slots;
+    const int slot = item - chunk * slots;        // (split, query tile)
+    const int split = slot / n_qtiles;
+    w.m_blk = slot - split * n_qtiles;
+    const int split_begin = split * tiles_per_split;
+    const int split_end = min(n_tiles, split_begin + tiles_per_split);
+    w.n_begin = split_begin + chunk * kTilesPerChunk;
+    w.n_end = min(split_end, w.n_begin + kTilesPerChunk);
     w.kb_begin = 0;
     w.kb_end = kb_total;
-    return w.n_begin < w.n_end;
+    w.tag = slot;
+    // aux: chunk index, bit 30 = last chunk of this split
+    const int last_chunk = (split_end - split_begin + kTilesPerChunk - 1) / kTilesPerChunk - 1;
+    w.aux = chunk | (chunk >= last_chunk ? (1 << 30) : 0);
+    return w.n_begin < w.n_end || chunk == 0;     // an empty split still emits its (padded) result
   }
 };
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // strict total order "a ranks before b": higher score first, lower index on ties
 __device__ __forceinline__ bool ranks_before(float ka, long long ia, float kb, long long ib) {
@@ -104,13 +133,32 @@ struct SearchEpilogue {
   int tcount;
   __device__ SearchEpilogue(const SearchParams& p_, float* s) : p(p_), invc_s(s), thr(kNegInf), cnt(0), tcount(0) {}
 
-  __device__ __forceinline__ long long ws_base(int row) const {
-    return (static_cast<long long>(blockIdx.x) * kBM + row) * kCap;
-  }
+  long long slot_row0;  // first state row of the current (split, query tile) slot
 
-  __device__ __forceinline__ void item_begin(const WorkItem&, int) {
-    thr = kNegInf;
-    cnt = 0;
+  __device__ __forceinline__ long long ws_base(int row) const { return (slot_row0 + row) * kCap; }
+
+  // Pick up the running top-k state of this query tile from whoever processed the previous chunk.
+  __device__ __forceinline__ void item_begin(const WorkItem& w, int row) {
+    slot_row0 = static_cast<long long>(w.tag) * kBM;
+    const int chunk = w.aux & 0x3fffffff;
+    if (chunk == 0) {
+      thr = kNegInf;
+      cnt = 0;
+      return;
+    }
+    if ((threadIdx.x & 31) == 0) {
+      unsigned spins = 0;
+      while (ld_acquire_gpu(p.done + w.tag) < chunk) {
+        __nanosleep(200);
+        if (++spins > (1u << 24)) {
+          printf("uniir: retrieval hand-off timeout (slot %d chunk %d)\n", w.tag, chunk);
+          __trap();
+        }
+      }
+    }
+    __syncwarp();
+    thr = __ldcg(p.g_thr + slot_row0 + row);
+    cnt = __ldcg(p.g_cnt + slot_row0 + row);
   }
 
   // Compact the buffers of the rows selected by `mask` (warp-uniform) to their top-k.
@@ -130,8 +178,9 @@ struct SearchEpilogue {
       for (int r = 0; r < 4; ++r) {
         const int e = r * 32 + lane;
         const bool ok = e < cntL;
-        key[r] = ok ? p.ws_scores[base + e] : kNegInf;
-        idx[r] = ok ? p.ws_idx[base + e] : 0x7fffffff;
+        // L2 loads: earlier chunks of this row were written by other SMs (L1 is not coherent)
+        key[r] = ok ? __ldcg(p.ws_scores + base + e) : kNegInf;
+        idx[r] = ok ? __ldcg(p.ws_idx + base + e) : 0x7fffffff;
       }
       warp_bitonic_desc<4, int>(key, idx);
       const int keep = min(cntL, p.k);
@@ -158,7 +207,7 @@ struct SearchEpilogue {
       if (final) {
         const long long q = static_cast<long long>(w.m_blk) * kBM + row0 + L;
         if (q < p.Q) {
-          const int split = w.n_begin / p.tiles_per_split;
+          const int split = w.tag / p.n_qtiles;
           const long long ob = (q * p.splits + split) * p.k;
           const float qi = p.q_inv[q];
 #pragma unroll
@@ -235,7 +284,16 @@ struct SearchEpilogue {
   }
 
   __device__ __forceinline__ void item_end(const WorkItem& w, int row) {
-    compact(0xffffffffu, row, true, w);
+    if (w.aux & (1 << 30)) {           // last chunk of the split: final sort + emit the partial list
+      compact(0xffffffffu, row, true, w);
+      return;
+    }
+    // hand the state over to the CTA that takes (this tile, next chunk)
+    p.g_thr[slot_row0 + row] = thr;
+    p.g_cnt[slot_row0 + row] = cnt;
+    __threadfence();
+    named_bar_sync(2, 128);
+    if (row == 0) st_release_gpu(p.done + w.tag, (w.aux & 0x3fffffff) + 1);
   }
 };
 
@@ -342,23 +400,24 @@ static void plan_splits(long long Q, long long N, int* splits, int* tiles_per_sp
   const int sms = num_sms();
   const int nq = static_cast<int>((Q + kBM - 1) / kBM);
   const int nt = static_cast<int>((N + kSearchBN - 1) / kSearchBN);
-  int best_s = 1;
-  double best_cost = 1e300;
-  for (int s = 1; s <= 32 && s <= nt; ++s) {
-    const int tps = (nt + s - 1) / s;
-    if (s > 1 && tps < 8) break;
-    const long long items = 1LL * nq * s;
-    const long long waves = (items + sms - 1) / sms;
-    // time ~ waves * (tiles per item + per-item fixed cost).  The fixed cost is the threshold
-    // ramp-up: ~k*ln(n/k) admissions per row before the running k-th best becomes selective,
-    // each a divergent slow-path event; measured at roughly 300 tile-times per item.
-    const double cost = static_cast<double>(waves) * (tps + 300.0);
-    if (cost < best_cost * 0.995) { best_cost = cost; best_s = s; }
+  // Enough independent (split, query tile) slots to keep every SM busy; one split when the query
+  // set alone provides them.  Each split needs a few tiles to be worth its ramp-up.
+  int s = 1;
+  if (nq < sms) {
+    s = (sms + nq - 1) / nq;
+    if (s > 32) s = 32;
+    while (s > 1 && (nt + s - 1) / s < 8) --s;
   }
-  *splits = best_s;
-  *tiles_per_split = (nt + best_s - 1) / best_s;
+  *splits = s;
+  *tiles_per_split = (nt + s - 1) / s;
   *n_tiles = nt;
   *n_qtiles = nq;
+}
+
+static size_t search_ws_bytes(int splits, int nq) {
+  const size_t rows = static_cast<size_t>(splits) * nq * kBM;
+  return rows * kCap * (sizeof(float) + sizeof(int)) + rows * (sizeof(float) + sizeof(int)) +
+         static_cast<size_t>(splits) * nq * sizeof(int) + 256;
 }
 
 }  // namespace uniir
@@ -389,7 +448,7 @@ extern "C" int uniir_ip_topk_plan(int64_t Q, int64_t N, int32_t k, int32_t* spli
   int s, tps, nt, nq;
   plan_splits(Q, N, &s, &tps, &nt, &nq);
   *splits = s;
-  *workspace_bytes = static_cast<size_t>(num_sms()) * kBM * kCap * (sizeof(float) + sizeof(int));
+  *workspace_bytes = search_ws_bytes(s, nq);
   return UNIIR_OK;
 }
 
@@ -408,7 +467,7 @@ extern "C" int uniir_ip_topk(const void* q, const float* q_inv, const void* c, c
   UNIIR_CHECK_ARG(splits == s, "uniir_ip_topk: splits=%d does not match uniir_ip_topk_plan (%d)",
                   splits, s);
   const int sms = num_sms();
-  const size_t need = static_cast<size_t>(sms) * kBM * kCap * (sizeof(float) + sizeof(int));
+  const size_t need = search_ws_bytes(s, nq);
   UNIIR_CHECK_ARG(workspace_bytes >= need, "uniir_ip_topk: workspace too small (%zu < %zu)",
                   workspace_bytes, need);
 
@@ -423,9 +482,15 @@ extern "C" int uniir_ip_topk(const void* q, const float* q_inv, const void* c, c
   p.n_tiles = nt; p.kb_total = (d + kBK - 1) / kBK;
   p.q_inv = q_inv; p.c_inv = c_inv;
   p.part_scores = part_scores; p.part_idx = part_idx;
+  const size_t rows = static_cast<size_t>(s) * nq * kBM;
+  p.n_chunks = (tps + kTilesPerChunk - 1) / kTilesPerChunk;
   p.ws_scores = static_cast<float*>(workspace);
-  p.ws_idx = reinterpret_cast<int*>(p.ws_scores + static_cast<size_t>(sms) * kBM * kCap);
-  SearchSched sched{nq, s, tps, nt, p.kb_total};
+  p.ws_idx = reinterpret_cast<int*>(p.ws_scores + rows * kCap);
+  p.g_thr = reinterpret_cast<float*>(p.ws_idx + rows * kCap);
+  p.g_cnt = reinterpret_cast<int*>(p.g_thr + rows);
+  p.done = p.g_cnt + rows;
+  UNIIR_CUDA_OK(cudaMemsetAsync(p.done, 0, static_cast<size_t>(s) * nq * sizeof(int), stream));
+  SearchSched sched{nq, s, tps, nt, p.kb_total, p.n_chunks};
 
   using SM = GemmSmem<kSearchBN>;
   const int smem_bytes = SM::kRingBytes + SM::kBarBytes + 2 * kSearchBN * sizeof(float) + 1024;
@@ -435,7 +500,8 @@ extern "C" int uniir_ip_topk(const void* q, const float* q_inv, const void* c, c
                                        smem_bytes));
     attr_set = true;
   }
-  const long long items = 1LL * nq * s;
+  const long long items = 1LL * nq * s * p.n_chunks;
+  UNIIR_CHECK_ARG(items < (1LL << 31), "uniir_ip_topk: too many work items");
   const int grid = items < sms ? static_cast<int>(items) : sms;
   const uint32_t idesc = make_idesc_f16(false, false, false, kBM, kSearchBN);
   ip_topk_kernel<<<grid, num_threads(4), smem_bytes, stream>>>(maps, p, sched, idesc);
