@@ -37,15 +37,27 @@ extern "C" int uniir_gemm_epi(const uniir_gemm_desc* d, void* stream_) {
     if (const char* e = getenv("UNIIR_GEMM_BN")) { const int v = atoi(e); if (v == 128 || (v == 256 && d->N > 128)) bn = v; }
   }
 
+  // CTA-pair path (256 x 256 tiles, cta_group::2): large, non-split problems whose epilogue has a pair
+  // instantiation.  UNIIR_GEMM_2CTA=0 disables, =1 forces where legal.
+  bool pair = false;
+  {
+    const char* e = getenv("UNIIR_GEMM_2CTA");
+    const int mode = e ? atoi(e) : 1;
+    const long long tiles2 = 1LL * ((d->M + 255) / 256) * ((d->N + 255) / 256);
+    pair = mode != 0 && bn == 256 && !atomic && d->M >= 256 && !(d->a_mn && !d->b_mn) &&
+           (mode == 1 ? tiles2 >= sms / 2 : true);
+  }
+
   GemmTensorMaps maps;
   int rc;
+  const int b_box = pair ? 128 : bn;
   if (!d->a_mn)
     rc = make_tmap_2d(&maps.a, d->A, d->in_dtype, d->K, d->M, d->lda, kBK, kBM);
   else
     rc = make_tmap_2d(&maps.a, d->A, d->in_dtype, d->M, d->K, d->lda, 64, kBK);
   if (rc) return rc;
   if (!d->b_mn)
-    rc = make_tmap_2d(&maps.b, d->B, d->in_dtype, d->K, d->N, d->ldb, kBK, bn);
+    rc = make_tmap_2d(&maps.b, d->B, d->in_dtype, d->K, d->N, d->ldb, kBK, b_box);
   else
     rc = make_tmap_2d(&maps.b, d->B, d->in_dtype, d->N, d->K, d->ldb, 64, kBK);
   if (rc) return rc;
@@ -90,6 +102,28 @@ extern "C" int uniir_gemm_epi(const uniir_gemm_desc* d, void* stream_) {
     epi = atomic ? EPI_ATOMIC : EPI_ACC32;
   if (getenv("UNIIR_GEMM_DYN")) epi = EPI_DYN;
 
+  if (pair) {
+    TileSched s2 = s;
+    s2.m_blocks = (d->M + 255) / 256;
+    s2.group_m = 8;
+#define UNIIR_GO2(A_, B_, E_) return launch_gemm_2cta<A_, B_, E_>(maps, p, s2, bf16, stream)
+    switch (epi) {
+      case EPI_STORE16: if (d->b_mn) UNIIR_GO2(false, true, EPI_STORE16); else UNIIR_GO2(false, false, EPI_STORE16);
+      case EPI_STORE32: if (!d->b_mn) UNIIR_GO2(false, false, EPI_STORE32); break;
+      case EPI_ACT: UNIIR_GO2(false, false, EPI_ACT);
+      case EPI_ACT_AUX: UNIIR_GO2(false, false, EPI_ACT_AUX);
+      case EPI_AGS: UNIIR_GO2(false, true, EPI_AGS);
+      case EPI_RES32: UNIIR_GO2(false, false, EPI_RES32);
+      case EPI_ACC32: UNIIR_GO2(true, true, EPI_ACC32);
+      default: break;   // no pair instantiation: fall through to the single-CTA kernels
+    }
+#undef UNIIR_GO2
+    // rebuild the B map for the single-CTA box
+    if (!d->b_mn) {
+      rc = make_tmap_2d(&maps.b, d->B, d->in_dtype, d->K, d->N, d->ldb, kBK, bn);
+      if (rc) return rc;
+    }
+  }
 #define UNIIR_GO(BN_, A_, B_, E_) return launch_gemm<BN_, A_, B_, E_>(maps, p, s, bf16, stream)
 #define UNIIR_BY_BN(A_, B_, E_) do { if (bn == 256) UNIIR_GO(256, A_, B_, E_); else UNIIR_GO(128, A_, B_, E_); } while (0)
   switch (epi) {

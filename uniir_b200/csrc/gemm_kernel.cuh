@@ -329,4 +329,49 @@ int launch_gemm_impl(const GemmTensorMaps& maps, const GemmEpiParams& p, const T
 // 4x-unrolled unit and the kernel grows to ~80 KB of SASS, which thrashes the instruction
 // cache (ncu: stall_no_inst on the epilogue FMULs).  The variants below cover the patterns the
 // CLIP towers use; anything else takes EPI_DYN.
+
+// ---- CTA-pair kernel (256 x 256 tiles, cta_group::2) -------------------------------------
+template <bool A_MN, bool B_MN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(num_threads(kGemmNE), 1)
+gemm_epi_kernel_2cta(const __grid_constant__ GemmTensorMaps maps, const GemmEpiParams p,
+                     const TileSched sched, const uint32_t idesc) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem_1024(smem_raw);
+  using SM = GemmSmem2<256>;
+  GemmEpilogue<256, EPI> epi(p, reinterpret_cast<float*>(smem + SM::kRingBytes + SM::kBarBytes));
+  gemm_body_2cta<256, A_MN, B_MN, kGemmNE>(&maps.a, &maps.b, idesc, sched, epi, smem);
+}
+
+template <bool A_MN, bool B_MN, int EPI>
+int launch_gemm_2cta(const GemmTensorMaps& maps, const GemmEpiParams& p, const TileSched& s, bool bf16,
+                     cudaStream_t stream);
+
+template <bool A_MN, bool B_MN, int EPI>
+int launch_gemm_2cta_impl(const GemmTensorMaps& maps, const GemmEpiParams& p, const TileSched& s, bool bf16,
+                          cudaStream_t stream) {
+  using SM = GemmSmem2<256>;
+  const int smem_bytes = SM::kRingBytes + SM::kBarBytes + kGemmNE * 4096 + 1024;
+  auto kern = gemm_epi_kernel_2cta<A_MN, B_MN, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    UNIIR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr_set = true;
+  }
+  const int items = s.m_blocks * s.n_blocks * s.split_k;
+  int pairs = num_sms() / 2;
+  if (items < pairs) pairs = items;
+  const uint32_t idesc = make_idesc_f16(bf16, A_MN, B_MN, 2 * kBM, 256);
+  kern<<<2 * pairs, num_threads(kGemmNE), smem_bytes, stream>>>(maps, p, s, idesc);
+  count_launch();
+  UNIIR_CUDA_OK(cudaGetLastError());
+  return UNIIR_OK;
+}
+
+#define UNIIR_INSTANTIATE_GEMM_2CTA(A_, B_, EPI_)                                                   \
+  template <>                                                                                       \
+  int launch_gemm_2cta<A_, B_, EPI_>(const GemmTensorMaps& m, const GemmEpiParams& p,               \
+                                     const TileSched& s, bool bf16, cudaStream_t st) {              \
+    return launch_gemm_2cta_impl<A_, B_, EPI_>(m, p, s, bf16, st);                                  \
+  }
+
 }  // namespace uniir
