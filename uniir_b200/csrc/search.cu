@@ -18,6 +18,7 @@
 // compacted (warp-cooperative bitonic sort) when it fills.
 #include <cuda_fp16.h>
 #include <float.h>
+#include <stdlib.h>
 
 #include "gemm_sm100.cuh"
 #include "host_util.cuh"
@@ -47,14 +48,14 @@ struct SearchParams {
 };
 
 struct SearchSched {
-  int n_qtiles, splits, tiles_per_split, n_tiles, kb_total, n_chunks;
-  __device__ __forceinline__ int num_items() const { return n_chunks * splits * n_qtiles; }
+  int n_units, splits, tiles_per_split, n_tiles, kb_total, n_chunks;   // unit = query tile (or tile pair)
+  __device__ __forceinline__ int num_items() const { return n_chunks * splits * n_units; }
   __device__ __forceinline__ bool get(int item, WorkItem& w) const {
-    const int slots = splits * n_qtiles;
+    const int slots = splits * n_units;
     const int chunk = item / slots;
-    const int slot = item - chunk * slots;        // (split, query tile)
-    const int split = slot / n_qtiles;
-    w.m_blk = slot - split * n_qtiles;
+    const int slot = item - chunk * slots;        // (split, unit)
+    const int split = slot / n_units;
+    w.m_blk = slot - split * n_units;
     const int split_begin = split * tiles_per_split;
     const int split_end = min(n_tiles, split_begin + tiles_per_split);
     w.n_begin = split_begin + chunk * kTilesPerChunk;
@@ -308,6 +309,19 @@ ip_topk_kernel(const __grid_constant__ GemmTensorMaps maps, const SearchParams p
   gemm_body<kSearchBN, false, false, 4>(&maps.a, &maps.b, idesc, sched, epi, smem);
 }
 
+// CTA-pair variant: two CTAs (one cluster) take two adjacent query tiles and share every candidate
+// tile through one 256-row cta_group::2 UMMA; each CTA stages half of the candidate tile.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(num_threads(4), 1)
+ip_topk_kernel_2cta(const __grid_constant__ GemmTensorMaps maps, const SearchParams p,
+                    const SearchSched sched, const uint32_t idesc) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem_1024(smem_raw);
+  using SM = GemmSmem2<kSearchBN>;
+  float* invc_s = reinterpret_cast<float*>(smem + SM::kRingBytes + SM::kBarBytes);
+  SearchEpilogue epi(p, invc_s);
+  gemm_body_2cta<kSearchBN, false, false, 4>(&maps.a, &maps.b, idesc, sched, epi, smem);
+}
+
 // ---------------------------------------------------------------------------------
 // inv-norm: one warp per row
 // ---------------------------------------------------------------------------------
@@ -395,16 +409,26 @@ __global__ void topk_merge_kernel(const float* __restrict__ in_s, const void* __
   }
 }
 
+static bool search_pairs() {
+  const char* e = getenv("UNIIR_SEARCH_2CTA");
+  return !(e && atoi(e) == 0);
+}
+
+// n_qtiles is the number of 128-row state slots per split (padded to an even count in pair mode)
 static void plan_splits(long long Q, long long N, int* splits, int* tiles_per_split, int* n_tiles,
                         int* n_qtiles) {
   const int sms = num_sms();
-  const int nq = static_cast<int>((Q + kBM - 1) / kBM);
+  const bool pairs = search_pairs();
+  int nq = static_cast<int>((Q + kBM - 1) / kBM);
+  if (pairs) nq = (nq + 1) / 2 * 2;
+  const int units = pairs ? nq / 2 : nq;          // schedulable units per chunk and split
+  const int workers = pairs ? sms / 2 : sms;
   const int nt = static_cast<int>((N + kSearchBN - 1) / kSearchBN);
-  // Enough independent (split, query tile) slots to keep every SM busy; one split when the query
-  // set alone provides them.  Each split needs a few tiles to be worth its ramp-up.
+  // Enough independent (split, unit) slots to keep every SM busy; one split when the query set
+  // alone provides them.  Each split needs a few tiles to be worth its ramp-up.
   int s = 1;
-  if (nq < sms) {
-    s = (sms + nq - 1) / nq;
+  if (units < workers) {
+    s = (workers + units - 1) / units;
     if (s > 32) s = 32;
     while (s > 1 && (nt + s - 1) / s < 8) --s;
   }
@@ -471,10 +495,11 @@ extern "C" int uniir_ip_topk(const void* q, const float* q_inv, const void* c, c
   UNIIR_CHECK_ARG(workspace_bytes >= need, "uniir_ip_topk: workspace too small (%zu < %zu)",
                   workspace_bytes, need);
 
+  const bool pairs = search_pairs();
   GemmTensorMaps maps;
   int rc = make_tmap_2d(&maps.a, q, UNIIR_F16, d, Q, d, kBK, kBM);
   if (rc) return rc;
-  rc = make_tmap_2d(&maps.b, c, UNIIR_F16, d, N, d, kBK, kSearchBN);
+  rc = make_tmap_2d(&maps.b, c, UNIIR_F16, d, N, d, kBK, pairs ? kSearchBN / 2 : kSearchBN);
   if (rc) return rc;
 
   SearchParams p;
@@ -490,21 +515,35 @@ extern "C" int uniir_ip_topk(const void* q, const float* q_inv, const void* c, c
   p.g_cnt = reinterpret_cast<int*>(p.g_thr + rows);
   p.done = p.g_cnt + rows;
   UNIIR_CUDA_OK(cudaMemsetAsync(p.done, 0, static_cast<size_t>(s) * nq * sizeof(int), stream));
-  SearchSched sched{nq, s, tps, nt, p.kb_total, p.n_chunks};
-
-  using SM = GemmSmem<kSearchBN>;
-  const int smem_bytes = SM::kRingBytes + SM::kBarBytes + 2 * kSearchBN * sizeof(float) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    UNIIR_CUDA_OK(cudaFuncSetAttribute(ip_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       smem_bytes));
-    attr_set = true;
-  }
-  const long long items = 1LL * nq * s * p.n_chunks;
+  const int units = pairs ? nq / 2 : nq;
+  SearchSched sched{units, s, tps, nt, p.kb_total, p.n_chunks};
+  const long long items = 1LL * units * s * p.n_chunks;
   UNIIR_CHECK_ARG(items < (1LL << 31), "uniir_ip_topk: too many work items");
-  const int grid = items < sms ? static_cast<int>(items) : sms;
-  const uint32_t idesc = make_idesc_f16(false, false, false, kBM, kSearchBN);
-  ip_topk_kernel<<<grid, num_threads(4), smem_bytes, stream>>>(maps, p, sched, idesc);
+
+  if (pairs) {
+    using SM = GemmSmem2<kSearchBN>;
+    const int smem_bytes = SM::kRingBytes + SM::kBarBytes + 2 * kSearchBN * sizeof(float) + 1024;
+    static bool attr2 = false;
+    if (!attr2) {
+      UNIIR_CUDA_OK(cudaFuncSetAttribute(ip_topk_kernel_2cta, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      attr2 = true;
+    }
+    int npairs = sms / 2;
+    if (items < npairs) npairs = static_cast<int>(items);
+    const uint32_t idesc = make_idesc_f16(false, false, false, 2 * kBM, kSearchBN);
+    ip_topk_kernel_2cta<<<2 * npairs, num_threads(4), smem_bytes, stream>>>(maps, p, sched, idesc);
+  } else {
+    using SM = GemmSmem<kSearchBN>;
+    const int smem_bytes = SM::kRingBytes + SM::kBarBytes + 2 * kSearchBN * sizeof(float) + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+      UNIIR_CUDA_OK(cudaFuncSetAttribute(ip_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      attr_set = true;
+    }
+    const int grid = items < sms ? static_cast<int>(items) : sms;
+    const uint32_t idesc = make_idesc_f16(false, false, false, kBM, kSearchBN);
+    ip_topk_kernel<<<grid, num_threads(4), smem_bytes, stream>>>(maps, p, sched, idesc);
+  }
   count_launch();
   UNIIR_CUDA_OK(cudaGetLastError());
   return UNIIR_OK;
