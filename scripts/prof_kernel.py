@@ -12,6 +12,8 @@ if which == "gemm_ags":
     print(ops.time_gemm_config({**base, "N": 4096, "K": 1024, "b_mn": True, "act": 1, "ags": True}, iters=3))
 elif which == "gemm_fc1":
     print(ops.time_gemm_config({**base, "N": 4096, "K": 1024, "bias": True, "act": 1, "aux": True}, iters=3))
+elif which == "gemm_fc2":
+    print(ops.time_gemm_config({**base, "N": 1024, "K": 4096, "bias": True, "out_dtype": torch.float32, "residual": torch.float32}, iters=3))
 elif which == "gemm_out":
     print(ops.time_gemm_config({**base, "N": 1024, "K": 1024, "bias": True, "out_dtype": torch.float32, "residual": torch.float32}, iters=3))
 elif which == "search":
