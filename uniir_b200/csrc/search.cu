@@ -31,7 +31,7 @@ constexpr int kMaxK = 64;
 constexpr float kNegInf = -INFINITY;
 constexpr float kFaissNeg = -3.4028234663852886e38f;
 
-constexpr int kTilesPerChunk = 64;   // 64 x 256 candidates x 1536 B = 25 MB: L2-resident per wave
+constexpr int kDefaultTilesPerChunk = 64;   // 64 x 256 candidates x 1536 B = 25 MB: L2-resident per wave
 
 struct SearchParams {
   long long Q, N;
@@ -48,7 +48,7 @@ struct SearchParams {
 };
 
 struct SearchSched {
-  int n_units, splits, tiles_per_split, n_tiles, kb_total, n_chunks;   // unit = query tile (or tile pair)
+  int n_units, splits, tiles_per_split, n_tiles, kb_total, n_chunks, tpc;   // unit = query tile (or tile pair); tpc = tiles per chunk
   __device__ __forceinline__ int num_items() const { return n_chunks * splits * n_units; }
   __device__ __forceinline__ bool get(int item, WorkItem& w) const {
     const int slots = splits * n_units;
@@ -58,13 +58,13 @@ struct SearchSched {
     w.m_blk = slot - split * n_units;
     const int split_begin = split * tiles_per_split;
     const int split_end = min(n_tiles, split_begin + tiles_per_split);
-    w.n_begin = split_begin + chunk * kTilesPerChunk;
-    w.n_end = min(split_end, w.n_begin + kTilesPerChunk);
+    w.n_begin = split_begin + chunk * tpc;
+    w.n_end = min(split_end, w.n_begin + tpc);
     w.kb_begin = 0;
     w.kb_end = kb_total;
     w.tag = slot;
     // aux: chunk index, bit 30 = last chunk of this split
-    const int last_chunk = (split_end - split_begin + kTilesPerChunk - 1) / kTilesPerChunk - 1;
+    const int last_chunk = (split_end - split_begin + tpc - 1) / tpc - 1;
     w.aux = chunk | (chunk >= last_chunk ? (1 << 30) : 0);
     return w.n_begin < w.n_end || chunk == 0;     // an empty split still emits its (padded) result
   }
@@ -508,7 +508,9 @@ extern "C" int uniir_ip_topk(const void* q, const float* q_inv, const void* c, c
   p.q_inv = q_inv; p.c_inv = c_inv;
   p.part_scores = part_scores; p.part_idx = part_idx;
   const size_t rows = static_cast<size_t>(s) * nq * kBM;
-  p.n_chunks = (tps + kTilesPerChunk - 1) / kTilesPerChunk;
+  int tpc = kDefaultTilesPerChunk;
+  if (const char* e = getenv("UNIIR_SEARCH_TPC")) { const int v = atoi(e); if (v >= 1) tpc = v; }
+  p.n_chunks = (tps + tpc - 1) / tpc;
   p.ws_scores = static_cast<float*>(workspace);
   p.ws_idx = reinterpret_cast<int*>(p.ws_scores + rows * kCap);
   p.g_thr = reinterpret_cast<float*>(p.ws_idx + rows * kCap);
@@ -516,7 +518,7 @@ extern "C" int uniir_ip_topk(const void* q, const float* q_inv, const void* c, c
   p.done = p.g_cnt + rows;
   UNIIR_CUDA_OK(cudaMemsetAsync(p.done, 0, static_cast<size_t>(s) * nq * sizeof(int), stream));
   const int units = pairs ? nq / 2 : nq;
-  SearchSched sched{units, s, tps, nt, p.kb_total, p.n_chunks};
+  SearchSched sched{units, s, tps, nt, p.kb_total, p.n_chunks, tpc};
   const long long items = 1LL * units * s * p.n_chunks;
   UNIIR_CHECK_ARG(items < (1LL << 31), "uniir_ip_topk: too many work items");
 
