@@ -214,25 +214,90 @@ class BLIPBertOracle(nn.Module):
 
 
 class BLIPFeatureFusionOracle(nn.Module):
-    """encode path of reference BLIPFeatureFusion (blip_ff.py:82-116, 259-287)."""
+    """Reference BLIPFeatureFusion restated: encode path (blip_ff.py:82-116, 259-287), momentum encoders
+    and queues (:41-63), contrastive loss with momentum distillation (:118-257), EMA (:289-292) and queue
+    update (:295-310).  Hard-negative variant of the loss is not restated (default hard_neg_num: 0)."""
 
-    def __init__(self, size="large"):
+    def __init__(self, size="large", embed_dim=None, queue_size=57600, momentum=0.995, dims=None, gather_fn=None):
         super().__init__()
-        self.dims = BLIP_CONFIGS[size]
+        self.dims = dims if dims is not None else BLIP_CONFIGS[size]
+        embed_dim = embed_dim or self.dims.t_width
         self.visual_encoder = BLIPViTOracle(self.dims)
         self.text_encoder = BLIPBertOracle(self.dims)
         for p in self.parameters():
-            if p.ndim >= 2:
-                nn.init.normal_(p, 0.0, 0.02)
-            else:
-                nn.init.normal_(p, 0.0, 0.02)
+            nn.init.normal_(p, 0.0, 0.02)
         for m in self.modules():
             if isinstance(m, nn.LayerNorm):
                 nn.init.normal_(m.weight, 1.0, 0.05)
+        self.visual_encoder_m = BLIPViTOracle(self.dims)
+        self.text_encoder_m = BLIPBertOracle(self.dims)
+        self.model_pairs = [[self.visual_encoder, self.visual_encoder_m], [self.text_encoder, self.text_encoder_m]]
+        self.copy_params()
+        self.register_buffer("query_queue", F.normalize(torch.randn(embed_dim, queue_size), dim=0))
+        self.register_buffer("cand_queue", F.normalize(torch.randn(embed_dim, queue_size), dim=0))
+        self.register_buffer("idx_queue", torch.full((1, queue_size), -100))
+        self.register_buffer("new_ptr_queue", torch.zeros(1, dtype=torch.long))
+        self.queue_size, self.momentum = queue_size, momentum
+        self.temp = nn.Parameter(0.07 * torch.ones([]))
+        self._gather = gather_fn or (lambda t: t)   # concat_all_gather (:323-332); identity for world size 1
 
-    def encode_multimodal_input(self, input_ids, attention_mask, image, txt_mask=None, img_mask=None):
-        img = self.visual_encoder(image.float())
-        return self.text_encoder(input_ids, attention_mask, img)
+    @torch.no_grad()
+    def copy_params(self):
+        for a, b in self.model_pairs:
+            for p, pm in zip(a.parameters(), b.parameters()):
+                pm.data.copy_(p.data)
+                pm.requires_grad = False
+
+    @torch.no_grad()
+    def _momentum_update(self):
+        for a, b in self.model_pairs:
+            for p, pm in zip(a.parameters(), b.parameters()):
+                pm.data = pm.data * self.momentum + p.data * (1.0 - self.momentum)
+
+    @torch.no_grad()
+    def _dequeue_and_enqueue(self, q, c, idxs):
+        idxs, q, c = self._gather(idxs), self._gather(q), self._gather(c)
+        n = q.shape[0]
+        ptr = int(self.new_ptr_queue)
+        assert self.queue_size % n == 0
+        self.query_queue[:, ptr:ptr + n] = q.T
+        self.cand_queue[:, ptr:ptr + n] = c.T
+        self.idx_queue[:, ptr:ptr + n] = idxs.T
+        self.new_ptr_queue[0] = (ptr + n) % self.queue_size
+
+    def encode_multimodal_input(self, input_ids, attention_mask, image, txt_mask=None, img_mask=None, use_momentum=False):
+        v, t = (self.visual_encoder_m, self.text_encoder_m) if use_momentum else (self.visual_encoder, self.text_encoder)
+        return t(input_ids, attention_mask, v(image.float()))
+
+    def compute_contrastive_loss(self, batch, alpha):
+        t = batch["txt_batched"]
+        ids, att, img = t["input_ids"], t["attention_mask"], batch["image_batched"]
+        pc_idx = torch.tensor(batch["p_did_list"]).view(-1, 1)
+        im = batch["index_mapping"]
+        assert "neg_cand_list" not in im, "hard-negative variant not restated"
+        with torch.no_grad():
+            self.temp.clamp_(0.001, 0.5)
+        emb = self.encode_multimodal_input(ids, att, img)
+        qi = torch.tensor(im["query"]).flatten()
+        pi = torch.tensor(im["pos_cand"]).flatten()
+        q, pc = F.normalize(emb[qi], dim=-1), F.normalize(emb[pi], dim=-1)
+        idx_all = torch.cat([pc_idx.t(), self.idx_queue.clone()], dim=1)
+        pos = torch.eq(pc_idx, idx_all).float()
+        sim_targets = pos / pos.sum(1, keepdim=True)
+        with torch.no_grad():
+            self._momentum_update()
+            emb_m = self.encode_multimodal_input(ids, att, img, use_momentum=True)
+            q_m, pc_m = F.normalize(emb_m[qi], dim=-1), F.normalize(emb_m[pi], dim=-1)
+            q_all = torch.cat([q_m.t(), self.query_queue.clone()], dim=1)
+            pc_all = torch.cat([pc_m.t(), self.cand_queue.clone()], dim=1)
+            t_q2pc = alpha * F.softmax(q_m @ pc_all / self.temp, dim=1) + (1 - alpha) * sim_targets
+            t_pc2q = alpha * F.softmax(pc_m @ q_all / self.temp, dim=1) + (1 - alpha) * sim_targets
+        s_q2pc = q @ pc_all / self.temp
+        s_pc2q = pc @ q_all / self.temp
+        loss = (-(F.log_softmax(s_q2pc, dim=1) * t_q2pc).sum(1).mean() - (F.log_softmax(s_pc2q, dim=1) * t_pc2q).sum(1).mean()) / 2
+        self._dequeue_and_enqueue(q_m, pc_m, pc_idx)
+        acc = pos.gather(1, s_q2pc.max(1)[1].unsqueeze(1)).squeeze().mean()
+        return {"loss": loss, "accuracy": acc}
 
     def encode_mbeir_batch(self, batch):   # blip_ff.py:264-287 (ValueError, not assert)
         id_list = batch.get("did_list") or batch.get("qid_list")
@@ -242,3 +307,6 @@ class BLIPFeatureFusionOracle(nn.Module):
         emb = self.encode_multimodal_input(t["input_ids"], t["attention_mask"], batch["image_batched"])
         assert emb.size(0) == len(id_list)
         return emb, id_list
+
+    def forward(self, batch, alpha=None, encode_mbeir_batch=False):
+        return self.encode_mbeir_batch(batch) if encode_mbeir_batch else self.compute_contrastive_loss(batch, alpha)

@@ -85,13 +85,13 @@ def blip_tiny():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from test_oracle_blip import _inputs
     torch.manual_seed(4321)
-    m = BLIPFeatureFusionOracle("tiny-test").eval()
+    m = BLIPFeatureFusionOracle("tiny-test", queue_size=64).eval()
     d = m.dims
     ids, att, img = _inputs(d, 6, 24, 5)
     with torch.no_grad():
         emb = m.encode_multimodal_input(ids, att, img)
     np.savez_compressed(os.path.join(OUT, "blip_tiny.npz"), ids=ids.numpy(), att=att.numpy(), img=img.numpy(), emb=emb.numpy(),
-                        **{"w:" + k: v.numpy() for k, v in m.state_dict().items()})
+                        **{"w:" + k: v.numpy() for k, v in m.state_dict().items() if k.startswith(("visual_encoder.", "text_encoder."))})
 
 
 if __name__ == "__main__":

@@ -65,3 +65,17 @@ def load():
     B.init_weights = lambda self: self.apply(self._init_weights)
     B.get_head_mask = lambda self, head_mask, n, *a, **k: [None] * n
     return vit, med
+
+
+def load_blip_ff():
+    """The reference BLIPFeatureFusion class itself (blip_ff.py), with the tokenizer download stubbed."""
+    load()
+    sys.modules["timm.models.hub"].download_cached_file = lambda *a, **k: None
+    blip = importlib.import_module("models.uniir_blip.backbone.blip")
+    blip.init_tokenizer = lambda: None
+    bf = importlib.import_module("models.uniir_blip.blip_featurefusion.blip_ff")
+    bf.init_tokenizer = lambda: None
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):   # concat_all_gather at world size 1
+        bf.concat_all_gather = lambda t: t
+    return bf
