@@ -205,6 +205,26 @@ int uniir_hardneg_loss(const float* emb, const int32_t* q_idx, const int32_t* p_
                        const float* logit_scale_log, float* loss_sum, float* correct_sum, float* d_emb,
                        float* d_logit_scale, void* stream);
 
+/* Backward of uniir_attn_fwd_ex (same addressing); dq rows at stride lddq, dk/dv rows at stride lddkv. */
+int uniir_attn_bwd_ex(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const void* out,
+                      int64_t ldo, const void* dout, int64_t lddo, const float* lse, int32_t B, int32_t Sq,
+                      int32_t Skv, int32_t H, int32_t causal, const int32_t* kv_len, float* delta_ws, void* dq,
+                      int64_t lddq, void* dk, void* dv, int64_t lddkv, void* stream);
+/* Momentum-encoder EMA over a flat segment (blip_ff.py:289-292) + its bf16 shadow. */
+int uniir_ema_update(float* p_m, const float* p, int64_t n, float momentum, void* p_m_bf16, void* stream);
+/* dz = dy * (1 - y^2): backward of the BERT pooler tanh (med.py:505-511); dz bf16. */
+int uniir_tanh_bwd(const float* dy, const float* y, int64_t n, void* dz_bf16, void* stream);
+/* fp32 out[M,N] = A[M,K] . B / (*temp); B stored [K,N] (b_kn=1) or [N,K] (b_kn=0).  BLIP logits
+ * q @ [pc_m^T | cand_queue] / temp (blip_ff.py:215-216,225-226) and the matching input gradients. */
+int uniir_sgemm_temp(const float* A, const float* B, int32_t b_kn, int32_t M, int32_t N, int32_t K,
+                     const float* temp, float* out, void* stream);
+/* Momentum-distillation soft-label cross entropy (blip_ff.py:164-178, 219-231, 250-252), one direction:
+ * S (online logits [bs,n], overwritten with dLoss/dS * gscale), Sm (momentum logits), pc_id [bs], id_all [n]
+ * (int64), loss_sum += sum_rows loss, acc_sum (optional) += sum_rows pos[argmax S], d_temp += dLoss/dtemp. */
+int uniir_blip_softce(float* S, const float* Sm, const int64_t* pc_id, const int64_t* id_all, int32_t bs, int32_t n,
+                      float alpha, float gscale, const float* temp, float* loss_sum, float* acc_sum, float* d_temp,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,8 +57,6 @@ def test_blip_ff_api_contract():
     b2 = dict(b); b2.pop("did_list")
     with pytest.raises(ValueError):
         m(b2, encode_mbeir_batch=True)
-    with pytest.raises(NotImplementedError):
-        m(b, alpha=0.4)
     keys = set(m.state_dict())
     for k in ("visual_encoder.patch_embed.proj.bias", "visual_encoder_m.blocks.0.attn.qkv.weight",
               "text_encoder.encoder.layer.0.crossattention.self.key.weight", "text_encoder.embeddings.position_ids",
@@ -89,3 +87,91 @@ def test_cross_attention_kernel_vs_reference():
     mask = (torch.arange(S)[None, :] >= lens[:, None]).float()[:, None, None, :] * -10000.0
     ref = ((q3 @ k3.transpose(-1, -2) * 0.125 + mask).softmax(-1) @ v3).transpose(1, 2).reshape(B * S, H * 64)
     assert ((o - ref).norm() / ref.norm()).item() < 6e-3
+
+
+def test_blip_ff_training_step_matches_oracle():
+    """Momentum-distillation loss with queue (blip_ff.py:118-257): loss, accuracy, all online gradients, temp
+    gradient, EMA'd momentum weights and queue contents over two consecutive steps vs the oracle (which is itself
+    pinned to the real reference class in tests/test_oracle_blip.py)."""
+    from oracle.blip_oracle import BLIPFeatureFusionOracle
+    from uniir_b200.blip_ff import BLIPFeatureFusion
+    from test_oracle_blip import _inputs
+    torch.manual_seed(3)
+    orc = BLIPFeatureFusionOracle("tiny-test", embed_dim=64, queue_size=16).eval()
+    m = BLIPFeatureFusion(vit="tiny-test", image_size=64, embed_dim=64, queue_size=16, micro_batch=8)
+    m.train_micro_batch = 8
+    missing, unexpected = m.load_state_dict(orc.state_dict(), strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    d = orc.dims
+    for step in range(2):
+        ids, att, img = _inputs(d, 16, 24, 20 + step)
+        b = dict(txt_batched={"input_ids": ids, "attention_mask": att}, image_batched=img, txt_mask_batched=None,
+                 image_mask_batched=None, p_did_list=[5, 6, 5, 7, 8, 9, 10, 11 + step],
+                 index_mapping={"query": [[2 * i] for i in range(8)], "pos_cand": [[2 * i + 1] for i in range(8)]})
+        orc.zero_grad()
+        ref = orc.compute_contrastive_loss(b, alpha=0.3); ref["loss"].backward()
+        if m._online.grad is not None:
+            for gbuf in m._online.grad.values():
+                gbuf.zero_()
+        out = m.compute_contrastive_loss(b, alpha=0.3)
+        m.backward_contrastive()
+        torch.cuda.synchronize()
+        assert abs(out["loss"].item() - ref["loss"].item()) < 2e-2 * max(1.0, abs(ref["loss"].item())), (out["loss"].item(), ref["loss"].item())
+        assert abs(out["accuracy"].item() - ref["accuracy"].item()) < 1e-6
+        worst = (1.0, "")
+        for n_, p_o in orc.named_parameters():
+            if p_o.grad is None:
+                continue
+            a, c = p_o.grad.flatten().double(), m._online.g(n_).cpu().flatten().double()
+            if a.numel() > 1:
+                cos = (torch.dot(a, c) / (a.norm() * c.norm() + 1e-30)).item()
+                worst = min(worst, (cos, n_))
+            else:
+                assert abs(a.item() - c.item()) < 5e-2 * max(1e-3, abs(a.item())), (n_, a.item(), c.item())
+        assert worst[0] > 0.99, worst
+        assert torch.equal(m.idx_queue.cpu(), orc.idx_queue) and int(m.new_ptr_queue) == int(orc.new_ptr_queue)
+        assert torch.nn.functional.cosine_similarity(m.cand_queue.cpu().t(), orc.cand_queue.t(), dim=-1).min() > 1 - 1e-3
+        wm, wo = m.get_parameter("visual_encoder_m.blocks.0.attn.qkv.weight").cpu(), orc.visual_encoder_m.blocks[0].attn.qkv.weight
+        assert torch.allclose(wm, wo, atol=1e-6)
+        # apply the same parameter update on both sides so step 2 starts from equal weights
+        with torch.no_grad():
+            for n_, p_o in orc.named_parameters():
+                if p_o.grad is not None:
+                    p_o -= 1e-2 * p_o.grad
+                    m.get_parameter(n_).copy_(p_o)
+
+
+def test_cross_attention_backward_kernel():
+    from uniir_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    B, Sq, Skv, H = 2, 100, 197, 3
+    q = torch.randn(B * Sq, H * 64, generator=g).bfloat16(); kv = torch.randn(B * Skv, 2 * H * 64, generator=g).bfloat16()
+    lens = None
+    qd, kvd = q.cuda(), kv.cuda()
+    lse = torch.empty(B, H, Sq, device="cuda")
+    out = ops.attn_fwd_ex(qd, kvd[:, :H * 64], kvd[:, H * 64:], B, Sq, Skv, H, lse=lse)
+    dout = torch.randn(B * Sq, H * 64, generator=g).bfloat16()
+    dq = torch.empty_like(qd); dkv = torch.empty_like(kvd)
+    ops.attn_bwd_ex(qd, kvd[:, :H * 64], kvd[:, H * 64:], out, dout.cuda(), lse, B, Sq, Skv, H, dq, dkv[:, :H * 64], dkv[:, H * 64:])
+    qf = q.float().requires_grad_(True); kvf = kv.float().requires_grad_(True)
+    qh = qf.view(B, Sq, H, 64).transpose(1, 2); kh = kvf[:, :H * 64].reshape(B, Skv, H, 64).transpose(1, 2)
+    vh = kvf[:, H * 64:].reshape(B, Skv, H, 64).transpose(1, 2)
+    ref = ((qh @ kh.transpose(-1, -2) * 0.125).softmax(-1) @ vh).transpose(1, 2).reshape(B * Sq, H * 64)
+    ref.backward(dout.float())
+    rel = lambda a, b: ((a.float().cpu() - b).norm() / b.norm()).item()
+    assert rel(dq, qf.grad) < 1.2e-2 and rel(dkv, kvf.grad) < 1.2e-2
+    # self-attention with a key-padding mask
+    S = 100
+    qkv = torch.randn(B * S, 3 * H * 64, generator=g).bfloat16(); qkvd = qkv.cuda()
+    lens = torch.tensor([100, 37], dtype=torch.int32).cuda()
+    D = H * 64
+    o = ops.attn_fwd_ex(qkvd[:, :D], qkvd[:, D:2 * D], qkvd[:, 2 * D:], B, S, S, H, kv_len=lens, lse=(l2 := torch.empty(B, H, S, device="cuda")))
+    do = torch.randn(B * S, D, generator=g).bfloat16()
+    dqkv = torch.zeros_like(qkvd)
+    ops.attn_bwd_ex(qkvd[:, :D], qkvd[:, D:2 * D], qkvd[:, 2 * D:], o, do.cuda(), l2, B, S, S, H, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], kv_len=lens)
+    x = qkv.float().requires_grad_(True)
+    q3, k3, v3 = x.view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+    mask = (torch.arange(S)[None, :] >= lens.cpu()[:, None]).float()[:, None, None, :] * -10000.0
+    r2 = ((q3 @ k3.transpose(-1, -2) * 0.125 + mask).softmax(-1) @ v3).transpose(1, 2).reshape(B * S, D)
+    r2.backward(do.float())
+    assert rel(dqkv, x.grad) < 1.2e-2

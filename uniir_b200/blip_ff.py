@@ -100,24 +100,46 @@ def blip_param_specs(d: BLIPDims, suffix=""):
         add(f"{l}.output.dense.weight", (H, d.t_inter), 0.02); add(f"{l}.output.dense.bias", (H,), 0.02)
         add(f"{l}.output.LayerNorm.weight", (H,), -1.0); add(f"{l}.output.LayerNorm.bias", (H,), 0.0)
     add(f"{t}.pooler.dense.weight", (H, H), 0.02); add(f"{t}.pooler.dense.bias", (H,), 0.02)
+    if not suffix:
+        add("temp", (), -3.0)   # LAST, so the momentum set's flat buffer is an exact prefix (EMA = one kernel)
     return sp
 
 
-class BLIPEncoder:
-    """ViT + cross-attention BERT forward for a fixed (micro-batch, text length)."""
+class _BertActs:
+    """Saved activations of one BERT layer for one micro-batch."""
 
-    def __init__(self, P: FlatParamModule, d: BLIPDims, mb, S, dev, suffix=""):
-        self.P, self.d, self.mb, self.S, self.dev = P, d, mb, S, dev
+    def __init__(self, T, H, I, Tv, B, nh, S, Sv, dev):
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.hb_in = torch.empty(T, H, **bf)
+        self.qkv = torch.empty(T, 3 * H, **bf); self.ctx1 = torch.empty(T, H, **bf); self.lse1 = torch.empty(B, nh, S, **f32)
+        self.t1 = torch.empty(T, H, **f32); self.m1 = torch.empty(T, **f32); self.r1 = torch.empty(T, **f32)
+        self.h1b = torch.empty(T, H, **bf)
+        self.q2 = torch.empty(T, H, **bf); self.kv2 = torch.empty(Tv, 2 * H, **bf); self.ctx2 = torch.empty(T, H, **bf)
+        self.lse2 = torch.empty(B, nh, S, **f32)
+        self.t2 = torch.empty(T, H, **f32); self.m2 = torch.empty(T, **f32); self.r2 = torch.empty(T, **f32)
+        self.h2b = torch.empty(T, H, **bf)
+        self.pre = torch.empty(T, I, **bf); self.act = torch.empty(T, I, **bf)
+        self.t3 = torch.empty(T, H, **f32); self.m3 = torch.empty(T, **f32); self.r3 = torch.empty(T, **f32)
+
+
+class BLIPEncoder:
+    """ViT + cross-attention BERT for a fixed (micro-batch, text length): forward, and (train=True) forward
+    with saved activations + backward."""
+
+    def __init__(self, P: FlatParamModule, d: BLIPDims, mb, S, dev, suffix="", train=False):
+        self.P, self.d, self.mb, self.S, self.dev, self.train = P, d, mb, S, dev, train
         self.v, self.t = f"visual_encoder{suffix}", f"text_encoder{suffix}"
         bf = dict(device=dev, dtype=torch.bfloat16)
         f32 = dict(device=dev, dtype=torch.float32)
-        self.vis = Tower(P, self.v, d.v_width, d.v_layers, d.v_heads, d.v_tokens, False, mb, dev, False,
+        self.vis = Tower(P, self.v, d.v_width, d.v_layers, d.v_heads, d.v_tokens, False, mb, dev, train,
                          names=Tower.TIMM_NAMES, act=L.ACT_GELU, eps=1e-6)
         Kp = 3 * d.patch * d.patch
         assert Kp % 8 == 0
+        Tv = mb * d.v_tokens
         self.col = torch.empty(mb * d.grid ** 2, Kp, **bf)
         self.patch = torch.empty(mb * d.grid ** 2, d.v_width, **bf)
-        self.img_tok = torch.empty(mb * d.v_tokens, d.v_width, **bf)
+        self.img_tok = torch.empty(Tv, d.v_width, **bf)
         T, H = mb * S, d.t_width
         self.h = torch.empty(T, H, **f32)
         self.tmp = torch.empty(T, H, **f32)
@@ -125,70 +147,178 @@ class BLIPEncoder:
         self.qkv = torch.empty(T, 3 * H, **bf)
         self.ctx = torch.empty(T, H, **bf)
         self.q = torch.empty(T, H, **bf)
-        self.kv = torch.empty(mb * d.v_tokens, 2 * H, **bf)
+        self.kv = torch.empty(Tv, 2 * H, **bf)
         self.inter = torch.empty(T, d.t_inter, **bf)
         self.pool = torch.empty(mb, H, **bf)
         self.emb = torch.empty(mb, H, **f32)
+        if train:
+            self.acts = [_BertActs(T, H, d.t_inter, Tv, mb, d.t_heads, S, d.v_tokens, dev) for _ in range(d.t_layers)]
+            self.emb_pre = torch.empty(T, H, **f32); self.me = torch.empty(T, **f32); self.re = torch.empty(T, **f32)
+            self.vn_m = torch.empty(Tv, **f32); self.vn_r = torch.empty(Tv, **f32)
+            self.dh = torch.empty(T, H, **f32)       # gradient of the fp32 hidden stream
+            self.dt = torch.empty(T, H, **f32)       # LN-backward output (grad of the pre-LN sum)
+            self.dtb = torch.empty(T, H, **bf)
+            self.d_ctx = torch.empty(T, H, **bf)
+            self.dqkv = torch.empty(T, 3 * H, **bf)
+            self.dq2 = torch.empty(T, H, **bf)
+            self.dkv2 = torch.empty(Tv, 2 * H, **bf)
+            self.d_pre = torch.empty(T, d.t_inter, **bf)
+            self.d_img = torch.empty(Tv, d.v_width, **f32)
+            self.dz = torch.empty(mb, H, **bf)
+            self.d_pool = torch.empty(mb, H, **bf)
+            self.d_patch = torch.empty(mb * d.grid ** 2, d.v_width, **bf)
+            self.delta = torch.empty(mb * d.t_heads * S, **f32)
+            self.att_len = None
+            self.ids = None
 
-    def _fused(self, first, rows, cols):
-        """[rows, cols] bf16 view starting at parameter `first` (adjacent parameters, see blip_param_specs)."""
+    def _fused(self, first, rows, cols, bufs=None):
+        """[rows, cols] view starting at parameter `first` (adjacent parameters, see blip_param_specs)."""
         decay, off, n, shape = self.P._index[first]
-        return self.P.flat16[decay][off:off + rows * cols].view(rows, cols)
+        return (bufs or self.P.flat16)[decay][off:off + rows * cols].view(rows, cols)
 
-    def _fused32(self, first, n):
+    def _fused1(self, first, n, bufs=None):
         decay, off, _, _ = self.P._index[first]
-        return self.P.flat[decay][off:off + n]
+        return (bufs or self.P.flat)[decay][off:off + n]
 
-    def forward(self, ids, att_len, img):
-        """ids int32 [mb,S]; att_len int32 [mb] (number of valid tokens: attention_mask is a prefix mask);
-        img fp32 [mb,3,H,W].  Returns pooled fused embedding fp32 [mb, 768] (buffer reused)."""
+    def forward(self, ids, att_len, img, save=False):
+        """ids int32 [mb,S]; att_len int32 [mb] (valid tokens: attention_mask is a prefix mask); img fp32
+        [mb,3,H,W].  Returns the pooled fused embedding fp32 [mb, H] (buffer reused)."""
         P, d, mb, S = self.P, self.d, self.mb, self.S
         w, w16 = P.w, P.w16
         v, t = self.v, self.t
+        assert not save or self.train
         # ---------------- ViT ----------------
         ops.patch_im2col(img, d.patch, self.col.shape[1], out=self.col)
         ops.gemm(self.col, w16(f"{v}.patch_embed.proj.weight").view(d.v_width, -1), bias=w(f"{v}.patch_embed.proj.bias"),
                  out=self.patch)
         ops.vision_embed_fwd(self.patch, w(f"{v}.cls_token").view(-1), w(f"{v}.pos_embed").view(d.v_tokens, d.v_width),
                              mb, d.v_tokens, d.v_width, out=self.vis.x.view(mb, d.v_tokens, d.v_width))
-        xo = self.vis.forward(False)
-        ops.layernorm_fwd(xo, w(f"{v}.norm.weight"), w(f"{v}.norm.bias"), 1e-6, out=self.img_tok)
+        xo = self.vis.forward(save)
+        ops.layernorm_fwd(xo, w(f"{v}.norm.weight"), w(f"{v}.norm.bias"), 1e-6, out=self.img_tok,
+                          stats=((self.vn_m, self.vn_r) if save else None))
         # ---------------- BERT ----------------
         H, nh = d.t_width, d.t_heads
+        e_pre = self.emb_pre if save else self.tmp
         ops.text_embed_fwd(ids, w(f"{t}.embeddings.word_embeddings.weight"),
-                           w(f"{t}.embeddings.position_embeddings.weight")[:S], out=self.tmp.view(mb, S, H))
-        ops.layernorm_fwd(self.tmp, w(f"{t}.embeddings.LayerNorm.weight"), w(f"{t}.embeddings.LayerNorm.bias"), 1e-12, out=self.h)
-        ops.cast_bf16(self.h, out=self.hb)
+                           w(f"{t}.embeddings.position_embeddings.weight")[:S], out=e_pre.view(mb, S, H))
+        ops.layernorm_fwd(e_pre, w(f"{t}.embeddings.LayerNorm.weight"), w(f"{t}.embeddings.LayerNorm.bias"), 1e-12,
+                          out=self.h, stats=((self.me, self.re) if save else None))
+        if save:
+            self.att_len, self.ids = att_len, ids
         for i in range(d.t_layers):
             l = f"{t}.encoder.layer.{i}"
+            a = self.acts[i] if save else None
+            hb_in = a.hb_in if save else self.hb
+            ops.cast_bf16(self.h, out=hb_in)
+            qkv, ctx1 = (a.qkv, a.ctx1) if save else (self.qkv, self.ctx)
             # self-attention (q|k|v fused), key-padding mask
-            ops.gemm(self.hb, self._fused(f"{l}.attention.self.query.weight", 3 * H, H),
-                     bias=self._fused32(f"{l}.attention.self.query.bias", 3 * H), out=self.qkv)
-            ops.attn_fwd_ex(self.qkv[:, :H], self.qkv[:, H:2 * H], self.qkv[:, 2 * H:], mb, S, S, nh, kv_len=att_len, out=self.ctx)
-            ops.gemm(self.ctx, w16(f"{l}.attention.output.dense.weight"), bias=w(f"{l}.attention.output.dense.bias"),
-                     residual=self.h, out=self.tmp)
-            ops.layernorm_fwd(self.tmp, w(f"{l}.attention.output.LayerNorm.weight"), w(f"{l}.attention.output.LayerNorm.bias"),
-                              1e-12, out=self.h)
-            ops.cast_bf16(self.h, out=self.hb)
+            ops.gemm(hb_in, self._fused(f"{l}.attention.self.query.weight", 3 * H, H),
+                     bias=self._fused1(f"{l}.attention.self.query.bias", 3 * H), out=qkv)
+            ops.attn_fwd_ex(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], mb, S, S, nh, kv_len=att_len, out=ctx1,
+                            lse=(a.lse1 if save else None))
+            t1 = a.t1 if save else self.tmp
+            ops.gemm(ctx1, w16(f"{l}.attention.output.dense.weight"), bias=w(f"{l}.attention.output.dense.bias"),
+                     residual=self.h, out=t1)
+            ops.layernorm_fwd(t1, w(f"{l}.attention.output.LayerNorm.weight"), w(f"{l}.attention.output.LayerNorm.bias"),
+                              1e-12, out=self.h, stats=((a.m1, a.r1) if save else None))
+            h1b = a.h1b if save else self.hb
+            ops.cast_bf16(self.h, out=h1b)
             # cross-attention into the image tokens (encoder mask is all ones, blip_ff.py:107)
-            ops.gemm(self.hb, w16(f"{l}.crossattention.self.query.weight"), bias=w(f"{l}.crossattention.self.query.bias"), out=self.q)
+            q2, kv2, ctx2 = (a.q2, a.kv2, a.ctx2) if save else (self.q, self.kv, self.ctx)
+            ops.gemm(h1b, w16(f"{l}.crossattention.self.query.weight"), bias=w(f"{l}.crossattention.self.query.bias"), out=q2)
             ops.gemm(self.img_tok, self._fused(f"{l}.crossattention.self.key.weight", 2 * H, d.v_width),
-                     bias=self._fused32(f"{l}.crossattention.self.key.bias", 2 * H), out=self.kv)
-            ops.attn_fwd_ex(self.q, self.kv[:, :H], self.kv[:, H:], mb, S, d.v_tokens, nh, out=self.ctx)
-            ops.gemm(self.ctx, w16(f"{l}.crossattention.output.dense.weight"), bias=w(f"{l}.crossattention.output.dense.bias"),
-                     residual=self.h, out=self.tmp)
-            ops.layernorm_fwd(self.tmp, w(f"{l}.crossattention.output.LayerNorm.weight"),
-                              w(f"{l}.crossattention.output.LayerNorm.bias"), 1e-12, out=self.h)
-            ops.cast_bf16(self.h, out=self.hb)
+                     bias=self._fused1(f"{l}.crossattention.self.key.bias", 2 * H), out=kv2)
+            ops.attn_fwd_ex(q2, kv2[:, :H], kv2[:, H:], mb, S, d.v_tokens, nh, out=ctx2, lse=(a.lse2 if save else None))
+            t2 = a.t2 if save else self.tmp
+            ops.gemm(ctx2, w16(f"{l}.crossattention.output.dense.weight"), bias=w(f"{l}.crossattention.output.dense.bias"),
+                     residual=self.h, out=t2)
+            ops.layernorm_fwd(t2, w(f"{l}.crossattention.output.LayerNorm.weight"),
+                              w(f"{l}.crossattention.output.LayerNorm.bias"), 1e-12, out=self.h,
+                              stats=((a.m2, a.r2) if save else None))
+            h2b = a.h2b if save else self.hb
+            ops.cast_bf16(self.h, out=h2b)
             # FFN
-            ops.gemm(self.hb, w16(f"{l}.intermediate.dense.weight"), bias=w(f"{l}.intermediate.dense.bias"), act=L.ACT_GELU,
-                     out=self.inter)
-            ops.gemm(self.inter, w16(f"{l}.output.dense.weight"), bias=w(f"{l}.output.dense.bias"), residual=self.h, out=self.tmp)
-            ops.layernorm_fwd(self.tmp, w(f"{l}.output.LayerNorm.weight"), w(f"{l}.output.LayerNorm.bias"), 1e-12, out=self.h)
-            ops.cast_bf16(self.h, out=self.hb)
+            pre, act = (a.pre, a.act) if save else (None, self.inter)
+            ops.gemm(h2b, w16(f"{l}.intermediate.dense.weight"), bias=w(f"{l}.intermediate.dense.bias"), act=L.ACT_GELU,
+                     aux_out=pre, out=act)
+            t3 = a.t3 if save else self.tmp
+            ops.gemm(act, w16(f"{l}.output.dense.weight"), bias=w(f"{l}.output.dense.bias"), residual=self.h, out=t3)
+            ops.layernorm_fwd(t3, w(f"{l}.output.LayerNorm.weight"), w(f"{l}.output.LayerNorm.bias"), 1e-12, out=self.h,
+                              stats=((a.m3, a.r3) if save else None))
+        ops.cast_bf16(self.h, out=self.hb)
         self.pool.copy_(self.hb.view(mb, S, H)[:, 0])
         ops.gemm(self.pool, w16(f"{t}.pooler.dense.weight"), bias=w(f"{t}.pooler.dense.bias"), act=L.ACT_TANH, out=self.emb)
         return self.emb
+
+    def backward(self, d_emb):
+        """d_emb fp32 [mb, H] = dLoss/d(pooled embedding) of the last forward(save=True).  Accumulates
+        parameter gradients into P.grad."""
+        P, d, mb, S = self.P, self.d, self.mb, self.S
+        w, w16, g = P.w, P.w16, P.g
+        v, t = self.v, self.t
+        H, nh, Sv = d.t_width, d.t_heads, d.v_tokens
+        G = P.grad
+        # ---- pooler: emb = tanh(W h[:,0] + b)
+        ops.tanh_bwd(d_emb, self.emb, self.dz)
+        ops.wgrad(self.dz, self.pool, g(f"{t}.pooler.dense.weight"))
+        ops.colsum_accum(self.dz, g(f"{t}.pooler.dense.bias"))
+        ops.gemm(self.dz, w16(f"{t}.pooler.dense.weight"), b_mn=True, out=self.d_pool)
+        self.dh.zero_()
+        self.dh.view(mb, S, H)[:, 0] = self.d_pool.float()
+        self.d_img.zero_()
+        for i in reversed(range(d.t_layers)):
+            l = f"{t}.encoder.layer.{i}"
+            a = self.acts[i]
+            # ---- FFN: h3 = LN(dense2(gelu(dense1(h2))) + h2)
+            ops.layernorm_bwd(self.dh, a.t3, a.m3, a.r3, w(f"{l}.output.LayerNorm.weight"), self.dt,
+                              g(f"{l}.output.LayerNorm.weight"), g(f"{l}.output.LayerNorm.bias"), accumulate=False, dx_bf16=self.dtb)
+            ops.wgrad(self.dtb, a.act, g(f"{l}.output.dense.weight"))
+            ops.colsum_accum(self.dtb, g(f"{l}.output.dense.bias"))
+            ops.gemm(self.dtb, w16(f"{l}.output.dense.weight"), b_mn=True, act=L.ACT_GELU, act_grad_src=a.pre, out=self.d_pre)
+            ops.wgrad(self.d_pre, a.h2b, g(f"{l}.intermediate.dense.weight"))
+            ops.colsum_accum(self.d_pre, g(f"{l}.intermediate.dense.bias"))
+            ops.gemm(self.d_pre, w16(f"{l}.intermediate.dense.weight"), b_mn=True, residual=self.dt, out=self.dh)
+            # ---- cross-attention: h2 = LN(dense(attn(q(h1), kv(img))) + h1)
+            ops.layernorm_bwd(self.dh, a.t2, a.m2, a.r2, w(f"{l}.crossattention.output.LayerNorm.weight"), self.dt,
+                              g(f"{l}.crossattention.output.LayerNorm.weight"), g(f"{l}.crossattention.output.LayerNorm.bias"),
+                              accumulate=False, dx_bf16=self.dtb)
+            ops.wgrad(self.dtb, a.ctx2, g(f"{l}.crossattention.output.dense.weight"))
+            ops.colsum_accum(self.dtb, g(f"{l}.crossattention.output.dense.bias"))
+            ops.gemm(self.dtb, w16(f"{l}.crossattention.output.dense.weight"), b_mn=True, out=self.d_ctx)
+            ops.attn_bwd_ex(a.q2, a.kv2[:, :H], a.kv2[:, H:], a.ctx2, self.d_ctx, a.lse2, mb, S, Sv, nh,
+                            self.dq2, self.dkv2[:, :H], self.dkv2[:, H:], delta=self.delta)
+            ops.wgrad(self.dq2, a.h1b, g(f"{l}.crossattention.self.query.weight"))
+            ops.colsum_accum(self.dq2, g(f"{l}.crossattention.self.query.bias"))
+            ops.gemm(self.dq2, w16(f"{l}.crossattention.self.query.weight"), b_mn=True, residual=self.dt, out=self.dh)
+            ops.wgrad(self.dkv2, self.img_tok, self._fused(f"{l}.crossattention.self.key.weight", 2 * H, d.v_width, G))
+            ops.colsum_accum(self.dkv2, self._fused1(f"{l}.crossattention.self.key.bias", 2 * H, G))
+            ops.gemm(self.dkv2, self._fused(f"{l}.crossattention.self.key.weight", 2 * H, d.v_width), b_mn=True,
+                     out=self.d_img, accumulate=True)
+            # ---- self-attention: h1 = LN(dense(attn(qkv(h_in))) + h_in)
+            ops.layernorm_bwd(self.dh, a.t1, a.m1, a.r1, w(f"{l}.attention.output.LayerNorm.weight"), self.dt,
+                              g(f"{l}.attention.output.LayerNorm.weight"), g(f"{l}.attention.output.LayerNorm.bias"),
+                              accumulate=False, dx_bf16=self.dtb)
+            ops.wgrad(self.dtb, a.ctx1, g(f"{l}.attention.output.dense.weight"))
+            ops.colsum_accum(self.dtb, g(f"{l}.attention.output.dense.bias"))
+            ops.gemm(self.dtb, w16(f"{l}.attention.output.dense.weight"), b_mn=True, out=self.d_ctx)
+            ops.attn_bwd_ex(a.qkv[:, :H], a.qkv[:, H:2 * H], a.qkv[:, 2 * H:], a.ctx1, self.d_ctx, a.lse1, mb, S, S, nh,
+                            self.dqkv[:, :H], self.dqkv[:, H:2 * H], self.dqkv[:, 2 * H:], kv_len=self.att_len, delta=self.delta)
+            ops.wgrad(self.dqkv, a.hb_in, self._fused(f"{l}.attention.self.query.weight", 3 * H, H, G))
+            ops.colsum_accum(self.dqkv, self._fused1(f"{l}.attention.self.query.bias", 3 * H, G))
+            ops.gemm(self.dqkv, self._fused(f"{l}.attention.self.query.weight", 3 * H, H), b_mn=True, residual=self.dt, out=self.dh)
+        # ---- embeddings: h0 = LN(word[ids] + pos)
+        ops.layernorm_bwd(self.dh, self.emb_pre, self.me, self.re, w(f"{t}.embeddings.LayerNorm.weight"), self.dt,
+                          g(f"{t}.embeddings.LayerNorm.weight"), g(f"{t}.embeddings.LayerNorm.bias"), accumulate=False)
+        ops.text_embed_bwd(self.dt.view(mb, S, H), self.ids, g(f"{t}.embeddings.word_embeddings.weight"),
+                           g(f"{t}.embeddings.position_embeddings.weight")[:S])
+        # ---- ViT: img_tok = LN_final(blocks(patch-embed(img)))
+        ops.layernorm_bwd(self.d_img, self.vis.x_out, self.vn_m, self.vn_r, w(f"{v}.norm.weight"), self.vis.dx,
+                          g(f"{v}.norm.weight"), g(f"{v}.norm.bias"), accumulate=False, dx_bf16=self.vis.dxb)
+        self.vis.backward()
+        ops.vision_embed_bwd(self.vis.dx.view(mb, Sv, d.v_width), mb, Sv, d.v_width, self.d_patch,
+                             g(f"{v}.cls_token").view(-1), g(f"{v}.pos_embed").view(Sv, d.v_width))
+        ops.wgrad(self.d_patch, self.col, g(f"{v}.patch_embed.proj.weight").view(d.v_width, -1))
+        ops.colsum_accum(self.d_patch, g(f"{v}.patch_embed.proj.bias"))
 
 
 class BLIPFeatureFusion(nn.Module):
@@ -224,8 +354,9 @@ class BLIPFeatureFusion(nn.Module):
         self.register_buffer("cand_queue", nn.functional.normalize(torch.randn(embed_dim, queue_size, generator=g), dim=0).to(dev))
         self.register_buffer("idx_queue", torch.full((1, queue_size), -100, device=dev))
         self.register_buffer("new_ptr_queue", torch.zeros(1, dtype=torch.long, device=dev))
-        self.temp = nn.Parameter(0.07 * torch.ones([], device=dev))
         self._enc = {}
+        self._train_state = None
+        self.train_micro_batch = 64
 
     # ---- reference surface -------------------------------------------------------------
     def get_img_preprocess_fn(self):
@@ -242,13 +373,25 @@ class BLIPFeatureFusion(nn.Module):
         self._mom.rebind_after_apply()
         return out
 
-    def _encoder(self, mb, S, momentum):
-        key = (mb, S, momentum)
+    def _encoder(self, mb, S, momentum, train=False):
+        key = (mb, S, momentum, train)
         if key not in self._enc:
-            self._enc = {k: v for k, v in self._enc.items() if k[2] != momentum}
+            self._enc = {k: v for k, v in self._enc.items() if (k[2], k[3]) != (momentum, train)}
             self._enc[key] = BLIPEncoder(self._mom if momentum else self._online, self.dims, mb, S, self.device_,
-                                         "_m" if momentum else "")
+                                         "_m" if momentum else "", train=train)
         return self._enc[key]
+
+
+
+    def _prep_txt(self, txt_dict_batched):
+        ids = txt_dict_batched["input_ids"] if isinstance(txt_dict_batched, dict) else txt_dict_batched.input_ids
+        att = txt_dict_batched["attention_mask"] if isinstance(txt_dict_batched, dict) else txt_dict_batched.attention_mask
+        dev = self.device_
+        ids = ids.to(dev, torch.int32).contiguous()
+        att = att.to(dev)
+        if not bool((att.cumsum(1) == torch.arange(1, att.shape[1] + 1, device=dev)).logical_or(att == 0).all()):
+            raise ValueError("attention_mask must be a prefix mask (padding='max_length' tokenisation)")
+        return ids, att.sum(1).to(torch.int32).contiguous()
 
     @torch.no_grad()
     def encode_multimodal_input(self, txt_dict_batched, image_batched, txt_mask=None, img_mask=None, use_momentum=False):
@@ -292,6 +435,100 @@ class BLIPFeatureFusion(nn.Module):
         assert embeddings.size(0) == len(id_list), "embeddings and id_batched must have the same batch size."
         return embeddings, id_list
 
+    # ---- training: momentum distillation + queue (blip_ff.py:118-257) ---------------------------
     def compute_contrastive_loss(self, batch, alpha):
-        raise NotImplementedError("BLIP_FF momentum-distillation / queue loss (blip_ff.py:118-257) is not built yet "
-                                  "(SURVEY.md 8 row a9); the encode path is available")
+        """Reference-compatible entry: returns {"loss", "accuracy"}; gradients are produced by
+        ``backward_contrastive`` (the fused engine path, uniir_b200.engine.train_step_blip)."""
+        loss, acc = self._loss_forward(batch, alpha)
+        return {"loss": loss, "accuracy": acc}
+
+    @torch.no_grad()
+    def _momentum_update(self):
+        for k in self._mom.flat:
+            ops.ema_update(self._mom.flat[k], self._online.flat[k][:self._mom.flat[k].numel()], self.momentum,
+                           self._mom.flat16[k])
+        self._mom.mark_shadow_fresh()
+
+    @torch.no_grad()
+    def _dequeue_and_enqueue(self, q_m, pc_m, pc_ids):
+        from . import dist_utils as du
+        idxs = du.all_gather_rows(pc_ids.view(-1, 1))
+        q_m, pc_m = du.all_gather_rows(q_m), du.all_gather_rows(pc_m)
+        n = q_m.shape[0]
+        ptr = int(self.new_ptr_queue)
+        assert self.queue_size % n == 0  # This is important (blip_ff.py:303)
+        self.query_queue[:, ptr:ptr + n] = q_m.T
+        self.cand_queue[:, ptr:ptr + n] = pc_m.T
+        self.idx_queue[:, ptr:ptr + n] = idxs.T
+        self.new_ptr_queue[0] = (ptr + n) % self.queue_size
+
+    @torch.no_grad()
+    def _loss_forward(self, batch, alpha):
+        im = batch["index_mapping"]
+        if "neg_cand_list" in im:
+            raise NotImplementedError("BLIP_FF hard-negative variant (blip_ff.py:127-131,160-171) is not built")
+        dev, E = self.device_, self.dims.t_width
+        P = self._online
+        P.w("temp").clamp_(0.001, 0.5)                                   # blip_ff.py:132-133
+        ids, lens = self._prep_txt(batch["txt_batched"])
+        img = batch["image_batched"].to(dev, torch.float32).contiguous()
+        q_idx = torch.tensor(im["query"], dtype=torch.int32).flatten().to(dev)
+        p_idx = torch.tensor(im["pos_cand"], dtype=torch.int32).flatten().to(dev)
+        pc_ids = torch.as_tensor(batch["p_did_list"]).to(dev, torch.int64).contiguous()
+        bs, n_items, S = q_idx.numel(), ids.shape[0], ids.shape[1]
+        txt = {"input_ids": ids, "attention_mask": (torch.arange(S, device=dev)[None, :] < lens[:, None]).long()}
+        emb = self.encode_multimodal_input(txt, img)                      # phase A, online (no activations kept)
+        self._momentum_update()                                           # blip_ff.py:182
+        emb_m = self.encode_multimodal_input(txt, img, use_momentum=True)
+        f32 = dict(device=dev, dtype=torch.float32)
+        qn, pn, qm, pm = (torch.empty(bs, E, **f32) for _ in range(4))
+        qnorm, pnorm, tmpn = torch.empty(bs, **f32), torch.empty(bs, **f32), torch.empty(bs, **f32)
+        lib = L.load()
+        L.check(lib.uniir_infonce_normalize(emb.data_ptr(), q_idx.data_ptr(), p_idx.data_ptr(), bs, E, qn.data_ptr(),
+                                            pn.data_ptr(), qnorm.data_ptr(), pnorm.data_ptr(), ops._stream()), "normalize")
+        L.check(lib.uniir_infonce_normalize(emb_m.data_ptr(), q_idx.data_ptr(), p_idx.data_ptr(), bs, E, qm.data_ptr(),
+                                            pm.data_ptr(), tmpn.data_ptr(), tmpn.data_ptr(), ops._stream()), "normalize")
+        q_all = torch.cat([qm.t(), self.query_queue], dim=1).contiguous()     # [E, bs+Qz]  (data movement only)
+        pc_all = torch.cat([pm.t(), self.cand_queue], dim=1).contiguous()
+        id_all = torch.cat([pc_ids, self.idx_queue[0]]).contiguous()
+        temp = P.w("temp")
+        S1, S1m = ops.sgemm_temp(qn, pc_all, True, temp), ops.sgemm_temp(qm, pc_all, True, temp)
+        S2, S2m = ops.sgemm_temp(pn, q_all, True, temp), ops.sgemm_temp(pm, q_all, True, temp)
+        acc_l = torch.zeros(4, **f32)     # loss q2pc, loss pc2q, acc, d_temp
+        gs = 0.5 / bs
+        ops.blip_softce(S1, S1m, pc_ids, id_all, float(alpha), gs, temp, acc_l[0:1], acc_l[2:3], acc_l[3:4])
+        ops.blip_softce(S2, S2m, pc_ids, id_all, float(alpha), gs, temp, acc_l[1:2], None, acc_l[3:4])
+        loss = (acc_l[0] + acc_l[1]) * gs
+        acc = acc_l[2] / bs
+        d_qn = ops.sgemm_temp(S1, pc_all, False, temp)                    # G @ pc_all^T / temp
+        d_pn = ops.sgemm_temp(S2, q_all, False, temp)
+        d_emb = torch.zeros(n_items, E, **f32)
+        L.check(lib.uniir_infonce_normalize_bwd(q_idx.data_ptr(), p_idx.data_ptr(), qn.data_ptr(), pn.data_ptr(),
+                                                qnorm.data_ptr(), pnorm.data_ptr(), d_qn.data_ptr(), d_pn.data_ptr(), bs, E,
+                                                d_emb.data_ptr(), ops._stream()), "normalize_bwd")
+        self._dequeue_and_enqueue(qm, pm, pc_ids)                         # blip_ff.py:247
+        self._train_state = dict(ids=ids, lens=lens, img=img, d_emb=d_emb, d_temp=acc_l[3].clone())
+        return loss.clone(), acc.clone()
+
+    @torch.no_grad()
+    def backward_contrastive(self):
+        """Phase C of the gradient cache: re-forward every micro-batch with saved activations and
+        backpropagate the cached embedding gradients into the flat gradient buffers."""
+        st = self._train_state
+        assert st is not None, "backward without forward"
+        P = self._online
+        P.ensure_grad()
+        P.g("temp").add_(st["d_temp"])
+        n, S = st["ids"].shape
+        mb = min(self.train_micro_batch, n)
+        if n % mb or mb % 8:
+            mb = next((m for m in range(mb - mb % 8, 7, -8) if n % m == 0), None)
+            if mb is None:
+                raise ValueError(f"batch of {n} items cannot be tiled by a micro-batch that is a multiple of 8")
+        enc = self._encoder(mb, S, False, train=True)
+        P.refresh_shadow()
+        for s in range(0, n, mb):
+            e = s + mb
+            enc.forward(st["ids"][s:e].contiguous(), st["lens"][s:e].contiguous(), st["img"][s:e].contiguous(), save=True)
+            enc.backward(st["d_emb"][s:e].contiguous())
+        self._train_state = None

@@ -96,6 +96,8 @@ struct AttnParams {
   long long ldq, ldkv, ldo;
   int Sq, Skv;
   const int* kv_len;         // optional [B]: keys >= kv_len[b] are masked (BERT padding mask)
+  __nv_bfloat16 *dq, *dk, *dv;     // backward outputs: dq rows stride lddq; dk/dv rows stride lddkv
+  long long lddq, lddkv, lddo;     // lddo: row stride of dout
   __nv_bfloat16* out;        // [B*S, D]
   float* lse;                // [B, H, S]
   const __nv_bfloat16* dout; // [B*S, D]
@@ -258,20 +260,19 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
 // delta[b,h,s] = sum_d dO[b,s,h,d] * O[b,s,h,d]; one warp per (b,s,h)
 __global__ void attn_delta_kernel(const AttnParams p) {
   const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const long long total = static_cast<long long>(p.B) * p.S * p.H;
+  const long long total = static_cast<long long>(p.B) * p.Sq * p.H;
   if (w >= total) return;
   const int lane = threadIdx.x & 31;
   const int h = w % p.H;
   const long long bs = w / p.H;
-  const long long off = bs * p.D + h * kHD + lane * 2;
-  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(p.dout + off);
-  const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162*>(p.out + off);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(p.dout + bs * p.lddo + h * kHD + lane * 2);
+  const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162*>(p.out + bs * p.ldo + h * kHD + lane * 2);
   float v = __bfloat162float(a.x) * __bfloat162float(c.x) + __bfloat162float(a.y) * __bfloat162float(c.y);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   if (lane == 0) {
-    const long long b = bs / p.S, s = bs % p.S;
-    p.delta[(b * p.H + h) * p.S + s] = v;
+    const long long b = bs / p.Sq, s_ = bs % p.Sq;
+    p.delta[(b * p.H + h) * p.Sq + s_] = v;
   }
 }
 
@@ -281,32 +282,32 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_bwd_dq_kernel(const Attn
   const uint32_t sK = s_u32(sm), sV = sK + spad * 128, sW = sV + spad * 128;
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long ld = 3LL * p.D;
-  const __nv_bfloat16* base = p.qkv + static_cast<long long>(b) * p.S * ld + h * kHD;
-  const __nv_bfloat16* dob = p.dout + static_cast<long long>(b) * p.S * p.D + h * kHD;
-  load_rows(sK, base + p.D, ld, p.S, spad);
-  load_rows(sV, base + 2 * p.D, ld, p.S, spad);
+  const __nv_bfloat16* qb = p.q + static_cast<long long>(b) * p.Sq * p.ldq + h * kHD;
+  const __nv_bfloat16* dob = p.dout + static_cast<long long>(b) * p.Sq * p.lddo + h * kHD;
+  const int kvl = p.kv_len ? min(p.kv_len[b], p.Skv) : p.Skv;
+  load_rows(sK, p.k + static_cast<long long>(b) * p.Skv * p.ldkv + h * kHD, p.ldkv, p.Skv, spad);
+  load_rows(sV, p.v + static_cast<long long>(b) * p.Skv * p.ldkv + h * kHD, p.ldkv, p.Skv, spad);
   cp_async_wait_all();
   __syncthreads();
   const uint32_t sQ = sW + warp * 4096, sDO = sQ + 2048;
-  const float* lp = p.lse + (static_cast<long long>(b) * p.H + h) * p.S;
-  const float* dp = p.delta + (static_cast<long long>(b) * p.H + h) * p.S;
+  const float* lp = p.lse + (static_cast<long long>(b) * p.H + h) * p.Sq;
+  const float* dp = p.delta + (static_cast<long long>(b) * p.H + h) * p.Sq;
   const float sc = p.scale * kLog2e;
-  __nv_bfloat16* ob = p.dqkv + static_cast<long long>(b) * p.S * ld + h * kHD;
-  const int n_qt = spad >> 4;
+  __nv_bfloat16* ob = p.dq + static_cast<long long>(b) * p.Sq * p.lddq + h * kHD;
+  const int n_qt = (p.Sq + 15) >> 4;
   for (int qt = warp; qt < n_qt; qt += kAttnWarps) {
     const int q0 = qt * 16;
     __syncwarp();
-    load_rows16_warp(sQ, base, ld, q0, p.S);
-    load_rows16_warp(sDO, dob, p.D, q0, p.S);
+    load_rows16_warp(sQ, qb, p.ldq, q0, p.Sq);
+    load_rows16_warp(sDO, dob, p.lddo, q0, p.Sq);
     cp_async_wait_all();
     __syncwarp();
     uint32_t qa[4][4], da[4][4];
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) { frag_a(sQ, 0, kk, qa[kk]); frag_a(sDO, 0, kk, da[kk]); }
     const int r0 = q0 + (lane >> 2), r1 = r0 + 8;
-    const float lse0 = (r0 < p.S) ? lp[r0] * kLog2e : 0.f, lse1 = (r1 < p.S) ? lp[r1] * kLog2e : 0.f;
-    const float dl0 = (r0 < p.S) ? dp[r0] : 0.f, dl1 = (r1 < p.S) ? dp[r1] : 0.f;
+    const float lse0 = (r0 < p.Sq) ? lp[r0] * kLog2e : 0.f, lse1 = (r1 < p.Sq) ? lp[r1] * kLog2e : 0.f;
+    const float dl0 = (r0 < p.Sq) ? dp[r0] : 0.f, dl1 = (r1 < p.Sq) ? dp[r1] : 0.f;
     float dq[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_bwd_dq_kernel(const Attn
           }
         }
       }
-      const bool need_mask = nt < 8 || k0 + kBlk > p.S || q0 + 16 > p.S || (p.causal && k0 + kBlk - 1 > q0);
+      const bool need_mask = nt < 8 || k0 + kBlk > kvl || q0 + 16 > p.Sq || (p.causal && k0 + kBlk - 1 > q0);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         s[j][0] = exp2f(fmaf(s[j][0], sc, -lse0)); s[j][1] = exp2f(fmaf(s[j][1], sc, -lse0));
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_bwd_dq_kernel(const Attn
           for (int e = 0; e < 4; ++e) {
             const int key = k0 + j * 8 + (lane & 3) * 2 + (e & 1);
             const int qr = (e < 2) ? r0 : r1;
-            if (j >= nt || key >= p.S || qr >= p.S || (p.causal && key > qr)) s[j][e] = 0.f;
+            if (j >= nt || key >= kvl || qr >= p.Sq || (p.causal && key > qr)) s[j][e] = 0.f;
           }
         }
       }
@@ -378,8 +379,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_bwd_dq_kernel(const Attn
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int col = j * 8 + (lane & 3) * 2;
-      if (r0 < p.S) *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(r0) * ld + col) = pack_bf16(dq[j][0] * p.scale, dq[j][1] * p.scale);
-      if (r1 < p.S) *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(r1) * ld + col) = pack_bf16(dq[j][2] * p.scale, dq[j][3] * p.scale);
+      if (r0 < p.Sq) *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(r0) * p.lddq + col) = pack_bf16(dq[j][0] * p.scale, dq[j][1] * p.scale);
+      if (r1 < p.Sq) *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(r1) * p.lddq + col) = pack_bf16(dq[j][2] * p.scale, dq[j][3] * p.scale);
     }
   }
 }
@@ -392,28 +393,31 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dkv_kernel(const AttnPa
   float* s_delta = s_lse + spad;
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long ld = 3LL * p.D;
-  const __nv_bfloat16* base = p.qkv + static_cast<long long>(b) * p.S * ld + h * kHD;
-  const __nv_bfloat16* dob = p.dout + static_cast<long long>(b) * p.S * p.D + h * kHD;
-  const float* lp = p.lse + (static_cast<long long>(b) * p.H + h) * p.S;
-  const float* dp = p.delta + (static_cast<long long>(b) * p.H + h) * p.S;
-  load_rows(sQ, base, ld, p.S, spad);
-  load_rows(sDO, dob, p.D, p.S, spad);
+  const __nv_bfloat16* qb = p.q + static_cast<long long>(b) * p.Sq * p.ldq + h * kHD;
+  const __nv_bfloat16* kb_ = p.k + static_cast<long long>(b) * p.Skv * p.ldkv + h * kHD;
+  const __nv_bfloat16* vb_ = p.v + static_cast<long long>(b) * p.Skv * p.ldkv + h * kHD;
+  const __nv_bfloat16* dob = p.dout + static_cast<long long>(b) * p.Sq * p.lddo + h * kHD;
+  const float* lp = p.lse + (static_cast<long long>(b) * p.H + h) * p.Sq;
+  const float* dp = p.delta + (static_cast<long long>(b) * p.H + h) * p.Sq;
+  const int kvl = p.kv_len ? min(p.kv_len[b], p.Skv) : p.Skv;
+  load_rows(sQ, qb, p.ldq, p.Sq, spad);          // spad = Sq rounded up to 16
+  load_rows(sDO, dob, p.lddo, p.Sq, spad);
   for (int i = threadIdx.x; i < spad; i += blockDim.x) {
-    s_lse[i] = (i < p.S) ? lp[i] * kLog2e : 0.f;
-    s_delta[i] = (i < p.S) ? dp[i] : 0.f;
+    s_lse[i] = (i < p.Sq) ? lp[i] * kLog2e : 0.f;
+    s_delta[i] = (i < p.Sq) ? dp[i] : 0.f;
   }
   cp_async_wait_all();
   __syncthreads();
   const uint32_t sKw = sW + warp * 4096, sVw = sKw + 2048;
   const float sc = p.scale * kLog2e;
-  __nv_bfloat16* ob = p.dqkv + static_cast<long long>(b) * p.S * ld + h * kHD;
-  const int n_kt = spad >> 4;
+  __nv_bfloat16* okb = p.dk + static_cast<long long>(b) * p.Skv * p.lddkv + h * kHD;
+  __nv_bfloat16* ovb = p.dv + static_cast<long long>(b) * p.Skv * p.lddkv + h * kHD;
+  const int n_kt = (p.Skv + 15) >> 4;
   for (int kt = warp; kt < n_kt; kt += kAttnWarps) {
     const int kbase = kt * 16;
     __syncwarp();
-    load_rows16_warp(sKw, base + p.D, ld, kbase, p.S);
-    load_rows16_warp(sVw, base + 2 * p.D, ld, kbase, p.S);
+    load_rows16_warp(sKw, kb_, p.ldkv, kbase, p.Skv);
+    load_rows16_warp(sVw, vb_, p.ldkv, kbase, p.Skv);
     cp_async_wait_all();
     __syncwarp();
     uint32_t ka[4][4], va[4][4];
@@ -451,7 +455,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dkv_kernel(const AttnPa
           }
         }
       }
-      const bool need_mask = nt < 8 || q0 + kBlk > p.S || kbase + 16 > p.S || (p.causal && kbase + 15 > q0);
+      const bool need_mask = nt < 8 || q0 + kBlk > p.Sq || kbase + 16 > kvl || (p.causal && kbase + 15 > q0);
       uint32_t pt[4][4], dst[4][4];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -466,7 +470,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dkv_kernel(const AttnPa
           for (int e = 0; e < 4; ++e) {
             const int q = q0 + j * 8 + (lane & 3) * 2 + (e & 1);
             const int key = (e < 2) ? key0 : key1;
-            if (j >= nt || key >= p.S || q >= p.S || (p.causal && key > q)) pe[e] = 0.f;
+            if (j >= nt || key >= kvl || q >= p.Sq || (p.causal && key > q)) pe[e] = 0.f;
           }
         }
         de[0] = pe[0] * (dpt[j][0] - dl.x); de[1] = pe[1] * (dpt[j][1] - dl.y);
@@ -496,13 +500,13 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dkv_kernel(const AttnPa
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int col = j * 8 + (lane & 3) * 2;
-      if (key0 < p.S) {
-        *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(key0) * ld + p.D + col) = pack_bf16(dk[j][0] * p.scale, dk[j][1] * p.scale);
-        *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(key0) * ld + 2 * p.D + col) = pack_bf16(dv[j][0], dv[j][1]);
+      if (key0 < p.Skv) {
+        *reinterpret_cast<uint32_t*>(okb + static_cast<long long>(key0) * p.lddkv + col) = pack_bf16(dk[j][0] * p.scale, dk[j][1] * p.scale);
+        *reinterpret_cast<uint32_t*>(ovb + static_cast<long long>(key0) * p.lddkv + col) = pack_bf16(dv[j][0], dv[j][1]);
       }
-      if (key1 < p.S) {
-        *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(key1) * ld + p.D + col) = pack_bf16(dk[j][2] * p.scale, dk[j][3] * p.scale);
-        *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(key1) * ld + 2 * p.D + col) = pack_bf16(dv[j][2], dv[j][3]);
+      if (key1 < p.Skv) {
+        *reinterpret_cast<uint32_t*>(okb + static_cast<long long>(key1) * p.lddkv + col) = pack_bf16(dk[j][2] * p.scale, dk[j][3] * p.scale);
+        *reinterpret_cast<uint32_t*>(ovb + static_cast<long long>(key1) * p.lddkv + col) = pack_bf16(dv[j][2], dv[j][3]);
       }
     }
   }
@@ -571,27 +575,66 @@ extern "C" int uniir_attn_fwd_ex(const void* q, int64_t ldq, const void* k, cons
   return attn_fwd_launch(p, stream);
 }
 
+static int attn_bwd_launch(AttnParams& p, void* stream) {
+  UNIIR_CHECK_ARG(p.Sq <= 768 && p.Skv <= 768, "uniir_attn_bwd: sequence length exceeds the head-resident limit of 768");
+  if (int rc = attn_set_smem()) return rc;
+  const int spad_kv = (p.Skv + 15) / 16 * 16, spad_q = (p.Sq + 15) / 16 * 16;
+  const long long warps = 1LL * p.B * p.Sq * p.H;
+  attn_delta_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, ST(stream)>>>(p);
+  attn_bwd_dq_kernel<<<dim3(p.H, p.B), kAttnThreads, attn_smem(spad_kv, true), ST(stream)>>>(p, spad_kv);
+  attn_bwd_dkv_kernel<<<dim3(p.H, p.B), kAttnThreads, attn_smem(spad_q, true), ST(stream)>>>(p, spad_q);
+  count_launch(3);
+  UNIIR_CUDA_OK(cudaGetLastError());
+  return UNIIR_OK;
+}
+
 extern "C" int uniir_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                               int32_t B, int32_t S, int32_t H, int32_t causal, float* delta_ws,
                               void* dqkv, void* stream) {
   UNIIR_CHECK_ARG(qkv && out && dout && lse && delta_ws && dqkv && B > 0 && S > 0 && H > 0,
                   "uniir_attn_bwd: bad args");
-  UNIIR_CHECK_ARG(S <= 768, "uniir_attn_bwd: S=%d exceeds the head-resident kernel's limit of 768", S);
-  if (int rc = attn_set_smem()) return rc;
   AttnParams p{};
+  p.D = H * kHD;
   p.qkv = static_cast<const __nv_bfloat16*>(qkv);
+  p.q = p.qkv; p.k = p.qkv + p.D; p.v = p.qkv + 2 * p.D;
+  p.ldq = p.ldkv = 3LL * p.D;
   p.out = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(out));
+  p.ldo = p.D;
   p.dout = static_cast<const __nv_bfloat16*>(dout);
+  p.lddo = p.D;
   p.lse = const_cast<float*>(lse);
   p.delta = delta_ws;
   p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
-  p.B = B; p.S = S; p.H = H; p.D = H * kHD; p.causal = causal; p.scale = 0.125f;
-  const int spad = (S + 15) / 16 * 16;
-  const long long warps = 1LL * B * S * H;
-  attn_delta_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, ST(stream)>>>(p);
-  attn_bwd_dq_kernel<<<dim3(H, B), kAttnThreads, attn_smem(spad, true), ST(stream)>>>(p, spad);
-  attn_bwd_dkv_kernel<<<dim3(H, B), kAttnThreads, attn_smem(spad, true), ST(stream)>>>(p, spad);
-  count_launch(3);
-  UNIIR_CUDA_OK(cudaGetLastError());
-  return UNIIR_OK;
+  p.dq = p.dqkv; p.dk = p.dqkv + p.D; p.dv = p.dqkv + 2 * p.D;
+  p.lddq = p.lddkv = 3LL * p.D;
+  p.B = B; p.S = S; p.Sq = p.Skv = S; p.H = H; p.causal = causal; p.scale = 0.125f;
+  return attn_bwd_launch(p, stream);
+}
+
+extern "C" int uniir_attn_bwd_ex(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                                 const void* out, int64_t ldo, const void* dout, int64_t lddo, const float* lse,
+                                 int32_t B, int32_t Sq, int32_t Skv, int32_t H, int32_t causal,
+                                 const int32_t* kv_len, float* delta_ws, void* dq, int64_t lddq, void* dk,
+                                 void* dv, int64_t lddkv, void* stream) {
+  UNIIR_CHECK_ARG(q && k && v && out && dout && lse && delta_ws && dq && dk && dv && B > 0 && Sq > 0 && Skv > 0 && H > 0,
+                  "uniir_attn_bwd_ex: bad args");
+  UNIIR_CHECK_ARG(ldq % 8 == 0 && ldkv % 8 == 0 && lddo % 8 == 0 && ldo % 2 == 0 && lddq % 2 == 0 && lddkv % 2 == 0,
+                  "uniir_attn_bwd_ex: strides must keep row alignment");
+  UNIIR_CHECK_ARG(!causal || Sq == Skv, "uniir_attn_bwd_ex: causal needs Sq == Skv");
+  AttnParams p{};
+  p.q = static_cast<const __nv_bfloat16*>(q);
+  p.k = static_cast<const __nv_bfloat16*>(k);
+  p.v = static_cast<const __nv_bfloat16*>(v);
+  p.ldq = ldq; p.ldkv = ldkv;
+  p.out = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(out));
+  p.ldo = ldo;
+  p.dout = static_cast<const __nv_bfloat16*>(dout);
+  p.lddo = lddo;
+  p.lse = const_cast<float*>(lse);
+  p.delta = delta_ws;
+  p.kv_len = kv_len;
+  p.dq = static_cast<__nv_bfloat16*>(dq); p.dk = static_cast<__nv_bfloat16*>(dk); p.dv = static_cast<__nv_bfloat16*>(dv);
+  p.lddq = lddq; p.lddkv = lddkv;
+  p.B = B; p.S = Sq; p.Sq = Sq; p.Skv = Skv; p.H = H; p.D = H * kHD; p.causal = causal; p.scale = 0.125f;
+  return attn_bwd_launch(p, stream);
 }

@@ -287,12 +287,12 @@ nce_bwd_g_kernel(const float* __restrict__ qn, const float* __restrict__ allp, i
 __global__ void __launch_bounds__(256)
 nce_sgemm_kernel(const float* __restrict__ A, long long a_rs, long long a_cs, const float* __restrict__ B,
                  long long b_rs, long long b_cs, int M, int N, int K,
-                 const float* __restrict__ logit_scale_log, float* __restrict__ C) {
+                 const float* __restrict__ logit_scale_log, float* __restrict__ C, int recip = 0) {
   __shared__ float As[kKC][kT + 1];
   __shared__ float Bs[kKC][kT + 1];
   const int m0 = blockIdx.y * kT, n0 = blockIdx.x * kT;
   const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
-  const float scale = __expf(*logit_scale_log);
+  const float scale = recip ? 1.f / *logit_scale_log : __expf(*logit_scale_log);
   float acc[4][4];
   sgemm_tile(A, a_rs, a_cs, B, b_rs, b_cs, M, N, K, m0, n0, acc, As, Bs);
 #pragma unroll
@@ -406,6 +406,81 @@ nce_hardneg_kernel(const float* __restrict__ emb, const int* __restrict__ q_idx,
   }
 }
 
+
+// ---------------------------------------------------------------------------------
+// BLIP momentum-distillation loss (reference blip_ff.py:204-231, 250-252), one CTA per row:
+//   S  = x . M / temp   (online logits, given)      Sm = x_m . M / temp  (momentum logits, given)
+//   t  = alpha * softmax(Sm) + (1-alpha) * pos / sum(pos),   pos_j = [pc_id[row] == id_all[j]]
+//   loss_row = -sum_j t_j log_softmax(S)_j = lse(S) - sum_j t_j S_j
+//   G  (in place of S) = (softmax(S) - t) * gscale        d temp += sum_j G_j * (-S_j / temp)
+//   accuracy term (q2pc direction only): pos[argmax_j S_j]
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ float cta_max(float v, float* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float t = -INFINITY;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) t = fmaxf(t, sh[i]);
+  return t;
+}
+
+__global__ void __launch_bounds__(256)
+blip_softce_kernel(float* __restrict__ S, const float* __restrict__ Sm, const long long* __restrict__ pc_id,
+                   const long long* __restrict__ id_all, int n, float alpha, float gscale,
+                   const float* __restrict__ temp, float* __restrict__ loss_sum, float* __restrict__ acc_sum,
+                   float* __restrict__ d_temp) {
+  __shared__ float sh[8];
+  __shared__ int sh_i[8];
+  const int row = blockIdx.x;
+  float* s = S + static_cast<long long>(row) * n;
+  const float* sm = Sm + static_cast<long long>(row) * n;
+  const long long my = pc_id[row];
+  float mx = -INFINITY, mxm = -INFINITY, npos = 0.f;
+  int amax = 0x7fffffff;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const float v = s[j];
+    if (v > mx) { mx = v; amax = j; }
+    mxm = fmaxf(mxm, sm[j]);
+    npos += (id_all[j] == my) ? 1.f : 0.f;
+  }
+  // arg-max with first-index tie break (torch.max)
+  const float gmx = cta_max(mx, sh);
+  int cand = (mx == gmx) ? amax : 0x7fffffff;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh_i[threadIdx.x >> 5] = cand;
+  __syncthreads();
+  int gam = 0x7fffffff;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) gam = min(gam, sh_i[i]);
+  const float gmxm = cta_max(mxm, sh);
+  npos = cta_sum(npos, sh);
+  float z = 0.f, zm = 0.f;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) { z += __expf(s[j] - gmx); zm += __expf(sm[j] - gmxm); }
+  z = cta_sum(z, sh);
+  zm = cta_sum(zm, sh);
+  const float lse = gmx + logf(z), inv_zm = 1.f / zm, inv_np = 1.f / npos, tmp = *temp;
+  float dot = 0.f, dt = 0.f;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const float v = s[j];
+    const float t = alpha * __expf(sm[j] - gmxm) * inv_zm + (1.f - alpha) * ((id_all[j] == my) ? inv_np : 0.f);
+    dot += t * v;
+    const float g = (__expf(v - lse) - t) * gscale;
+    s[j] = g;
+    dt -= g * v / tmp;
+  }
+  dot = cta_sum(dot, sh);
+  dt = cta_sum(dt, sh);
+  if (threadIdx.x == 0) {
+    atomicAdd(loss_sum, lse - dot);
+    atomicAdd(d_temp, dt);
+    if (acc_sum) atomicAdd(acc_sum, (id_all[gam] == my) ? 1.f : 0.f);
+  }
+}
+
 static int nce_carve(void* workspace, size_t bytes, int bs, int nct, int nrt, NceWs* ws) {
   char* p = static_cast<char*>(workspace);
   const size_t per = static_cast<size_t>(bs) * nct;
@@ -510,6 +585,29 @@ extern "C" int uniir_hardneg_loss(const float* emb, const int32_t* q_idx, const 
   const int k = in_batch_neg_num < bs - 1 ? in_batch_neg_num : bs - 1;  // clip_sf.py:110
   nce_hardneg_kernel<<<bs, 128, 0, ST(stream)>>>(emb, q_idx, p_idx, n_idx, bs, neg_num, k < 0 ? 0 : k, E,
                                                   logit_scale_log, loss_sum, correct_sum, d_emb, d_logit_scale);
+  count_launch();
+  UNIIR_CUDA_OK(cudaGetLastError());
+  return UNIIR_OK;
+}
+
+/* out[M,N] = (A[M,K] . B)/(*temp) with B given as [K,N] (b_kn=1) or [N,K] (b_kn=0), fp32 */
+extern "C" int uniir_sgemm_temp(const float* A, const float* B, int32_t b_kn, int32_t M, int32_t N, int32_t K,
+                                const float* temp, float* out, void* stream) {
+  UNIIR_CHECK_ARG(A && B && temp && out && M > 0 && N > 0 && K > 0, "uniir_sgemm_temp: bad args");
+  nce_sgemm_kernel<<<dim3((N + kT - 1) / kT, (M + kT - 1) / kT), 256, 0, ST(stream)>>>(
+      A, K, 1, B, b_kn ? 1 : K, b_kn ? N : 1, M, N, K, temp, out, 1);
+  count_launch();
+  UNIIR_CUDA_OK(cudaGetLastError());
+  return UNIIR_OK;
+}
+
+extern "C" int uniir_blip_softce(float* S, const float* Sm, const int64_t* pc_id, const int64_t* id_all, int32_t bs,
+                                 int32_t n, float alpha, float gscale, const float* temp, float* loss_sum,
+                                 float* acc_sum, float* d_temp, void* stream) {
+  UNIIR_CHECK_ARG(S && Sm && pc_id && id_all && temp && loss_sum && d_temp && bs > 0 && n > 0, "uniir_blip_softce: bad args");
+  blip_softce_kernel<<<bs, 256, 0, ST(stream)>>>(S, Sm, reinterpret_cast<const long long*>(pc_id),
+                                                 reinterpret_cast<const long long*>(id_all), n, alpha, gscale, temp,
+                                                 loss_sum, acc_sum, d_temp);
   count_launch();
   UNIIR_CUDA_OK(cudaGetLastError());
   return UNIIR_OK;

@@ -378,6 +378,35 @@ __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float
   }
 }
 
+// momentum encoder EMA (reference blip_ff.py:289-292): p_m = m*p_m + (1-m)*p over a flat segment,
+// also refreshing the momentum encoder's bf16 shadow
+__global__ void ema_kernel(float* __restrict__ pm, const float* __restrict__ p, long long n, float m,
+                           __nv_bfloat16* __restrict__ pm16) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  if (i + 3 < n) {
+    float4 a = *reinterpret_cast<float4*>(pm + i);
+    const float4 b = *reinterpret_cast<const float4*>(p + i);
+    a.x = a.x * m + b.x * (1.f - m); a.y = a.y * m + b.y * (1.f - m);
+    a.z = a.z * m + b.z * (1.f - m); a.w = a.w * m + b.w * (1.f - m);
+    *reinterpret_cast<float4*>(pm + i) = a;
+    if (pm16) *reinterpret_cast<uint2*>(pm16 + i) = pack4_bf16(a.x, a.y, a.z, a.w);
+  } else {
+    for (long long j = i; j < n; ++j) {
+      const float a = pm[j] * m + p[j] * (1.f - m);
+      pm[j] = a;
+      if (pm16) pm16[j] = __float2bfloat16(a);
+    }
+  }
+}
+
+// dz = dy * (1 - y*y) (tanh backward; BERT pooler), bf16 out for the following GEMMs
+__global__ void tanh_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, long long n,
+                                __nv_bfloat16* __restrict__ dz) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) dz[i] = __float2bfloat16(dy[i] * (1.f - y[i] * y[i]));
+}
+
 }  // namespace uniir
 
 using namespace uniir;
@@ -542,6 +571,24 @@ extern "C" int uniir_adamw_step(float* p, float* g, float* m, float* v, void* p_
   const long long t = (n + 3) / 4;
   adamw_kernel<<<(unsigned)((t + 255) / 256), 256, 0, ST(stream)>>>(
       p, g, m, v, static_cast<__nv_bfloat16*>(p_bf16), n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale);
+  count_launch();
+  UNIIR_CUDA_OK(cudaGetLastError());
+  return UNIIR_OK;
+}
+
+extern "C" int uniir_ema_update(float* p_m, const float* p, int64_t n, float momentum, void* p_m_bf16, void* stream) {
+  UNIIR_CHECK_ARG(p_m && p && n >= 0, "uniir_ema_update: bad args");
+  if (n == 0) return UNIIR_OK;
+  const long long t = (n + 3) / 4;
+  ema_kernel<<<(unsigned)((t + 255) / 256), 256, 0, ST(stream)>>>(p_m, p, n, momentum, static_cast<__nv_bfloat16*>(p_m_bf16));
+  count_launch();
+  UNIIR_CUDA_OK(cudaGetLastError());
+  return UNIIR_OK;
+}
+extern "C" int uniir_tanh_bwd(const float* dy, const float* y, int64_t n, void* dz_bf16, void* stream) {
+  UNIIR_CHECK_ARG(dy && y && dz_bf16 && n >= 0, "uniir_tanh_bwd: bad args");
+  if (n == 0) return UNIIR_OK;
+  tanh_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(dy, y, n, static_cast<__nv_bfloat16*>(dz_bf16));
   count_launch();
   UNIIR_CUDA_OK(cudaGetLastError());
   return UNIIR_OK;

@@ -142,3 +142,16 @@ def train_one_epoch(model, data_loader, optimizer, epoch, gpu_id, scheduler, glo
         stats["loss"], stats["inbatch_accuracy"] = t[0].item(), t[1].item()
     print("Averaged stats:", stats)
     return stats
+
+
+def train_step_blip(model, batch, optimizer: FlatAdamW, alpha, scheduler=None):
+    """One BLIP_FF optimisation step (reference uniir_blip/engine.py:9-66 inner loop): momentum-distillation
+    loss with gradient caching, flat gradient all-reduce, fused AdamW (single group, wd 0.05,
+    uniir_blip/train.py:193-197)."""
+    loss, acc = model._loss_forward(batch, alpha)
+    model.backward_contrastive()
+    allreduce_grads(model._online)
+    optimizer.step()
+    if scheduler is not None:
+        scheduler.step()
+    return loss, acc

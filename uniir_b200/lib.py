@@ -76,6 +76,11 @@ _SIGS = {
     "uniir_infonce_normalize": (C.c_int, [VP, VP, VP, I32, I32, VP, VP, VP, VP, VP]),
     "uniir_infonce_fwd": (C.c_int, [VP, VP, I32, I32, I32, VP, I32, VP, VP, VP, VP, C.c_size_t, VP]),
     "uniir_infonce_bwd": (C.c_int, [VP, VP, I32, I32, I32, VP, I32, VP, VP, VP, VP, VP, VP, VP]),
+    "uniir_attn_bwd_ex": (C.c_int, [VP, I64, VP, VP, I64, VP, I64, VP, I64, VP, I32, I32, I32, I32, I32, VP, VP, VP, I64, VP, VP, I64, VP]),
+    "uniir_ema_update": (C.c_int, [VP, VP, I64, C.c_float, VP, VP]),
+    "uniir_tanh_bwd": (C.c_int, [VP, VP, I64, VP, VP]),
+    "uniir_sgemm_temp": (C.c_int, [VP, VP, I32, I32, I32, I32, VP, VP, VP]),
+    "uniir_blip_softce": (C.c_int, [VP, VP, VP, VP, I32, I32, C.c_float, C.c_float, VP, VP, VP, VP, VP]),
     "uniir_hardneg_loss": (C.c_int, [VP, VP, VP, VP, I32, I32, I32, I32, VP, VP, VP, VP, VP, VP]),
     "uniir_infonce_normalize_bwd": (C.c_int, [VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, VP, VP]),
 }

@@ -436,3 +436,41 @@ def hardneg_loss(emb, q_idx, p_idx, n_idx, in_batch_neg_num, logit_scale, d_logi
                                         sums[1:2].data_ptr(), d_emb.data_ptr(), d_logit_scale.data_ptr(), _stream()),
             "uniir_hardneg_loss")
     return sums[0] / bs, sums[1] / bs, d_emb
+
+
+def attn_bwd_ex(q, k, v, out, dout, lse, B, Sq, Skv, H, dq, dk, dv, *, causal=False, kv_len=None, delta=None):
+    """Backward of attn_fwd_ex; dq/dk/dv are preallocated bf16 row-strided views (dk, dv share a stride)."""
+    if delta is None:
+        delta = torch.empty(B * H * Sq, device=q.device, dtype=torch.float32)
+    assert dk.stride(0) == dv.stride(0) and k.stride(0) == v.stride(0)
+    L.check(L.load().uniir_attn_bwd_ex(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), out.data_ptr(),
+                                       out.stride(0), dout.data_ptr(), dout.stride(0), lse.data_ptr(), B, Sq, Skv, H,
+                                       int(causal), _ptr(kv_len), delta.data_ptr(), dq.data_ptr(), dq.stride(0),
+                                       dk.data_ptr(), dv.data_ptr(), dk.stride(0), _stream()), "uniir_attn_bwd_ex")
+
+
+def ema_update(p_m, p, momentum, p_m16=None):
+    L.check(L.load().uniir_ema_update(p_m.data_ptr(), p.data_ptr(), p.numel(), momentum, _ptr(p_m16), _stream()),
+            "uniir_ema_update")
+
+
+def tanh_bwd(dy, y, out):
+    L.check(L.load().uniir_tanh_bwd(dy.data_ptr(), y.data_ptr(), y.numel(), out.data_ptr(), _stream()), "uniir_tanh_bwd")
+
+
+def sgemm_temp(a, b, b_kn, temp, out=None):
+    """fp32 (a @ b or a @ b.T) / temp with b stored [K,N] (b_kn) or [N,K]."""
+    M, K = a.shape
+    N = b.shape[1] if b_kn else b.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    L.check(L.load().uniir_sgemm_temp(a.data_ptr(), b.data_ptr(), int(b_kn), M, N, K, temp.data_ptr(), out.data_ptr(),
+                                      _stream()), "uniir_sgemm_temp")
+    return out
+
+
+def blip_softce(S, Sm, pc_id, id_all, alpha, gscale, temp, loss_sum, acc_sum, d_temp):
+    bs, n = S.shape
+    L.check(L.load().uniir_blip_softce(S.data_ptr(), Sm.data_ptr(), pc_id.data_ptr(), id_all.data_ptr(), bs, n, alpha,
+                                       gscale, temp.data_ptr(), loss_sum.data_ptr(), _ptr(acc_sum), d_temp.data_ptr(),
+                                       _stream()), "uniir_blip_softce")

@@ -131,6 +131,8 @@ class FlatParamModule(nn.Module):
                 view.fill_(1.0)
             elif std == -2.0:
                 view.fill_(math.log(100.0))  # pretrained logit_scale
+            elif std == -3.0:
+                view.fill_(0.07)             # BLIP temperature (blip_ff.py:61)
             elif std > 0:
                 view.copy_(torch.empty(shape, dtype=torch.float32).normal_(0.0, std, generator=gen))
             self._register(name, nn.Parameter(view))
