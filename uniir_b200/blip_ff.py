@@ -345,7 +345,7 @@ class BLIPFeatureFusion(nn.Module):
         for name, *_ in self._mom._specs:
             self.get_parameter(name).requires_grad_(False)          # blip_ff.py:283-287 copy_params
         for k in self._mom.flat:
-            self._mom.flat[k].copy_(self._online.flat[k])
+            self._mom.flat[k].copy_(self._online.flat[k][:self._mom.flat[k].numel()])
         for enc in ("text_encoder", "text_encoder_m"):
             self.get_submodule(f"{enc}.embeddings").register_buffer(
                 "position_ids", torch.arange(d.max_pos, device=dev).expand((1, -1)))
