@@ -192,6 +192,11 @@ def run_reference(args, rank):
     if args.workload == "search":
         cb, dt = cpu_search_reference(args.steps, args.warmup)
         metric, unit, cfg = "queries_per_sec_top50", "queries/s", {"workload": "dense_retrieval_190k_x_5.6M_d768_fp16_top50"}
+    elif args.workload == "blip":
+        cb, dt = cpu_blip_reference(args.steps, args.warmup)
+        metric, unit = "contrastive_pairs_per_sec", "pairs/s"
+        cfg = {"workload": "BLIP_FF ViT-L/16 + BERT-base momentum-distillation training step (BASELINE configs[2])",
+               "global_batch": BLIP_GLOBAL_BATCH}
     else:
         cb, dt = cpu_train_reference(args.steps, args.warmup)
         metric, unit = "contrastive_pairs_per_sec", "pairs/s"
@@ -437,13 +442,144 @@ def run_embed(args, rank, world, dev, peaks):
                     "d2h_bytes_per_step": B * 768 * 2 * world, "ms_per_step": ms_e2e}}
 
 
+def synth_blip_batch(dims, pairs, seed, device, step=0):
+    """SURVEY.md 8d BLIP inputs: input_ids [B,100] = [101, U{1000..vocab-3} x L, 102, 0..], prefix attention
+    mask, randn images, query = even rows / pos_cand = odd rows, distinct positive-candidate ids."""
+    n, S = 2 * pairs, 100
+    g = torch.Generator().manual_seed(seed)
+    L_ = torch.randint(1, S - 1, (n,), generator=g)
+    ids = torch.randint(1000, dims.vocab - 2, (n, S), generator=g)
+    pos = torch.arange(S)[None, :]
+    ids = torch.where(pos == 0, torch.full_like(ids, 101), ids)
+    ids = torch.where(pos == (L_ + 1)[:, None], torch.full_like(ids, 102), ids)
+    att = (pos <= (L_ + 1)[:, None]).long()
+    ids = ids * att
+    gd = torch.Generator(device=device).manual_seed(seed)
+    img = torch.randn(n, 3, dims.image_size, dims.image_size, generator=gd, device=device)
+    return dict(txt_batched={"input_ids": ids.to(device), "attention_mask": att.to(device)}, image_batched=img,
+                txt_mask_batched=None, image_mask_batched=None,
+                p_did_list=torch.arange(pairs, dtype=torch.int64) + (seed * 1_000_003 + step * pairs),
+                index_mapping={"query": [[2 * i] for i in range(pairs)], "pos_cand": [[2 * i + 1] for i in range(pairs)]})
+
+
+BLIP_GLOBAL_BATCH = 2048
+BLIP_FLOPS_PER_PAIR = 1.212e12     # SURVEY.md 8d (algorithmic fwd+bwd of the online encoders; momentum forward not credited)
+
+
+def run_train_blip(args, rank, world, dev, peaks):
+    """BASELINE configs[2]: BLIP_FF ViT-L/16 + BERT-base cross-attention encoder, momentum distillation with
+    a 57344-entry queue, global batch 2048 pairs, text length 100."""
+    from collections import Counter
+    from uniir_b200 import lib, ops
+    from uniir_b200.blip_ff import BLIPFeatureFusion
+    from uniir_b200.engine import FlatAdamW, train_step_blip
+    pairs = BLIP_GLOBAL_BATCH // world
+    model = BLIPFeatureFusion(vit="large", image_size=224, embed_dim=768, queue_size=57344, device=dev, micro_batch=256)
+    model.train_micro_batch = args.blip_micro_batch
+    opt = FlatAdamW(model._online, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05)
+    batch = synth_blip_batch(model.dims, pairs, 2023 + rank, dev)
+    state = {}
+
+    def step():
+        state["loss"], state["acc"] = train_step_blip(model, batch, opt, alpha=0.4)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index or 0); sampler.start()
+    l0 = lib.launch_count() + ops.graph_launches()
+    ms = timed(step, args.steps, world)
+    launches = lib.launch_count() + ops.graph_launches() - l0
+    clocks = sampler.stop()
+    value = BLIP_GLOBAL_BATCH / (ms / 1e3)
+
+    hb = {"ids": batch["txt_batched"]["input_ids"].cpu().pin_memory(), "att": batch["txt_batched"]["attention_mask"].cpu().pin_memory(),
+          "img": torch.empty(batch["image_batched"].shape, pin_memory=True).copy_(batch["image_batched"])}
+    h2d = sum(v.numel() * v.element_size() for v in hb.values())
+
+    def e2e_step():
+        gb = dict(batch)
+        gb["txt_batched"] = {"input_ids": hb["ids"].to(dev, non_blocking=True), "attention_mask": hb["att"].to(dev, non_blocking=True)}
+        gb["image_batched"] = hb["img"].to(dev, non_blocking=True)
+        loss, _ = train_step_blip(model, gb, opt, alpha=0.4)
+        state["e2e_loss"] = loss.item()
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, 1, world)
+
+    sink = []
+    ops.set_gemm_profiler(sink)
+    step()
+    ops.set_gemm_profiler(None)
+    torch.cuda.synchronize()
+    keyf = lambda c: tuple(sorted((k, str(v)) for k, v in c.items()))
+    uniq, counts = {}, Counter()
+    for c in sink:
+        uniq[keyf(c)] = c
+        counts[keyf(c)] += 1
+    g_ms = g_fl = 0.0
+    for k_, c in uniq.items():
+        t = ops.time_gemm_config(c, iters=5, device=dev)
+        g_ms += t * counts[k_]
+        g_fl += 2.0 * c["M"] * c["N"] * c["K"] * counts[k_]
+    achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    roof = {"bound": "tensor", "kernel": "uniir::gemm_epi_kernel (tcgen05.mma kind::f16, TMA-fed, TMEM accum)",
+            "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
+            "peak_src": f"{peaks['src']} sustained bf16 (kernel timed inside a long step)", "launches": len(sink),
+            "distinct_configs": len(uniq), "gemm_share_of_step": g_ms / ms if ms else None, "traffic": None,
+            "step_algorithmic_tflops": BLIP_FLOPS_PER_PAIR * BLIP_GLOBAL_BATCH / world / (ms / 1e3) / 1e12}
+    out = {"metric": "contrastive_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": "BLIP_FF ViT-L/16 + BERT-base momentum-distillation training step (BASELINE configs[2])",
+                      "model": "BLIP_FF large", "global_batch": BLIP_GLOBAL_BATCH, "pairs_per_gpu": pairs, "queue_size": 57344,
+                      "seq_len": "197 vision tokens + 100 text tokens per item, 2 items per pair", "micro_batch_items": model.train_micro_batch,
+                      "parallelism": f"dp{world}", "grad_cache": "embedding-level (1 extra online forward + momentum forward, not credited)",
+                      "l2": "inputs+weights+activations per step >> 126 MB L2 (no flush needed)"},
+           "clocks": clocks, "gpu_launches": launches, "roofline": roof,
+           "e2e": {"value": BLIP_GLOBAL_BATCH / (ms_e2e / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": h2d * world,
+                   "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e},
+           "loss": float(state["loss"].item()), "accuracy": float(state["acc"].item())}
+    del model, opt, batch, hb
+    torch.cuda.empty_cache()
+    return out
+
+
+def cpu_blip_reference(steps, warmup, pairs=2):
+    from oracle.blip_oracle import BLIPFeatureFusionOracle
+    cores = _cpu_threads()
+    torch.manual_seed(2023)
+    model = BLIPFeatureFusionOracle("large", embed_dim=768, queue_size=57344)
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=0.05)
+    b = synth_blip_batch(model.dims, pairs, 2023, torch.device("cpu"))
+    b["p_did_list"] = b["p_did_list"].tolist()
+
+    def step():
+        out = model.compute_contrastive_loss(b, alpha=0.4)
+        out["loss"].backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": pairs / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": f"oracle BLIP_FF large fp32, {pairs} pairs/step (of the {BLIP_GLOBAL_BATCH}-pair batch), online+momentum "
+                      f"forward, loss, backward, AdamW, {steps} timed steps"}, dt
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train", "search", "embed"])
+    ap.add_argument("--workload", default="train", choices=["train", "search", "embed", "blip"])
+    ap.add_argument("--blip-micro-batch", type=int, default=64)
     ap.add_argument("--micro-batch", type=int, default=128, help="encoder items per micro-batch")
     ap.add_argument("--no-extra", action="store_true", help="skip the attached retrieval measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -469,6 +605,10 @@ def main():
     peaks = load_peaks()
     if args.workload == "embed":
         out = run_embed(args, rank, world, dev, peaks)
+    elif args.workload == "blip":
+        out = run_train_blip(args, rank, world, dev, peaks)
+        if rank == 0 and not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"], _ = cpu_blip_reference(1, 1)
     elif args.workload == "search":
         out = run_search(args, rank, world, dev, peaks)
         if rank == 0 and not args.no_cpu_baseline and world == 1:
