@@ -80,9 +80,10 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def synth_batch(dims, pairs, seed, device, pinned=False):
+def synth_batch(dims, pairs, seed, device, pinned=False, mask_mix="ones"):
     """SURVEY.md 8d synthetic inputs: randn images (CLIP-normalised images are ~N(0,1)), token ids
-    [SOT, U x L, EOT, 0..], all-ones masks, query = even rows / pos_cand = odd rows."""
+    [SOT, U x L, EOT, 0..], all-ones masks, query = even rows / pos_cand = odd rows.
+    mask_mix="mbeir": the second SURVEY 8d configuration, 1/3 text-only, 1/3 image-only, 1/3 both."""
     from uniir_b200.preprocess import synthetic_clip_tokens
     n = 2 * pairs
     g = torch.Generator().manual_seed(seed)
@@ -100,7 +101,13 @@ def synth_batch(dims, pairs, seed, device, pinned=False):
         ones = torch.ones(n, dtype=torch.long)
         if pinned:
             ids, ones = ids.pin_memory(), ones.pin_memory()
-    return dict(txt_batched=ids, image_batched=img, txt_mask_batched=ones, image_mask_batched=ones.clone(),
+    mt, mv = ones, ones.clone()
+    if mask_mix == "mbeir":
+        kind = torch.arange(n, device=ones.device) % 3          # 0: text-only, 1: image-only, 2: both
+        mt, mv = (kind != 1).long(), (kind != 0).long()
+        if pinned:
+            mt, mv = mt.pin_memory(), mv.pin_memory()
+    return dict(txt_batched=ids, image_batched=img, txt_mask_batched=mt, image_mask_batched=mv,
                 index_mapping={"query": [[2 * i] for i in range(pairs)], "pos_cand": [[2 * i + 1] for i in range(pairs)]})
 
 
@@ -224,7 +231,8 @@ def run_train(args, rank, world, dev, peaks):
     pairs = GLOBAL_BATCH // world
     model = CLIPScoreFusion(MODEL, device=dev, config=Cfg, micro_batch=args.micro_batch)
     opt = FlatAdamW(model.clip_model, lr=1e-5, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.2)
-    batch = synth_batch(model.dims, pairs, 2023 + rank, dev)
+    batch = synth_batch(model.dims, pairs, 2023 + rank, dev, mask_mix=args.mask_mix)
+    model.skip_masked_towers = not args.no_tower_skip
     state = {}
 
     def step():
@@ -298,7 +306,10 @@ def run_train(args, rank, world, dev, peaks):
                       "micro_batch_items": model._train_mb if hasattr(model, "_train_mb") else args.micro_batch,
                       "seq_len": "257 vision tokens + 77 text tokens per item, 2 items per pair",
                       "parallelism": f"dp{world}", "grad_cache": "embedding-level (1 extra forward, not credited)",
-                      "l2": "inputs+weights+activations per step >> 126 MB L2 (no flush needed)"},
+                      "l2": "inputs+weights+activations per step >> 126 MB L2 (no flush needed)",
+                      "masks": ("all ones (both modalities present)" if args.mask_mix == "ones" else
+                                "1/3 text-only, 1/3 image-only, 1/3 both; masked towers "
+                                + ("encoded and multiplied by 0 (reference behaviour)" if args.no_tower_skip else "skipped"))},
            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof,
            "loss": float(state["loss"].item()), "accuracy": float(state["acc"].item())}
     del model, opt, batch, hb
@@ -583,6 +594,9 @@ def main():
     ap.add_argument("--micro-batch", type=int, default=128, help="encoder items per micro-batch")
     ap.add_argument("--no-extra", action="store_true", help="skip the attached retrieval measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mask-mix", default="ones", choices=["ones", "mbeir"],
+                    help="train workload: modality masks (SURVEY 8d); 'mbeir' = 1/3 text-only, 1/3 image-only, 1/3 both")
+    ap.add_argument("--no-tower-skip", action="store_true", help="encode masked modalities like the reference does")
     ap.add_argument("--search-q", type=int, default=SEARCH_Q)
     ap.add_argument("--search-n", type=int, default=SEARCH_N)
     args = ap.parse_args()

@@ -115,12 +115,15 @@ int uniir_layernorm_fwd(const float* x, int64_t ldx, const int32_t* row_index, c
                         const float* beta, float eps, int64_t rows, int32_t D, void* y, int64_t ldy,
                         int32_t y_dtype, float* mean, float* rstd, void* stream);
 /* dx[src row] (+)= LN backward; dgamma/dbeta += column sums (atomic fp32); dx_bf16 (optional,
- * same row addressing as dx) receives a bf16 copy of the updated dx (next GEMM's operand). */
+ * same row addressing as dx) receives a bf16 copy of the updated dx (next GEMM's operand);
+ * dcolsum [D] (optional) += column sums of the updated dx over the processed rows = the bias
+ * gradient of the linear layer this dx flows into next (autograd's sum over tokens), fused here
+ * so that no separate pass reads dx again. */
 int uniir_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_dtype, const float* x, int64_t ldx,
                         const int32_t* row_index, const float* mean, const float* rstd,
                         const float* gamma, int64_t rows, int32_t D, float* dx, int64_t lddx,
                         int32_t dx_accumulate, float* dgamma, float* dbeta, void* dx_bf16,
-                        void* stream);
+                        float* dcolsum, void* stream);
 /* visual.conv1 (stride = kernel = patch, no bias; clip_ff.py:36) as im2col:
  * img fp32 [B,3,H,W] -> bf16 [B*(H/P)^2, Kpad], k = c*P*P + py*P + px, zero padded. */
 int uniir_patch_im2col(const float* img, int32_t B, int32_t H, int32_t W, int32_t P, int32_t Kpad,
@@ -142,6 +145,16 @@ int uniir_score_fuse_fwd(const float* t, const float* v, const int64_t* mt, cons
                          int32_t E, float* out, void* stream);
 int uniir_score_fuse_bwd(const float* d, const int64_t* mt, const int64_t* mv, int64_t B, int32_t E,
                          void* dt_bf16, void* dv_bf16, void* stream);
+/* Score fusion over compacted rows -- the reference encodes "" / a black image for a missing
+ * modality and multiplies the result by mask 0 (clip_sf.py:53-63, mbeir_dataset.py:503-504); here a
+ * tower only sees the rows whose mask is non-zero and its term is scattered back:
+ *   scatter   : out[rows[r],:] += mask[rows[r]] * emb[r,:]                         r < n
+ *   gather_bwd: d[r,:] = bf16(mask[rows[r]] * d_out[rows[r],:]) for r < n, 0 for n <= r < n_pad
+ * rows int32 [n] (batch row of each compact row), mask int64 [B], emb/out/d_out fp32 [*,E]. */
+int uniir_score_fuse_scatter(const float* emb, const int32_t* rows, const int64_t* mask, int32_t n,
+                             int32_t E, float* out, void* stream);
+int uniir_score_fuse_gather_bwd(const float* d_out, const int32_t* rows, const int64_t* mask, int32_t n,
+                                int32_t n_pad, int32_t E, void* d_bf16, void* stream);
 /* out[n] += sum_m dy[m,n]  (bias gradients; dy bf16). */
 int uniir_colsum_accum(const void* dy, int64_t M, int32_t N, int64_t ld, float* out, void* stream);
 int uniir_pad_cast_bf16(const float* src, int64_t rows, int32_t K, int32_t Kpad, void* dst, void* stream);
@@ -169,6 +182,11 @@ int uniir_attn_fwd(const void* qkv, int32_t B, int32_t S, int32_t H, int32_t cau
 int uniir_attn_fwd_ex(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, int32_t B,
                       int32_t Sq, int32_t Skv, int32_t H, int32_t causal, const int32_t* kv_len, void* out,
                       int64_t ldo, float* lse, void* stream);
+/* Forward implementation switch: 0 = mma.sync head-resident kernel, 1 = tcgen05 kernel (scores of a
+ * 128-query tile in TMEM, P staged in shared memory, K/V of the next head prefetched by TMA) wherever
+ * Skv <= 304, falling back to 0 elsewhere.  Default: environment UNIIR_ATTN_TC (unset = 0).
+ * Returns the previous mode.  Both compute the same function; tests compare them. */
+int uniir_attn_set_mode(int32_t mode);
 int uniir_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int32_t B,
                    int32_t S, int32_t H, int32_t causal, float* delta_ws /* [B*H*S] */, void* dqkv,
                    void* stream);

@@ -41,8 +41,9 @@ def _pair(name, mb, seed=0):
     return orc, mine
 
 
-def _check_against_oracle(name, bs, mb, min_grad_cos):
+def _check_against_oracle(name, bs, mb, min_grad_cos, skip_masked=True):
     orc, mine = _pair(name, mb)
+    mine.skip_masked_towers = skip_masked
     b = _batch(orc.clip_model.dims, bs)
     ref = orc(b)
     ref["loss"].backward()
@@ -71,6 +72,38 @@ def _check_against_oracle(name, bs, mb, min_grad_cos):
 def test_tiny_model_matches_oracle_with_and_without_microbatching():
     _check_against_oracle("tiny-test", 8, 16, 0.995)    # one micro-batch
     _check_against_oracle("tiny-test", 12, 8, 0.995)    # 3 micro-batches: gradient cache is exact
+
+
+def test_tiny_model_matches_oracle_without_tower_skipping():
+    """_batch() has text-only and image-only items: by default they never enter the masked tower (compacted
+    rows); this is the reference-shaped path that encodes every row in both towers and multiplies by the mask."""
+    _check_against_oracle("tiny-test", 12, 8, 0.995, skip_masked=False)
+
+
+def test_skipping_masked_towers_changes_nothing():
+    """rows with mask 0 are not encoded.  Embeddings must equal the encode-everything path
+    (each row's tower output does not depend on its neighbours), loss equal, gradients equal up to the order of
+    the atomic accumulations.  Mix: text-only, image-only, both, neither; counts that do not fill a micro-batch."""
+    from uniir_b200.clip_sf import CLIPScoreFusion
+    res = {}
+    for skip in (False, True):
+        m = CLIPScoreFusion("tiny-test", device="cuda", micro_batch=8, seed=5)
+        m.skip_masked_towers = skip
+        b = _batch(m.dims, 12, seed=7)
+        g = torch.Generator().manual_seed(11)
+        b["txt_mask_batched"] = (torch.rand(24, generator=g) < 0.6).long()
+        b["image_mask_batched"] = (torch.rand(24, generator=g) < 0.5).long()
+        b["txt_mask_batched"][0] = b["image_mask_batched"][0] = 0      # an item with neither modality
+        gb = _cuda(b)
+        emb = m.encode_multimodal_input(gb["txt_batched"], gb["image_batched"], gb["txt_mask_batched"], gb["image_mask_batched"])
+        loss, acc = m._loss_forward(gb); m._loss_backward(gb, None)
+        res[skip] = (emb.clone(), loss.item(), {n: m.clip_model.g(n).clone() for n, *_ in m.clip_model._specs})
+    assert res[True][0][0].abs().max().item() == 0
+    assert torch.allclose(res[True][0], res[False][0], atol=1e-6, rtol=1e-6)
+    assert abs(res[True][1] - res[False][1]) < 1e-5 * max(1.0, abs(res[False][1]))
+    for n, ga in res[False][2].items():
+        gb_ = res[True][2][n]
+        assert (ga - gb_).norm() <= 2e-3 * (ga.norm() + 1e-12), n
 
 
 def test_vit_b32_batch4_matches_oracle():

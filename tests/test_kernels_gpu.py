@@ -83,8 +83,9 @@ def test_gemm_rejects_bad_arguments(ops):
         ops.gemm(A, A)
 
 
-@pytest.mark.parametrize("D,rows", [(1024, 300), (768, 77), (128, 50), (512, 9)])
+@pytest.mark.parametrize("D,rows", [(1024, 300), (768, 77), (128, 50), (512, 9), (1024, 2571), (64, 1), (2048, 37), (36, 19)])
 def test_layernorm_fwd_bwd(ops, D, rows):
+    """D <= 1024 runs the warp-per-row kernels, wider rows the CTA-per-row ones; both must match torch."""
     g = torch.Generator().manual_seed(D)
     x = torch.randn(rows, D, generator=g) * 2 + 0.5
     w, b = torch.randn(D, generator=g), torch.randn(D, generator=g)
@@ -97,6 +98,30 @@ def test_layernorm_fwd_bwd(ops, D, rows):
     dx = torch.ones(rows, D, device=dev); dg = torch.zeros(D, device=dev); db = torch.zeros(D, device=dev)
     ops.layernorm_bwd(dy.to(dev), x.to(dev), mean, rstd, w.to(dev), dx, dg, db)
     assert rel(dx - 1, xr.grad) < 1e-5 and rel(dg, wr.grad) < 1e-5 and rel(db, br.grad) < 1e-5
+    # fused bias-gradient output: column sums of the updated dx (here dx = 1 + LN grad), plus the bf16 copy;
+    # fp32 dy and accumulate=False exercise the other load / store variants
+    dx2 = torch.ones(rows, D, device=dev); dxb = torch.zeros(rows, D, device=dev, dtype=torch.bfloat16)
+    dg2 = torch.zeros(D, device=dev); db2 = torch.zeros(D, device=dev); dc = torch.full((D,), 2.0, device=dev)
+    ops.layernorm_bwd(dy.to(dev), x.to(dev), mean, rstd, w.to(dev), dx2, dg2, db2, dx_bf16=dxb, dcolsum=dc)
+    assert rel(dx2, dx) < 1e-6 and rel(dg2, wr.grad) < 1e-5 and rel(db2, br.grad) < 1e-5   # template variants may contract FMAs differently
+    assert rel(dxb, dx) < 5e-3
+    tol = 1e-5 if D <= 1024 else 3e-3            # wide rows take the column sums from the bf16 copy
+    assert ((dc - 2).cpu() - (1 + xr.grad).sum(0)).abs().max() < tol * (1 + xr.grad).abs().sum(0).max()
+    dx3 = torch.full((rows, D), 7.0, device=dev); dg3 = torch.zeros(D, device=dev); db3 = torch.zeros(D, device=dev)
+    ops.layernorm_bwd(dy.float().to(dev), x.to(dev), mean, rstd, w.to(dev), dx3, dg3, db3, accumulate=False)
+    assert rel(dx3, xr.grad) < 1e-5 and rel(dg3, wr.grad) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,ld", [(2571, 3072, 3072), (100, 4096, 4096), (33, 768, 2304), (7, 64, 64), (1000, 36, 36), (513, 264, 264)])
+def test_colsum_accum(ops, M, N, ld):
+    """Bias gradient = column sums of bf16 dy; N % 8 == 0 takes the 128-bit kernel (also on a strided view)."""
+    g = torch.Generator().manual_seed(M + N)
+    full = torch.randn(M, ld, generator=g).bfloat16()
+    dy = full[:, :N]
+    out = torch.full((N,), 3.0, device=dev)
+    ops.colsum_accum(full.to(dev)[:, :N], out)
+    ref = dy.float().sum(0)
+    assert ((out - 3).cpu() - ref).abs().max() < 1e-4 * dy.float().abs().sum(0).max()
 
 
 def test_layernorm_gathered_rows_and_embed_kernels(ops):
@@ -145,6 +170,56 @@ def test_attention_fwd_bwd(ops, B, S, H, causal):
     ref.backward(dout.float())
     dqkv = ops.attn_bwd(qkv.to(dev), out, dout.to(dev), lse, B, S, H, causal)
     assert rel(dqkv, qr.grad) < 1e-2   # bf16 P / dS operands
+
+
+@pytest.mark.parametrize("B,S,H,causal", [(2, 64, 1, False), (3, 257, 4, False), (5, 77, 3, True), (2, 197, 2, False),
+                                           (2, 50, 2, False), (1, 130, 2, True), (2, 100, 1, False), (1, 132, 1, False),
+                                           (1, 304, 2, False), (20, 257, 16, False), (40, 77, 12, True), (1, 128, 1, True)])
+def test_attention_fwd_tcgen05(ops, B, S, H, causal):
+    """The tcgen05 forward (attention_tc.cu) against the fp32 reference and against the mma.sync kernel: one
+    128-query tile, several tiles, the 1..4-row CUDA-core tail (257, 130, 132), persistence over more heads than
+    SMs (320 and 480 heads: K/V double buffering, every barrier wraps), causal masking."""
+    g = torch.Generator().manual_seed(S + B)
+    qkv = (torch.randn(B * S, 3 * H * 64, generator=g) * 1.5).bfloat16()
+    ref, rlse = _attn_ref(qkv.float(), B, S, H, causal)
+    out0, lse0 = ops.attn_fwd(qkv.to(dev), B, S, H, causal)
+    prev = ops.attn_set_mode(1)
+    try:
+        out1, lse1 = ops.attn_fwd(qkv.to(dev), B, S, H, causal)
+        torch.cuda.synchronize()
+    finally:
+        ops.attn_set_mode(prev)
+    assert rel(out1, ref) < 6e-3 and (lse1.cpu() - rlse).abs().max() < 1e-3
+    assert rel(out1, out0) < 6e-3 and (lse1 - lse0).abs().max() < 1e-3
+
+
+def test_attention_fwd_tcgen05_cross_attention_with_key_padding(ops):
+    """BLIP shapes: text queries (100) over image keys (197), and BERT self-attention with a key-padding mask;
+    q / k / v are column slices of packed projections (row stride != 64 H)."""
+    g = torch.Generator().manual_seed(5)
+    B, Sq, Skv, H = 3, 100, 197, 12
+    q = (torch.randn(B * Sq, H * 64, generator=g)).bfloat16().to(dev)
+    kv = (torch.randn(B * Skv, 2 * H * 64, generator=g)).bfloat16().to(dev)
+    qkv = (torch.randn(B * Sq, 3 * H * 64, generator=g)).bfloat16().to(dev)
+    kvl = torch.tensor([100, 17, 1], dtype=torch.int32, device=dev)
+    res = {}
+    for mode in (0, 1):
+        prev = ops.attn_set_mode(mode)
+        try:
+            lse_x = torch.empty(B, H, Sq, device=dev); lse_s = torch.empty(B, H, Sq, device=dev)
+            ox = ops.attn_fwd_ex(q, kv[:, :H * 64], kv[:, H * 64:], B, Sq, Skv, H, lse=lse_x)
+            os_ = ops.attn_fwd_ex(qkv[:, :H * 64], qkv[:, H * 64:2 * H * 64], qkv[:, 2 * H * 64:], B, Sq, Sq, H, kv_len=kvl, lse=lse_s)
+            torch.cuda.synchronize()
+        finally:
+            ops.attn_set_mode(prev)
+        res[mode] = (ox, lse_x, os_, lse_s)
+    assert rel(res[1][0], res[0][0]) < 6e-3 and (res[1][1] - res[0][1]).abs().max() < 1e-3
+    assert rel(res[1][2], res[0][2]) < 6e-3 and (res[1][3] - res[0][3]).abs().max() < 1e-3
+    # and against fp32 for the cross-attention case
+    qf = q.float().cpu().view(B, Sq, H, 64).transpose(1, 2); kf = kv[:, :H * 64].float().cpu().view(B, Skv, H, 64).transpose(1, 2)
+    vf = kv[:, H * 64:].float().cpu().view(B, Skv, H, 64).transpose(1, 2)
+    ref = ((qf @ kf.transpose(-1, -2) * 0.125).softmax(-1) @ vf).transpose(1, 2).reshape(B * Sq, H * 64)
+    assert rel(res[1][0], ref) < 6e-3
 
 
 def test_adamw_matches_torch(ops):

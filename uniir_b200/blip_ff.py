@@ -271,9 +271,9 @@ class BLIPEncoder:
             a = self.acts[i]
             # ---- FFN: h3 = LN(dense2(gelu(dense1(h2))) + h2)
             ops.layernorm_bwd(self.dh, a.t3, a.m3, a.r3, w(f"{l}.output.LayerNorm.weight"), self.dt,
-                              g(f"{l}.output.LayerNorm.weight"), g(f"{l}.output.LayerNorm.bias"), accumulate=False, dx_bf16=self.dtb)
+                              g(f"{l}.output.LayerNorm.weight"), g(f"{l}.output.LayerNorm.bias"), accumulate=False, dx_bf16=self.dtb,
+                              dcolsum=g(f"{l}.output.dense.bias"))
             ops.wgrad(self.dtb, a.act, g(f"{l}.output.dense.weight"))
-            ops.colsum_accum(self.dtb, g(f"{l}.output.dense.bias"))
             ops.gemm(self.dtb, w16(f"{l}.output.dense.weight"), b_mn=True, act=L.ACT_GELU, act_grad_src=a.pre, out=self.d_pre)
             ops.wgrad(self.d_pre, a.h2b, g(f"{l}.intermediate.dense.weight"))
             ops.colsum_accum(self.d_pre, g(f"{l}.intermediate.dense.bias"))
@@ -281,9 +281,9 @@ class BLIPEncoder:
             # ---- cross-attention: h2 = LN(dense(attn(q(h1), kv(img))) + h1)
             ops.layernorm_bwd(self.dh, a.t2, a.m2, a.r2, w(f"{l}.crossattention.output.LayerNorm.weight"), self.dt,
                               g(f"{l}.crossattention.output.LayerNorm.weight"), g(f"{l}.crossattention.output.LayerNorm.bias"),
-                              accumulate=False, dx_bf16=self.dtb)
+                              accumulate=False, dx_bf16=self.dtb,
+                              dcolsum=g(f"{l}.crossattention.output.dense.bias"))
             ops.wgrad(self.dtb, a.ctx2, g(f"{l}.crossattention.output.dense.weight"))
-            ops.colsum_accum(self.dtb, g(f"{l}.crossattention.output.dense.bias"))
             ops.gemm(self.dtb, w16(f"{l}.crossattention.output.dense.weight"), b_mn=True, out=self.d_ctx)
             ops.attn_bwd_ex(a.q2, a.kv2[:, :H], a.kv2[:, H:], a.ctx2, self.d_ctx, a.lse2, mb, S, Sv, nh,
                             self.dq2, self.dkv2[:, :H], self.dkv2[:, H:], delta=self.delta)
@@ -297,9 +297,9 @@ class BLIPEncoder:
             # ---- self-attention: h1 = LN(dense(attn(qkv(h_in))) + h_in)
             ops.layernorm_bwd(self.dh, a.t1, a.m1, a.r1, w(f"{l}.attention.output.LayerNorm.weight"), self.dt,
                               g(f"{l}.attention.output.LayerNorm.weight"), g(f"{l}.attention.output.LayerNorm.bias"),
-                              accumulate=False, dx_bf16=self.dtb)
+                              accumulate=False, dx_bf16=self.dtb,
+                              dcolsum=g(f"{l}.attention.output.dense.bias"))
             ops.wgrad(self.dtb, a.ctx1, g(f"{l}.attention.output.dense.weight"))
-            ops.colsum_accum(self.dtb, g(f"{l}.attention.output.dense.bias"))
             ops.gemm(self.dtb, w16(f"{l}.attention.output.dense.weight"), b_mn=True, out=self.d_ctx)
             ops.attn_bwd_ex(a.qkv[:, :H], a.qkv[:, H:2 * H], a.qkv[:, 2 * H:], a.ctx1, self.d_ctx, a.lse1, mb, S, S, nh,
                             self.dqkv[:, :H], self.dqkv[:, H:2 * H], self.dqkv[:, 2 * H:], kv_len=self.att_len, delta=self.delta)
@@ -313,8 +313,9 @@ class BLIPEncoder:
                            g(f"{t}.embeddings.position_embeddings.weight")[:S])
         # ---- ViT: img_tok = LN_final(blocks(patch-embed(img)))
         ops.layernorm_bwd(self.d_img, self.vis.x_out, self.vn_m, self.vn_r, w(f"{v}.norm.weight"), self.vis.dx,
-                          g(f"{v}.norm.weight"), g(f"{v}.norm.bias"), accumulate=False, dx_bf16=self.vis.dxb)
-        self.vis.backward()
+                          g(f"{v}.norm.weight"), g(f"{v}.norm.bias"), accumulate=False, dx_bf16=self.vis.dxb,
+                          dcolsum=self.vis.top_bias_grad())
+        self.vis.backward(top_bias_done=True)
         ops.vision_embed_bwd(self.vis.dx.view(mb, Sv, d.v_width), mb, Sv, d.v_width, self.d_patch,
                              g(f"{v}.cls_token").view(-1), g(f"{v}.pos_embed").view(Sv, d.v_width))
         ops.wgrad(self.d_patch, self.col, g(f"{v}.patch_embed.proj.weight").view(d.v_width, -1))

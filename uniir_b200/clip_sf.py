@@ -74,6 +74,7 @@ class CLIPScoreFusion(nn.Module):
             self.in_batch_neg_num = config.data_config.in_batch_neg_num
         self.micro_batch = micro_batch
         self.use_cuda_graphs = True
+        self.skip_masked_towers = True   # rows with mask 0 never enter that tower (same result)
         self._enc = {}
         self._nce = None
         self._train_state = None
@@ -164,8 +165,19 @@ class CLIPScoreFusion(nn.Module):
         self.clip_model.refresh_shadow()
         enc.refresh_weights()
 
+    def _mask_plan(self, mt, mv):
+        """None when every item has both modalities (the fused two-tower pass runs); otherwise the batch
+        rows each tower has to encode, as int32 device tensors.  Costs one small device->host read."""
+        if not self.skip_masked_towers:
+            return None
+        nz = torch.stack([mt != 0, mv != 0])
+        if bool(nz.all()):
+            return None
+        return (nz[0].nonzero().flatten().to(torch.int32).contiguous(),
+                nz[1].nonzero().flatten().to(torch.int32).contiguous())
+
     def _embed_into(self, emb, txt, img, mt, mv, enc=None):
-        """Forward (no activations saved) in micro-batches; the tail chunk is padded."""
+        """Forward (no activations saved) in micro-batches; the tail chunk is padded.  Returns the mask plan."""
         n = txt.shape[0]
         txt, img = self._prep(txt, img)
         mt = mt.to(self.device_, torch.int64).contiguous()
@@ -173,10 +185,21 @@ class CLIPScoreFusion(nn.Module):
         mb = self._pick_mb(n, False) if enc is None else enc.mb
         enc = enc or self._encoder(mb, False)
         self._sync_weights(enc)
-        for s in range(0, n, mb):
-            e = min(n, s + mb)  # a ragged tail is zero-padded inside set_inputs; padded rows are dropped
-            enc.set_inputs(txt[s:e], img[s:e], mt[s:e], mv[s:e])
-            emb[s:e].copy_(enc.embed(self.use_cuda_graphs)[:e - s])
+        plan = self._mask_plan(mt, mv)
+        if plan is None:
+            for s in range(0, n, mb):
+                e = min(n, s + mb)  # a ragged tail is zero-padded inside set_inputs; padded rows are dropped
+                enc.set_inputs(txt[s:e], img[s:e], mt[s:e], mv[s:e])
+                emb[s:e].copy_(enc.embed(self.use_cuda_graphs)[:e - s])
+            return None
+        # each tower encodes only its unmasked rows; out = mt * text + mv * image is scattered back
+        emb.zero_()
+        for tower, rows, src, mask in (("text", plan[0], txt, mt), ("vision", plan[1], img, mv)):
+            for s in range(0, rows.numel(), mb):
+                r = rows[s:s + mb]
+                enc.set_tower_input(tower, src, r)
+                ops.score_fuse_scatter(enc.run_tower(tower, False, self.use_cuda_graphs), r, mask, emb)
+        return plan
 
     def _world(self):
         if getattr(self, "gather_embeddings", False):
@@ -210,7 +233,7 @@ class CLIPScoreFusion(nn.Module):
         st["mt"] = batch["txt_mask_batched"].to(dev, torch.int64).contiguous()
         st["mv"] = batch["image_mask_batched"].to(dev, torch.int64).contiguous()
         emb = torch.empty(n_items, E, device=dev, dtype=torch.float32)
-        self._embed_into(emb, st["txt"], st["img"], st["mt"], st["mv"], enc=enc)
+        st["plan"] = self._embed_into(emb, st["txt"], st["img"], st["mt"], st["mv"], enc=enc)
         if "neg_cand_list" in im:   # hard-negative branch (clip_sf.py:105-131): no gather, fused fwd+bwd
             n_idx = torch.tensor(im["neg_cand_list"], dtype=torch.int32).to(dev).contiguous()
             P = self.clip_model
@@ -253,8 +276,20 @@ class CLIPScoreFusion(nn.Module):
             d_emb = torch.zeros(st["n_items"], E, device=self.device_, dtype=torch.float32)
             nce.normalize_bwd(st["q_idx"], st["p_idx"], d_pn, d_emb, off)
         mb = enc.mb
-        for s in range(0, st["n_items"], mb):
-            e = s + mb
-            enc.set_inputs(st["txt"][s:e], st["img"][s:e], st["mt"][s:e], st["mv"][s:e], d_emb[s:e])
-            enc.fwdbwd(self.use_cuda_graphs)
+        if st["plan"] is None:
+            for s in range(0, st["n_items"], mb):
+                e = s + mb
+                enc.set_inputs(st["txt"][s:e], st["img"][s:e], st["mt"][s:e], st["mv"][s:e], d_emb[s:e])
+                enc.fwdbwd(self.use_cuda_graphs)
+        else:
+            # masked towers skipped: per tower, re-forward + backward over its compacted rows; the rows that
+            # pad the last micro-batch carry a zero output gradient, so they add nothing to any parameter
+            d_emb = d_emb.contiguous()
+            for tower, rows, src, mask, d_in in (("text", st["plan"][0], st["txt"], st["mt"], enc.d_t),
+                                                 ("vision", st["plan"][1], st["img"], st["mv"], enc.d_v)):
+                for s in range(0, rows.numel(), mb):
+                    r = rows[s:s + mb]
+                    enc.set_tower_input(tower, src, r)
+                    ops.score_fuse_gather_bwd(d_emb, r, mask, out=d_in)
+                    enc.run_tower(tower, True, self.use_cuda_graphs)
         self._train_state = None

@@ -121,8 +121,16 @@ class Tower:
             ops.gemm(act, w16(n("mlp.c_proj.weight")), bias=w(n("mlp.c_proj.bias")), residual=x_mid, out=x_out)
         return self.x_out if save else self.x
 
-    # ---- backward: self.dx holds dL/dx_out on entry, dL/dx_in on exit; self.dxb = bf16(self.dx)
-    def backward(self):
+    def top_bias_grad(self):
+        """Gradient buffer of the last block's c_proj bias: pass it as `dcolsum` to the LayerNorm backward
+        that produces this tower's incoming dx / dxb and call backward(top_bias_done=True)."""
+        return self.P.g(self._n(self.nl - 1, "mlp.c_proj.bias"))
+
+    # ---- backward: self.dx holds dL/dx_out on entry, dL/dx_in on exit; self.dxb = bf16(self.dx).
+    # The bias gradients of out_proj / c_proj are the column sums of the residual-stream gradient;
+    # the LayerNorm backward that produces that gradient emits them (dcolsum), so only the wide
+    # d_pre / d_qkv matrices need a separate column-sum pass.
+    def backward(self, top_bias_done=False):
         P, dx, dxb, B, S, H = self.P, self.dx, self.dxb, self.mb, self.S, self.H
         for i in reversed(range(self.nl)):
             a = self.acts[i]
@@ -130,24 +138,25 @@ class Tower:
             w16 = lambda leaf: P.w16(self._n(i, leaf))
             # ---- MLP branch: x_out = x_mid + c_proj(quickgelu(c_fc(ln_2(x_mid))))
             ops.wgrad(dxb, a.act, g("mlp.c_proj.weight"))
-            ops.colsum_accum(dxb, g("mlp.c_proj.bias"))
+            if i == self.nl - 1 and not top_bias_done:
+                ops.colsum_accum(dxb, g("mlp.c_proj.bias"))
             ops.gemm(dxb, w16("mlp.c_proj.weight"), b_mn=True, act=self.act, act_grad_src=a.pre,
                      out=self.d_big)
             ops.wgrad(self.d_big, a.h2, g("mlp.c_fc.weight"))
             ops.colsum_accum(self.d_big, g("mlp.c_fc.bias"))
             ops.gemm(self.d_big, w16("mlp.c_fc.weight"), b_mn=True, out=self.d_h)
             ops.layernorm_bwd(self.d_h, a.x_mid, a.m2, a.r2, P.w(self._n(i, "ln_2.weight")), dx,
-                              g("ln_2.weight"), g("ln_2.bias"), dx_bf16=dxb)
+                              g("ln_2.weight"), g("ln_2.bias"), dx_bf16=dxb, dcolsum=g("attn.out_proj.bias"))
             # ---- attention branch: x_mid = x_in + out_proj(attn(in_proj(ln_1(x_in))))
             ops.wgrad(dxb, a.att, g("attn.out_proj.weight"))
-            ops.colsum_accum(dxb, g("attn.out_proj.bias"))
             ops.gemm(dxb, w16("attn.out_proj.weight"), b_mn=True, out=self.d_h)
             ops.attn_bwd(a.qkv, a.att, self.d_h, a.lse, B, S, H, self.causal, dqkv=self.dqkv, delta=self.delta)
             ops.wgrad(self.dqkv, a.h1, g("attn.in_proj_weight"))
             ops.colsum_accum(self.dqkv, g("attn.in_proj_bias"))
             ops.gemm(self.dqkv, w16("attn.in_proj_weight"), b_mn=True, out=self.d_h)
             ops.layernorm_bwd(self.d_h, a.x_in, a.m1, a.r1, P.w(self._n(i, "ln_1.weight")), dx,
-                              g("ln_1.weight"), g("ln_1.bias"), dx_bf16=dxb)
+                              g("ln_1.weight"), g("ln_1.bias"), dx_bf16=dxb,
+                              dcolsum=(P.g(self._n(i - 1, "mlp.c_proj.bias")) if i > 0 else None))
 
 
 class CLIPEncoder:
@@ -257,8 +266,9 @@ class CLIPEncoder:
         self.vis.dxb.zero_()
         ops.layernorm_bwd(self.d_pool_v, self.vis.x_out, self.vp_m, self.vp_r, P.w("visual.ln_post.weight"),
                           self.vis.dx, P.g("visual.ln_post.weight"), P.g("visual.ln_post.bias"),
-                          row_index=self.cls_rows, accumulate=False, dx_bf16=self.vis.dxb)
-        self.vis.backward()
+                          row_index=self.cls_rows, accumulate=False, dx_bf16=self.vis.dxb,
+                          dcolsum=self.vis.top_bias_grad())
+        self.vis.backward(top_bias_done=True)
         ops.layernorm_bwd(self.vis.dx, self.x0, self.pre_m, self.pre_r, P.w("visual.ln_pre.weight"),
                           self.dx0, P.g("visual.ln_pre.weight"), P.g("visual.ln_pre.bias"), accumulate=False)
         ops.vision_embed_bwd(self.dx0, mb, d.v_tokens, d.v_width, self.d_patch, P.g("visual.class_embedding"),
@@ -275,8 +285,9 @@ class CLIPEncoder:
         self.txt.dxb.zero_()
         ops.layernorm_bwd(self.d_pool_t, self.txt.x_out, self.tp_m, self.tp_r, P.w("ln_final.weight"),
                           self.txt.dx, P.g("ln_final.weight"), P.g("ln_final.bias"),
-                          row_index=self.eot_rows, accumulate=False, dx_bf16=self.txt.dxb)
-        self.txt.backward()
+                          row_index=self.eot_rows, accumulate=False, dx_bf16=self.txt.dxb,
+                          dcolsum=self.txt.top_bias_grad())
+        self.txt.backward(top_bias_done=True)
         ops.text_embed_bwd(self.txt.dx, self.ids, P.g("token_embedding.weight"), P.g("positional_embedding"))
 
     # ---- backward from d t_emb / d v_emb (bf16 [mb, E]); accumulates into P.grad -----
@@ -296,6 +307,40 @@ class CLIPEncoder:
         self.forward(self.in_ids, self.in_img, save=True)
         ops.score_fuse_bwd(self.in_demb, self.in_mt, self.in_mv, out=(self.d_t, self.d_v))
         self.backward(self.d_t, self.d_v)
+
+    # ---- single-tower passes over COMPACTED rows.  The reference encodes "" / a black
+    # image for a missing modality and multiplies the result by its 0 mask (clip_sf.py:53-63); here
+    # the caller hands each tower only the rows whose mask is non-zero. ---------------------------
+    def _body_embed_text(self):
+        self._text_fwd(self.in_ids, save=False)
+
+    def _body_embed_vision(self):
+        self._vision_fwd(self.in_img, save=False)
+
+    def _body_fwdbwd_text(self):
+        self._text_fwd(self.in_ids, save=True)
+        self._text_bwd(self.d_t)
+
+    def _body_fwdbwd_vision(self):
+        self._vision_fwd(self.in_img, save=True)
+        self._vision_bwd(self.d_v)
+
+    def set_tower_input(self, tower, src, rows):
+        """Gather batch rows `rows` (int32, <= mb of them) of the token ids / images into the static input
+        buffer of one tower; the unused tail is zeroed (finite activations, zero gradient)."""
+        buf = self.in_ids if tower == "text" else self.in_img
+        n = rows.numel()
+        torch.index_select(src, 0, rows, out=buf[:n])
+        if n < self.mb:
+            buf[n:].zero_()
+
+    def run_tower(self, tower, train, use_graph=True):
+        """train=False: forward -> fp32 [mb, E] embedding of that tower.  train=True: forward with saved
+        activations + backward from self.d_t / self.d_v (bf16 [mb, E], set by the caller)."""
+        body = {("text", False): self._body_embed_text, ("vision", False): self._body_embed_vision,
+                ("text", True): self._body_fwdbwd_text, ("vision", True): self._body_fwdbwd_vision}[(tower, train)]
+        self._run(f"{'fwdbwd' if train else 'embed'}_{tower}", body, use_graph)
+        return self.t_emb if tower == "text" else self.v_emb
 
     def _run(self, key, body, use_graph):
         """First call runs eagerly (sets kernel attributes, warms allocators), second call

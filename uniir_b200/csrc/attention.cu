@@ -532,7 +532,17 @@ static int attn_set_smem() {
   return UNIIR_OK;
 }
 
+namespace uniir {
+int attn_fwd_tc_try(const __nv_bfloat16* q, long long ldq, const __nv_bfloat16* k, const __nv_bfloat16* v,
+                    long long ldkv, int B, int Sq, int Skv, int H, int causal, const int* kv_len,
+                    __nv_bfloat16* out, long long ldo, float* lse, float scale, void* stream);   // attention_tc.cu
+}
+
 static int attn_fwd_launch(AttnParams& p, void* stream) {
+  // tcgen05 forward (attention_tc.cu) when enabled and the key range fits; > 0 means "not applicable"
+  const int tc = attn_fwd_tc_try(p.q, p.ldq, p.k, p.v, p.ldkv, p.B, p.Sq, p.Skv, p.H, p.causal, p.kv_len, p.out,
+                                 p.ldo, p.lse, p.scale, stream);
+  if (tc <= 0) return tc;
   UNIIR_CHECK_ARG(p.Skv <= 768, "uniir_attn_fwd: Skv=%d exceeds the head-resident kernel's limit of 768", p.Skv);
   if (int rc = attn_set_smem()) return rc;
   const int spad = (p.Skv + 15) / 16 * 16;

@@ -175,6 +175,163 @@ __global__ void layernorm_bwd_kernel(const void* __restrict__ dy, long long lddy
 }
 
 // ---------------------------------------------------------------------------------
+// Warp-per-row LayerNorm (D <= 1024): the row lives in the registers of one warp (NV float4
+// per lane, lane-interleaved so every access is a full 512 B line group), statistics by warp
+// shuffles only -- no __syncthreads, no shared memory; several rows per CTA and ~10 KB per
+// warp in flight keep HBM busy.  Same arithmetic as the CTA-per-row kernels above (two-pass
+// centred variance in fp32), which remain the path for wider rows.
+// ---------------------------------------------------------------------------------
+constexpr int kLnWarpsFwd = 4;
+template <int NV>
+__global__ void __launch_bounds__(kLnWarpsFwd * 32)
+layernorm_fwd_warp_kernel(const float* __restrict__ x, long long ldx, const int* __restrict__ row_index,
+                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                          int D, long long rows, void* __restrict__ y, long long ldy, int y_f32,
+                          float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const long long r = static_cast<long long>(blockIdx.x) * kLnWarpsFwd + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const long long src = row_index ? row_index[r] : r;
+  const float* xr = x + src * ldx;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + i * 32) * 4;
+    v[i] = (c < D) ? __ldcs(reinterpret_cast<const float4*>(xr + c)) : make_float4(0, 0, 0, 0);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + i * 32) * 4;
+    if (c < D) {
+      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (cc * cc + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / D + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[r] = mean;
+    if (rstd_out) rstd_out[r] = rstd;
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + i * 32) * 4;
+    if (c < D) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+      const float o0 = (v[i].x - mean) * rstd * g.x + b.x, o1 = (v[i].y - mean) * rstd * g.y + b.y;
+      const float o2 = (v[i].z - mean) * rstd * g.z + b.z, o3 = (v[i].w - mean) * rstd * g.w + b.w;
+      if (y_f32)
+        *reinterpret_cast<float4*>(static_cast<float*>(y) + r * ldy + c) = make_float4(o0, o1, o2, o3);
+      else
+        *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(y) + r * ldy + c) = pack4_bf16(o0, o1, o2, o3);
+    }
+  }
+}
+
+// Backward, warp per row, 8 warps per CTA, each warp walking rows r0+w, r0+w+8, ... of the
+// CTA's strip.  dgamma / dbeta (and, when `dcolsum` is given, the column sums of the UPDATED dx
+// -- the bias gradient of the linear layer whose output gradient this dx is, which saves a
+// separate pass over dx) accumulate per lane in registers, are reduced over the CTA's warps
+// through shared memory and leave with one atomicAdd per column per CTA.
+constexpr int kLnWarpsBwd = 8;
+template <int NV, bool COLSUM, bool DY_F32>
+__global__ void __launch_bounds__(kLnWarpsBwd * 32)
+layernorm_bwd_warp_kernel(const void* __restrict__ dy, long long lddy,
+                          const float* __restrict__ x, long long ldx, const int* __restrict__ row_index,
+                          const float* __restrict__ mean, const float* __restrict__ rstd,
+                          const float* __restrict__ gamma, int D, long long rows, int rows_per_cta,
+                          float* __restrict__ dx, long long lddx, int dx_accumulate,
+                          float* __restrict__ dgamma, float* __restrict__ dbeta,
+                          __nv_bfloat16* __restrict__ dx16, float* __restrict__ dcolsum) {
+  __shared__ float4 red[kLnWarpsBwd][NV * 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float4 dg[NV], db[NV], dc[COLSUM ? NV : 1];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    dg[i] = db[i] = make_float4(0, 0, 0, 0);
+    if (COLSUM) dc[i] = make_float4(0, 0, 0, 0);
+  }
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  const long long r1 = min(rows, r0 + rows_per_cta);
+  for (long long r = r0 + w; r < r1; r += kLnWarpsBwd) {
+    const long long src = row_index ? row_index[r] : r;
+    const float mu = mean[r], rs = rstd[r];
+    float4 xh[NV], d[NV], old[NV];
+    uint2 raw[DY_F32 ? 1 : NV];
+    // Issue EVERY load of the row before the first use: nothing in this loop may consume a loaded
+    // value (ncu showed the bf16 unpack placed here serialising the row into NV memory round trips).
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + i * 32) * 4;
+      if (c < D) {
+        xh[i] = __ldcs(reinterpret_cast<const float4*>(x + src * ldx + c));
+        if (DY_F32) d[i] = __ldcs(reinterpret_cast<const float4*>(static_cast<const float*>(dy) + r * lddy + c));
+        else raw[DY_F32 ? 0 : i] = __ldcs(reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(dy) + r * lddy + c));
+        if (dx_accumulate) old[i] = *reinterpret_cast<const float4*>(dx + src * lddx + c);
+      }
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + i * 32) * 4;
+      if (c < D) {
+        if (!DY_F32) d[i] = unpack4_bf16(raw[DY_F32 ? 0 : i]);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));   // 4 KB, L1-resident
+        xh[i] = make_float4((xh[i].x - mu) * rs, (xh[i].y - mu) * rs, (xh[i].z - mu) * rs, (xh[i].w - mu) * rs);
+        dg[i].x += d[i].x * xh[i].x; dg[i].y += d[i].y * xh[i].y;
+        dg[i].z += d[i].z * xh[i].z; dg[i].w += d[i].w * xh[i].w;
+        db[i].x += d[i].x; db[i].y += d[i].y; db[i].z += d[i].z; db[i].w += d[i].w;
+        d[i] = make_float4(d[i].x * g.x, d[i].y * g.y, d[i].z * g.z, d[i].w * g.w);   // from here on: g * dy
+        s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
+        s2 += (d[i].x * xh[i].x + d[i].y * xh[i].y) + (d[i].z * xh[i].z + d[i].w * xh[i].w);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {   // the two reductions share the shuffle latency
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float m1 = s1 / D, m2 = s2 / D;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + i * 32) * 4;
+      if (c < D) {
+        float4 o;
+        o.x = rs * (d[i].x - m1 - xh[i].x * m2);
+        o.y = rs * (d[i].y - m1 - xh[i].y * m2);
+        o.z = rs * (d[i].z - m1 - xh[i].z * m2);
+        o.w = rs * (d[i].w - m1 - xh[i].w * m2);
+        if (dx_accumulate) { o.x += old[i].x; o.y += old[i].y; o.z += old[i].z; o.w += old[i].w; }
+        *reinterpret_cast<float4*>(dx + src * lddx + c) = o;
+        if (dx16) *reinterpret_cast<uint2*>(dx16 + src * lddx + c) = pack4_bf16(o.x, o.y, o.z, o.w);
+        if (COLSUM) { dc[i].x += o.x; dc[i].y += o.y; dc[i].z += o.z; dc[i].w += o.w; }
+      }
+    }
+  }
+  // CTA reduction of the column sums: [warp][column-vector] in shared memory, one output at a time
+  float* outs[3] = {dgamma, dbeta, dcolsum};
+#pragma unroll
+  for (int which = 0; which < (COLSUM ? 3 : 2); ++which) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[w][lane + i * 32] = which == 0 ? dg[i] : (which == 1 ? db[i] : dc[COLSUM ? i : 0]);
+    __syncthreads();
+    const float* rf = reinterpret_cast<const float*>(&red[0][0]);
+    for (int col = threadIdx.x; col < D; col += kLnWarpsBwd * 32) {
+      // column `col` sits in vector (col/4) at lane-interleaved slot: c = (lane + 32 i)*4 -> slot = c/4
+      float t = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < kLnWarpsBwd; ++ww) t += rf[(ww * NV * 32 + (col >> 2)) * 4 + (col & 3)];
+      atomicAdd(outs[which] + col, t);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
 // im2col for the stride=patch conv: img fp32 [B,3,H,W] -> bf16 [B*g*g, Kpad],
 // k = c*P*P + py*P + px (conv weight [out, c, py, px] flattened), zero padded to Kpad.
 // ---------------------------------------------------------------------------------
@@ -288,6 +445,32 @@ __global__ void fuse_bwd_kernel(const float* __restrict__ d, const long long* __
   dv[i] = __float2bfloat16(d[i] * static_cast<float>(mv[r]));
 }
 
+// Score fusion over COMPACTED rows (masked towers are skipped: a text-only item never enters the
+// image tower).  `rows[r]` is the batch row that compact row r came from:
+//   scatter:  out[rows[r], :] += mask[rows[r]] * emb[r, :]            (clip_sf.py:61-63, one tower's term)
+//   gather :  d[r, :] = bf16(mask[rows[r]] * d_out[rows[r], :])  for r < n, 0 for n <= r < n_pad
+__global__ void fuse_scatter_kernel(const float* __restrict__ emb, const int* __restrict__ rows,
+                                    const long long* __restrict__ mask, int n, int E, float* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(n) * E) return;
+  const int r = static_cast<int>(i / E), c = static_cast<int>(i % E);
+  const long long dst = rows[r];
+  out[dst * E + c] += static_cast<float>(mask[dst]) * emb[i];
+}
+__global__ void fuse_gather_bwd_kernel(const float* __restrict__ d_out, const int* __restrict__ rows,
+                                       const long long* __restrict__ mask, int n, int n_pad, int E,
+                                       __nv_bfloat16* __restrict__ d) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(n_pad) * E) return;
+  const int r = static_cast<int>(i / E), c = static_cast<int>(i % E);
+  float v = 0.f;
+  if (r < n) {
+    const long long src = rows[r];
+    v = static_cast<float>(mask[src]) * d_out[src * E + c];
+  }
+  d[i] = __float2bfloat16(v);
+}
+
 // bias gradient: out[n] += sum_m dy[m, n]; CTA = 64 columns x a strip of rows
 __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ dy, long long M, int N, long long ld,
                               int rows_per_cta, float* __restrict__ out) {
@@ -302,6 +485,53 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ dy, long long M,
   sh[sub][threadIdx.x & 63] = acc;
   __syncthreads();
   if (sub == 0 && col < N) atomicAdd(out + col, sh[0][threadIdx.x] + sh[1][threadIdx.x] + sh[2][threadIdx.x] + sh[3][threadIdx.x]);
+}
+
+// 128-bit version (N, ld multiples of 8, 16 B-aligned base): a warp reads 512 contiguous bytes of a
+// row (256 columns, 8 per lane), the CTA's 8 warps take rows r0+w, r0+w+8, ... of the strip four at
+// a time, partial sums meet in shared memory, one atomicAdd per column per CTA.
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const __nv_bfloat16* __restrict__ dy, long long M, int N, long long ld, int rows_per_cta,
+                  float* __restrict__ out) {
+  __shared__ float sh[8][256 + 8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col0 = blockIdx.x * 256 + lane * 8;
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_cta;
+  const long long r1 = min(M, r0 + rows_per_cta);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (col0 < N) {
+    const __nv_bfloat16* base = dy + col0;
+    long long r = r0 + w;
+    for (; r + 24 < r1; r += 32) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = __ldcs(reinterpret_cast<const uint4*>(base + (r + 8 * k) * ld));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 lo = unpack4_bf16(make_uint2(u[k].x, u[k].y)), hi = unpack4_bf16(make_uint2(u[k].z, u[k].w));
+        acc[0] += lo.x; acc[1] += lo.y; acc[2] += lo.z; acc[3] += lo.w;
+        acc[4] += hi.x; acc[5] += hi.y; acc[6] += hi.z; acc[7] += hi.w;
+      }
+    }
+    for (; r < r1; r += 8) {
+      const uint4 u = __ldcs(reinterpret_cast<const uint4*>(base + r * ld));
+      const float4 lo = unpack4_bf16(make_uint2(u.x, u.y)), hi = unpack4_bf16(make_uint2(u.z, u.w));
+      acc[0] += lo.x; acc[1] += lo.y; acc[2] += lo.z; acc[3] += lo.w;
+      acc[4] += hi.x; acc[5] += hi.y; acc[6] += hi.z; acc[7] += hi.w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[w][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) t += sh[ww][threadIdx.x];
+    atomicAdd(out + col, t);
+  }
 }
 
 // fp32 [rows, K] -> bf16 [rows, Kpad] (zero pad); and the reverse accumulate for its gradient
@@ -421,12 +651,22 @@ extern "C" int uniir_layernorm_fwd(const float* x, int64_t ldx, const int32_t* r
                   "uniir_layernorm_fwd: bad args (D=%d must be a multiple of 4, <= 4096)", D);
   UNIIR_CHECK_ARG(y_dtype == UNIIR_BF16 || y_dtype == UNIIR_F32, "uniir_layernorm_fwd: y dtype");
   if (rows == 0) return UNIIR_OK;
-  const int threads = 256;
-  const int vecs = (D / 4 + threads - 1) / threads;
   const int f32 = y_dtype == UNIIR_F32;
+  if (D <= 1024) {
+    // warp per row
+    const int nv = (D + 127) / 128;
+    const unsigned grid = static_cast<unsigned>((rows + kLnWarpsFwd - 1) / kLnWarpsFwd);
+#define LN_FWD_W(V) layernorm_fwd_warp_kernel<V><<<grid, kLnWarpsFwd * 32, 0, ST(stream)>>>(x, ldx, row_index, gamma, beta, eps, D, rows, y, ldy, f32, mean, rstd)
+    if (nv <= 1) LN_FWD_W(1); else if (nv <= 2) LN_FWD_W(2); else if (nv <= 4) LN_FWD_W(4);
+    else if (nv <= 6) LN_FWD_W(6); else LN_FWD_W(8);
+#undef LN_FWD_W
+  } else {
+    const int threads = 256;
+    const int vecs = (D / 4 + threads - 1) / threads;
 #define LN_FWD(V) layernorm_fwd_kernel<V><<<(unsigned)rows, threads, 0, ST(stream)>>>(x, ldx, row_index, gamma, beta, eps, D, y, ldy, f32, mean, rstd)
-  if (vecs <= 1) LN_FWD(1); else if (vecs <= 2) LN_FWD(2); else LN_FWD(4);
+    if (vecs <= 2) LN_FWD(2); else LN_FWD(4);
 #undef LN_FWD
+  }
   count_launch();
   UNIIR_CUDA_OK(cudaGetLastError());
   return UNIIR_OK;
@@ -436,22 +676,52 @@ extern "C" int uniir_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_dtyp
                                    int64_t ldx, const int32_t* row_index, const float* mean,
                                    const float* rstd, const float* gamma, int64_t rows, int32_t D,
                                    float* dx, int64_t lddx, int32_t dx_accumulate, float* dgamma,
-                                   float* dbeta, void* dx_bf16, void* stream) {
+                                   float* dbeta, void* dx_bf16, float* dcolsum, void* stream) {
   UNIIR_CHECK_ARG(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && D > 0 && D % 4 == 0 && D <= 4096,
                   "uniir_layernorm_bwd: bad args");
   if (rows == 0) return UNIIR_OK;
-  const int threads = 256;
-  const int vecs = (D / 4 + threads - 1) / threads;
-  // ~4 CTAs per SM keeps the dgamma/dbeta atomics to a few thousand per column
-  long long ctas = 4LL * num_sms();
-  int rpc = static_cast<int>((rows + ctas - 1) / ctas);
-  if (rpc < 1) rpc = 1;
-  const unsigned grid = static_cast<unsigned>((rows + rpc - 1) / rpc);
   const int f32 = dy_dtype == UNIIR_F32;
-#define LN_BWD(V) layernorm_bwd_kernel<V><<<grid, threads, 0, ST(stream)>>>(dy, lddy, f32, x, ldx, row_index, mean, rstd, gamma, D, rows, rpc, dx, lddx, dx_accumulate, dgamma, dbeta, static_cast<__nv_bfloat16*>(dx_bf16))
-  if (vecs <= 1) LN_BWD(1); else if (vecs <= 2) LN_BWD(2); else LN_BWD(4);
+  __nv_bfloat16* dx16 = static_cast<__nv_bfloat16*>(dx_bf16);
+  if (D <= 1024) {
+    // warp per row; 2 CTAs of 8 warps per SM-worth of strips keeps the atomics at ~300 per column
+    long long ctas = 2LL * num_sms();
+    long long rpc = (rows + ctas - 1) / ctas;
+    rpc = (rpc + kLnWarpsBwd - 1) / kLnWarpsBwd * kLnWarpsBwd;
+    const unsigned grid = static_cast<unsigned>((rows + rpc - 1) / rpc);
+    const int nv = (D + 127) / 128;
+#define LN_BWD_L(V, C, F)                                                                                    \
+  layernorm_bwd_warp_kernel<V, C, F><<<grid, kLnWarpsBwd * 32, 0, ST(stream)>>>(                             \
+      dy, lddy, x, ldx, row_index, mean, rstd, gamma, D, rows, (int)rpc, dx, lddx, dx_accumulate, dgamma,    \
+      dbeta, dx16, dcolsum)
+#define LN_BWD_W(V)                                                                                          \
+  do {                                                                                                       \
+    if (dcolsum) { if (f32) LN_BWD_L(V, true, true); else LN_BWD_L(V, true, false); }                        \
+    else         { if (f32) LN_BWD_L(V, false, true); else LN_BWD_L(V, false, false); }                      \
+  } while (0)
+    if (nv <= 1) LN_BWD_W(1); else if (nv <= 2) LN_BWD_W(2); else if (nv <= 4) LN_BWD_W(4);
+    else if (nv <= 6) LN_BWD_W(6); else LN_BWD_W(8);
+#undef LN_BWD_W
+#undef LN_BWD_L
+    count_launch();
+  } else {
+    const int threads = 256;
+    const int vecs = (D / 4 + threads - 1) / threads;
+    // ~4 CTAs per SM keeps the dgamma/dbeta atomics to a few thousand per column
+    long long ctas = 4LL * num_sms();
+    int rpc = static_cast<int>((rows + ctas - 1) / ctas);
+    if (rpc < 1) rpc = 1;
+    const unsigned grid = static_cast<unsigned>((rows + rpc - 1) / rpc);
+#define LN_BWD(V) layernorm_bwd_kernel<V><<<grid, threads, 0, ST(stream)>>>(dy, lddy, f32, x, ldx, row_index, mean, rstd, gamma, D, rows, rpc, dx, lddx, dx_accumulate, dgamma, dbeta, dx16)
+    if (vecs <= 2) LN_BWD(2); else LN_BWD(4);
 #undef LN_BWD
-  count_launch();
+    count_launch();
+    if (dcolsum) {
+      // wide rows: the column sums of the updated dx take the separate pass
+      UNIIR_CHECK_ARG(row_index == nullptr && dx16, "uniir_layernorm_bwd: dcolsum with D > 1024 needs dx_bf16 and no row_index");
+      const int r = uniir_colsum_accum(dx16, rows, D, lddx, dcolsum, stream);
+      if (r != UNIIR_OK) return r;
+    }
+  }
   UNIIR_CUDA_OK(cudaGetLastError());
   return UNIIR_OK;
 }
@@ -524,12 +794,43 @@ extern "C" int uniir_score_fuse_bwd(const float* d, const int64_t* mt, const int
   UNIIR_CUDA_OK(cudaGetLastError());
   return UNIIR_OK;
 }
+extern "C" int uniir_score_fuse_scatter(const float* emb, const int32_t* rows, const int64_t* mask, int32_t n,
+                                        int32_t E, float* out, void* stream) {
+  UNIIR_CHECK_ARG(emb && rows && mask && out && n >= 0 && E > 0, "uniir_score_fuse_scatter: bad args");
+  if (n == 0) return UNIIR_OK;
+  const long long t = static_cast<long long>(n) * E;
+  fuse_scatter_kernel<<<(unsigned)((t + 255) / 256), 256, 0, ST(stream)>>>(emb, rows, reinterpret_cast<const long long*>(mask), n, E, out);
+  count_launch();
+  UNIIR_CUDA_OK(cudaGetLastError());
+  return UNIIR_OK;
+}
+extern "C" int uniir_score_fuse_gather_bwd(const float* d_out, const int32_t* rows, const int64_t* mask, int32_t n,
+                                           int32_t n_pad, int32_t E, void* d_bf16, void* stream) {
+  UNIIR_CHECK_ARG(d_out && rows && mask && d_bf16 && n >= 0 && n_pad >= n && E > 0, "uniir_score_fuse_gather_bwd: bad args");
+  if (n_pad == 0) return UNIIR_OK;
+  const long long t = static_cast<long long>(n_pad) * E;
+  fuse_gather_bwd_kernel<<<(unsigned)((t + 255) / 256), 256, 0, ST(stream)>>>(
+      d_out, rows, reinterpret_cast<const long long*>(mask), n, n_pad, E, static_cast<__nv_bfloat16*>(d_bf16));
+  count_launch();
+  UNIIR_CUDA_OK(cudaGetLastError());
+  return UNIIR_OK;
+}
 extern "C" int uniir_colsum_accum(const void* dy, int64_t M, int32_t N, int64_t ld, float* out, void* stream) {
   UNIIR_CHECK_ARG(dy && out && M >= 0 && N > 0, "uniir_colsum_accum: bad args");
   if (M == 0) return UNIIR_OK;
-  const int rpc = 512;
-  dim3 grid((N + 63) / 64, static_cast<unsigned>((M + rpc - 1) / rpc));
-  colsum_kernel<<<grid, 256, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(dy), M, N, ld, rpc, out);
+  const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(dy);
+  if (N % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
+    const int nbx = (N + 255) / 256;
+    long long strips = (8LL * num_sms() + nbx - 1) / nbx;
+    long long rpc = (M + strips - 1) / strips;
+    rpc = (rpc + 31) / 32 * 32;
+    dim3 grid(nbx, static_cast<unsigned>((M + rpc - 1) / rpc));
+    colsum_vec_kernel<<<grid, 256, 0, ST(stream)>>>(p, M, N, ld, static_cast<int>(rpc), out);
+  } else {
+    const int rpc = 512;
+    dim3 grid((N + 63) / 64, static_cast<unsigned>((M + rpc - 1) / rpc));
+    colsum_kernel<<<grid, 256, 0, ST(stream)>>>(p, M, N, ld, rpc, out);
+  }
   count_launch();
   UNIIR_CUDA_OK(cudaGetLastError());
   return UNIIR_OK;

@@ -55,7 +55,7 @@ _SIGS = {
                                    C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "uniir_layernorm_fwd": (C.c_int, [VP, I64, VP, VP, VP, C.c_float, I64, I32, VP, I64, I32, VP, VP, VP]),
-    "uniir_layernorm_bwd": (C.c_int, [VP, I64, I32, VP, I64, VP, VP, VP, VP, I64, I32, VP, I64, I32, VP, VP, VP, VP]),
+    "uniir_layernorm_bwd": (C.c_int, [VP, I64, I32, VP, I64, VP, VP, VP, VP, I64, I32, VP, I64, I32, VP, VP, VP, VP, VP]),
     "uniir_patch_im2col": (C.c_int, [VP, I32, I32, I32, I32, I32, VP, VP]),
     "uniir_vision_embed_fwd": (C.c_int, [VP, VP, VP, I32, I32, I32, VP, VP]),
     "uniir_vision_embed_bwd": (C.c_int, [VP, I32, I32, I32, VP, VP, VP, VP]),
@@ -63,6 +63,8 @@ _SIGS = {
     "uniir_text_embed_bwd": (C.c_int, [VP, VP, I32, I32, I32, VP, VP, VP]),
     "uniir_score_fuse_fwd": (C.c_int, [VP, VP, VP, VP, I64, I32, VP, VP]),
     "uniir_score_fuse_bwd": (C.c_int, [VP, VP, VP, I64, I32, VP, VP, VP]),
+    "uniir_score_fuse_scatter": (C.c_int, [VP, VP, VP, I32, I32, VP, VP]),
+    "uniir_score_fuse_gather_bwd": (C.c_int, [VP, VP, VP, I32, I32, I32, VP, VP]),
     "uniir_colsum_accum": (C.c_int, [VP, I64, I32, I64, VP, VP]),
     "uniir_pad_cast_bf16": (C.c_int, [VP, I64, I32, I32, VP, VP]),
     "uniir_unpad_accum": (C.c_int, [VP, I64, I32, I32, VP, VP]),
@@ -72,6 +74,7 @@ _SIGS = {
     "uniir_attn_fwd": (C.c_int, [VP, I32, I32, I32, I32, VP, VP, VP]),
     "uniir_attn_fwd_ex": (C.c_int, [VP, I64, VP, VP, I64, I32, I32, I32, I32, I32, VP, VP, I64, VP, VP]),
     "uniir_attn_bwd": (C.c_int, [VP, VP, VP, VP, I32, I32, I32, I32, VP, VP, VP]),
+    "uniir_attn_set_mode": (C.c_int, [I32]),
     "uniir_infonce_workspace_bytes": (C.c_size_t, [I32, I32]),
     "uniir_infonce_normalize": (C.c_int, [VP, VP, VP, I32, I32, VP, VP, VP, VP, VP]),
     "uniir_infonce_fwd": (C.c_int, [VP, VP, I32, I32, I32, VP, I32, VP, VP, VP, VP, C.c_size_t, VP]),

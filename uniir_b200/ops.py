@@ -190,7 +190,9 @@ def layernorm_fwd(x, gamma, beta, eps, *, rows=None, ldx=None, row_index=None, o
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, *, rows=None, ldx=None, lddx=None,
-                  row_index=None, accumulate=True, dx_bf16=None):
+                  row_index=None, accumulate=True, dx_bf16=None, dcolsum=None):
+    """dcolsum fp32 [D] (optional) += column sums of the updated dx: the bias gradient of the linear layer
+    whose output gradient this dx is (saves the separate colsum_accum pass over dx_bf16)."""
     D = gamma.numel()
     if rows is None:
         rows = mean.numel()
@@ -198,7 +200,7 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, *, rows=None, ldx
                                          _ptr(row_index), mean.data_ptr(), rstd.data_ptr(),
                                          gamma.data_ptr(), rows, D, dx.data_ptr(), lddx or (ldx or D),
                                          int(accumulate), dgamma.data_ptr(), dbeta.data_ptr(), _ptr(dx_bf16),
-                                         _stream()),
+                                         _ptr(dcolsum), _stream()),
             "uniir_layernorm_bwd")
 
 
@@ -267,6 +269,22 @@ def score_fuse_bwd(d, mt, mv, out=None):
     return dt, dv
 
 
+def score_fuse_scatter(emb, rows, mask, out):
+    """out[rows[r]] += mask[rows[r]] * emb[r] for the first rows.numel() rows of emb (compacted tower output)."""
+    n, E = rows.numel(), out.shape[1]
+    assert emb.dtype == torch.float32 and out.dtype == torch.float32 and rows.dtype == torch.int32 and mask.dtype == torch.int64
+    L.check(L.load().uniir_score_fuse_scatter(emb.data_ptr(), rows.data_ptr(), mask.data_ptr(), n, E, out.data_ptr(),
+                                              _stream()), "uniir_score_fuse_scatter")
+
+
+def score_fuse_gather_bwd(d_out, rows, mask, out):
+    """out[r] = bf16(mask[rows[r]] * d_out[rows[r]]) for r < rows.numel(), zero for the padding rows of out."""
+    n, (n_pad, E) = rows.numel(), out.shape
+    assert d_out.dtype == torch.float32 and out.dtype == torch.bfloat16 and rows.dtype == torch.int32
+    L.check(L.load().uniir_score_fuse_gather_bwd(d_out.data_ptr(), rows.data_ptr(), mask.data_ptr(), n, n_pad, E,
+                                                 out.data_ptr(), _stream()), "uniir_score_fuse_gather_bwd")
+
+
 def colsum_accum(dy, out):
     M, N = dy.shape
     assert dy.dtype == torch.bfloat16 and dy.stride(1) == 1 and out.dtype == torch.float32
@@ -305,6 +323,11 @@ def adamw_step(p, g, m, v, p16, lr, betas, eps, wd, step, grad_scale=1.0):
 # ----------------------------------------------------------------------------------------
 # attention
 # ----------------------------------------------------------------------------------------
+def attn_set_mode(mode):
+    """0 = mma.sync forward kernel, 1 = tcgen05 forward kernel where Skv <= 304.  Returns the previous mode."""
+    return L.load().uniir_attn_set_mode(int(mode))
+
+
 def attn_fwd(qkv, B, S, H, causal, out=None, lse=None, need_lse=True):
     assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.shape == (B * S, 3 * H * 64)
     if out is None:
