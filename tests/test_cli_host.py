@@ -69,3 +69,85 @@ def test_index_file_roundtrip_without_gpu(tmp_path):
     write_index(p, emb, ids)
     with np.load(p) as z:
         assert (z["embeddings"] == emb).all() and (z["ids"] == ids).all() and z["embeddings"].dtype == np.float16
+
+
+def _ref_select(retrieved, pos, neg, num_hard_negs):
+    """Literal restatement of reference mbeir_retriever.py:667-684 (the oracle for select_hard_negatives)."""
+    hard_negatives = [doc_id for doc_id in retrieved if doc_id not in pos and doc_id not in neg]
+    if 0 < len(hard_negatives) < num_hard_negs:
+        multiplier = num_hard_negs // len(hard_negatives)
+        remainder = num_hard_negs % len(hard_negatives)
+        hard_negatives = hard_negatives * multiplier + hard_negatives[:remainder]
+    return hard_negatives[:num_hard_negs]
+
+
+def test_hard_negative_selection_matches_reference_rule():
+    from uniir_b200.mbeir_retriever import select_hard_negatives
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        k = int(rng.integers(0, 12))
+        retrieved = [f"1:{int(x)}" for x in rng.integers(0, 15, size=k)]
+        pos = [f"1:{int(x)}" for x in rng.integers(0, 15, size=int(rng.integers(0, 4)))]
+        neg = [f"1:{int(x)}" for x in rng.integers(0, 15, size=int(rng.integers(0, 4)))]
+        n = int(rng.integers(1, 9))
+        assert select_hard_negatives(retrieved, pos, neg, n) == _ref_select(retrieved, pos, neg, n)
+    assert select_hard_negatives([], ["1:1"], [], 3) == []                 # nothing retrieved: stays empty
+    assert select_hard_negatives(["1:2"], [], [], 3) == ["1:2"] * 3         # short list repeats cyclically
+
+
+def test_id_hashing_matches_reference():
+    from uniir_b200 import mbeir_retriever as mr
+    assert mr.hash_qid("9:123") == 9 * 500000 + 123 and mr.unhash_qid(mr.hash_qid("9:123")) == "9:123"
+    assert mr.hash_did("3:9999999") == 3 * 10000000 + 9999999 and mr.unhash_did(np.int64(39999999)) == "3:9999999"
+    path = "/root/reference/src/data/preprocessing/utils.py"
+    if os.path.exists(path):   # pin against the reference's own constants (not on the GPU box)
+        src = open(path).read()
+        assert "DATASET_CAN_NUM_UPPER_BOUND = 10000000" in src and "DATASET_QUERY_NUM_UPPER_BOUND = 500000" in src
+
+
+def test_run_hard_negative_mining_end_to_end_with_injected_search(tmp_path):
+    """File formats + flow of run_hard_negative_mining (reference :606-708) on a toy corpus; the search itself
+    (GPU kernel, tested in test_search_gpu.py) is injected as exact numpy cosine top-k."""
+    import json
+    from types import SimpleNamespace as NS
+    from uniir_b200 import mbeir_retriever as mr
+    rng = np.random.default_rng(1)
+    n_c, n_q, d, k = 40, 6, 16, 8
+    cand = rng.standard_normal((n_c, d)).astype(np.float16)
+    dids = np.array([mr.hash_did(f"2:{i + 1}") for i in range(n_c)], dtype=np.int64)
+    q = rng.standard_normal((n_q, d)).astype(np.float16)
+    qids = np.array([mr.hash_qid(f"2:{i + 1}") for i in range(n_q)], dtype=np.int64)
+    uniir, data = tmp_path / "uniir", tmp_path / "mbeir"
+    suffix = "CLIP_SF/Large/Instruct/InBatch/"
+    (uniir / "embed" / suffix / "train").mkdir(parents=True)
+    np.save(uniir / "embed" / suffix / "train" / "mbeir_agg_train_embed.npy", q)
+    np.save(uniir / "embed" / suffix / "train" / "mbeir_agg_train_ids.npy", qids)
+    mr.write_index(str(uniir / "index" / suffix / "cand_pool" / "mbeir_union_cand_pool.index"), cand, dids)
+    (data / "train").mkdir(parents=True)
+    entries = [dict(qid=f"2:{i + 1}", pos_cand_list=[f"2:{i + 1}"], neg_cand_list=[f"2:{i + 2}"]) for i in range(n_q)]
+    with open(data / "train" / "mbeir_agg_train.jsonl", "w") as f:
+        for e in entries:
+            f.write(json.dumps(e) + "\n")
+
+    def np_search(query_embed_path, cand_index_path, batch_size=10, num_cand_to_retrieve=10):
+        qq = np.load(query_embed_path).astype(np.float32)
+        with np.load(cand_index_path) as z:
+            cc, ids = z["embeddings"].astype(np.float32), z["ids"]
+        qq /= np.linalg.norm(qq, axis=1, keepdims=True); cc /= np.linalg.norm(cc, axis=1, keepdims=True)
+        sc = qq @ cc.T
+        order = np.argsort(-sc, axis=1)[:, :num_cand_to_retrieve]
+        return np.take_along_axis(sc, order, 1), ids[order]
+
+    cfg = NS(uniir_dir=str(uniir), mbeir_data_dir=str(data), experiment=NS(path_suffix=suffix),
+             retrieval_config=NS(embed_dir_name="embed", index_dir_name="index", hard_negs_dir_name="hard_negs", k=k,
+                                 num_hard_negs=3, train_datasets_config=NS(enable_retrieve=True, datasets_name=["AGG"],
+                                                                           correspond_cand_pools_name=["UNION"])))
+    out = mr.run_hard_negative_mining(cfg, search_fn=np_search)
+    assert out.endswith("train/hard_negs/mbeir_agg_hard_negs_train.jsonl")
+    got = [json.loads(l) for l in open(out)]
+    _, I = np_search(str(uniir / "embed" / suffix / "train" / "mbeir_agg_train_embed.npy"),
+                     str(uniir / "index" / suffix / "cand_pool" / "mbeir_union_cand_pool.index"), num_cand_to_retrieve=k)
+    for i, e in enumerate(got):
+        want = _ref_select([mr.unhash_did(x) for x in I[i]], entries[i]["pos_cand_list"], entries[i]["neg_cand_list"], 3)
+        assert e["qid"] == entries[i]["qid"] and e["neg_cand_list"] == entries[i]["neg_cand_list"] + want
+        assert len(want) == 3 and not set(want) & set(entries[i]["pos_cand_list"])

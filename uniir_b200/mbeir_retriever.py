@@ -96,6 +96,95 @@ def compute_recall_at_k(relevant_docs, retrieved_indices, k):
     return 1.0 if set(relevant_docs).intersection(set(retrieved_indices[:k])) else 0.0
 
 
+# ----------------------------------------------------------------------------------------------
+# Hard-negative mining (reference mbeir_retriever.py:606-708).  The search is the fused
+# kernel (whole training query set in one launch, k = retrieval_config.k); the selection rule and the
+# jsonl in/out formats are the reference's.
+# ----------------------------------------------------------------------------------------------
+DATASET_CAN_NUM_UPPER_BOUND = 10000000   # reference src/data/preprocessing/utils.py:47-48
+DATASET_QUERY_NUM_UPPER_BOUND = 500000
+
+
+def hash_qid(qid):
+    dataset_id, data_within_id = map(int, qid.split(":"))
+    return dataset_id * DATASET_QUERY_NUM_UPPER_BOUND + data_within_id
+
+
+def unhash_qid(hashed_qid):
+    return f"{int(hashed_qid) // DATASET_QUERY_NUM_UPPER_BOUND}:{int(hashed_qid) % DATASET_QUERY_NUM_UPPER_BOUND}"
+
+
+def hash_did(did):
+    dataset_id, data_within_id = map(int, did.split(":"))
+    return dataset_id * DATASET_CAN_NUM_UPPER_BOUND + data_within_id
+
+
+def unhash_did(hashed_did):
+    return f"{int(hashed_did) // DATASET_CAN_NUM_UPPER_BOUND}:{int(hashed_did) % DATASET_CAN_NUM_UPPER_BOUND}"
+
+
+def select_hard_negatives(retrieved_dids, pos_cand_list, neg_cand_list, num_hard_negs):
+    """mbeir_retriever.py:667-684: retrieved documents (best first) that are neither positives nor already
+    negatives; a short list is repeated cyclically up to num_hard_negs; then truncated."""
+    known = set(pos_cand_list) | set(neg_cand_list)
+    hard = [d for d in retrieved_dids if d not in known]
+    if 0 < len(hard) < num_hard_negs:
+        hard = hard * (num_hard_negs // len(hard)) + hard[:num_hard_negs % len(hard)]
+    elif len(hard) == 0:
+        print("Warning: hard_negatives list is empty.")
+    return hard[:num_hard_negs]
+
+
+def mine_hard_negatives(query_data_list, query_ids, retrieved_indices, num_hard_negs):
+    """Extends every query's neg_cand_list in place (mbeir_retriever.py:658-685).  query_ids: hashed int64 [Q] in
+    the order of query_data_list; retrieved_indices: int64 [Q,k] hashed dids, best first (-1 = no result)."""
+    assert len(query_ids) == len(retrieved_indices) == len(query_data_list)
+    for i, hashed in enumerate(query_ids):
+        query_data = query_data_list[i]
+        assert unhash_qid(hashed) == query_data["qid"]
+        dids = [unhash_did(idx) for idx in retrieved_indices[i] if idx >= 0]
+        query_data["neg_cand_list"].extend(
+            select_hard_negatives(dids, query_data["pos_cand_list"], query_data["neg_cand_list"], num_hard_negs))
+    return query_data_list
+
+
+def run_hard_negative_mining(config, search_fn=None):
+    """Drop-in for the reference function of the same name: reads the training jsonl + query embeddings,
+    searches the first candidate pool with k = retrieval_config.k, writes
+    {mbeir_data_dir}/train/{hard_negs_dir_name}/mbeir_{dataset}_hard_negs_train.jsonl."""
+    import json
+    search_fn = search_fn or search_index
+    rc = config.retrieval_config
+    expt = config.experiment.path_suffix
+    tcfg = rc.train_datasets_config
+    assert tcfg.enable_retrieve, "Hard negative mining is not enabled for training data"
+    dataset_name = tcfg.datasets_name[0].lower()            # only the first dataset / pool, like the reference
+    cand_pool_name = tcfg.correspond_cand_pools_name[0].lower()
+    split = "train"
+    query_data_path = os.path.join(config.mbeir_data_dir, "train", f"mbeir_{dataset_name}_{split}.jsonl")
+    with open(query_data_path) as f:
+        query_data_list = [json.loads(line) for line in f if line.strip()]
+    embed_dir = os.path.join(config.uniir_dir, rc.embed_dir_name, expt, split)
+    query_ids = np.load(os.path.join(embed_dir, f"mbeir_{dataset_name}_{split}_ids.npy"))
+    embed_path = os.path.join(embed_dir, f"mbeir_{dataset_name}_{split}_embed.npy")
+    index_path = os.path.join(config.uniir_dir, rc.index_dir_name, expt, "cand_pool",
+                              f"mbeir_{cand_pool_name}_cand_pool.index")
+    print("-" * 30)
+    print(f"Hard Negative mining, Datasets: {dataset_name}, Candidate Pools: {cand_pool_name}")
+    print("-" * 30)
+    _, retrieved = search_fn(embed_path, index_path, batch_size=query_ids.shape[0], num_cand_to_retrieve=rc.k)
+    mine_hard_negatives(query_data_list, query_ids, retrieved, rc.num_hard_negs)
+    out_path = os.path.join(config.mbeir_data_dir, "train", rc.hard_negs_dir_name,
+                            f"mbeir_{dataset_name}_hard_negs_{split}.jsonl")
+    os.makedirs(os.path.dirname(out_path), exist_ok=True)
+    with open(out_path, "w") as f:
+        for entry in query_data_list:
+            f.write(json.dumps(entry) + "\n")
+    print(f"MBEIR Train Data with Hard Negatives saved to {out_path}")
+    print(f"Total number of entries in {out_path}: {len(query_data_list)}")
+    return out_path
+
+
 def parse_arguments():
     p = argparse.ArgumentParser(description="FAISS-free index / retrieval pipeline on B200")
     p.add_argument("--uniir_dir", type=str, default="/data/UniIR")
@@ -116,9 +205,11 @@ def main():
     config.mbeir_data_dir = args.mbeir_data_dir
     if args.enable_create_index:
         create_index(config)
-    if args.enable_retrieval or args.enable_hard_negative_mining:
-        raise NotImplementedError("run_retrieval / run_hard_negative_mining keep the reference's Python metric and "
-                                  "TSV code; import search_index from this module into it (INTEGRATION.md)")
+    if args.enable_hard_negative_mining:
+        run_hard_negative_mining(config)
+    if args.enable_retrieval:
+        raise NotImplementedError("run_retrieval keeps the reference's Python metric / run-file / TSV code (SURVEY a13); "
+                                  "import search_index from this module into it (INTEGRATION.md)")
 
 
 if __name__ == "__main__":
