@@ -184,9 +184,12 @@ int uniir_attn_fwd_ex(const void* q, int64_t ldq, const void* k, const void* v, 
                       int64_t ldo, float* lse, void* stream);
 /* Forward implementation switch: 0 = mma.sync head-resident kernel, 1 = tcgen05 kernel (scores of a
  * 128-query tile in TMEM, P staged in shared memory, K/V of the next head prefetched by TMA) wherever
- * Skv <= 304, falling back to 0 elsewhere.  Default: environment UNIIR_ATTN_TC (unset = 0).
+ * Skv <= 272, falling back to 0 elsewhere.  Default: environment UNIIR_ATTN_TC (unset = 0).
  * Returns the previous mode.  Both compute the same function; tests compare them. */
 int uniir_attn_set_mode(int32_t mode);
+/* Diagnostic: device buffer of 3 x 256 int64 that receives SM-clock timestamps of CTA 0's phases in the
+ * tcgen05 forward (softmax warp / MMA thread / tail warp; scripts/trace_attn.py prints them); null = off. */
+int uniir_attn_set_trace(void* device_buf_3x256_int64);
 int uniir_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int32_t B,
                    int32_t S, int32_t H, int32_t causal, float* delta_ws /* [B*H*S] */, void* dqkv,
                    void* stream);

@@ -174,7 +174,7 @@ def test_attention_fwd_bwd(ops, B, S, H, causal):
 
 @pytest.mark.parametrize("B,S,H,causal", [(2, 64, 1, False), (3, 257, 4, False), (5, 77, 3, True), (2, 197, 2, False),
                                            (2, 50, 2, False), (1, 130, 2, True), (2, 100, 1, False), (1, 132, 1, False),
-                                           (1, 304, 2, False), (20, 257, 16, False), (40, 77, 12, True), (1, 128, 1, True)])
+                                           (1, 272, 2, False), (1, 304, 2, False), (20, 257, 16, False), (40, 77, 12, True), (1, 128, 1, True)])
 def test_attention_fwd_tcgen05(ops, B, S, H, causal):
     """The tcgen05 forward (attention_tc.cu) against the fp32 reference and against the mma.sync kernel: one
     128-query tile, several tiles, the 1..4-row CUDA-core tail (257, 130, 132), persistence over more heads than

@@ -24,6 +24,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
     "-DUNIIR_BUILDING=1",
 ]
+# diagnostics builds, e.g. UNIIR_NVCC_EXTRA=-DUNIIR_ATTN_TRACE for scripts/trace_attn.py
+NVCC_FLAGS += os.environ.get("UNIIR_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

@@ -324,7 +324,7 @@ def adamw_step(p, g, m, v, p16, lr, betas, eps, wd, step, grad_scale=1.0):
 # attention
 # ----------------------------------------------------------------------------------------
 def attn_set_mode(mode):
-    """0 = mma.sync forward kernel, 1 = tcgen05 forward kernel where Skv <= 304.  Returns the previous mode."""
+    """0 = mma.sync forward kernel, 1 = tcgen05 forward kernel where Skv <= 272.  Returns the previous mode."""
     return L.load().uniir_attn_set_mode(int(mode))
 
 
