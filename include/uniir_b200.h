@@ -182,16 +182,23 @@ int uniir_attn_fwd(const void* qkv, int32_t B, int32_t S, int32_t H, int32_t cau
 int uniir_attn_fwd_ex(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, int32_t B,
                       int32_t Sq, int32_t Skv, int32_t H, int32_t causal, const int32_t* kv_len, void* out,
                       int64_t ldo, float* lse, void* stream);
-/* Forward implementation switch: 0 = mma.sync head-resident kernel, 1 = tcgen05 kernel (scores of a
- * 128-query tile in TMEM, P staged in shared memory, K/V of the next head prefetched by TMA) wherever
- * Skv <= 272, falling back to 0 elsewhere.  Default: environment UNIIR_ATTN_TC (unset = 0).
- * Returns the previous mode.  Both compute the same function; tests compare them. */
+/* Implementation switch (bit mask): bit 0 = tcgen05 forward (scores of a 128-query tile in TMEM, P staged in
+ * shared memory, K/V of the next head prefetched by TMA) wherever Skv <= 272 and not causal; bit 1 = tcgen05
+ * backward (attention_bwd_tc.cu: S^T / dP^T of a 128-key tile in TMEM, P^T / dS^T staged in shared memory,
+ * dK / dV / dQ accumulated in TMEM) wherever Sq <= 260; bit 2 = take the tcgen05 kernels also for the shapes
+ * where they measured slower (causal forward); 0 = the mma.sync head-resident kernels everywhere, which are
+ * also the fallback for shapes the tcgen05 kernels do not take.  Default 3; environment UNIIR_ATTN_TC
+ * overrides.  Returns the previous mode.  Both families compute the same function; tests compare them. */
 int uniir_attn_set_mode(int32_t mode);
 /* Diagnostic: device buffer of 3 x 256 int64 that receives SM-clock timestamps of CTA 0's phases in the
  * tcgen05 forward (softmax warp / MMA thread / tail warp; scripts/trace_attn.py prints them); null = off. */
 int uniir_attn_set_trace(void* device_buf_3x256_int64);
+/* Backward workspace (fp32 elements, 16-byte aligned): delta = rowsum(dO o O), the base-2 LSE and the dS of
+ * the key columns beyond the last full 128-key tile, each padded to 16 rows per head. */
+int64_t uniir_attn_bwd_workspace_floats(int32_t B, int32_t Sq, int32_t Skv, int32_t H);
 int uniir_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int32_t B,
-                   int32_t S, int32_t H, int32_t causal, float* delta_ws /* [B*H*S] */, void* dqkv,
+                   int32_t S, int32_t H, int32_t causal,
+                   float* delta_ws /* uniir_attn_bwd_workspace_floats(B, S, S, H) floats */, void* dqkv,
                    void* stream);
 
 /* ------------------------------------------------------------------------------------
@@ -226,7 +233,8 @@ int uniir_hardneg_loss(const float* emb, const int32_t* q_idx, const int32_t* p_
                        const float* logit_scale_log, float* loss_sum, float* correct_sum, float* d_emb,
                        float* d_logit_scale, void* stream);
 
-/* Backward of uniir_attn_fwd_ex (same addressing); dq rows at stride lddq, dk/dv rows at stride lddkv. */
+/* Backward of uniir_attn_fwd_ex (same addressing); dq rows at stride lddq, dk/dv rows at stride lddkv;
+ * delta_ws: uniir_attn_bwd_workspace_floats(B, Sq, Skv, H) floats. */
 int uniir_attn_bwd_ex(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const void* out,
                       int64_t ldo, const void* dout, int64_t lddo, const float* lse, int32_t B, int32_t Sq,
                       int32_t Skv, int32_t H, int32_t causal, const int32_t* kv_len, float* delta_ws, void* dq,

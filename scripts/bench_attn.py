@@ -1,5 +1,6 @@
-"""Attention forward: mma.sync head-resident kernel (mode 0) vs tcgen05 kernel (mode 1) at the tower shapes.
-Algorithmic FLOPs = 4 * B * H * Sq * Skv * 64 (halved for the causal text tower).  CUDA events, 20 launches.
+"""Attention forward and backward: mma.sync head-resident kernels (mode 0) vs tcgen05 kernels (mode bits 1 =
+forward, 2 = backward) at the tower shapes.  Algorithmic FLOPs = 4 * B * H * Sq * Skv * 64 forward, 2.5 x that
+backward (halved for the causal text tower).  CUDA events, 20 launches.
 
     python scripts/bench_attn.py [--json gpurun_out/attn.json] [--once]
 """
@@ -43,8 +44,8 @@ def main():
         flops = 4.0 * B * H * S * S * 64 * (0.5 if causal else 1.0)
         row = dict(shape=name, B=B, S=S, H=H, causal=causal, algorithmic_flops=flops)
         outs = {}
-        for mode in (0, 1):
-            prev = ops.attn_set_mode(mode)
+        for mode, m in ((0, 0), (1, 5)):     # 5 = tcgen05 forward forced (also for the causal text shape)
+            prev = ops.attn_set_mode(m)
             try:
                 ms = timeit(lambda: ops.attn_fwd(qkv, B, S, H, causal, out=out, lse=lse))
                 outs[mode] = out.clone()
@@ -53,6 +54,23 @@ def main():
             row[f"ms_mode{mode}"] = ms
             row[f"tflops_mode{mode}"] = flops / ms / 1e9
         row["max_abs_diff"] = (outs[0].float() - outs[1].float()).abs().max().item()
+        # backward (delta + dQ + dK/dV; tcgen05: prep + one fused kernel)
+        dout = torch.randn(B * S, H * 64, device=dev).bfloat16()
+        dqkv = torch.empty_like(qkv)
+        ws = torch.empty(ops.attn_bwd_ws_floats(B, S, S, H), device=dev)
+        grads = {}
+        for mode in (0, 2):
+            prev = ops.attn_set_mode(mode)
+            try:
+                ms = timeit(lambda: ops.attn_bwd(qkv, out, dout, lse, B, S, H, causal, dqkv=dqkv, delta=ws))
+                grads[mode] = dqkv.clone()
+            finally:
+                ops.attn_set_mode(prev)
+            row[f"bwd_ms_mode{mode}"] = ms
+            row[f"bwd_tflops_mode{mode}"] = 2.5 * flops / ms / 1e9
+        row["bwd_rel_diff"] = ((grads[0].float() - grads[2].float()).norm() / grads[0].float().norm()).item()
+        print(f"{name:28s} bwd: mma.sync {row['bwd_ms_mode0'] * 1e3:8.1f} us ({row['bwd_tflops_mode0']:6.1f} TF/s)   "
+              f"tcgen05 {row['bwd_ms_mode2'] * 1e3:8.1f} us ({row['bwd_tflops_mode2']:6.1f} TF/s)   rel diff {row['bwd_rel_diff']:.3e}")
         res.append(row)
         print(f"{name:28s} mma.sync {row['ms_mode0'] * 1e3:8.1f} us ({row['tflops_mode0']:6.1f} TF/s)   "
               f"tcgen05 {row['ms_mode1'] * 1e3:8.1f} us ({row['tflops_mode1']:6.1f} TF/s)   max|diff| {row['max_abs_diff']:.3e}")

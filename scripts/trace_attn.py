@@ -6,7 +6,7 @@ import torch
 from uniir_b200 import ops, lib
 B, S, H = (int(x) for x in sys.argv[1:4]) if len(sys.argv) > 3 else (128, 257, 16)
 qkv = torch.randn(B * S, 3 * H * 64, device="cuda").bfloat16()
-ops.attn_set_mode(1)
+ops.attn_set_mode(5)
 for _ in range(2):
     ops.attn_fwd(qkv, B, S, H, False)
 buf = torch.zeros(3 * 256, dtype=torch.int64, device="cuda")

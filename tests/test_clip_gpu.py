@@ -168,7 +168,13 @@ def test_train_step_graphs_equal_eager_and_loss_decreases():
         opt = FlatAdamW(m.clip_model, lr=1e-3)
         gb = _cuda(_batch(m.dims, 16))
         res[use] = [train_step(m, gb, opt)[0].item() for _ in range(5)]
-    assert all(abs(a - b) < 2e-3 * max(1, abs(a)) for a, b in zip(res[False], res[True]))
+    # Same kernels, same inputs: the first loss is identical.  Gradients are reproducible only to ~5e-7 relative
+    # (fp32 atomics in the split-K weight gradients and column sums; scripts/check_determinism.py), and five
+    # lr=1e-3 Adam steps on this tiny model amplify that: two runs of the SAME mode differ by up to ~1 % at
+    # step 5 (gpurun_out/c10_modes.log), so later steps are compared loosely.
+    assert res[False][0] == res[True][0]
+    assert all(abs(a - b) < 1e-3 * abs(a) for a, b in zip(res[False][:2], res[True][:2]))
+    assert all(abs(a - b) < 3e-2 * max(1, abs(a)) for a, b in zip(res[False], res[True]))
     assert res[True][-1] < 0.2 * res[True][0]
 
 

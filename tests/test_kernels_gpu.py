@@ -182,8 +182,12 @@ def test_attention_fwd_tcgen05(ops, B, S, H, causal):
     g = torch.Generator().manual_seed(S + B)
     qkv = (torch.randn(B * S, 3 * H * 64, generator=g) * 1.5).bfloat16()
     ref, rlse = _attn_ref(qkv.float(), B, S, H, causal)
-    out0, lse0 = ops.attn_fwd(qkv.to(dev), B, S, H, causal)
-    prev = ops.attn_set_mode(1)
+    prev = ops.attn_set_mode(0)
+    try:
+        out0, lse0 = ops.attn_fwd(qkv.to(dev), B, S, H, causal)
+    finally:
+        ops.attn_set_mode(prev)
+    prev = ops.attn_set_mode(5)
     try:
         out1, lse1 = ops.attn_fwd(qkv.to(dev), B, S, H, causal)
         torch.cuda.synchronize()
@@ -203,7 +207,7 @@ def test_attention_fwd_tcgen05_cross_attention_with_key_padding(ops):
     qkv = (torch.randn(B * Sq, 3 * H * 64, generator=g)).bfloat16().to(dev)
     kvl = torch.tensor([100, 17, 1], dtype=torch.int32, device=dev)
     res = {}
-    for mode in (0, 1):
+    for mode in (0, 5):
         prev = ops.attn_set_mode(mode)
         try:
             lse_x = torch.empty(B, H, Sq, device=dev); lse_s = torch.empty(B, H, Sq, device=dev)
@@ -213,13 +217,75 @@ def test_attention_fwd_tcgen05_cross_attention_with_key_padding(ops):
         finally:
             ops.attn_set_mode(prev)
         res[mode] = (ox, lse_x, os_, lse_s)
-    assert rel(res[1][0], res[0][0]) < 6e-3 and (res[1][1] - res[0][1]).abs().max() < 1e-3
-    assert rel(res[1][2], res[0][2]) < 6e-3 and (res[1][3] - res[0][3]).abs().max() < 1e-3
+    assert rel(res[5][0], res[0][0]) < 6e-3 and (res[5][1] - res[0][1]).abs().max() < 1e-3
+    assert rel(res[5][2], res[0][2]) < 6e-3 and (res[5][3] - res[0][3]).abs().max() < 1e-3
     # and against fp32 for the cross-attention case
     qf = q.float().cpu().view(B, Sq, H, 64).transpose(1, 2); kf = kv[:, :H * 64].float().cpu().view(B, Skv, H, 64).transpose(1, 2)
     vf = kv[:, H * 64:].float().cpu().view(B, Skv, H, 64).transpose(1, 2)
     ref = ((qf @ kf.transpose(-1, -2) * 0.125).softmax(-1) @ vf).transpose(1, 2).reshape(B * Sq, H * 64)
-    assert rel(res[1][0], ref) < 6e-3
+    assert rel(res[5][0], ref) < 6e-3
+
+
+@pytest.mark.parametrize("B,S,H,causal", [(1, 64, 1, False), (3, 257, 4, False), (5, 77, 3, True), (2, 197, 2, False),
+                                           (2, 50, 2, False), (1, 130, 2, True), (2, 100, 1, False), (1, 132, 1, False),
+                                           (1, 256, 2, False), (20, 257, 16, False), (40, 77, 12, True), (1, 128, 1, True)])
+def test_attention_bwd_tcgen05(ops, B, S, H, causal):
+    """The tcgen05 backward (attention_bwd_tc.cu) against the fp32 autograd reference and the mma.sync kernels:
+    one and two 128-key tiles, partial 64-query chunks, the CUDA-core tail of 257 / 130 / 132 (key columns and
+    query rows beyond the last full tile, prep kernel), persistence over more heads than SMs, causal masks."""
+    g = torch.Generator().manual_seed(S + B)
+    qkv = (torch.randn(B * S, 3 * H * 64, generator=g) * 1.5).bfloat16()
+    dout = torch.randn(B * S, H * 64, generator=g).bfloat16()
+    qr = qkv.float().requires_grad_(True)
+    ref, _ = _attn_ref(qr, B, S, H, causal)
+    ref.backward(dout.float())
+    prev = ops.attn_set_mode(0)
+    try:
+        out, lse = ops.attn_fwd(qkv.to(dev), B, S, H, causal)
+        g0 = ops.attn_bwd(qkv.to(dev), out, dout.to(dev), lse, B, S, H, causal)
+    finally:
+        ops.attn_set_mode(prev)
+    prev = ops.attn_set_mode(2)
+    try:
+        g2 = ops.attn_bwd(qkv.to(dev), out, dout.to(dev), lse, B, S, H, causal)
+        torch.cuda.synchronize()
+    finally:
+        ops.attn_set_mode(prev)
+    D = H * 64
+    for i in range(3):   # dq, dk, dv separately
+        assert rel(g2[:, i * D:(i + 1) * D], qr.grad[:, i * D:(i + 1) * D]) < 1e-2   # bf16 P / dS operands
+        assert rel(g2[:, i * D:(i + 1) * D], g0[:, i * D:(i + 1) * D]) < 1e-2
+
+
+def test_attention_bwd_tcgen05_cross_attention_with_key_padding(ops):
+    """BLIP shapes: text queries (100) over image keys (197) and BERT self-attention with a key-padding mask, on
+    column slices of packed projections; tcgen05 backward against the mma.sync kernels."""
+    g = torch.Generator().manual_seed(6)
+    B, Sq, Skv, H = 3, 100, 197, 12
+    D = H * 64
+    q = torch.randn(B * Sq, D, generator=g).bfloat16().to(dev)
+    kv = torch.randn(B * Skv, 2 * D, generator=g).bfloat16().to(dev)
+    qkv = torch.randn(B * Sq, 3 * D, generator=g).bfloat16().to(dev)
+    dout = torch.randn(B * Sq, D, generator=g).bfloat16().to(dev)
+    kvl = torch.tensor([100, 17, 1], dtype=torch.int32, device=dev)
+    lse_x = torch.empty(B, H, Sq, device=dev); lse_s = torch.empty(B, H, Sq, device=dev)
+    ox = ops.attn_fwd_ex(q, kv[:, :D], kv[:, D:], B, Sq, Skv, H, lse=lse_x)
+    os_ = ops.attn_fwd_ex(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B, Sq, Sq, H, kv_len=kvl, lse=lse_s)
+    res = {}
+    for mode in (0, 2):
+        prev = ops.attn_set_mode(mode)
+        try:
+            dq = torch.zeros(B * Sq, D, device=dev, dtype=torch.bfloat16); dkv = torch.zeros(B * Skv, 2 * D, device=dev, dtype=torch.bfloat16)
+            ops.attn_bwd_ex(q, kv[:, :D], kv[:, D:], ox, dout, lse_x, B, Sq, Skv, H, dq, dkv[:, :D], dkv[:, D:])
+            dqkv = torch.zeros(B * Sq, 3 * D, device=dev, dtype=torch.bfloat16)
+            ops.attn_bwd_ex(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], os_, dout, lse_s, B, Sq, Sq, H,
+                            dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], kv_len=kvl)
+            torch.cuda.synchronize()
+        finally:
+            ops.attn_set_mode(prev)
+        res[mode] = (dq, dkv, dqkv)
+    for a, b in zip(res[2], res[0]):
+        assert rel(a, b) < 1e-2
 
 
 def test_adamw_matches_torch(ops):

@@ -167,7 +167,8 @@ class BLIPEncoder:
             self.dz = torch.empty(mb, H, **bf)
             self.d_pool = torch.empty(mb, H, **bf)
             self.d_patch = torch.empty(mb * d.grid ** 2, d.v_width, **bf)
-            self.delta = torch.empty(mb * d.t_heads * S, **f32)
+            self.delta = torch.empty(max(ops.attn_bwd_ws_floats(mb, S, S, d.t_heads),
+                                         ops.attn_bwd_ws_floats(mb, S, Tv // mb, d.t_heads)), **f32)
             self.att_len = None
             self.ids = None
 

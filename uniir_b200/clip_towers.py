@@ -67,7 +67,7 @@ class Tower:
             self.d_big = torch.empty(T, 4 * D, **bf)   # d_pre
             self.d_h = torch.empty(T, D, **bf)         # d_h1 / d_h2 / d_att
             self.dqkv = torch.empty(T, 3 * D, **bf)
-            self.delta = torch.empty(mb * heads * S, **f32)
+            self.delta = torch.empty(ops.attn_bwd_ws_floats(mb, S, S, heads), **f32)
             # the no-save forward (gradient-cache phase A) borrows block 0's buffers as scratch
             a0 = self.acts[0]
             self.h, self.qkv, self.att, self.big = a0.h1, a0.qkv, a0.att, a0.act

@@ -585,7 +585,24 @@ extern "C" int uniir_attn_fwd_ex(const void* q, int64_t ldq, const void* k, cons
   return attn_fwd_launch(p, stream);
 }
 
+namespace uniir {
+long long attn_bwd_ws_floats(int B, int Sq, int Skv, int H);   // attention_bwd_tc.cu
+int attn_bwd_tc_try(const __nv_bfloat16* q, long long ldq, const __nv_bfloat16* k, const __nv_bfloat16* v,
+                    long long ldkv, const __nv_bfloat16* out, long long ldo, const __nv_bfloat16* dout,
+                    long long lddo, const float* lse, int B, int Sq, int Skv, int H, int causal, const int* kv_len,
+                    float* ws, __nv_bfloat16* dq, long long lddq, __nv_bfloat16* dk, __nv_bfloat16* dv,
+                    long long lddkv, float scale, void* stream);
+}
+
+extern "C" int64_t uniir_attn_bwd_workspace_floats(int32_t B, int32_t Sq, int32_t Skv, int32_t H) {
+  return attn_bwd_ws_floats(B, Sq, Skv, H);
+}
+
 static int attn_bwd_launch(AttnParams& p, void* stream) {
+  // tcgen05 backward (attention_bwd_tc.cu) when enabled and the shape fits; > 0 means "not applicable"
+  const int tc = attn_bwd_tc_try(p.q, p.ldq, p.k, p.v, p.ldkv, p.out, p.ldo, p.dout, p.lddo, p.lse, p.B, p.Sq, p.Skv,
+                                 p.H, p.causal, p.kv_len, p.delta, p.dq, p.lddq, p.dk, p.dv, p.lddkv, p.scale, stream);
+  if (tc <= 0) return tc;
   UNIIR_CHECK_ARG(p.Sq <= 768 && p.Skv <= 768, "uniir_attn_bwd: sequence length exceeds the head-resident limit of 768");
   if (int rc = attn_set_smem()) return rc;
   const int spad_kv = (p.Skv + 15) / 16 * 16, spad_q = (p.Sq + 15) / 16 * 16;

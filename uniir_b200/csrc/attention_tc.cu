@@ -21,6 +21,7 @@
 // alternate chunk ownership of the two warps per SM sub-partition in pass 2, a 3-deep P ring.
 #include <cuda_bf16.h>
 
+#include "attn_tc_common.cuh"
 #include "gemm_sm100.cuh"
 #include "host_util.cuh"
 
@@ -51,28 +52,6 @@ struct AttnTcParams {
   float scale;
   long long* trace;                  // diagnostic: SM-clock timestamps of CTA 0's phases (null = off)
 };
-
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float lg2_approx(float x) {
-  float y;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
-  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<const uint32_t*>(&v);
-}
-__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
-
-// byte offset of 16-byte chunk `ch` of row `r` in a [rows x 64] bf16 tile with the TMA 128B swizzle
-__device__ __forceinline__ uint32_t sw128(int r, int ch) {
-  return static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128 + ((ch ^ (r & 7)) << 4));
-}
 
 // diagnostic timeline: role r (0 softmax warp 2, 1 MMA thread, 2 tail warp), slot i < 256
 #ifdef UNIIR_ATTN_TRACE   // build with -DUNIIR_ATTN_TRACE for scripts/trace_attn.py; off by default (register pressure)
@@ -474,14 +453,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc_kernel(const __grid
 
 using namespace uniir;
 
-// mode: 0 = mma.sync head-resident kernels (attention.cu), 1 = tcgen05 forward where it applies.
+// mode bits: 1 = tcgen05 forward, 2 = tcgen05 backward (attention_bwd_tc.cu), wherever they apply and pay off;
+// 4 = also where they apply but measured slower (the causal 77-token forward); 0 = the mma.sync head-resident
+// kernels (attention.cu) everywhere.  Default 3; environment UNIIR_ATTN_TC overrides.
 static int g_attn_tc_mode = -1;
 static int attn_tc_mode() {
   if (g_attn_tc_mode < 0) {
     const char* e = getenv("UNIIR_ATTN_TC");
-    g_attn_tc_mode = e ? (atoi(e) != 0) : 0;
+    g_attn_tc_mode = e ? (atoi(e) & 7) : 3;
   }
   return g_attn_tc_mode;
+}
+namespace uniir {
+int attn_tc_mode_bits() { return attn_tc_mode(); }
 }
 static long long* g_attn_tc_trace = nullptr;
 extern "C" int uniir_attn_set_trace(void* device_buf_3x256_int64) {
@@ -490,7 +474,7 @@ extern "C" int uniir_attn_set_trace(void* device_buf_3x256_int64) {
 }
 extern "C" int uniir_attn_set_mode(int32_t mode) {
   const int prev = attn_tc_mode();
-  g_attn_tc_mode = mode != 0;
+  g_attn_tc_mode = mode & 7;
   return prev;
 }
 
@@ -500,7 +484,8 @@ namespace uniir {
 int attn_fwd_tc_try(const __nv_bfloat16* q, long long ldq, const __nv_bfloat16* k, const __nv_bfloat16* v,
                     long long ldkv, int B, int Sq, int Skv, int H, int causal, const int* kv_len,
                     __nv_bfloat16* out, long long ldo, float* lse, float scale, void* stream) {
-  if (!attn_tc_mode()) return 1;
+  if (!(attn_tc_mode() & 1)) return 1;
+  if (causal && !(attn_tc_mode() & 4)) return 1;   // CLIP text tower (77 tokens): 33.6 us vs 32.2 us for mma.sync
   if (Skv > kTcMaxKv || ldo % 8 != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0) return 1;
   AttnTcParams p{};
   p.q = q; p.ldq = ldq; p.ldo = ldo; p.out = out; p.lse = lse; p.kv_len = kv_len;

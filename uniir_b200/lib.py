@@ -75,6 +75,7 @@ _SIGS = {
     "uniir_attn_fwd_ex": (C.c_int, [VP, I64, VP, VP, I64, I32, I32, I32, I32, I32, VP, VP, I64, VP, VP]),
     "uniir_attn_bwd": (C.c_int, [VP, VP, VP, VP, I32, I32, I32, I32, VP, VP, VP]),
     "uniir_attn_set_mode": (C.c_int, [I32]),
+    "uniir_attn_bwd_workspace_floats": (C.c_int64, [I32, I32, I32, I32]),
     "uniir_attn_set_trace": (C.c_int, [VP]),
     "uniir_infonce_workspace_bytes": (C.c_size_t, [I32, I32]),
     "uniir_infonce_normalize": (C.c_int, [VP, VP, VP, I32, I32, VP, VP, VP, VP, VP]),

@@ -324,8 +324,15 @@ def adamw_step(p, g, m, v, p16, lr, betas, eps, wd, step, grad_scale=1.0):
 # attention
 # ----------------------------------------------------------------------------------------
 def attn_set_mode(mode):
-    """0 = mma.sync forward kernel, 1 = tcgen05 forward kernel where Skv <= 272.  Returns the previous mode."""
+    """Bit mask: 1 = tcgen05 forward where Skv <= 272 (non-causal), 2 = tcgen05 backward where Sq <= 260, 4 = also
+    the shapes where tcgen05 measured slower (causal forward); 0 = mma.sync kernels.  Default 3.  Returns the
+    previous mode."""
     return L.load().uniir_attn_set_mode(int(mode))
+
+
+def attn_bwd_ws_floats(B, Sq, Skv, H):
+    """fp32 elements of the backward workspace (delta, base-2 LSE, tail-column dS)."""
+    return int(L.load().uniir_attn_bwd_workspace_floats(B, Sq, Skv, H))
 
 
 def attn_fwd(qkv, B, S, H, causal, out=None, lse=None, need_lse=True):
@@ -356,7 +363,7 @@ def attn_bwd(qkv, out, dout, lse, B, S, H, causal, dqkv=None, delta=None):
     if dqkv is None:
         dqkv = torch.empty_like(qkv)
     if delta is None:
-        delta = torch.empty(B * H * S, device=qkv.device, dtype=torch.float32)
+        delta = torch.empty(attn_bwd_ws_floats(B, S, S, H), device=qkv.device, dtype=torch.float32)
     L.check(L.load().uniir_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), B, S, H,
                                     int(causal), delta.data_ptr(), dqkv.data_ptr(), _stream()),
             "uniir_attn_bwd")
@@ -464,7 +471,7 @@ def hardneg_loss(emb, q_idx, p_idx, n_idx, in_batch_neg_num, logit_scale, d_logi
 def attn_bwd_ex(q, k, v, out, dout, lse, B, Sq, Skv, H, dq, dk, dv, *, causal=False, kv_len=None, delta=None):
     """Backward of attn_fwd_ex; dq/dk/dv are preallocated bf16 row-strided views (dk, dv share a stride)."""
     if delta is None:
-        delta = torch.empty(B * H * Sq, device=q.device, dtype=torch.float32)
+        delta = torch.empty(attn_bwd_ws_floats(B, Sq, Skv, H), device=q.device, dtype=torch.float32)
     assert dk.stride(0) == dv.stride(0) and k.stride(0) == v.stride(0)
     L.check(L.load().uniir_attn_bwd_ex(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), out.data_ptr(),
                                        out.stride(0), dout.data_ptr(), dout.stride(0), lse.data_ptr(), B, Sq, Skv, H,
