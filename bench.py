@@ -228,11 +228,14 @@ def run_train(args, rank, world, dev, peaks):
         class model: gather_embeddings = world > 1
         class data_config: in_batch_neg_num = 0
 
-    pairs = GLOBAL_BATCH // world
+    GB = GLOBAL_BATCH if args.pairs_per_gpu is None else args.pairs_per_gpu * world   # BASELINE configs[1] unless emulating a rank
+    pairs = GB // world
     model = CLIPScoreFusion(MODEL, device=dev, config=Cfg, micro_batch=args.micro_batch)
     opt = FlatAdamW(model.clip_model, lr=1e-5, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.2)
     batch = synth_batch(model.dims, pairs, 2023 + rank, dev, mask_mix=args.mask_mix)
     model.skip_masked_towers = not args.no_tower_skip
+    if args.retain is not None:
+        model.retain_micro_batches = args.retain
     state = {}
 
     def step():
@@ -247,7 +250,7 @@ def run_train(args, rank, world, dev, peaks):
     ms = timed(step, args.steps, world)
     launches = lib.launch_count() + ops.graph_launches() - l0   # direct launches + kernels replayed from CUDA graphs
     clocks = sampler.stop()
-    value = GLOBAL_BATCH / (ms / 1e3)
+    value = GB / (ms / 1e3)
 
     # ---- end-to-end through the public API with HOST (pinned) buffers -------------------
     hb = {k: (torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) if torch.is_tensor(v) else v)
@@ -261,7 +264,7 @@ def run_train(args, rank, world, dev, peaks):
 
     e2e_step()
     ms_e2e = timed(e2e_step, max(1, min(2, args.steps)), world)
-    e2e = {"value": GLOBAL_BATCH / (ms_e2e / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": h2d * world,
+    e2e = {"value": GB / (ms_e2e / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": h2d * world,
            "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e}
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM), timed live with CUDA events -----
@@ -297,15 +300,18 @@ def run_train(args, rank, world, dev, peaks):
             "frac": achieved / peaks["bf16_sustained"], "peak_src": f"{peaks['src']} sustained bf16 (kernel timed inside a long step)",
             "launches": len(prof), "distinct_configs": len(uniq), "gemm_share_of_step": g_ms / ms if ms else None,
             "traffic": _ncu_traffic("gemm"),
-            "step_algorithmic_tflops": FLOPS_PER_PAIR * GLOBAL_BATCH / world / (ms / 1e3) / 1e12}
+            "step_algorithmic_tflops": FLOPS_PER_PAIR * GB / world / (ms / 1e3) / 1e12}
     out = {"metric": "contrastive_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-           "config": {"workload": f"CLIP_SF {MODEL} in-batch contrastive training step (BASELINE configs[1])",
-                      "model": f"CLIP_SF {MODEL}", "global_batch": GLOBAL_BATCH, "pairs_per_gpu": pairs,
+           "config": {"workload": f"CLIP_SF {MODEL} in-batch contrastive training step (BASELINE configs[1])"
+                                  + ("" if args.pairs_per_gpu is None else f" -- DIAGNOSTIC: {pairs} pairs per GPU, not the 4096-pair batch"),
+                      "model": f"CLIP_SF {MODEL}", "global_batch": GB, "pairs_per_gpu": pairs,
                       "micro_batch_items": model._train_mb if hasattr(model, "_train_mb") else args.micro_batch,
                       "seq_len": "257 vision tokens + 77 text tokens per item, 2 items per pair",
-                      "parallelism": f"dp{world}", "grad_cache": "embedding-level (1 extra forward, not credited)",
+                      "parallelism": f"dp{world}",
+                      "grad_cache": f"embedding-level: extra forward (not credited) for {n_mb - getattr(model, '_n_retained', 0)} of "
+                                    f"{n_mb} micro-batches per GPU; {getattr(model, '_n_retained', 0)} keep their activations in HBM",
                       "l2": "inputs+weights+activations per step >> 126 MB L2 (no flush needed)",
                       "masks": ("all ones (both modalities present)" if args.mask_mix == "ones" else
                                 "1/3 text-only, 1/3 image-only, 1/3 both; masked towers "
@@ -597,6 +603,12 @@ def main():
     ap.add_argument("--mask-mix", default="ones", choices=["ones", "mbeir"],
                     help="train workload: modality masks (SURVEY 8d); 'mbeir' = 1/3 text-only, 1/3 image-only, 1/3 both")
     ap.add_argument("--no-tower-skip", action="store_true", help="encode masked modalities like the reference does")
+    ap.add_argument("--retain", type=lambda s: s if s == "auto" else int(s), default=None,
+                    help="micro-batches whose activations stay in HBM between the embedding pass and the backward "
+                         "(default: auto = as many as fit)")
+    ap.add_argument("--pairs-per-gpu", type=int, default=None,
+                    help="diagnostic: run this many pairs on this GPU (emulates one rank of a larger job; the JSON "
+                         "line then reports that batch, not BASELINE's)")
     ap.add_argument("--search-q", type=int, default=SEARCH_Q)
     ap.add_argument("--search-n", type=int, default=SEARCH_N)
     args = ap.parse_args()

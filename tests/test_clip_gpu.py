@@ -106,6 +106,37 @@ def test_skipping_masked_towers_changes_nothing():
         assert (ga - gb_).norm() <= 2e-3 * (ga.norm() + 1e-12), n
 
 
+def test_retained_micro_batches_skip_the_reforward_and_change_nothing():
+    """Gradient caching re-runs each micro-batch forward before its backward; micro-batches whose activations are
+    kept from the embedding pass (extra encoders, as many as HBM holds) skip that.  Same loss, same gradients (up
+    to the order of the atomic accumulations), fewer kernels; eager, graph capture and graph replay."""
+    from uniir_b200 import lib as L
+    from uniir_b200 import ops as ops_
+    from uniir_b200.clip_sf import CLIPScoreFusion
+    res = {}
+    for keep in (0, 2, "auto"):
+        m = CLIPScoreFusion("tiny-test", device="cuda", micro_batch=8, seed=5)
+        m.retain_micro_batches = keep
+        b = _batch(m.dims, 16, seed=7)
+        b["txt_mask_batched"] = torch.ones(32, dtype=torch.long); b["image_mask_batched"] = torch.ones(32, dtype=torch.long)
+        gb = _cuda(b)
+        for it in range(3):          # eager, capture, replay
+            if m.clip_model.grad is not None:
+                for g_ in m.clip_model.grad.values():
+                    g_.zero_()
+            n0 = L.launch_count() + ops_.graph_launches()
+            loss, acc = m._loss_forward(gb); m._loss_backward(gb, None)
+            torch.cuda.synchronize()
+            launches = L.launch_count() + ops_.graph_launches() - n0   # direct + replayed from CUDA graphs
+        assert m._n_retained == {0: 0, 2: 2, "auto": 4}[keep]
+        res[keep] = (loss.item(), {n: m.clip_model.g(n).clone() for n, *_ in m.clip_model._specs}, launches)
+    for keep in (2, "auto"):
+        assert abs(res[keep][0] - res[0][0]) < 1e-6 * max(1.0, abs(res[0][0]))
+        for n, ga in res[0][1].items():
+            assert (ga - res[keep][1][n]).norm() <= 2e-3 * (ga.norm() + 1e-12), (keep, n)
+    assert res["auto"][2] < res[2][2] < res[0][2]     # each retained micro-batch saves one forward
+
+
 def test_vit_b32_batch4_matches_oracle():
     """BASELINE configs[0]: CLIP_SF ViT-B/32 in-batch contrastive step, batch 4."""
     _check_against_oracle("ViT-B/32", 4, 8, 0.995)

@@ -75,6 +75,13 @@ class CLIPScoreFusion(nn.Module):
         self.micro_batch = micro_batch
         self.use_cuda_graphs = True
         self.skip_masked_towers = True   # rows with mask 0 never enter that tower (same result)
+        # Gradient caching runs every micro-batch forward twice (embeddings first, activations again before its
+        # backward).  As many micro-batches as HBM holds keep their activations from the first pass instead
+        # (one extra encoder = one extra set of activation buffers each): "auto" sizes that from free memory,
+        # an int forces it, 0 disables.  Same arithmetic, one forward less for those micro-batches.
+        self.retain_micro_batches = "auto"
+        self.retain_reserve_bytes = 16 << 30   # left free for the loss, NCCL and allocator slack under "auto"
+        self._retained = []
         self._enc = {}
         self._nce = None
         self._train_state = None
@@ -176,8 +183,38 @@ class CLIPScoreFusion(nn.Module):
         return (nz[0].nonzero().flatten().to(torch.int32).contiguous(),
                 nz[1].nonzero().flatten().to(torch.int32).contiguous())
 
-    def _embed_into(self, emb, txt, img, mt, mv, enc=None):
-        """Forward (no activations saved) in micro-batches; the tail chunk is padded.  Returns the mask plan."""
+    def _retained_encoders(self, enc, n_mb):
+        """Extra training encoders whose activations survive from the embedding pass to the backward pass."""
+        want = self.retain_micro_batches
+        if self._retained and (self._retained[0].mb != enc.mb or self._retained[0].P is not enc.P):
+            self._retained = []
+        if want == "auto":
+            if not getattr(self, "_retain_sized", None) == enc.mb:
+                # cost of one encoder = what the main one took; keep `retain_reserve_bytes` free
+                torch.cuda.synchronize()
+                per = max(enc.bytes_allocated, 1)
+                free, _ = torch.cuda.mem_get_info(self.device_)
+                free += torch.cuda.memory_reserved(self.device_) - torch.cuda.memory_allocated(self.device_)
+                self._retain_auto = max(0, int((free - self.retain_reserve_bytes) // per))
+                self._retain_sized = enc.mb
+            want = self._retain_auto
+        want = max(0, min(int(want), n_mb))
+        while len(self._retained) < want:
+            try:
+                r = CLIPEncoder(self.clip_model, self.dims, enc.mb, self.device_, True)
+            except torch.cuda.OutOfMemoryError:
+                torch.cuda.empty_cache()
+                if self.retain_micro_batches == "auto":
+                    self._retain_auto = len(self._retained)
+                break
+            r.conv_w16 = enc.conv_w16        # one bf16 copy of the patch-embedding weight (refresh_weights)
+            self._retained.append(r)
+        return self._retained[:want]
+
+    def _embed_into(self, emb, txt, img, mt, mv, enc=None, retain=False):
+        """Forward in micro-batches; the tail chunk is padded.  Returns the mask plan.  retain=True (training,
+        every item has both modalities): the first micro-batches run on the retained encoders and keep their
+        activations for _loss_backward."""
         n = txt.shape[0]
         txt, img = self._prep(txt, img)
         mt = mt.to(self.device_, torch.int64).contiguous()
@@ -186,9 +223,16 @@ class CLIPScoreFusion(nn.Module):
         enc = enc or self._encoder(mb, False)
         self._sync_weights(enc)
         plan = self._mask_plan(mt, mv)
+        self._n_retained = 0
         if plan is None:
-            for s in range(0, n, mb):
+            kept = self._retained_encoders(enc, n // mb) if (retain and n % mb == 0) else []
+            self._n_retained = len(kept)
+            for i, s in enumerate(range(0, n, mb)):
                 e = min(n, s + mb)  # a ragged tail is zero-padded inside set_inputs; padded rows are dropped
+                if i < len(kept):
+                    kept[i].set_inputs(txt[s:e], img[s:e], mt[s:e], mv[s:e])
+                    emb[s:e].copy_(kept[i].fwd_save(self.use_cuda_graphs))
+                    continue
                 enc.set_inputs(txt[s:e], img[s:e], mt[s:e], mv[s:e])
                 emb[s:e].copy_(enc.embed(self.use_cuda_graphs)[:e - s])
             return None
@@ -233,7 +277,8 @@ class CLIPScoreFusion(nn.Module):
         st["mt"] = batch["txt_mask_batched"].to(dev, torch.int64).contiguous()
         st["mv"] = batch["image_mask_batched"].to(dev, torch.int64).contiguous()
         emb = torch.empty(n_items, E, device=dev, dtype=torch.float32)
-        st["plan"] = self._embed_into(emb, st["txt"], st["img"], st["mt"], st["mv"], enc=enc)
+        st["plan"] = self._embed_into(emb, st["txt"], st["img"], st["mt"], st["mv"], enc=enc, retain=True)
+        st["n_retained"] = self._n_retained
         if "neg_cand_list" in im:   # hard-negative branch (clip_sf.py:105-131): no gather, fused fwd+bwd
             n_idx = torch.tensor(im["neg_cand_list"], dtype=torch.int32).to(dev).contiguous()
             P = self.clip_model
@@ -277,8 +322,11 @@ class CLIPScoreFusion(nn.Module):
             nce.normalize_bwd(st["q_idx"], st["p_idx"], d_pn, d_emb, off)
         mb = enc.mb
         if st["plan"] is None:
-            for s in range(0, st["n_items"], mb):
+            for i, s in enumerate(range(0, st["n_items"], mb)):
                 e = s + mb
+                if i < st["n_retained"]:     # activations kept since the embedding pass: backward only
+                    self._retained[i].bwd_only(d_emb[s:e], self.use_cuda_graphs)
+                    continue
                 enc.set_inputs(st["txt"][s:e], st["img"][s:e], st["mt"][s:e], st["mv"][s:e], d_emb[s:e])
                 enc.fwdbwd(self.use_cuda_graphs)
         else:

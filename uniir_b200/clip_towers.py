@@ -165,6 +165,7 @@ class CLIPEncoder:
     def __init__(self, params: FlatParamModule, dims: CLIPDims, mb: int, dev, train: bool):
         self.P, self.d, self.mb, self.dev, self.train = params, dims, mb, dev, train
         d = dims
+        mem0 = torch.cuda.memory_allocated(dev)
         bf = dict(device=dev, dtype=torch.bfloat16)
         f32 = dict(device=dev, dtype=torch.float32)
         self.vis = Tower(params, "visual.transformer", d.v_width, d.v_layers, d.v_heads, d.v_tokens, False,
@@ -203,6 +204,7 @@ class CLIPEncoder:
             self.d_v = torch.zeros(mb, d.embed_dim, **bf)
         self._graphs = {}
         self._side = None
+        self.bytes_allocated = torch.cuda.memory_allocated(dev) - mem0   # what one more encoder like this costs
 
     def refresh_weights(self):
         d = self.d
@@ -308,6 +310,16 @@ class CLIPEncoder:
         ops.score_fuse_bwd(self.in_demb, self.in_mt, self.in_mv, out=(self.d_t, self.d_v))
         self.backward(self.d_t, self.d_v)
 
+    # ---- retained micro-batches: an encoder that is not reused between the embedding pass and the
+    # backward pass keeps its activations, so the gradient-cache re-forward is skipped for it ----
+    def _body_fwd_save(self):
+        t, v = self.forward(self.in_ids, self.in_img, save=True)
+        ops.score_fuse_fwd(t, v, self.in_mt, self.in_mv, out=self.out_emb)
+
+    def _body_bwd_only(self):
+        ops.score_fuse_bwd(self.in_demb, self.in_mt, self.in_mv, out=(self.d_t, self.d_v))
+        self.backward(self.d_t, self.d_v)
+
     # ---- single-tower passes over COMPACTED rows.  The reference encodes "" / a black
     # image for a missing modality and multiplies the result by its 0 mask (clip_sf.py:53-63); here
     # the caller hands each tower only the rows whose mask is non-zero. ---------------------------
@@ -383,3 +395,13 @@ class CLIPEncoder:
 
     def fwdbwd(self, use_graph=True):
         self._run("fwdbwd", self._body_fwdbwd, use_graph)
+
+    def fwd_save(self, use_graph=True):
+        """Forward that keeps the activations (this encoder must not run anything else until bwd_only)."""
+        self._run("fwd_save", self._body_fwd_save, use_graph)
+        return self.out_emb
+
+    def bwd_only(self, d_emb, use_graph=True):
+        """Backward from the activations kept by the last fwd_save()."""
+        self.in_demb.copy_(d_emb, non_blocking=True)
+        self._run("bwd_only", self._body_bwd_only, use_graph)
