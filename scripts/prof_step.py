@@ -11,6 +11,7 @@ pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 mb = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 m = CLIPScoreFusion("ViT-L/14", device="cuda", micro_batch=mb)
 m.use_cuda_graphs = False
+m.retain_micro_batches = 0      # profile the common micro-batch: embedding pass, then re-forward + backward
 opt = FlatAdamW(m.clip_model, lr=1e-5)
 b = bench.synth_batch(m.dims, pairs, 1, torch.device("cuda"))
 train_step(m, b, opt)            # warm-up (ncu: skipped with -s)

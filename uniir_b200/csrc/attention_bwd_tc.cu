@@ -34,8 +34,9 @@
 
 namespace uniir {
 
-constexpr int kBwThreads = 448;      // warp 0 TMA, warp 1 MMA, warps 2-9 elementwise, warps 10-13 epilogue
-constexpr int kBwEwThreads = 256;
+// warp 0 TMA, warp 1 MMA, EW elementwise warps (8: two 16-query units of a chunk per thread; 16: one), then 4
+// epilogue warps
+constexpr int bw_threads(int ew_warps) { return 64 + 32 * ew_warps + 128; }
 constexpr int kBwEpThreads = 128;
 constexpr int kBwStages = 4;         // Q_i / dO_i / stats ring
 constexpr int kBwTailMax = 4;        // leftover key columns / query rows handled by the prep kernel
@@ -43,6 +44,7 @@ constexpr int kBwMaxQTiles = 2;      // dQ accumulators in TMEM
 constexpr float kBwLog2e = 1.4426950408889634f;
 // TMEM columns
 constexpr int kColS = 0, kColDP = 128, kColDK = 256, kColDV = 320, kColDQ = 384;
+static_assert(kColDV == kColDK + 64, "the dK/dV epilogue walks both accumulators as one 128-column range");
 
 struct AttnBwdTcParams {
   CUtensorMap tmQ64, tmQ16, tmDO64, tmDO16;   // box 64 cols x 64 / 16 rows
@@ -324,7 +326,10 @@ __device__ __forceinline__ void bw_store32(__nv_bfloat16* dst, const uint32_t (&
                        pack2_bf16(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
 }
 
-__global__ void __launch_bounds__(kBwThreads, 1) attn_bwd_tc_kernel(const __grid_constant__ AttnBwdTcParams p) {
+template <int EW>
+__global__ void __launch_bounds__(bw_threads(EW), 1) attn_bwd_tc_kernel(const __grid_constant__ AttnBwdTcParams p) {
+  constexpr int kBwEwThreads = 32 * EW;
+  constexpr int kUnits = 16 / EW;            // 16-query units per thread and chunk (4 units x 4 lane quarters / EW warps)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem_al = align_smem_1024(smem_raw);
   if (smem_al - smem_raw > kBwSmemSlack) __trap();
@@ -475,11 +480,11 @@ __global__ void __launch_bounds__(kBwThreads, 1) attn_bwd_tc_kernel(const __grid
       if (pdA.valid) back(pdA, true);
       if (pdB.valid) back(pdB, true);
     }
-  } else if (warp < 10) {
+  } else if (warp < 2 + EW) {
     // =============================== elementwise ===============================
-    const int ew = warp - 2;                 // 0..7
+    const int ew = warp - 2;                 // 0..EW-1
     const int quarter = warp & 3;            // TMEM lanes [32 quarter, +32)
-    const int half = ew >> 2;                // which 32 of the chunk's 64 query columns
+    const int part = ew >> 2;                // which 64 / (EW / 4) of the chunk's 64 query columns
     const int rit = quarter * 32 + lane;     // key row in the tile
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const float sc = p.scale * kBwLog2e;
@@ -509,28 +514,26 @@ __global__ void __launch_bounds__(kBwThreads, 1) attn_bwd_tc_kernel(const __grid
           // warp beyond some query of the chunk
           const bool masked = (wkey0 + 31 >= kvl) || (p.causal && (wkey0 + 31 > 64 * i));
           {
-            // this thread's two 16-query units; all four TMEM loads in flight before the first exponential
-            const int u0 = 2 * half, u1 = 2 * half + 1;
-            const bool on0 = 16 * u0 < nq, on1 = 16 * u1 < nq;
-            uint32_t s0[16], dp0[16], s1[16], dp1[16];
-            if (on0) {
-              tmem_ld_32x32b_x16(tlane + kColS + 64 * tb + 16 * u0, s0);
-              tmem_ld_32x32b_x16(tlane + kColDP + 64 * tb + 16 * u0, dp0);
-            }
-            if (on1) {
-              tmem_ld_32x32b_x16(tlane + kColS + 64 * tb + 16 * u1, s1);
-              tmem_ld_32x32b_x16(tlane + kColDP + 64 * tb + 16 * u1, dp1);
+            // this thread's 16-query units; all of its TMEM loads in flight before the first exponential
+            uint32_t s[kUnits][16], dp[kUnits][16];
+#pragma unroll
+            for (int uu = 0; uu < kUnits; ++uu) {
+              const int u = kUnits * part + uu;
+              if (16 * u < nq) {
+                tmem_ld_32x32b_x16(tlane + kColS + 64 * tb + 16 * u, s[uu]);
+                tmem_ld_32x32b_x16(tlane + kColDP + 64 * tb + 16 * u, dp[uu]);
+              }
             }
             tmem_ld_wait();
-            // causal: key may attend to queries >= key, i.e. unit columns >= key - (64 i + 16 u)
-            const int qm0 = p.causal ? key - (64 * i + 16 * u0) : 0, qm1 = p.causal ? key - (64 * i + 16 * u1) : 0;
-            if (on0) {
-              if (masked) bw_unit<true>(s0, dp0, st_lse, st_dl, u0, sc, p.scale, key_ok, qm0, pbuf, dsbuf, rit);
-              else bw_unit<false>(s0, dp0, st_lse, st_dl, u0, sc, p.scale, key_ok, qm0, pbuf, dsbuf, rit);
-            }
-            if (on1) {
-              if (masked) bw_unit<true>(s1, dp1, st_lse, st_dl, u1, sc, p.scale, key_ok, qm1, pbuf, dsbuf, rit);
-              else bw_unit<false>(s1, dp1, st_lse, st_dl, u1, sc, p.scale, key_ok, qm1, pbuf, dsbuf, rit);
+#pragma unroll
+            for (int uu = 0; uu < kUnits; ++uu) {
+              const int u = kUnits * part + uu;
+              if (16 * u < nq) {
+                // causal: key may attend to queries >= key, i.e. unit columns >= key - (64 i + 16 u)
+                const int qm = p.causal ? key - (64 * i + 16 * u) : 0;
+                if (masked) bw_unit<true>(s[uu], dp[uu], st_lse, st_dl, u, sc, p.scale, key_ok, qm, pbuf, dsbuf, rit);
+                else bw_unit<false>(s[uu], dp[uu], st_lse, st_dl, u, sc, p.scale, key_ok, qm, pbuf, dsbuf, rit);
+              }
             }
           }
           tc_fence_before();
@@ -556,15 +559,11 @@ __global__ void __launch_bounds__(kBwThreads, 1) attn_bwd_tc_kernel(const __grid
         tc_fence_after();
         const long long off = (static_cast<long long>(b) * p.Skv + key) * p.lddkv + h * 64;
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          uint32_t a[32], c[32];
-          tmem_ld_32x32b_x32(tlane + kColDK + 32 * hf, a);
-          tmem_ld_32x32b_x32(tlane + kColDV + 32 * hf, c);
+        for (int part = 0; part < 4; ++part) {     // dK[0:32], dK[32:64], dV[0:32], dV[32:64]: one TMEM load at a time
+          uint32_t a[32];
+          tmem_ld_32x32b_x32(tlane + kColDK + 32 * part, a);      // kColDV == kColDK + 64
           tmem_ld_wait();
-          if (key < p.Skv) {
-            bw_store32(p.dk + off + 32 * hf, a);
-            bw_store32(p.dv + off + 32 * hf, c);
-          }
+          if (key < p.Skv) bw_store32((part < 2 ? p.dk : p.dv) + off + 32 * (part & 1), a);
         }
         tc_fence_before();
         mbar_arrive(sm.akv_free);
@@ -680,16 +679,21 @@ int attn_bwd_tc_try(const __nv_bfloat16* q, long long ldq, const __nv_bfloat16* 
   if ((rc = make_tmap_2d(&p.tmDO16, dout, UNIIR_BF16, cols, rows_q, lddo, 64, 16))) return rc;
   if ((rc = make_tmap_2d(&p.tmK, k, UNIIR_BF16, cols, rows_k, ldkv, 64, 128))) return rc;
   if ((rc = make_tmap_2d(&p.tmV, v, UNIIR_BF16, cols, rows_k, ldkv, 64, 128))) return rc;
-  static bool smem_set = false;
-  if (!smem_set) {
-    UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwSmemBytes));
-    smem_set = true;
+  // 8 elementwise warps (two 16-query units per thread) by default; UNIIR_ATTN_BWD_EW=16 selects the 16-warp
+  // variant (one unit per thread), measured 3 % slower on B200 (ViT-L/14 shape: 390 us vs 379 us with prep)
+  static int ew16 = -1;
+  if (ew16 < 0) {
+    const char* e = getenv("UNIIR_ATTN_BWD_EW");
+    ew16 = (e && atoi(e) == 16);
+    UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwSmemBytes));
+    UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwSmemBytes));
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   attn_bwd_prep_kernel<<<dim3(H, B), kPrepThreads, 0, st>>>(pp);
   const int heads = B * H;
   const int grid = heads < num_sms() ? heads : num_sms();
-  attn_bwd_tc_kernel<<<grid, kBwThreads, kBwSmemBytes, st>>>(p);
+  if (ew16) attn_bwd_tc_kernel<16><<<grid, bw_threads(16), kBwSmemBytes, st>>>(p);
+  else attn_bwd_tc_kernel<8><<<grid, bw_threads(8), kBwSmemBytes, st>>>(p);
   count_launch(2);
   UNIIR_CUDA_OK(cudaGetLastError());
   return UNIIR_OK;
