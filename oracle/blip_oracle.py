@@ -175,7 +175,8 @@ class _BertLayer(nn.Module):
 
     def forward(self, h, mask, enc, enc_mask):
         a = self.attention(h, h, mask)
-        a = self.crossattention(a, enc, enc_mask)
+        if enc is not None:          # mode="multimodal"; mode="text" skips the cross-attention (med.py:368-383)
+            a = self.crossattention(a, enc, enc_mask)
         return self.output.LayerNorm(self.output.dense(F.gelu(self.intermediate.dense(a))) + a)
 
 
@@ -199,18 +200,23 @@ class _Encoder(nn.Module):
 
 
 class BLIPBertOracle(nn.Module):
-    def __init__(self, d: BLIPDims):
+    def __init__(self, d: BLIPDims, add_pooling_layer=True):
         super().__init__()
         self.embeddings = _Embeddings(d)
         self.encoder = _Encoder(d)
-        self.pooler = _Dense(d.t_width, d.t_width)
+        if add_pooling_layer:
+            self.pooler = _Dense(d.t_width, d.t_width)
 
-    def forward(self, input_ids, attention_mask, encoder_hidden_states):
+    def hidden(self, input_ids, attention_mask, encoder_hidden_states=None):
+        """last_hidden_state; encoder_hidden_states=None is the reference's mode="text" (no cross-attention)."""
         mask = (1.0 - attention_mask[:, None, None, :].float()) * -10000.0        # med.py:687-688
         h = self.embeddings(input_ids.long())
         for lyr in self.encoder.layer:
             h = lyr(h, mask, encoder_hidden_states, None)   # image mask is all ones (blip_ff.py:107)
-        return torch.tanh(self.pooler.dense(h[:, 0]))
+        return h
+
+    def forward(self, input_ids, attention_mask, encoder_hidden_states):
+        return torch.tanh(self.pooler.dense(self.hidden(input_ids, attention_mask, encoder_hidden_states)[:, 0]))
 
 
 class BLIPFeatureFusionOracle(nn.Module):
@@ -277,7 +283,8 @@ class BLIPFeatureFusionOracle(nn.Module):
         assert "neg_cand_list" not in im, "hard-negative variant not restated"
         with torch.no_grad():
             self.temp.clamp_(0.001, 0.5)
-        emb = self.encode_multimodal_input(ids, att, img)
+        mt, mv = batch.get("txt_mask_batched"), batch.get("image_mask_batched")   # ignored by FF, applied by SF
+        emb = self.encode_multimodal_input(ids, att, img, mt, mv)
         qi = torch.tensor(im["query"]).flatten()
         pi = torch.tensor(im["pos_cand"]).flatten()
         q, pc = F.normalize(emb[qi], dim=-1), F.normalize(emb[pi], dim=-1)
@@ -286,7 +293,7 @@ class BLIPFeatureFusionOracle(nn.Module):
         sim_targets = pos / pos.sum(1, keepdim=True)
         with torch.no_grad():
             self._momentum_update()
-            emb_m = self.encode_multimodal_input(ids, att, img, use_momentum=True)
+            emb_m = self.encode_multimodal_input(ids, att, img, mt, mv, use_momentum=True)
             q_m, pc_m = F.normalize(emb_m[qi], dim=-1), F.normalize(emb_m[pi], dim=-1)
             q_all = torch.cat([q_m.t(), self.query_queue.clone()], dim=1)
             pc_all = torch.cat([pc_m.t(), self.cand_queue.clone()], dim=1)
@@ -310,3 +317,58 @@ class BLIPFeatureFusionOracle(nn.Module):
 
     def forward(self, batch, alpha=None, encode_mbeir_batch=False):
         return self.encode_mbeir_batch(batch) if encode_mbeir_batch else self.compute_contrastive_loss(batch, alpha)
+
+
+class BLIPScoreFusionOracle(BLIPFeatureFusionOracle):
+    """Reference BLIPScoreFusion restated (blip_scorefusion/blip_sf.py:11-332): ViT class token -> vision_proj,
+    BERT in mode="text" (cross-attention layers present but skipped and frozen, no pooler) [CLS] -> text_proj,
+    each multiplied by its modality mask and summed (:97-172).  Momentum encoders, queues, loss, EMA and queue
+    update are the BLIP_FF ones (:174-330 is the same code), inherited."""
+
+    def __init__(self, size="large", embed_dim=768, queue_size=57600, momentum=0.995, dims=None, gather_fn=None):
+        nn.Module.__init__(self)
+        self.dims = dims if dims is not None else BLIP_CONFIGS[size]
+        d = self.dims
+        self.visual_encoder = BLIPViTOracle(d)
+        self.text_encoder = BLIPBertOracle(d, add_pooling_layer=False)
+        self.vision_proj = nn.Linear(d.v_width, embed_dim)
+        self.text_proj = nn.Linear(d.t_width, embed_dim)
+        for p in self.parameters():
+            nn.init.normal_(p, 0.0, 0.02)
+        for m in self.modules():
+            if isinstance(m, nn.LayerNorm):
+                nn.init.normal_(m.weight, 1.0, 0.05)
+        for n, p in self.text_encoder.named_parameters():      # blip_sf.py:75-78
+            if "crossattention" in n:
+                p.requires_grad = False
+        self.visual_encoder_m = BLIPViTOracle(d)
+        self.vision_proj_m = nn.Linear(d.v_width, embed_dim)
+        self.text_encoder_m = BLIPBertOracle(d, add_pooling_layer=False)
+        self.text_proj_m = nn.Linear(d.t_width, embed_dim)
+        self.model_pairs = [[self.visual_encoder, self.visual_encoder_m], [self.vision_proj, self.vision_proj_m],
+                            [self.text_encoder, self.text_encoder_m], [self.text_proj, self.text_proj_m]]
+        self.copy_params()
+        self.register_buffer("query_queue", F.normalize(torch.randn(embed_dim, queue_size), dim=0))
+        self.register_buffer("cand_queue", F.normalize(torch.randn(embed_dim, queue_size), dim=0))
+        self.register_buffer("idx_queue", torch.full((1, queue_size), -100))
+        self.register_buffer("new_ptr_queue", torch.zeros(1, dtype=torch.long))
+        self.queue_size, self.momentum = queue_size, momentum
+        self.temp = nn.Parameter(0.07 * torch.ones([]))
+        self._gather = gather_fn or (lambda t: t)
+
+    def encode_multimodal_input(self, input_ids, attention_mask, image, txt_mask=None, img_mask=None, use_momentum=False):
+        v, vp, t, tp = ((self.visual_encoder_m, self.vision_proj_m, self.text_encoder_m, self.text_proj_m) if use_momentum
+                        else (self.visual_encoder, self.vision_proj, self.text_encoder, self.text_proj))
+        txt = tp(t.hidden(input_ids, attention_mask)[:, 0, :]) * txt_mask.unsqueeze(-1)        # blip_sf.py:97-121,168
+        img = vp(v(image.float())[:, 0, :]) * img_mask.unsqueeze(-1)                           # :123-143,169
+        return img + txt                                                                       # :145-156
+
+    def encode_mbeir_batch(self, batch):
+        id_list = batch.get("did_list") or batch.get("qid_list")
+        if id_list is None:
+            raise ValueError("id_list not found in batch.")
+        t = batch["txt_batched"]
+        emb = self.encode_multimodal_input(t["input_ids"], t["attention_mask"], batch["image_batched"],
+                                           batch["txt_mask_batched"], batch["image_mask_batched"])
+        assert emb.size(0) == len(id_list)
+        return emb, id_list

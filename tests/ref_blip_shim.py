@@ -79,3 +79,17 @@ def load_blip_ff():
     if not (dist.is_available() and dist.is_initialized()):   # concat_all_gather at world size 1
         bf.concat_all_gather = lambda t: t
     return bf
+
+
+def load_blip_sf():
+    """The reference BLIPScoreFusion class itself (blip_scorefusion/blip_sf.py), tokenizer download stubbed."""
+    load()
+    sys.modules["timm.models.hub"].download_cached_file = lambda *a, **k: None
+    blip = importlib.import_module("models.uniir_blip.backbone.blip")
+    blip.init_tokenizer = lambda: None
+    bs = importlib.import_module("models.uniir_blip.blip_scorefusion.blip_sf")
+    bs.init_tokenizer = lambda: None
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):   # concat_all_gather at world size 1
+        bs.concat_all_gather = lambda t: t
+    return bs

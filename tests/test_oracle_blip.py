@@ -9,7 +9,7 @@ import torch
 
 import ref_blip_shim
 from conftest import GOLDEN
-from oracle.blip_oracle import BLIP_CONFIGS, BLIPFeatureFusionOracle
+from oracle.blip_oracle import BLIP_CONFIGS, BLIPFeatureFusionOracle, BLIPScoreFusionOracle
 
 
 def _inputs(d, B, S, seed):
@@ -103,3 +103,52 @@ def test_training_loss_matches_reference_class(tmp_path):
         assert torch.equal(ref.idx_queue, orc.idx_queue) and torch.equal(ref.new_ptr_queue, orc.new_ptr_queue)
         assert torch.allclose(ref.cand_queue, orc.cand_queue, atol=1e-6)
         assert torch.allclose(ref.visual_encoder_m.blocks[0].attn.qkv.weight, orc.visual_encoder_m.blocks[0].attn.qkv.weight, atol=1e-7)
+
+
+@pytest.mark.skipif(not ref_blip_shim.available(), reason="reference tree not present (GPU box): golden vectors cover it")
+def test_blip_sf_restatement_matches_reference_class(tmp_path):
+    """The REAL reference BLIPScoreFusion (blip_sf.py) vs the oracle restatement: state-dict keys, masked
+    score-fusion embeddings (online and momentum), and two consecutive training steps (loss, accuracy, gradients
+    incl. the frozen cross-attention, EMA'd weights, queues)."""
+    import types
+    from oracle.blip_oracle import BLIPDims
+    bs = ref_blip_shim.load_blip_sf()
+    cfg = dict(json.load(open("/root/reference/src/models/uniir_blip/backbone/configs/med_config.json")))
+    cfg.update(hidden_size=64, intermediate_size=256, num_attention_heads=1, num_hidden_layers=2, vocab_size=600,
+               max_position_embeddings=128, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    p = tmp_path / "med.json"; p.write_text(json.dumps(cfg))
+    torch.manual_seed(0)
+    ref = bs.BLIPScoreFusion(med_config=str(p), image_size=64, vit="base", embed_dim=48, queue_size=16, config=None).eval()
+    d = BLIPDims(image_size=64, patch=16, v_width=768, v_layers=12, v_heads=12, t_width=64, t_layers=2, t_heads=1,
+                 t_inter=256, vocab=600, max_pos=128)
+    orc = BLIPScoreFusionOracle(dims=d, embed_dim=48, queue_size=16).eval()
+    missing, unexpected = orc.load_state_dict(ref.state_dict(), strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    assert {n for n, q in ref.named_parameters() if not q.requires_grad} == {n for n, q in orc.named_parameters() if not q.requires_grad}
+    ids, att, img = _inputs(d, 8, 20, 3)
+    mt = torch.tensor([1, 1, 0, 1, 1, 0, 1, 1]); mv = torch.tensor([1, 0, 1, 1, 1, 1, 0, 1])
+    txt_ns = types.SimpleNamespace(input_ids=ids, attention_mask=att)
+    with torch.no_grad():
+        for mom in (False, True):
+            e_ref = ref.encode_multimodal_input(txt_ns, img, mt, mv, use_momentum=mom)
+            e_orc = orc.encode_multimodal_input(ids, att, img, mt, mv, use_momentum=mom)
+            assert torch.allclose(e_orc, e_ref, atol=1e-5, rtol=1e-4), (e_orc - e_ref).abs().max()
+    for step in range(2):
+        ids, att, img = _inputs(d, 8, 20, 10 + step)
+        mk = lambda: dict(image_batched=img, txt_mask_batched=mt, image_mask_batched=mv, p_did_list=[7, 8, 7, 9 + step],
+                          index_mapping={"query": [[0], [2], [4], [6]], "pos_cand": [[1], [3], [5], [7]]})
+        br = mk(); br["txt_batched"] = types.SimpleNamespace(input_ids=ids, attention_mask=att)
+        bo = mk(); bo["txt_batched"] = {"input_ids": ids, "attention_mask": att}
+        ref.zero_grad(); orc.zero_grad()
+        o_r = ref.compute_contrastive_loss(br, alpha=0.3); o_r["loss"].backward()
+        o_o = orc.compute_contrastive_loss(bo, alpha=0.3); o_o["loss"].backward()
+        assert abs(o_r["loss"].item() - o_o["loss"].item()) < 1e-5 and abs(o_r["accuracy"].item() - o_o["accuracy"].item()) < 1e-6
+        for n in ("temp", "text_proj.weight", "vision_proj.bias", "text_encoder.encoder.layer.1.attention.self.key.weight",
+                  "visual_encoder.blocks.3.attn.qkv.weight", "visual_encoder.patch_embed.proj.bias"):
+            a, b = ref.get_parameter(n).grad, orc.get_parameter(n).grad
+            assert torch.allclose(a, b, atol=1e-6, rtol=1e-4), n
+        assert ref.get_parameter("text_encoder.encoder.layer.0.crossattention.self.key.weight").grad is None
+        assert orc.get_parameter("text_encoder.encoder.layer.0.crossattention.self.key.weight").grad is None
+        assert torch.equal(ref.idx_queue, orc.idx_queue) and torch.equal(ref.new_ptr_queue, orc.new_ptr_queue)
+        assert torch.allclose(ref.cand_queue, orc.cand_queue, atol=1e-6)
+        assert torch.allclose(ref.text_proj_m.weight, orc.text_proj_m.weight, atol=1e-7)
