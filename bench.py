@@ -481,6 +481,9 @@ def synth_blip_batch(dims, pairs, seed, device, step=0):
 
 BLIP_GLOBAL_BATCH = 2048
 BLIP_FLOPS_PER_PAIR = 1.212e12     # SURVEY.md 8d (algorithmic fwd+bwd of the online encoders; momentum forward not credited)
+# BLIP_SF: ViT-L/16 123.1 G + BERT-base in text mode at 100 tokens (12 x (QKV 0.354 + attention 0.031 + out 0.118 +
+# FFN 0.944) = 17.4 G) = 140.5 GFLOP per item forward; x 2 items x (3 online + 1 momentum forward)
+BLIP_SF_FLOPS_PER_PAIR = 1.124e12
 
 
 def run_train_blip(args, rank, world, dev, peaks):
@@ -489,9 +492,13 @@ def run_train_blip(args, rank, world, dev, peaks):
     from collections import Counter
     from uniir_b200 import lib, ops
     from uniir_b200.blip_ff import BLIPFeatureFusion
+    from uniir_b200.blip_sf import BLIPScoreFusion
     from uniir_b200.engine import FlatAdamW, train_step_blip
     pairs = BLIP_GLOBAL_BATCH // world
-    model = BLIPFeatureFusion(vit="large", image_size=224, embed_dim=768, queue_size=57344, device=dev, micro_batch=256)
+    sf = args.blip_model == "sf"      # BLIP_SF (text-mode BERT + projection heads), same step otherwise
+    flops_per_pair = BLIP_SF_FLOPS_PER_PAIR if sf else BLIP_FLOPS_PER_PAIR
+    model = (BLIPScoreFusion if sf else BLIPFeatureFusion)(vit="large", image_size=224, embed_dim=768, queue_size=57344,
+                                                           device=dev, micro_batch=256)
     model.train_micro_batch = args.blip_micro_batch
     opt = FlatAdamW(model._online, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05)
     batch = synth_blip_batch(model.dims, pairs, 2023 + rank, dev)
@@ -544,12 +551,13 @@ def run_train_blip(args, rank, world, dev, peaks):
             "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
             "peak_src": f"{peaks['src']} sustained bf16 (kernel timed inside a long step)", "launches": len(sink),
             "distinct_configs": len(uniq), "gemm_share_of_step": g_ms / ms if ms else None, "traffic": None,
-            "step_algorithmic_tflops": BLIP_FLOPS_PER_PAIR * BLIP_GLOBAL_BATCH / world / (ms / 1e3) / 1e12}
+            "step_algorithmic_tflops": flops_per_pair * BLIP_GLOBAL_BATCH / world / (ms / 1e3) / 1e12}
     out = {"metric": "contrastive_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "bf16", "data": "synthetic",
-           "config": {"workload": "BLIP_FF ViT-L/16 + BERT-base momentum-distillation training step (BASELINE configs[2])",
-                      "model": "BLIP_FF large", "global_batch": BLIP_GLOBAL_BATCH, "pairs_per_gpu": pairs, "queue_size": 57344,
+           "config": {"workload": ("BLIP_SF ViT-L/16 + text-mode BERT-base momentum-distillation training step (SURVEY 8f-3; BASELINE configs[2] shape)"
+                                   if sf else "BLIP_FF ViT-L/16 + BERT-base momentum-distillation training step (BASELINE configs[2])"),
+                      "model": "BLIP_SF large" if sf else "BLIP_FF large", "global_batch": BLIP_GLOBAL_BATCH, "pairs_per_gpu": pairs, "queue_size": 57344,
                       "seq_len": "197 vision tokens + 100 text tokens per item, 2 items per pair", "micro_batch_items": model.train_micro_batch,
                       "parallelism": f"dp{world}", "grad_cache": "embedding-level (1 extra online forward + momentum forward, not credited)",
                       "l2": "inputs+weights+activations per step >> 126 MB L2 (no flush needed)"},
@@ -597,6 +605,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="train", choices=["train", "search", "embed", "blip"])
     ap.add_argument("--blip-micro-batch", type=int, default=64)
+    ap.add_argument("--blip-model", default="ff", choices=["ff", "sf"], help="--workload blip: BLIP_FF (configs[2]) or BLIP_SF")
     ap.add_argument("--micro-batch", type=int, default=128, help="encoder items per micro-batch")
     ap.add_argument("--no-extra", action="store_true", help="skip the attached retrieval measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")

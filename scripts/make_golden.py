@@ -94,7 +94,28 @@ def blip_tiny():
                         **{"w:" + k: v.numpy() for k, v in m.state_dict().items() if k.startswith(("visual_encoder.", "text_encoder."))})
 
 
+def blip_sf_tiny():
+    """BLIP_SF (blip_sf.py) masked score-fusion embeddings of the oracle, which tests/test_oracle_blip.py pins
+    against the real reference class."""
+    from oracle.blip_oracle import BLIPScoreFusionOracle
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_oracle_blip import _inputs
+    torch.manual_seed(8765)
+    m = BLIPScoreFusionOracle("tiny-test", embed_dim=64, queue_size=64).eval()
+    ids, att, img = _inputs(m.dims, 6, 24, 6)
+    mt = torch.tensor([1, 1, 0, 1, 0, 1]); mv = torch.tensor([1, 0, 1, 1, 1, 0])
+    with torch.no_grad():
+        emb = m.encode_multimodal_input(ids, att, img, mt, mv)
+    keep = ("visual_encoder.", "text_encoder.", "vision_proj.", "text_proj.")
+    np.savez_compressed(os.path.join(OUT, "blip_sf_tiny.npz"), ids=ids.numpy(), att=att.numpy(), img=img.numpy(), mt=mt.numpy(),
+                        mv=mv.numpy(), emb=emb.numpy(),
+                        **{"w:" + k: v.numpy() for k, v in m.state_dict().items() if k.startswith(keep)})
+
+
 if __name__ == "__main__":
-    clip_tiny(); search_small(); infonce(); blip_tiny()
+    if "--only-blip-sf" in sys.argv:
+        blip_sf_tiny()
+    else:
+        clip_tiny(); search_small(); infonce(); blip_tiny(); blip_sf_tiny()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -152,3 +152,43 @@ def test_blip_sf_restatement_matches_reference_class(tmp_path):
         assert torch.equal(ref.idx_queue, orc.idx_queue) and torch.equal(ref.new_ptr_queue, orc.new_ptr_queue)
         assert torch.allclose(ref.cand_queue, orc.cand_queue, atol=1e-6)
         assert torch.allclose(ref.text_proj_m.weight, orc.text_proj_m.weight, atol=1e-7)
+
+
+def test_blip_sf_golden_vectors():
+    g = np.load(os.path.join(GOLDEN, "blip_sf_tiny.npz"))
+    m = BLIPScoreFusionOracle("tiny-test", embed_dim=64, queue_size=64).eval()
+    missing, unexpected = m.load_state_dict({k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w:")}, strict=False)
+    assert not unexpected and all("_m." in k or k in ("query_queue", "cand_queue", "idx_queue", "new_ptr_queue", "temp") for k in missing)
+    with torch.no_grad():
+        e = m.encode_multimodal_input(torch.from_numpy(g["ids"]), torch.from_numpy(g["att"]), torch.from_numpy(g["img"]),
+                                      torch.from_numpy(g["mt"]), torch.from_numpy(g["mv"]))
+    assert np.allclose(e.numpy(), g["emb"], atol=1e-5)
+    assert np.abs(g["emb"][2] - g["emb"][4]).max() > 1e-3     # image-only rows differ; masks were applied, not ignored
+
+
+@pytest.mark.parametrize("mode", ["ff", "sf"])
+def test_product_parameter_layout_equals_the_reference_state_dict(mode):
+    """uniir_b200's flat parameter specs (names, shapes; online and momentum sets) against the oracle classes, whose
+    state dicts load into / from the real reference classes with strict key equality (tests above)."""
+    from uniir_b200.blip_ff import BLIP_CONFIGS as PCFG, blip_param_specs
+    d = PCFG["tiny-test"]
+    orc = (BLIPFeatureFusionOracle("tiny-test", embed_dim=48, queue_size=16) if mode == "ff"
+           else BLIPScoreFusionOracle("tiny-test", embed_dim=48, queue_size=16))
+    want = {k: tuple(v.shape) for k, v in orc.named_parameters()}
+    got = {}
+    for sfx in ("", "_m"):
+        for name, shape, decay, _ in blip_param_specs(d, sfx, mode, 48):
+            assert name not in got
+            got[name] = tuple(shape)
+            if mode == "sf":       # frozen cross-attention -> the segment without weight decay / gradients
+                assert decay == (".crossattention." not in name), name
+            else:
+                assert decay, name
+    assert got == want, (sorted(set(got) ^ set(want))[:10])
+    # the momentum set is an exact prefix of the online set in each flat segment (EMA = one kernel per segment)
+    on, mo = blip_param_specs(d, "", mode, 48), blip_param_specs(d, "_m", mode, 48)
+    for seg in (True, False):
+        a = [(n, s) for n, s, dc, _ in on if dc == seg]
+        b = [(n, s) for n, s, dc, _ in mo if dc == seg]
+        assert [s for _, s in a[:len(b)]] == [s for _, s in b]
+        assert len(a) - len(b) == (1 if seg else 0)      # temp, last in the decayed segment

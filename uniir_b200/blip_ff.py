@@ -58,12 +58,16 @@ BLIP_CONFIGS = {
 }
 
 
-def blip_param_specs(d: BLIPDims, suffix=""):
+def blip_param_specs(d: BLIPDims, suffix="", mode="ff", embed_dim=None):
     """[(name, shape, decay, std)].  q/k/v (and cross k/v) weights, then their biases, are adjacent so the
     fused [3D, D] / [2D, Dv] projection matrices are plain views of the flat buffer.  `decay` is True for
-    everything: the reference uses one AdamW group with wd 0.05 (uniir_blip/train.py:193-197)."""
+    every trained parameter: the reference uses one AdamW group with wd 0.05 (uniir_blip/train.py:193-197).
+    mode "sf" (BLIPScoreFusion, blip_sf.py:36-50): no pooler, vision_proj / text_proj heads, and the
+    cross-attention parameters -- present in the checkpoint, frozen (:75-78) and never used in mode="text" --
+    go to the second flat segment, which gets no weight decay and never sees a gradient, so the fused AdamW
+    leaves them exactly as loaded (torch's AdamW skips parameters without a gradient)."""
     sp = []
-    add = lambda n, shape, std: sp.append((n, tuple(shape), True, std))
+    add = lambda n, shape, std: sp.append((n, tuple(shape), not (mode == "sf" and ".crossattention." in n), std))
     v, t = f"visual_encoder{suffix}", f"text_encoder{suffix}"
     D = d.v_width
     add(f"{v}.cls_token", (1, 1, D), 0.02)
@@ -99,7 +103,11 @@ def blip_param_specs(d: BLIPDims, suffix=""):
         add(f"{l}.intermediate.dense.weight", (d.t_inter, H), 0.02); add(f"{l}.intermediate.dense.bias", (d.t_inter,), 0.02)
         add(f"{l}.output.dense.weight", (H, d.t_inter), 0.02); add(f"{l}.output.dense.bias", (H,), 0.02)
         add(f"{l}.output.LayerNorm.weight", (H,), -1.0); add(f"{l}.output.LayerNorm.bias", (H,), 0.0)
-    add(f"{t}.pooler.dense.weight", (H, H), 0.02); add(f"{t}.pooler.dense.bias", (H,), 0.02)
+    if mode == "ff":
+        add(f"{t}.pooler.dense.weight", (H, H), 0.02); add(f"{t}.pooler.dense.bias", (H,), 0.02)
+    else:
+        add(f"vision_proj{suffix}.weight", (embed_dim, D), 0.02); add(f"vision_proj{suffix}.bias", (embed_dim,), 0.02)
+        add(f"text_proj{suffix}.weight", (embed_dim, H), 0.02); add(f"text_proj{suffix}.bias", (embed_dim,), 0.02)
     if not suffix:
         add("temp", (), -3.0)   # LAST, so the momentum set's flat buffer is an exact prefix (EMA = one kernel)
     return sp
@@ -108,17 +116,20 @@ def blip_param_specs(d: BLIPDims, suffix=""):
 class _BertActs:
     """Saved activations of one BERT layer for one micro-batch."""
 
-    def __init__(self, T, H, I, Tv, B, nh, S, Sv, dev):
+    def __init__(self, T, H, I, Tv, B, nh, S, Sv, dev, cross=True):
         bf = dict(device=dev, dtype=torch.bfloat16)
         f32 = dict(device=dev, dtype=torch.float32)
         self.hb_in = torch.empty(T, H, **bf)
         self.qkv = torch.empty(T, 3 * H, **bf); self.ctx1 = torch.empty(T, H, **bf); self.lse1 = torch.empty(B, nh, S, **f32)
         self.t1 = torch.empty(T, H, **f32); self.m1 = torch.empty(T, **f32); self.r1 = torch.empty(T, **f32)
         self.h1b = torch.empty(T, H, **bf)
-        self.q2 = torch.empty(T, H, **bf); self.kv2 = torch.empty(Tv, 2 * H, **bf); self.ctx2 = torch.empty(T, H, **bf)
-        self.lse2 = torch.empty(B, nh, S, **f32)
-        self.t2 = torch.empty(T, H, **f32); self.m2 = torch.empty(T, **f32); self.r2 = torch.empty(T, **f32)
-        self.h2b = torch.empty(T, H, **bf)
+        if cross:
+            self.q2 = torch.empty(T, H, **bf); self.kv2 = torch.empty(Tv, 2 * H, **bf); self.ctx2 = torch.empty(T, H, **bf)
+            self.lse2 = torch.empty(B, nh, S, **f32)
+            self.t2 = torch.empty(T, H, **f32); self.m2 = torch.empty(T, **f32); self.r2 = torch.empty(T, **f32)
+            self.h2b = torch.empty(T, H, **bf)
+        else:
+            self.h2b = self.h1b          # mode="text": the FFN reads the self-attention block's output
         self.pre = torch.empty(T, I, **bf); self.act = torch.empty(T, I, **bf)
         self.t3 = torch.empty(T, H, **f32); self.m3 = torch.empty(T, **f32); self.r3 = torch.empty(T, **f32)
 
@@ -127,8 +138,11 @@ class BLIPEncoder:
     """ViT + cross-attention BERT for a fixed (micro-batch, text length): forward, and (train=True) forward
     with saved activations + backward."""
 
-    def __init__(self, P: FlatParamModule, d: BLIPDims, mb, S, dev, suffix="", train=False):
+    def __init__(self, P: FlatParamModule, d: BLIPDims, mb, S, dev, suffix="", train=False, mode="ff", embed_dim=None):
+        """mode "ff": feature fusion (cross-attention BERT over all image tokens, pooler).  mode "sf": score fusion
+        (blip_sf.py:97-172): BERT in mode="text", [CLS] -> text_proj; ViT class token -> vision_proj; masked sum."""
         self.P, self.d, self.mb, self.S, self.dev, self.train = P, d, mb, S, dev, train
+        self.mode, self.sfx = mode, suffix
         self.v, self.t = f"visual_encoder{suffix}", f"text_encoder{suffix}"
         bf = dict(device=dev, dtype=torch.bfloat16)
         f32 = dict(device=dev, dtype=torch.float32)
@@ -150,9 +164,20 @@ class BLIPEncoder:
         self.kv = torch.empty(Tv, 2 * H, **bf)
         self.inter = torch.empty(T, d.t_inter, **bf)
         self.pool = torch.empty(mb, H, **bf)
-        self.emb = torch.empty(mb, H, **f32)
+        self.emb = torch.empty(mb, H if mode == "ff" else embed_dim, **f32)
+        if mode == "sf":
+            self.cls_rows = (torch.arange(mb, device=dev, dtype=torch.int32) * d.v_tokens).contiguous()
+            self.v_pool = torch.empty(mb, d.v_width, **bf)
+            self.t_emb = torch.empty(mb, embed_dim, **f32)
+            self.v_emb = torch.empty(mb, embed_dim, **f32)
+            self.ones = torch.ones(mb, device=dev, dtype=torch.int64)
+            self.mt = self.mv = self.ones
+            if train:
+                self.d_t = torch.empty(mb, embed_dim, **bf); self.d_v = torch.empty(mb, embed_dim, **bf)
+                self.d_vpool = torch.empty(mb, d.v_width, **bf)
         if train:
-            self.acts = [_BertActs(T, H, d.t_inter, Tv, mb, d.t_heads, S, d.v_tokens, dev) for _ in range(d.t_layers)]
+            self.acts = [_BertActs(T, H, d.t_inter, Tv, mb, d.t_heads, S, d.v_tokens, dev, cross=(mode == "ff"))
+                         for _ in range(d.t_layers)]
             self.emb_pre = torch.empty(T, H, **f32); self.me = torch.empty(T, **f32); self.re = torch.empty(T, **f32)
             self.vn_m = torch.empty(Tv, **f32); self.vn_r = torch.empty(Tv, **f32)
             self.dh = torch.empty(T, H, **f32)       # gradient of the fp32 hidden stream
@@ -181,12 +206,14 @@ class BLIPEncoder:
         decay, off, _, _ = self.P._index[first]
         return (bufs or self.P.flat)[decay][off:off + n]
 
-    def forward(self, ids, att_len, img, save=False):
+    def forward(self, ids, att_len, img, save=False, mt=None, mv=None):
         """ids int32 [mb,S]; att_len int32 [mb] (valid tokens: attention_mask is a prefix mask); img fp32
-        [mb,3,H,W].  Returns the pooled fused embedding fp32 [mb, H] (buffer reused)."""
+        [mb,3,H,W]; mt / mv int64 [mb] modality masks (mode "sf" only; default all ones).  Returns the embedding
+        fp32 [mb, H] (ff: pooled fused feature) or [mb, embed_dim] (sf: masked score fusion); buffer reused."""
         P, d, mb, S = self.P, self.d, self.mb, self.S
         w, w16 = P.w, P.w16
         v, t = self.v, self.t
+        ff = self.mode == "ff"
         assert not save or self.train
         # ---------------- ViT ----------------
         ops.patch_im2col(img, d.patch, self.col.shape[1], out=self.col)
@@ -195,8 +222,13 @@ class BLIPEncoder:
         ops.vision_embed_fwd(self.patch, w(f"{v}.cls_token").view(-1), w(f"{v}.pos_embed").view(d.v_tokens, d.v_width),
                              mb, d.v_tokens, d.v_width, out=self.vis.x.view(mb, d.v_tokens, d.v_width))
         xo = self.vis.forward(save)
-        ops.layernorm_fwd(xo, w(f"{v}.norm.weight"), w(f"{v}.norm.bias"), 1e-6, out=self.img_tok,
-                          stats=((self.vn_m, self.vn_r) if save else None))
+        if ff:
+            ops.layernorm_fwd(xo, w(f"{v}.norm.weight"), w(f"{v}.norm.bias"), 1e-6, out=self.img_tok,
+                              stats=((self.vn_m, self.vn_r) if save else None))
+        else:   # only the class token is used (blip_sf.py:136-143): final norm on those rows, then vision_proj
+            ops.layernorm_fwd(xo, w(f"{v}.norm.weight"), w(f"{v}.norm.bias"), 1e-6, row_index=self.cls_rows,
+                              out=self.v_pool, stats=((self.vn_m[:mb], self.vn_r[:mb]) if save else None))
+            ops.gemm(self.v_pool, w16(f"vision_proj{self.sfx}.weight"), bias=w(f"vision_proj{self.sfx}.bias"), out=self.v_emb)
         # ---------------- BERT ----------------
         H, nh = d.t_width, d.t_heads
         e_pre = self.emb_pre if save else self.tmp
@@ -224,20 +256,23 @@ class BLIPEncoder:
                               1e-12, out=self.h, stats=((a.m1, a.r1) if save else None))
             h1b = a.h1b if save else self.hb
             ops.cast_bf16(self.h, out=h1b)
-            # cross-attention into the image tokens (encoder mask is all ones, blip_ff.py:107)
-            q2, kv2, ctx2 = (a.q2, a.kv2, a.ctx2) if save else (self.q, self.kv, self.ctx)
-            ops.gemm(h1b, w16(f"{l}.crossattention.self.query.weight"), bias=w(f"{l}.crossattention.self.query.bias"), out=q2)
-            ops.gemm(self.img_tok, self._fused(f"{l}.crossattention.self.key.weight", 2 * H, d.v_width),
-                     bias=self._fused1(f"{l}.crossattention.self.key.bias", 2 * H), out=kv2)
-            ops.attn_fwd_ex(q2, kv2[:, :H], kv2[:, H:], mb, S, d.v_tokens, nh, out=ctx2, lse=(a.lse2 if save else None))
-            t2 = a.t2 if save else self.tmp
-            ops.gemm(ctx2, w16(f"{l}.crossattention.output.dense.weight"), bias=w(f"{l}.crossattention.output.dense.bias"),
-                     residual=self.h, out=t2)
-            ops.layernorm_fwd(t2, w(f"{l}.crossattention.output.LayerNorm.weight"),
-                              w(f"{l}.crossattention.output.LayerNorm.bias"), 1e-12, out=self.h,
-                              stats=((a.m2, a.r2) if save else None))
-            h2b = a.h2b if save else self.hb
-            ops.cast_bf16(self.h, out=h2b)
+            if ff:
+                # cross-attention into the image tokens (encoder mask is all ones, blip_ff.py:107)
+                q2, kv2, ctx2 = (a.q2, a.kv2, a.ctx2) if save else (self.q, self.kv, self.ctx)
+                ops.gemm(h1b, w16(f"{l}.crossattention.self.query.weight"), bias=w(f"{l}.crossattention.self.query.bias"), out=q2)
+                ops.gemm(self.img_tok, self._fused(f"{l}.crossattention.self.key.weight", 2 * H, d.v_width),
+                         bias=self._fused1(f"{l}.crossattention.self.key.bias", 2 * H), out=kv2)
+                ops.attn_fwd_ex(q2, kv2[:, :H], kv2[:, H:], mb, S, d.v_tokens, nh, out=ctx2, lse=(a.lse2 if save else None))
+                t2 = a.t2 if save else self.tmp
+                ops.gemm(ctx2, w16(f"{l}.crossattention.output.dense.weight"), bias=w(f"{l}.crossattention.output.dense.bias"),
+                         residual=self.h, out=t2)
+                ops.layernorm_fwd(t2, w(f"{l}.crossattention.output.LayerNorm.weight"),
+                                  w(f"{l}.crossattention.output.LayerNorm.bias"), 1e-12, out=self.h,
+                                  stats=((a.m2, a.r2) if save else None))
+                h2b = a.h2b if save else self.hb
+                ops.cast_bf16(self.h, out=h2b)
+            else:
+                h2b = h1b        # mode="text" (med.py:368-383): no cross-attention, the FFN follows directly
             # FFN
             pre, act = (a.pre, a.act) if save else (None, self.inter)
             ops.gemm(h2b, w16(f"{l}.intermediate.dense.weight"), bias=w(f"{l}.intermediate.dense.bias"), act=L.ACT_GELU,
@@ -248,7 +283,13 @@ class BLIPEncoder:
                               stats=((a.m3, a.r3) if save else None))
         ops.cast_bf16(self.h, out=self.hb)
         self.pool.copy_(self.hb.view(mb, S, H)[:, 0])
-        ops.gemm(self.pool, w16(f"{t}.pooler.dense.weight"), bias=w(f"{t}.pooler.dense.bias"), act=L.ACT_TANH, out=self.emb)
+        if ff:
+            ops.gemm(self.pool, w16(f"{t}.pooler.dense.weight"), bias=w(f"{t}.pooler.dense.bias"), act=L.ACT_TANH, out=self.emb)
+            return self.emb
+        ops.gemm(self.pool, w16(f"text_proj{self.sfx}.weight"), bias=w(f"text_proj{self.sfx}.bias"), out=self.t_emb)
+        self.mt = self.ones if mt is None else mt
+        self.mv = self.ones if mv is None else mv
+        ops.score_fuse_fwd(self.t_emb, self.v_emb, self.mt, self.mv, out=self.emb)   # txt * txt_mask + img * img_mask
         return self.emb
 
     def backward(self, d_emb):
@@ -259,14 +300,22 @@ class BLIPEncoder:
         v, t = self.v, self.t
         H, nh, Sv = d.t_width, d.t_heads, d.v_tokens
         G = P.grad
-        # ---- pooler: emb = tanh(W h[:,0] + b)
-        ops.tanh_bwd(d_emb, self.emb, self.dz)
-        ops.wgrad(self.dz, self.pool, g(f"{t}.pooler.dense.weight"))
-        ops.colsum_accum(self.dz, g(f"{t}.pooler.dense.bias"))
-        ops.gemm(self.dz, w16(f"{t}.pooler.dense.weight"), b_mn=True, out=self.d_pool)
+        ff = self.mode == "ff"
+        if ff:
+            # ---- pooler: emb = tanh(W h[:,0] + b)
+            ops.tanh_bwd(d_emb, self.emb, self.dz)
+            ops.wgrad(self.dz, self.pool, g(f"{t}.pooler.dense.weight"))
+            ops.colsum_accum(self.dz, g(f"{t}.pooler.dense.bias"))
+            ops.gemm(self.dz, w16(f"{t}.pooler.dense.weight"), b_mn=True, out=self.d_pool)
+            self.d_img.zero_()
+        else:
+            # ---- emb = mt * text_proj(h[:,0]) + mv * vision_proj(norm(x)[:,0])
+            ops.score_fuse_bwd(d_emb, self.mt, self.mv, out=(self.d_t, self.d_v))
+            ops.wgrad(self.d_t, self.pool, g(f"text_proj{self.sfx}.weight"))
+            ops.colsum_accum(self.d_t, g(f"text_proj{self.sfx}.bias"))
+            ops.gemm(self.d_t, w16(f"text_proj{self.sfx}.weight"), b_mn=True, out=self.d_pool)
         self.dh.zero_()
         self.dh.view(mb, S, H)[:, 0] = self.d_pool.float()
-        self.d_img.zero_()
         for i in reversed(range(d.t_layers)):
             l = f"{t}.encoder.layer.{i}"
             a = self.acts[i]
@@ -279,22 +328,23 @@ class BLIPEncoder:
             ops.wgrad(self.d_pre, a.h2b, g(f"{l}.intermediate.dense.weight"))
             ops.colsum_accum(self.d_pre, g(f"{l}.intermediate.dense.bias"))
             ops.gemm(self.d_pre, w16(f"{l}.intermediate.dense.weight"), b_mn=True, residual=self.dt, out=self.dh)
-            # ---- cross-attention: h2 = LN(dense(attn(q(h1), kv(img))) + h1)
-            ops.layernorm_bwd(self.dh, a.t2, a.m2, a.r2, w(f"{l}.crossattention.output.LayerNorm.weight"), self.dt,
-                              g(f"{l}.crossattention.output.LayerNorm.weight"), g(f"{l}.crossattention.output.LayerNorm.bias"),
-                              accumulate=False, dx_bf16=self.dtb,
-                              dcolsum=g(f"{l}.crossattention.output.dense.bias"))
-            ops.wgrad(self.dtb, a.ctx2, g(f"{l}.crossattention.output.dense.weight"))
-            ops.gemm(self.dtb, w16(f"{l}.crossattention.output.dense.weight"), b_mn=True, out=self.d_ctx)
-            ops.attn_bwd_ex(a.q2, a.kv2[:, :H], a.kv2[:, H:], a.ctx2, self.d_ctx, a.lse2, mb, S, Sv, nh,
-                            self.dq2, self.dkv2[:, :H], self.dkv2[:, H:], delta=self.delta)
-            ops.wgrad(self.dq2, a.h1b, g(f"{l}.crossattention.self.query.weight"))
-            ops.colsum_accum(self.dq2, g(f"{l}.crossattention.self.query.bias"))
-            ops.gemm(self.dq2, w16(f"{l}.crossattention.self.query.weight"), b_mn=True, residual=self.dt, out=self.dh)
-            ops.wgrad(self.dkv2, self.img_tok, self._fused(f"{l}.crossattention.self.key.weight", 2 * H, d.v_width, G))
-            ops.colsum_accum(self.dkv2, self._fused1(f"{l}.crossattention.self.key.bias", 2 * H, G))
-            ops.gemm(self.dkv2, self._fused(f"{l}.crossattention.self.key.weight", 2 * H, d.v_width), b_mn=True,
-                     out=self.d_img, accumulate=True)
+            # ---- cross-attention: h2 = LN(dense(attn(q(h1), kv(img))) + h1)   (mode "sf": absent, dh passes through)
+            if ff:
+                ops.layernorm_bwd(self.dh, a.t2, a.m2, a.r2, w(f"{l}.crossattention.output.LayerNorm.weight"), self.dt,
+                                  g(f"{l}.crossattention.output.LayerNorm.weight"), g(f"{l}.crossattention.output.LayerNorm.bias"),
+                                  accumulate=False, dx_bf16=self.dtb,
+                                  dcolsum=g(f"{l}.crossattention.output.dense.bias"))
+                ops.wgrad(self.dtb, a.ctx2, g(f"{l}.crossattention.output.dense.weight"))
+                ops.gemm(self.dtb, w16(f"{l}.crossattention.output.dense.weight"), b_mn=True, out=self.d_ctx)
+                ops.attn_bwd_ex(a.q2, a.kv2[:, :H], a.kv2[:, H:], a.ctx2, self.d_ctx, a.lse2, mb, S, Sv, nh,
+                                self.dq2, self.dkv2[:, :H], self.dkv2[:, H:], delta=self.delta)
+                ops.wgrad(self.dq2, a.h1b, g(f"{l}.crossattention.self.query.weight"))
+                ops.colsum_accum(self.dq2, g(f"{l}.crossattention.self.query.bias"))
+                ops.gemm(self.dq2, w16(f"{l}.crossattention.self.query.weight"), b_mn=True, residual=self.dt, out=self.dh)
+                ops.wgrad(self.dkv2, self.img_tok, self._fused(f"{l}.crossattention.self.key.weight", 2 * H, d.v_width, G))
+                ops.colsum_accum(self.dkv2, self._fused1(f"{l}.crossattention.self.key.bias", 2 * H, G))
+                ops.gemm(self.dkv2, self._fused(f"{l}.crossattention.self.key.weight", 2 * H, d.v_width), b_mn=True,
+                         out=self.d_img, accumulate=True)
             # ---- self-attention: h1 = LN(dense(attn(qkv(h_in))) + h_in)
             ops.layernorm_bwd(self.dh, a.t1, a.m1, a.r1, w(f"{l}.attention.output.LayerNorm.weight"), self.dt,
                               g(f"{l}.attention.output.LayerNorm.weight"), g(f"{l}.attention.output.LayerNorm.bias"),
@@ -312,10 +362,21 @@ class BLIPEncoder:
                           g(f"{t}.embeddings.LayerNorm.weight"), g(f"{t}.embeddings.LayerNorm.bias"), accumulate=False)
         ops.text_embed_bwd(self.dt.view(mb, S, H), self.ids, g(f"{t}.embeddings.word_embeddings.weight"),
                            g(f"{t}.embeddings.position_embeddings.weight")[:S])
-        # ---- ViT: img_tok = LN_final(blocks(patch-embed(img)))
-        ops.layernorm_bwd(self.d_img, self.vis.x_out, self.vn_m, self.vn_r, w(f"{v}.norm.weight"), self.vis.dx,
-                          g(f"{v}.norm.weight"), g(f"{v}.norm.bias"), accumulate=False, dx_bf16=self.vis.dxb,
-                          dcolsum=self.vis.top_bias_grad())
+        if ff:
+            # ---- ViT: img_tok = LN_final(blocks(patch-embed(img)))
+            ops.layernorm_bwd(self.d_img, self.vis.x_out, self.vn_m, self.vn_r, w(f"{v}.norm.weight"), self.vis.dx,
+                              g(f"{v}.norm.weight"), g(f"{v}.norm.bias"), accumulate=False, dx_bf16=self.vis.dxb,
+                              dcolsum=self.vis.top_bias_grad())
+        else:
+            # ---- ViT: v_emb = vision_proj(LN_final(x_out)[class-token rows])
+            ops.wgrad(self.d_v, self.v_pool, g(f"vision_proj{self.sfx}.weight"))
+            ops.colsum_accum(self.d_v, g(f"vision_proj{self.sfx}.bias"))
+            ops.gemm(self.d_v, w16(f"vision_proj{self.sfx}.weight"), b_mn=True, out=self.d_vpool)
+            self.vis.dx.zero_()
+            self.vis.dxb.zero_()
+            ops.layernorm_bwd(self.d_vpool, self.vis.x_out, self.vn_m[:mb], self.vn_r[:mb], w(f"{v}.norm.weight"), self.vis.dx,
+                              g(f"{v}.norm.weight"), g(f"{v}.norm.bias"), row_index=self.cls_rows, accumulate=False,
+                              dx_bf16=self.vis.dxb, dcolsum=self.vis.top_bias_grad())
         self.vis.backward(top_bias_done=True)
         ops.vision_embed_bwd(self.vis.dx.view(mb, Sv, d.v_width), mb, Sv, d.v_width, self.d_patch,
                              g(f"{v}.cls_token").view(-1), g(f"{v}.pos_embed").view(Sv, d.v_width))
@@ -324,6 +385,8 @@ class BLIPEncoder:
 
 
 class BLIPFeatureFusion(nn.Module):
+    MODE = "ff"     # BLIPScoreFusion (blip_sf.py) overrides: same loss / queues / EMA, different encoder head
+
     def __init__(self, med_config="backbone/configs/med_config.json", image_size=224, vit="base", vit_grad_ckpt=False,
                  vit_ckpt_layer=0, embed_dim=768, queue_size=57600, momentum=0.995, config=None, device="cuda",
                  micro_batch=256, seed=2023):
@@ -342,10 +405,15 @@ class BLIPFeatureFusion(nn.Module):
         self.dims, self.device_, self.micro_batch = d, dev, micro_batch
         self.image_size, self.queue_size, self.momentum, self.embed_dim, self.config = image_size, queue_size, momentum, embed_dim, config
         # online + momentum encoders as two flat parameter sets with identical layouts (EMA = one kernel)
-        self._online = FlatParamModule(blip_param_specs(d), dev, seed=seed, root=self)
-        self._mom = FlatParamModule(blip_param_specs(d, "_m"), dev, seed=seed, root=self)
+        self._out_dim = d.t_width if self.MODE == "ff" else embed_dim     # width of the fused embedding
+        self._online = FlatParamModule(blip_param_specs(d, "", self.MODE, embed_dim), dev, seed=seed, root=self)
+        self._mom = FlatParamModule(blip_param_specs(d, "_m", self.MODE, embed_dim), dev, seed=seed, root=self)
         for name, *_ in self._mom._specs:
             self.get_parameter(name).requires_grad_(False)          # blip_ff.py:283-287 copy_params
+        if self.MODE == "sf":                                       # blip_sf.py:75-78
+            for name, *_ in self._online._specs:
+                if ".crossattention." in name:
+                    self.get_parameter(name).requires_grad_(False)
         for k in self._mom.flat:
             self._mom.flat[k].copy_(self._online.flat[k][:self._mom.flat[k].numel()])
         for enc in ("text_encoder", "text_encoder_m"):
@@ -380,8 +448,17 @@ class BLIPFeatureFusion(nn.Module):
         if key not in self._enc:
             self._enc = {k: v for k, v in self._enc.items() if (k[2], k[3]) != (momentum, train)}
             self._enc[key] = BLIPEncoder(self._mom if momentum else self._online, self.dims, mb, S, self.device_,
-                                         "_m" if momentum else "", train=train)
+                                         "_m" if momentum else "", train=train, mode=self.MODE, embed_dim=self.embed_dim)
         return self._enc[key]
+
+    def _masks(self, txt_mask, img_mask, n):
+        """Modality masks as int64 [n] device tensors (score fusion); None for feature fusion, which ignores them."""
+        if self.MODE == "ff":
+            return None, None
+        one = torch.ones(n, dtype=torch.int64, device=self.device_)
+        mt = one if txt_mask is None else txt_mask.to(self.device_, torch.int64).reshape(n).contiguous()
+        mv = one if img_mask is None else img_mask.to(self.device_, torch.int64).reshape(n).contiguous()
+        return mt, mv
 
 
 
@@ -397,7 +474,8 @@ class BLIPFeatureFusion(nn.Module):
 
     @torch.no_grad()
     def encode_multimodal_input(self, txt_dict_batched, image_batched, txt_mask=None, img_mask=None, use_momentum=False):
-        """blip_ff.py:82-116.  txt_mask / img_mask are accepted and ignored, exactly like the reference."""
+        """blip_ff.py:82-116: txt_mask / img_mask are accepted and ignored, exactly like the reference.
+        blip_sf.py:158-172 (MODE "sf"): text_proj(text [CLS]) * txt_mask + vision_proj(image class token) * img_mask."""
         ids = txt_dict_batched["input_ids"] if isinstance(txt_dict_batched, dict) else txt_dict_batched.input_ids
         att = txt_dict_batched["attention_mask"] if isinstance(txt_dict_batched, dict) else txt_dict_batched.attention_mask
         dev = self.device_
@@ -412,15 +490,21 @@ class BLIPFeatureFusion(nn.Module):
         enc = self._encoder(mb, S, use_momentum)
         P = self._mom if use_momentum else self._online
         P.refresh_shadow()
-        out = torch.empty(n, self.dims.t_width, device=dev, dtype=torch.float32)
+        out = torch.empty(n, self._out_dim, device=dev, dtype=torch.float32)
+        mt, mv = self._masks(txt_mask, img_mask, n)
         for s in range(0, n, mb):
             e = min(n, s + mb)
             i_c, l_c, im_c = ids[s:e], lens[s:e], img[s:e]
+            mt_c, mv_c = (None, None) if mt is None else (mt[s:e], mv[s:e])
             if e - s < mb:
                 pad = mb - (e - s)
                 i_c = torch.cat([i_c, i_c.new_zeros(pad, S)]); l_c = torch.cat([l_c, l_c.new_ones(pad)])
                 im_c = torch.cat([im_c, im_c.new_zeros(pad, *im_c.shape[1:])])
-            out[s:e] = enc.forward(i_c.contiguous(), l_c.contiguous(), im_c.contiguous())[:e - s]
+                if mt is not None:
+                    mt_c = torch.cat([mt_c, mt_c.new_zeros(pad)]); mv_c = torch.cat([mv_c, mv_c.new_zeros(pad)])
+            out[s:e] = enc.forward(i_c.contiguous(), l_c.contiguous(), im_c.contiguous(),
+                                   mt=None if mt_c is None else mt_c.contiguous(),
+                                   mv=None if mv_c is None else mv_c.contiguous())[:e - s]
         return out
 
     def forward(self, batch, alpha=None, encode_mbeir_batch=False):
@@ -469,7 +553,7 @@ class BLIPFeatureFusion(nn.Module):
         im = batch["index_mapping"]
         if "neg_cand_list" in im:
             raise NotImplementedError("BLIP_FF hard-negative variant (blip_ff.py:127-131,160-171) is not built")
-        dev, E = self.device_, self.dims.t_width
+        dev, E = self.device_, self._out_dim
         P = self._online
         P.w("temp").clamp_(0.001, 0.5)                                   # blip_ff.py:132-133
         ids, lens = self._prep_txt(batch["txt_batched"])
@@ -479,9 +563,10 @@ class BLIPFeatureFusion(nn.Module):
         pc_ids = torch.as_tensor(batch["p_did_list"]).to(dev, torch.int64).contiguous()
         bs, n_items, S = q_idx.numel(), ids.shape[0], ids.shape[1]
         txt = {"input_ids": ids, "attention_mask": (torch.arange(S, device=dev)[None, :] < lens[:, None]).long()}
-        emb = self.encode_multimodal_input(txt, img)                      # phase A, online (no activations kept)
+        mt, mv = self._masks(batch.get("txt_mask_batched"), batch.get("image_mask_batched"), n_items)
+        emb = self.encode_multimodal_input(txt, img, mt, mv)              # phase A, online (no activations kept)
         self._momentum_update()                                           # blip_ff.py:182
-        emb_m = self.encode_multimodal_input(txt, img, use_momentum=True)
+        emb_m = self.encode_multimodal_input(txt, img, mt, mv, use_momentum=True)
         f32 = dict(device=dev, dtype=torch.float32)
         qn, pn, qm, pm = (torch.empty(bs, E, **f32) for _ in range(4))
         qnorm, pnorm, tmpn = torch.empty(bs, **f32), torch.empty(bs, **f32), torch.empty(bs, **f32)
@@ -509,7 +594,7 @@ class BLIPFeatureFusion(nn.Module):
                                                 qnorm.data_ptr(), pnorm.data_ptr(), d_qn.data_ptr(), d_pn.data_ptr(), bs, E,
                                                 d_emb.data_ptr(), ops._stream()), "normalize_bwd")
         self._dequeue_and_enqueue(qm, pm, pc_ids)                         # blip_ff.py:247
-        self._train_state = dict(ids=ids, lens=lens, img=img, d_emb=d_emb, d_temp=acc_l[3].clone())
+        self._train_state = dict(ids=ids, lens=lens, img=img, d_emb=d_emb, d_temp=acc_l[3].clone(), mt=mt, mv=mv)
         return loss.clone(), acc.clone()
 
     @torch.no_grad()
@@ -531,6 +616,8 @@ class BLIPFeatureFusion(nn.Module):
         P.refresh_shadow()
         for s in range(0, n, mb):
             e = s + mb
-            enc.forward(st["ids"][s:e].contiguous(), st["lens"][s:e].contiguous(), st["img"][s:e].contiguous(), save=True)
+            enc.forward(st["ids"][s:e].contiguous(), st["lens"][s:e].contiguous(), st["img"][s:e].contiguous(), save=True,
+                        mt=None if st["mt"] is None else st["mt"][s:e].contiguous(),
+                        mv=None if st["mv"] is None else st["mv"][s:e].contiguous())
             enc.backward(st["d_emb"][s:e].contiguous())
         self._train_state = None

@@ -137,7 +137,7 @@ def save_embeddings(embed_path, ids_path, emb, ids):
 
 
 def build_model_from_config(config):
-    """The ``CLIPScoreFusion`` and ``BLIPFeatureFusion`` arms of reference common/utils.py:64-152 on the B200
+    """The ``CLIPScoreFusion``, ``BLIPFeatureFusion`` and ``BLIPScoreFusion`` arms of reference common/utils.py:64-152 on the B200
     backend (same config fields, same checkpoint layout ``torch.load(path)["model"]``)."""
     name = config.model.name
     mc = config.model
@@ -145,15 +145,17 @@ def build_model_from_config(config):
         from .clip_sf import CLIPScoreFusion
         model = CLIPScoreFusion(model_name=mc.clip_vision_model_name,
                                 download_root=os.path.join(config.uniir_dir, mc.pretrained_clip_model_dir))
-    elif name == "BLIPFeatureFusion":
-        from .blip_ff import BLIPFeatureFusion
-        model = BLIPFeatureFusion(med_config=os.path.join("../models/uniir_blip", "backbone/configs/med_config.json"),
-                                  image_size=mc.image_size, vit=mc.vit, vit_grad_ckpt=mc.vit_grad_ckpt,
-                                  vit_ckpt_layer=mc.vit_ckpt_layer, embed_dim=mc.embed_dim, queue_size=mc.queue_size,
-                                  config=mc)
+    elif name in ("BLIPFeatureFusion", "BLIPScoreFusion"):     # common/utils.py:97-152
+        if name == "BLIPFeatureFusion":
+            from .blip_ff import BLIPFeatureFusion as cls
+        else:
+            from .blip_sf import BLIPScoreFusion as cls
+        model = cls(med_config=os.path.join("../models/uniir_blip", "backbone/configs/med_config.json"),
+                    image_size=mc.image_size, vit=mc.vit, vit_grad_ckpt=mc.vit_grad_ckpt,
+                    vit_ckpt_layer=mc.vit_ckpt_layer, embed_dim=mc.embed_dim, queue_size=mc.queue_size, config=mc)
     else:
-        raise NotImplementedError(f"model {name!r}: CLIPScoreFusion and BLIPFeatureFusion are built on the B200 path "
-                                  "(CLIPFeatureFusion / BLIPScoreFusion: SURVEY 8f-3)")
+        raise NotImplementedError(f"model {name!r}: CLIPScoreFusion, BLIPFeatureFusion and BLIPScoreFusion are built on "
+                                  "the B200 path (CLIPFeatureFusion: SURVEY 8f-3)")
     ckpt = os.path.join(config.uniir_dir, mc.ckpt_config.ckpt_dir, mc.ckpt_config.ckpt_name)
     assert os.path.exists(ckpt), f"Checkpoint file {ckpt} does not exist."
     print(f"loading {name} checkpoint from {ckpt}")
