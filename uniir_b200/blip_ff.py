@@ -1,11 +1,12 @@
 """Drop-in for the reference ``BLIPFeatureFusion`` (src/models/uniir_blip/blip_featurefusion/
-blip_ff.py:11-332) on the B200-native kernels -- ENCODE PATH.
+blip_ff.py:11-332) on the B200-native kernels, and the shared machinery of
+``BLIPScoreFusion`` (blip_sf.py; ``BLIPEncoder(mode="sf")``).
 
-Built this round: constructor / state-dict layout (online + momentum encoders, queues, temp: reference
-checkpoints load with a plain ``load_state_dict``), ``encode_multimodal_input``, ``forward(batch,
-encode_mbeir_batch=True)`` / ``encode_mbeir_batch`` (embedding extraction and retrieval with BLIP_FF).
-Not built yet: ``compute_contrastive_loss`` (momentum distillation + queue, row a9) raises
-NotImplementedError.
+Built: constructor / state-dict layout (online + momentum encoders, queues, temp: reference checkpoints load
+with a plain ``load_state_dict``), ``encode_multimodal_input``, ``forward(batch, encode_mbeir_batch=True)`` /
+``encode_mbeir_batch``, and the momentum-distillation training step (``compute_contrastive_loss`` +
+``backward_contrastive``, driven by ``engine.train_step_blip``): EMA, queue, soft-label cross-entropy, gradient
+caching.  Not built: the hard-negative variant of the loss (blip_ff.py:127-131,160-171).
 
 Arithmetic (vendored reference code, restated in oracle/blip_oracle.py and pinned against the shimmed
 reference modules): ViT-L/16 with biased patch-embed, pre-LN blocks (eps 1e-6), exact GELU, final norm, all
