@@ -258,8 +258,9 @@ def run_train(args, rank, world, dev, peaks):
     h2d = sum(v.numel() * v.element_size() for v in hb.values() if torch.is_tensor(v))
 
     def e2e_step():
-        gb = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in hb.items()}
-        loss, acc = train_step(model, gb, opt)
+        # the public call with the pinned HOST batch: the model uploads it (images in micro-batch chunks on a copy
+        # stream, overlapped with the towers; everything else up front) -- every byte of `h2d` crosses PCIe each step
+        loss, acc = train_step(model, hb, opt)
         state["e2e_loss"] = loss.item()  # device -> host read of the step's result
 
     e2e_step()
@@ -438,8 +439,7 @@ def run_embed(args, rank, world, dev, peaks):
     hb = {k: (torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) if torch.is_tensor(v) else v) for k, v in b.items()}
 
     def e2e_step():
-        gb = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in hb.items()}
-        emb, _ = model(gb, encode_mbeir_batch=True)
+        emb, _ = model(hb, encode_mbeir_batch=True)      # pinned host batch in, uploaded in chunks by the model
         state["host"] = emb.half().cpu()
 
     e2e_step()

@@ -137,6 +137,29 @@ def test_retained_micro_batches_skip_the_reforward_and_change_nothing():
     assert res["auto"][2] < res[2][2] < res[0][2]     # each retained micro-batch saves one forward
 
 
+def test_pinned_host_batch_is_uploaded_in_chunks_and_changes_nothing():
+    """End-to-end path: a pinned host batch goes straight into the public call; the images are uploaded in
+    micro-batch chunks on a copy stream (overlapped with the towers).  Same loss and gradients as a device batch."""
+    from uniir_b200.clip_sf import CLIPScoreFusion
+    res = {}
+    for where in ("device", "pinned"):
+        m = CLIPScoreFusion("tiny-test", device="cuda", micro_batch=8, seed=5)
+        b = _batch(m.dims, 16, seed=9)
+        b["txt_mask_batched"] = torch.ones(32, dtype=torch.long); b["image_mask_batched"] = torch.ones(32, dtype=torch.long)
+        gb = _cuda(b) if where == "device" else {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()}
+        for it in range(3):          # eager, capture, replay
+            if m.clip_model.grad is not None:
+                for g_ in m.clip_model.grad.values():
+                    g_.zero_()
+            loss, acc = m._loss_forward(gb); m._loss_backward(gb, None)
+        torch.cuda.synchronize()
+        assert (m._upload is None) and (where == "device" or m._h2d_stream is not None)
+        res[where] = (loss.item(), {n: m.clip_model.g(n).clone() for n, *_ in m.clip_model._specs})
+    assert abs(res["pinned"][0] - res["device"][0]) < 1e-6 * max(1.0, abs(res["device"][0]))
+    for n, ga in res["device"][1].items():
+        assert (ga - res["pinned"][1][n]).norm() <= 2e-3 * (ga.norm() + 1e-12), n
+
+
 def test_vit_b32_batch4_matches_oracle():
     """BASELINE configs[0]: CLIP_SF ViT-B/32 in-batch contrastive step, batch 4."""
     _check_against_oracle("ViT-B/32", 4, 8, 0.995)

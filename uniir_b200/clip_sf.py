@@ -82,6 +82,8 @@ class CLIPScoreFusion(nn.Module):
         self.retain_micro_batches = "auto"
         self.retain_reserve_bytes = 16 << 30   # left free for the loss, NCCL and allocator slack under "auto"
         self._retained = []
+        self._upload = None          # (chunk, events) of an image upload in flight (_prep / _wait_upload)
+        self._h2d_stream = None
         self._enc = {}
         self._nce = None
         self._train_state = None
@@ -163,10 +165,42 @@ class CLIPScoreFusion(nn.Module):
         cap = 64 if train else 256
         return min(cap, n)
 
-    def _prep(self, txt, img):
-        txt = txt.to(self.device_, torch.int32).contiguous()
-        img = img.to(self.device_, torch.float32).contiguous()
+    def _prep(self, txt, img, chunk=None):
+        """Inputs on the device.  A pinned host image batch (the end-to-end path: 602 KB per item, 4.9 GB for the
+        4096-pair batch) is uploaded on a side stream in micro-batch chunks, each with an event, so that only the
+        first chunk's copy is exposed and the rest overlaps the towers (`_wait_upload` before a chunk is read)."""
+        txt = txt.to(self.device_, torch.int32, non_blocking=True).contiguous()
+        if (chunk and img.device.type == "cpu" and img.is_pinned() and img.dtype == torch.float32 and img.is_contiguous()
+                and img.shape[0] > chunk):
+            main = torch.cuda.current_stream(self.device_)
+            if self._h2d_stream is None:
+                self._h2d_stream = torch.cuda.Stream(device=self.device_)
+            side = self._h2d_stream
+            dev = torch.empty(img.shape, device=self.device_, dtype=torch.float32)
+            side.wait_stream(main)           # the allocator may hand out memory the main stream is still using
+            dev.record_stream(side)
+            events = []
+            with torch.cuda.stream(side):
+                for s in range(0, img.shape[0], chunk):
+                    dev[s:s + chunk].copy_(img[s:s + chunk], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    events.append(ev)
+            self._upload = (chunk, events)
+            return txt, dev
+        img = img.to(self.device_, torch.float32, non_blocking=True).contiguous()
         return txt, img
+
+    def _wait_upload(self, s=None, e=None):
+        """Make the current stream wait for the uploaded image rows [s, e) (all rows if None)."""
+        up = self._upload
+        if up is None:
+            return
+        chunk, events = up
+        lo, hi = (0, len(events)) if s is None else (s // chunk, (e + chunk - 1) // chunk)
+        cur = torch.cuda.current_stream(self.device_)
+        for ev in events[lo:hi]:
+            cur.wait_event(ev)
 
     def _sync_weights(self, enc):
         self.clip_model.refresh_shadow()
@@ -216,10 +250,10 @@ class CLIPScoreFusion(nn.Module):
         every item has both modalities): the first micro-batches run on the retained encoders and keep their
         activations for _loss_backward."""
         n = txt.shape[0]
-        txt, img = self._prep(txt, img)
+        mb = self._pick_mb(n, False) if enc is None else enc.mb
+        txt, img = self._prep(txt, img, chunk=mb)     # no-op for device tensors (training: uploaded by _loss_forward)
         mt = mt.to(self.device_, torch.int64).contiguous()
         mv = mv.to(self.device_, torch.int64).contiguous()
-        mb = self._pick_mb(n, False) if enc is None else enc.mb
         enc = enc or self._encoder(mb, False)
         self._sync_weights(enc)
         plan = self._mask_plan(mt, mv)
@@ -229,14 +263,18 @@ class CLIPScoreFusion(nn.Module):
             self._n_retained = len(kept)
             for i, s in enumerate(range(0, n, mb)):
                 e = min(n, s + mb)  # a ragged tail is zero-padded inside set_inputs; padded rows are dropped
+                self._wait_upload(s, e)
                 if i < len(kept):
                     kept[i].set_inputs(txt[s:e], img[s:e], mt[s:e], mv[s:e])
                     emb[s:e].copy_(kept[i].fwd_save(self.use_cuda_graphs))
                     continue
                 enc.set_inputs(txt[s:e], img[s:e], mt[s:e], mv[s:e])
                 emb[s:e].copy_(enc.embed(self.use_cuda_graphs)[:e - s])
+            self._upload = None
             return None
         # each tower encodes only its unmasked rows; out = mt * text + mv * image is scattered back
+        self._wait_upload()
+        self._upload = None
         emb.zero_()
         for tower, rows, src, mask in (("text", plan[0], txt, mt), ("vision", plan[1], img, mv)):
             for s in range(0, rows.numel(), mb):
@@ -273,7 +311,7 @@ class CLIPScoreFusion(nn.Module):
         enc = self._encoder(mb, True)
         self._train_mb = mb
         st = dict(q_idx=q_idx, p_idx=p_idx, bs=bs, n_items=n_items, rank=rank, world=world, enc=enc)
-        st["txt"], st["img"] = self._prep(batch["txt_batched"], batch["image_batched"])
+        st["txt"], st["img"] = self._prep(batch["txt_batched"], batch["image_batched"], chunk=mb)
         st["mt"] = batch["txt_mask_batched"].to(dev, torch.int64).contiguous()
         st["mv"] = batch["image_mask_batched"].to(dev, torch.int64).contiguous()
         emb = torch.empty(n_items, E, device=dev, dtype=torch.float32)

@@ -112,6 +112,8 @@ def train_one_epoch(model, data_loader, optimizer, epoch, gpu_id, scheduler, glo
     for i, batch in enumerate(data_loader):
         for key in batch:
             if isinstance(batch[key], torch.Tensor):
+                if fast and key == "image_batched" and batch[key].is_pinned():
+                    continue    # the model uploads pinned images in micro-batch chunks, overlapped with the towers
                 batch[key] = batch[key].to(gpu_id, non_blocking=True)
         counter += 1
         stepping = counter == accumulation_steps
