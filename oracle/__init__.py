@@ -15,6 +15,11 @@ Parity status (see DESIGN.md "Oracle"):
     restatement against an independent second implementation, ``transformers.CLIPModel``
     (tests/test_oracle_clip.py), and against committed golden vectors in tests/golden/.
   * CLIP_SF loss / fusion / embed API: restated from clip_sf.py:53-168.
+  * BLIP_FF / BLIP_SF (oracle/blip_oracle.py): the arithmetic is vendored in the reference (backbone/vit.py,
+    med.py, blip_ff.py, blip_sf.py); the restatements are pinned against those UNMODIFIED modules / classes
+    imported through shims (tests/test_oracle_blip.py, tests/ref_blip_shim.py): pinned by the reference itself.
+  * CLIP_FF (oracle/clip_ff_oracle.py; oracle only, no product path yet): the T5 fusion stack is pinned against
+    transformers' own T5Stack, the class the reference instantiates (tests/test_oracle_clip_ff.py).
   * FAISS IndexFlatIP search: faiss-gpu is absent; restated from its documented
     semantics + call sites mbeir_retriever.py:69-103,188-232.
 """
