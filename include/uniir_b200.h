@@ -40,6 +40,7 @@ extern "C" {
 #define UNIIR_ACT_QUICKGELU 1 /* x*sigmoid(1.702x): upstream CLIP QuickGELU */
 #define UNIIR_ACT_GELU 2      /* exact erf GELU: BLIP vit.py:39 / med.py:308 */
 #define UNIIR_ACT_TANH 3      /* BERT pooler, med.py:505-511 (forward only) */
+#define UNIIR_ACT_RELU 4      /* T5 DenseReluDense of the CLIP_FF fusion stack (clip_ff.py:82-98) */
 
 int uniir_abi_version(void);
 const char* uniir_last_error(void);
@@ -124,6 +125,13 @@ int uniir_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_dtype, const fl
                         const float* gamma, int64_t rows, int32_t D, float* dx, int64_t lddx,
                         int32_t dx_accumulate, float* dgamma, float* dbeta, void* dx_bf16,
                         float* dcolsum, void* stream);
+/* T5LayerNorm (RMS norm, no mean subtraction, no bias): y = x * rsqrt(mean(x^2) + eps) * gamma; x fp32 rows at stride
+ * ldx, y bf16 or fp32 rows at stride ldy.  transformers T5LayerNorm as used by the CLIP_FF fusion stack. */
+int uniir_rmsnorm_fwd(const float* x, int64_t ldx, const float* gamma, float eps, int64_t rows, int32_t D, void* y,
+                      int64_t ldy, int32_t y_dtype, void* stream);
+/* out[b, :] = mean over the S token rows of x[b, :, :] (x fp32 [B, S, D] contiguous): the mean pooling that ends
+ * CLIPFeatureFusion.encode_multimodal_input (clip_ff.py:185-192). */
+int uniir_token_mean(const float* x, int32_t B, int32_t S, int32_t D, float* out, void* stream);
 /* visual.conv1 (stride = kernel = patch, no bias; clip_ff.py:36) as im2col:
  * img fp32 [B,3,H,W] -> bf16 [B*(H/P)^2, Kpad], k = c*P*P + py*P + px, zero padded. */
 int uniir_patch_im2col(const float* img, int32_t B, int32_t H, int32_t W, int32_t P, int32_t Kpad,
@@ -193,6 +201,13 @@ int uniir_attn_set_mode(int32_t mode);
 /* Diagnostic: device buffer of 3 x 256 int64 that receives SM-clock timestamps of CTA 0's phases in the
  * tcgen05 forward (softmax warp / MMA thread / tail warp; scripts/trace_attn.py prints them); null = off. */
 int uniir_attn_set_trace(void* device_buf_3x256_int64);
+/* Attention forward with an additive score bias and a caller-chosen scale: softmax(scale * QK^T + bias) V, bias fp32
+ * [H, Sq, Skv] shared by all batch rows (T5 relative-position bias of the CLIP_FF fusion encoder, clip_ff.py:82-98,
+ * 178-183: transformers' T5Attention adds `position_bias` to unscaled scores, i.e. scale = 1).  Addressing as
+ * uniir_attn_fwd_ex; mma.sync kernel (Skv <= 768). */
+int uniir_attn_fwd_bias(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, int32_t B, int32_t Sq,
+                        int32_t Skv, int32_t H, float scale, const float* bias, void* out, int64_t ldo, float* lse,
+                        void* stream);
 /* Backward workspace (fp32 elements, 16-byte aligned): delta = rowsum(dO o O), the base-2 LSE and the dS of
  * the key columns beyond the last full 128-key tile, each padded to 16 rows per head. */
 int64_t uniir_attn_bwd_workspace_floats(int32_t B, int32_t Sq, int32_t Skv, int32_t H);

@@ -80,3 +80,24 @@ def test_clip_ff_model_contract():
     assert emb.shape == (B, d.embed_dim) and idl == [5, 6, 7, 8]
     with pytest.raises(AssertionError):
         m({**b2, "did_list": ["1:2"] * B}, encode_mbeir_batch=True)
+
+
+@pytest.mark.parametrize("name", ["tiny-test", "ViT-B/32"])
+def test_product_parameter_layout_equals_the_oracle_state_dict(name):
+    """uniir_b200.clip_ff's flat parameter specs (names, shapes) against the oracle's state dict (reference layout:
+    clip_model.* without text_projection, t5_layers.* with transformers' T5Stack names), and the product's host-side
+    bucketing table against transformers' own function."""
+    from transformers.models.t5.modeling_t5 import T5Attention
+    from uniir_b200.clip_ff import clip_ff_param_specs, t5_heads, t5_relative_position_bucket as product_bucket
+    from uniir_b200.params import CLIP_CONFIGS
+    orc = CLIPFeatureFusionOracle(name)
+    want = {k: tuple(v.shape) for k, v in orc.state_dict().items()}
+    got = {n: tuple(s) for n, s, _, _ in clip_ff_param_specs(CLIP_CONFIGS[name], t5_heads(name))}
+    assert got == want, sorted(set(got) ^ set(want))[:10]
+    specs = [n for n, *_ in clip_ff_param_specs(CLIP_CONFIGS[name], t5_heads(name))]
+    for i in range(2):      # q, k, v adjacent: the fused projection is a view of the flat buffer
+        j = specs.index(f"t5_layers.block.{i}.layer.0.SelfAttention.q.weight")
+        assert specs[j + 1].endswith("SelfAttention.k.weight") and specs[j + 2].endswith("SelfAttention.v.weight")
+    pos = torch.arange(334)
+    ref = T5Attention._relative_position_bucket(pos[None, :] - pos[:, None], bidirectional=True, num_buckets=32, max_distance=128)
+    assert torch.equal(product_bucket(334), ref)

@@ -1,0 +1,75 @@
+"""GPU parity of the CLIP_FF encode path (uniir_b200/clip_ff.py) against the oracle, whose T5 stack is
+pinned against transformers' T5Stack (tests/test_oracle_clip_ff.py).
+
+These tests were written in a session that had no GPU time left: the kernels they exercise (uniir_rmsnorm_fwd,
+uniir_attn_fwd_bias, the ReLU epilogue, uniir_token_mean) compile for sm_100a but have not run on hardware yet.
+They are therefore xfail(strict=False) -- XPASS means the path is confirmed and the marker can go -- and the file
+sorts last so that it cannot mask any confirmed test."""
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="CLIP_FF kernels not yet confirmed on a B200")]
+dev = "cuda"
+
+
+def test_new_kernels_against_torch():
+    from uniir_b200 import lib as L
+    from uniir_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    # RMS norm (T5LayerNorm), bf16 and fp32 outputs
+    x = torch.randn(501, 768, generator=g) * 2; w = torch.randn(768, generator=g)
+    ref = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6) * w
+    y32 = ops.rmsnorm_fwd(x.to(dev), w.to(dev), 1e-6, out=torch.empty(501, 768, device=dev))
+    y16 = ops.rmsnorm_fwd(x.to(dev), w.to(dev), 1e-6, out=torch.empty(501, 768, device=dev, dtype=torch.bfloat16))
+    assert (y32.cpu() - ref).abs().max() < 1e-5 and ((y16.float().cpu() - ref).norm() / ref.norm()) < 5e-3
+    # token mean
+    t = torch.randn(5, 334, 768, generator=g)
+    assert (ops.token_mean(t.to(dev)).cpu() - t.mean(1)).abs().max() < 1e-5
+    # ReLU epilogue
+    a = torch.randn(200, 64, generator=g).bfloat16(); b = torch.randn(256, 64, generator=g).bfloat16()
+    out = torch.empty(200, 256, device=dev, dtype=torch.bfloat16)
+    ops.gemm(a.to(dev), b.to(dev), act=L.ACT_RELU, out=out)
+    r = torch.relu(a.float() @ b.float().t())
+    assert ((out.float().cpu() - r).norm() / r.norm()) < 6e-3 and out.min().item() >= 0
+    # attention with an additive score bias and no 1/sqrt(d) scaling (T5), S = 334 and a short ragged S
+    for B, S, H in ((2, 334, 12), (3, 94, 2)):
+        qkv = (torch.randn(B * S, 3 * H * 64, generator=g) * 0.3).bfloat16()
+        bias = torch.randn(H, S, S, generator=g)
+        D = H * 64
+        o = ops.attn_fwd_bias(qkv.to(dev)[:, :D], qkv.to(dev)[:, D:2 * D], qkv.to(dev)[:, 2 * D:], B, S, S, H, bias.to(dev),
+                              scale=1.0).float().cpu()
+        q, k, v = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+        rr = ((q @ k.transpose(-1, -2) + bias).softmax(-1) @ v).transpose(1, 2).reshape(B * S, D)
+        assert ((o - rr).norm() / rr.norm()).item() < 6e-3
+
+
+def test_clip_ff_encode_matches_oracle_and_api_contract():
+    from oracle.clip_ff_oracle import CLIPFeatureFusionOracle
+    from uniir_b200.clip_ff import CLIPFeatureFusion
+    torch.manual_seed(11)
+    orc = CLIPFeatureFusionOracle("tiny-test").eval()
+    with torch.no_grad():      # T5 weights at a scale where the fusion stack matters
+        for n, p in orc.t5_layers.named_parameters():
+            p.normal_(0.0, 0.08) if "layer_norm" not in n else p.normal_(1.0, 0.1)
+    m = CLIPFeatureFusion("tiny-test", device=dev, micro_batch=4)
+    missing, unexpected = m.load_state_dict(orc.state_dict(), strict=True)
+    d = orc.clip_model.dims
+    g = torch.Generator().manual_seed(5)
+    B = 6                                  # micro-batch 4: one full chunk and a ragged tail
+    ids = torch.zeros(B, d.context, dtype=torch.long)
+    for i in range(B):
+        n = int(torch.randint(1, d.context - 2, (1,), generator=g))
+        ids[i, 0] = d.vocab - 2; ids[i, 1:1 + n] = torch.randint(1, d.vocab - 2, (n,), generator=g); ids[i, 1 + n] = d.vocab - 1
+    img = torch.randn(B, 3, d.image_size, d.image_size, generator=g)
+    one = torch.ones(B, dtype=torch.long)
+    with torch.no_grad():
+        ref = orc.encode_multimodal_input(ids, img, one, one)
+    out = m.encode_multimodal_input(ids.to(dev), img.to(dev), one.to(dev), 0 * one.to(dev)).cpu()   # masks ignored
+    cos = torch.nn.functional.cosine_similarity(out, ref, dim=-1)
+    assert cos.min().item() > 1 - 1e-3, cos
+    emb, idl = m({"txt_batched": ids, "image_batched": img, "txt_mask_batched": one, "image_mask_batched": one,
+                  "did_list": list(range(10, 10 + B))}, encode_mbeir_batch=True)
+    assert emb.shape == (B, d.embed_dim) and idl == list(range(10, 10 + B))
+    with pytest.raises(NotImplementedError):
+        m({"txt_batched": ids, "image_batched": img, "txt_mask_batched": one, "image_mask_batched": one,
+           "index_mapping": {"query": [[0]], "pos_cand": [[1]]}})

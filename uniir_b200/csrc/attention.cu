@@ -96,6 +96,7 @@ struct AttnParams {
   long long ldq, ldkv, ldo;
   int Sq, Skv;
   const int* kv_len;         // optional [B]: keys >= kv_len[b] are masked (BERT padding mask)
+  const float* bias;         // optional fp32 [H, Sq, Skv] added to scale * QK^T (T5 relative-position bias; forward only)
   __nv_bfloat16 *dq, *dk, *dv;     // backward outputs: dq rows stride lddq; dk/dv rows stride lddkv
   long long lddq, lddkv, lddo;     // lddo: row stride of dout
   __nv_bfloat16* out;        // [B*S, D]
@@ -137,6 +138,9 @@ __device__ __forceinline__ void load_rows16_warp(uint32_t dst, const __nv_bfloat
   }
 }
 
+// BIAS = false is the tower kernel; BIAS = true adds p.bias[h, q, key] (in score units: divided by the scale
+// that rides in the exp2 FFMA) -- a separate instantiation, so the tower path compiles exactly as before.
+template <bool BIAS>
 __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams p, int spad) {
   extern __shared__ __align__(128) uint8_t sm[];
   const uint32_t sK = s_u32(sm), sV = sK + spad * 128, sQ0 = sV + spad * 128;
@@ -183,6 +187,20 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
             frag_b_nk(bK, j, kk, bb);
             mma_bf16(s[j], qa[kk], bb[0], bb[1]);
             mma_bf16(s[j + 1], qa[kk], bb[2], bb[3]);
+          }
+        }
+      }
+      if constexpr (BIAS) {
+        const float inv_scale = 1.f / p.scale;
+        const float* bh = p.bias + static_cast<long long>(h) * p.Sq * p.Skv;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int key = k0 + j * 8 + (lane & 3) * 2 + (e & 1);
+            const int qr = (e < 2) ? r0 : r1;
+            if (j < nt && key < p.Skv && qr < p.Sq)
+              s[j][e] = fmaf(__ldg(bh + static_cast<long long>(qr) * p.Skv + key), inv_scale, s[j][e]);
           }
         }
       }
@@ -524,7 +542,8 @@ static int attn_set_smem() {
   static bool done = false;
   if (!done) {
     const int mx = 227 * 1024;
-    UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     done = true;
@@ -540,13 +559,16 @@ int attn_fwd_tc_try(const __nv_bfloat16* q, long long ldq, const __nv_bfloat16* 
 
 static int attn_fwd_launch(AttnParams& p, void* stream) {
   // tcgen05 forward (attention_tc.cu) when enabled and the key range fits; > 0 means "not applicable"
-  const int tc = attn_fwd_tc_try(p.q, p.ldq, p.k, p.v, p.ldkv, p.B, p.Sq, p.Skv, p.H, p.causal, p.kv_len, p.out,
-                                 p.ldo, p.lse, p.scale, stream);
-  if (tc <= 0) return tc;
+  if (!p.bias) {     // the tcgen05 kernel takes no score bias
+    const int tc = attn_fwd_tc_try(p.q, p.ldq, p.k, p.v, p.ldkv, p.B, p.Sq, p.Skv, p.H, p.causal, p.kv_len, p.out,
+                                   p.ldo, p.lse, p.scale, stream);
+    if (tc <= 0) return tc;
+  }
   UNIIR_CHECK_ARG(p.Skv <= 768, "uniir_attn_fwd: Skv=%d exceeds the head-resident kernel's limit of 768", p.Skv);
   if (int rc = attn_set_smem()) return rc;
   const int spad = (p.Skv + 15) / 16 * 16;
-  attn_fwd_kernel<<<dim3(p.H, p.B), kAttnThreads, attn_smem(spad, false), ST(stream)>>>(p, spad);
+  if (p.bias) attn_fwd_kernel<true><<<dim3(p.H, p.B), kAttnThreads, attn_smem(spad, false), ST(stream)>>>(p, spad);
+  else attn_fwd_kernel<false><<<dim3(p.H, p.B), kAttnThreads, attn_smem(spad, false), ST(stream)>>>(p, spad);
   count_launch();
   UNIIR_CUDA_OK(cudaGetLastError());
   return UNIIR_OK;
@@ -582,6 +604,23 @@ extern "C" int uniir_attn_fwd_ex(const void* q, int64_t ldq, const void* k, cons
   p.out = static_cast<__nv_bfloat16*>(out);
   p.lse = lse;
   p.B = B; p.S = Sq; p.H = H; p.D = H * kHD; p.causal = causal; p.scale = 0.125f;
+  return attn_fwd_launch(p, stream);
+}
+
+extern "C" int uniir_attn_fwd_bias(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, int32_t B,
+                                   int32_t Sq, int32_t Skv, int32_t H, float scale, const float* bias, void* out,
+                                   int64_t ldo, float* lse, void* stream) {
+  UNIIR_CHECK_ARG(q && k && v && out && bias && B > 0 && Sq > 0 && Skv > 0 && H > 0 && scale > 0.f, "uniir_attn_fwd_bias: bad args");
+  UNIIR_CHECK_ARG(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 2 == 0, "uniir_attn_fwd_bias: strides must keep 16 B row alignment");
+  AttnParams p{};
+  p.q = static_cast<const __nv_bfloat16*>(q);
+  p.k = static_cast<const __nv_bfloat16*>(k);
+  p.v = static_cast<const __nv_bfloat16*>(v);
+  p.ldq = ldq; p.ldkv = ldkv; p.ldo = ldo;
+  p.Sq = Sq; p.Skv = Skv; p.bias = bias;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.lse = lse;
+  p.B = B; p.S = Sq; p.H = H; p.D = H * kHD; p.causal = 0; p.scale = scale;
   return attn_fwd_launch(p, stream);
 }
 

@@ -58,6 +58,7 @@ __device__ __forceinline__ float act_fwd(float x, int act) {
   if (act == UNIIR_ACT_QUICKGELU) return x * qg_sigmoid(x);
   if (act == UNIIR_ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
   if (act == UNIIR_ACT_TANH) return tanhf(x);
+  if (act == UNIIR_ACT_RELU) return fmaxf(x, 0.f);
   return x;
 }
 __device__ __forceinline__ float act_bwd(float x, int act) {
@@ -69,6 +70,7 @@ __device__ __forceinline__ float act_bwd(float x, int act) {
     const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
     return cdf + x * 0.3989422804014327f * __expf(-0.5f * x * x);
   }
+  if (act == UNIIR_ACT_RELU) return x > 0.f ? 1.f : 0.f;
   return 1.f;
 }
 

@@ -232,6 +232,54 @@ layernorm_fwd_warp_kernel(const float* __restrict__ x, long long ldx, const int*
   }
 }
 
+// T5LayerNorm: y = x * rsqrt(mean(x^2) + eps) * gamma.  Warp per row like the LayerNorm forward above.
+template <int NV>
+__global__ void __launch_bounds__(kLnWarpsFwd * 32)
+rmsnorm_fwd_warp_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma, float eps, int D,
+                        long long rows, void* __restrict__ y, long long ldy, int y_f32) {
+  const int lane = threadIdx.x & 31;
+  const long long r = static_cast<long long>(blockIdx.x) * kLnWarpsFwd + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float* xr = x + r * ldx;
+  float4 v[NV];
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + i * 32) * 4;
+    v[i] = (c < D) ? __ldcs(reinterpret_cast<const float4*>(xr + c)) : make_float4(0, 0, 0, 0);
+    q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / D + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + i * 32) * 4;
+    if (c < D) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float o0 = v[i].x * rstd * g.x, o1 = v[i].y * rstd * g.y, o2 = v[i].z * rstd * g.z, o3 = v[i].w * rstd * g.w;
+      if (y_f32)
+        *reinterpret_cast<float4*>(static_cast<float*>(y) + r * ldy + c) = make_float4(o0, o1, o2, o3);
+      else
+        *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(y) + r * ldy + c) = pack4_bf16(o0, o1, o2, o3);
+    }
+  }
+}
+
+// out[b, c..c+3] = mean_s x[b, s, c..c+3]; one thread per float4 column of one item, consecutive threads on
+// consecutive columns (coalesced rows)
+__global__ void token_mean_kernel(const float* __restrict__ x, int S, int D, float* __restrict__ out) {
+  const int b = blockIdx.y, c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c >= D) return;
+  const float* xb = x + static_cast<long long>(b) * S * D + c;
+  float4 a = make_float4(0, 0, 0, 0);
+#pragma unroll 4
+  for (int s = 0; s < S; ++s) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(xb + static_cast<long long>(s) * D));
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  const float inv = 1.f / S;
+  *reinterpret_cast<float4*>(out + static_cast<long long>(b) * D + c) = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+}
+
 // Backward, warp per row, 8 warps per CTA, each warp walking rows r0+w, r0+w+8, ... of the
 // CTA's strip.  dgamma / dbeta (and, when `dcolsum` is given, the column sums of the UPDATED dx
 // -- the bias gradient of the linear layer whose output gradient this dx is, which saves a
@@ -667,6 +715,33 @@ extern "C" int uniir_layernorm_fwd(const float* x, int64_t ldx, const int32_t* r
     if (vecs <= 2) LN_FWD(2); else LN_FWD(4);
 #undef LN_FWD
   }
+  count_launch();
+  UNIIR_CUDA_OK(cudaGetLastError());
+  return UNIIR_OK;
+}
+
+extern "C" int uniir_rmsnorm_fwd(const float* x, int64_t ldx, const float* gamma, float eps, int64_t rows, int32_t D,
+                                 void* y, int64_t ldy, int32_t y_dtype, void* stream) {
+  UNIIR_CHECK_ARG(x && gamma && y && D > 0 && D % 4 == 0 && D <= 1024 && ldx % 4 == 0 && ldy % 4 == 0,
+                  "uniir_rmsnorm_fwd: bad args (D must be a multiple of 4, at most 1024)");
+  UNIIR_CHECK_ARG(y_dtype == UNIIR_F32 || y_dtype == UNIIR_BF16, "uniir_rmsnorm_fwd: y must be fp32 or bf16");
+  if (rows == 0) return UNIIR_OK;
+  const int f32 = y_dtype == UNIIR_F32;
+  const int nv = (D + 127) / 128;
+  const unsigned grid = static_cast<unsigned>((rows + kLnWarpsFwd - 1) / kLnWarpsFwd);
+#define RMS_FWD_W(V) rmsnorm_fwd_warp_kernel<V><<<grid, kLnWarpsFwd * 32, 0, ST(stream)>>>(x, ldx, gamma, eps, D, rows, y, ldy, f32)
+  if (nv <= 1) RMS_FWD_W(1); else if (nv <= 2) RMS_FWD_W(2); else if (nv <= 4) RMS_FWD_W(4);
+  else if (nv <= 6) RMS_FWD_W(6); else RMS_FWD_W(8);
+#undef RMS_FWD_W
+  count_launch();
+  UNIIR_CUDA_OK(cudaGetLastError());
+  return UNIIR_OK;
+}
+
+extern "C" int uniir_token_mean(const float* x, int32_t B, int32_t S, int32_t D, float* out, void* stream) {
+  UNIIR_CHECK_ARG(x && out && B > 0 && S > 0 && D > 0 && D % 4 == 0 && B <= 65535, "uniir_token_mean: bad args");
+  const int threads = 128;
+  token_mean_kernel<<<dim3((D / 4 + threads - 1) / threads, B), threads, 0, ST(stream)>>>(x, S, D, out);
   count_launch();
   UNIIR_CUDA_OK(cudaGetLastError());
   return UNIIR_OK;

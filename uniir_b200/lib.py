@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libuniir_b200.so")
 
 BF16, F16, F32 = 0, 1, 2
-ACT_NONE, ACT_QUICKGELU, ACT_GELU, ACT_TANH = 0, 1, 2, 3
+ACT_NONE, ACT_QUICKGELU, ACT_GELU, ACT_TANH, ACT_RELU = 0, 1, 2, 3, 4
 
 
 class UniirError(RuntimeError):
@@ -74,6 +74,9 @@ _SIGS = {
     "uniir_attn_fwd": (C.c_int, [VP, I32, I32, I32, I32, VP, VP, VP]),
     "uniir_attn_fwd_ex": (C.c_int, [VP, I64, VP, VP, I64, I32, I32, I32, I32, I32, VP, VP, I64, VP, VP]),
     "uniir_attn_bwd": (C.c_int, [VP, VP, VP, VP, I32, I32, I32, I32, VP, VP, VP]),
+    "uniir_attn_fwd_bias": (C.c_int, [VP, I64, VP, VP, I64, I32, I32, I32, I32, C.c_float, VP, VP, I64, VP, VP]),
+    "uniir_rmsnorm_fwd": (C.c_int, [VP, I64, VP, C.c_float, I64, I32, VP, I64, I32, VP]),
+    "uniir_token_mean": (C.c_int, [VP, I32, I32, I32, VP, VP]),
     "uniir_attn_set_mode": (C.c_int, [I32]),
     "uniir_attn_bwd_workspace_floats": (C.c_int64, [I32, I32, I32, I32]),
     "uniir_attn_set_trace": (C.c_int, [VP]),

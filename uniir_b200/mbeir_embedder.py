@@ -137,14 +137,17 @@ def save_embeddings(embed_path, ids_path, emb, ids):
 
 
 def build_model_from_config(config):
-    """The ``CLIPScoreFusion``, ``BLIPFeatureFusion`` and ``BLIPScoreFusion`` arms of reference common/utils.py:64-152 on the B200
+    """The four arms of reference common/utils.py:64-152 (CLIP_SF, CLIP_FF [encode path], BLIP_SF, BLIP_FF) on the B200
     backend (same config fields, same checkpoint layout ``torch.load(path)["model"]``)."""
     name = config.model.name
     mc = config.model
-    if name == "CLIPScoreFusion":
-        from .clip_sf import CLIPScoreFusion
-        model = CLIPScoreFusion(model_name=mc.clip_vision_model_name,
-                                download_root=os.path.join(config.uniir_dir, mc.pretrained_clip_model_dir))
+    if name in ("CLIPScoreFusion", "CLIPFeatureFusion"):       # common/utils.py:67-110
+        if name == "CLIPScoreFusion":
+            from .clip_sf import CLIPScoreFusion as cls
+        else:
+            from .clip_ff import CLIPFeatureFusion as cls      # encode path only (embedding extraction / retrieval)
+        model = cls(model_name=mc.clip_vision_model_name,
+                    download_root=os.path.join(config.uniir_dir, mc.pretrained_clip_model_dir))
     elif name in ("BLIPFeatureFusion", "BLIPScoreFusion"):     # common/utils.py:97-152
         if name == "BLIPFeatureFusion":
             from .blip_ff import BLIPFeatureFusion as cls
@@ -154,8 +157,8 @@ def build_model_from_config(config):
                     image_size=mc.image_size, vit=mc.vit, vit_grad_ckpt=mc.vit_grad_ckpt,
                     vit_ckpt_layer=mc.vit_ckpt_layer, embed_dim=mc.embed_dim, queue_size=mc.queue_size, config=mc)
     else:
-        raise NotImplementedError(f"model {name!r}: CLIPScoreFusion, BLIPFeatureFusion and BLIPScoreFusion are built on "
-                                  "the B200 path (CLIPFeatureFusion: SURVEY 8f-3)")
+        raise NotImplementedError(f"model {name!r}: the reference knows CLIPScoreFusion, CLIPFeatureFusion, "
+                                  "BLIPScoreFusion and BLIPFeatureFusion (common/utils.py:64-152)")
     ckpt = os.path.join(config.uniir_dir, mc.ckpt_config.ckpt_dir, mc.ckpt_config.ckpt_name)
     assert os.path.exists(ckpt), f"Checkpoint file {ckpt} does not exist."
     print(f"loading {name} checkpoint from {ckpt}")

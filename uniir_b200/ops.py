@@ -204,6 +204,27 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, *, rows=None, ldx
             "uniir_layernorm_bwd")
 
 
+def rmsnorm_fwd(x, gamma, eps, out):
+    """T5LayerNorm: out = x * rsqrt(mean(x^2) + eps) * gamma; x fp32 [rows, D] contiguous, out bf16 or fp32."""
+    _require_cuda(x)
+    D = gamma.numel()
+    rows = x.numel() // D
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous() and out.numel() == x.numel()
+    L.check(L.load().uniir_rmsnorm_fwd(x.data_ptr(), D, gamma.data_ptr(), eps, rows, D, out.data_ptr(), D, _DT[out.dtype],
+                                       _stream()), "uniir_rmsnorm_fwd")
+    return out
+
+
+def token_mean(x, out=None):
+    """x fp32 [B, S, D] contiguous -> mean over the S tokens, fp32 [B, D]."""
+    B, S, D = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    if out is None:
+        out = torch.empty(B, D, device=x.device, dtype=torch.float32)
+    L.check(L.load().uniir_token_mean(x.data_ptr(), B, S, D, out.data_ptr(), _stream()), "uniir_token_mean")
+    return out
+
+
 def patch_im2col(img, P, Kpad, out=None):
     B, C3, H, W = img.shape
     assert C3 == 3 and img.dtype == torch.float32 and img.is_contiguous()
@@ -356,6 +377,20 @@ def attn_fwd_ex(q, k, v, B, Sq, Skv, H, *, causal=False, kv_len=None, out=None, 
     L.check(L.load().uniir_attn_fwd_ex(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), B, Sq, Skv, H,
                                        int(causal), _ptr(kv_len), out.data_ptr(), out.stride(0), _ptr(lse), _stream()),
             "uniir_attn_fwd_ex")
+    return out
+
+
+def attn_fwd_bias(q, k, v, B, Sq, Skv, H, bias, scale=1.0, out=None, lse=None):
+    """softmax(scale * q k^T + bias) v with bias fp32 [H, Sq, Skv] shared by all batch rows (T5 relative-position
+    bias; T5 does not scale the scores).  q / k / v: bf16 row-strided views as in attn_fwd_ex."""
+    assert q.dtype == torch.bfloat16 and q.stride(1) == 1 and k.stride(1) == 1 and v.stride(1) == 1
+    assert k.stride(0) == v.stride(0)
+    assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.shape == (H, Sq, Skv)
+    if out is None:
+        out = torch.empty(B * Sq, H * 64, device=q.device, dtype=torch.bfloat16)
+    L.check(L.load().uniir_attn_fwd_bias(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), B, Sq, Skv, H,
+                                         float(scale), bias.data_ptr(), out.data_ptr(), out.stride(0), _ptr(lse), _stream()),
+            "uniir_attn_fwd_bias")
     return out
 
 
