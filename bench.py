@@ -200,9 +200,10 @@ def run_reference(args, rank):
         cb, dt = cpu_search_reference(args.steps, args.warmup)
         metric, unit, cfg = "queries_per_sec_top50", "queries/s", {"workload": "dense_retrieval_190k_x_5.6M_d768_fp16_top50"}
     elif args.workload == "blip":
-        cb, dt = cpu_blip_reference(args.steps, args.warmup)
+        cb, dt = cpu_blip_reference(args.steps, args.warmup, sf=args.blip_model == "sf")
         metric, unit = "contrastive_pairs_per_sec", "pairs/s"
-        cfg = {"workload": "BLIP_FF ViT-L/16 + BERT-base momentum-distillation training step (BASELINE configs[2])",
+        cfg = {"workload": ("BLIP_SF" if args.blip_model == "sf" else "BLIP_FF")
+               + " ViT-L/16 + BERT-base momentum-distillation training step (BASELINE configs[2])",
                "global_batch": BLIP_GLOBAL_BATCH}
     else:
         cb, dt = cpu_train_reference(args.steps, args.warmup)
@@ -570,15 +571,18 @@ def run_train_blip(args, rank, world, dev, peaks):
     return out
 
 
-def cpu_blip_reference(steps, warmup, pairs=2):
-    from oracle.blip_oracle import BLIPFeatureFusionOracle
+def cpu_blip_reference(steps, warmup, pairs=2, sf=False):
+    from oracle.blip_oracle import BLIPFeatureFusionOracle, BLIPScoreFusionOracle
     cores = _cpu_threads()
     torch.manual_seed(2023)
-    model = BLIPFeatureFusionOracle("large", embed_dim=768, queue_size=57344)
+    model = (BLIPScoreFusionOracle if sf else BLIPFeatureFusionOracle)("large", embed_dim=768, queue_size=57344)
     params = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=0.05)
     b = synth_blip_batch(model.dims, pairs, 2023, torch.device("cpu"))
     b["p_did_list"] = b["p_did_list"].tolist()
+    if sf:      # score fusion multiplies by the modality masks (blip_sf.py:168-169): both present
+        b["txt_mask_batched"] = torch.ones(2 * pairs, dtype=torch.long)
+        b["image_mask_batched"] = torch.ones(2 * pairs, dtype=torch.long)
 
     def step():
         out = model.compute_contrastive_loss(b, alpha=0.4)
@@ -593,7 +597,7 @@ def cpu_blip_reference(steps, warmup, pairs=2):
         step()
     dt = (time.perf_counter() - t0) / steps
     return {"value": pairs / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
-            "sample": f"oracle BLIP_FF large fp32, {pairs} pairs/step (of the {BLIP_GLOBAL_BATCH}-pair batch), online+momentum "
+            "sample": f"oracle {'BLIP_SF' if sf else 'BLIP_FF'} large fp32, {pairs} pairs/step (of the {BLIP_GLOBAL_BATCH}-pair batch), online+momentum "
                       f"forward, loss, backward, AdamW, {steps} timed steps"}, dt
 
 
@@ -643,7 +647,7 @@ def main():
     elif args.workload == "blip":
         out = run_train_blip(args, rank, world, dev, peaks)
         if rank == 0 and not args.no_cpu_baseline and world == 1:
-            out["cpu_baseline"], _ = cpu_blip_reference(1, 1)
+            out["cpu_baseline"], _ = cpu_blip_reference(1, 1, sf=args.blip_model == "sf")
     elif args.workload == "search":
         out = run_search(args, rank, world, dev, peaks)
         if rank == 0 and not args.no_cpu_baseline and world == 1:
