@@ -36,7 +36,7 @@ namespace uniir {
 
 // warp 0 TMA, warp 1 MMA, EW elementwise warps (8: two 16-query units of a chunk per thread; 16: one), then 4
 // epilogue warps
-constexpr int bw_threads(int ew_warps) { return 64 + 32 * ew_warps + 128; }
+constexpr int bw_threads(int ew_warps, bool fold = false) { return 64 + 32 * ew_warps + 128 + (fold ? 64 : 0); }
 constexpr int kBwEpThreads = 128;
 constexpr int kBwStages = 4;         // Q_i / dO_i / stats ring
 constexpr int kBwTailMax = 4;        // leftover key columns / query rows handled by the prep kernel
@@ -52,8 +52,11 @@ struct AttnBwdTcParams {
   const float* lse2;        // [B*H, sq_pad]  LSE * log2(e), +inf in the padding
   const float* delta_s;     // [B*H, sq_pad]  delta * scale
   const float* ds_col;      // [B*H, tail_k, sq_pad]  dS of the tail key columns (fp32), for the dQ epilogue
+  float* fold_ws;           // FOLD: per CTA 2 x sq_pad (dS of the tail key column, by head parity) + 192 floats
   const __nv_bfloat16* k;   // tail key rows are read directly in the dQ epilogue
   long long ldkv;
+  const __nv_bfloat16 *v_g, *q_g, *do_g;   // FOLD: tail rows of V, Q, dO
+  long long ldq_g, lddo_g;
   __nv_bfloat16 *dq, *dk, *dv;
   long long lddq, lddkv;
   const int* kv_len;
@@ -77,6 +80,7 @@ struct BwSmem {
   uint64_t *chunk_done;             // [2]  the 256 elementwise threads have read TMEM buffer g & 1 and staged P^T / dS^T
   uint64_t *bufs_free;              // [2]  the dV / dK / dQ MMAs of chunk g (and every earlier MMA) have retired
   uint64_t *akv_full, *akv_free, *dq_full, *dq_free;
+  uint64_t *tail_done;               // [2] FOLD: the tail warps have published dS of the tail key column (by head parity)
   uint32_t* tmem_ptr;
 };
 __device__ __forceinline__ BwSmem bw_carve(uint8_t* base) {
@@ -98,6 +102,7 @@ __device__ __forceinline__ BwSmem bw_carve(uint8_t* base) {
   s.chunk_done = b; b += 2;
   s.bufs_free = b; b += 2;
   s.akv_full = b++; s.akv_free = b++; s.dq_full = b++; s.dq_free = b++;
+  s.tail_done = b; b += 2;
   s.tmem_ptr = reinterpret_cast<uint32_t*>(b);
   return s;
 }
@@ -105,7 +110,7 @@ __device__ __forceinline__ BwSmem bw_carve(uint8_t* base) {
 // it at a smaller alignment (checked in the kernel: a larger shift traps instead of overrunning)
 constexpr int kBwSmemSlack = 512;
 constexpr int kBwSmemBytes = kBwSmemSlack + 2 * kBwStages * 8192 + 10 * 16384 + kBwStages * 512 +
-                             (2 * kBwStages + 14) * 8 + 16;
+                             (2 * kBwStages + 16) * 8 + 16;
 static_assert(kBwSmemBytes <= 227 * 1024, "shared memory budget");
 
 // ---------------------------------------------------------------------------------------------------
@@ -122,6 +127,15 @@ struct AttnBwdPrepParams {
   int B, H, Sq, Skv, causal, sq_pad, n_kt, tail_k, n_qt, tail_q;
   float scale;
 };
+
+__device__ __forceinline__ float bw_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float2 bw_ld_bf2(const __nv_bfloat16* p) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
 
 // 64-wide dot product of two bf16 rows held as 8 x uint4
 __device__ __forceinline__ float dot64(const uint4 (&a)[8], const uint4 (&b)[8]) {
@@ -326,8 +340,12 @@ __device__ __forceinline__ void bw_store32(__nv_bfloat16* dst, const uint32_t (&
                        pack2_bf16(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
 }
 
-template <int EW>
-__global__ void __launch_bounds__(bw_threads(EW), 1) attn_bwd_tc_kernel(const __grid_constant__ AttnBwdTcParams p) {
+// FOLD (opt-in, UNIIR_ATTN_BWD_FOLD=1; NOT yet run on hardware -- written after this round's GPU time was spent, the
+// default instantiation <8, false> is unchanged): two more warps compute the tail key column and the tail query
+// row (257 = 2 x 128 + 1) from the operands already in shared memory, in registers, instead of the prep kernel's
+// second pass over Q / K / V / dO in HBM.  Only tail_k <= 1 and tail_q <= 1.
+template <int EW, bool FOLD = false>
+__global__ void __launch_bounds__(bw_threads(EW, FOLD), 1) attn_bwd_tc_kernel(const __grid_constant__ AttnBwdTcParams p) {
   constexpr int kBwEwThreads = 32 * EW;
   constexpr int kUnits = 16 / EW;            // 16-query units per thread and chunk (4 units x 4 lane quarters / EW warps)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -340,9 +358,10 @@ __global__ void __launch_bounds__(bw_threads(EW), 1) attn_bwd_tc_kernel(const __
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&p.tmQ64); tma_prefetch_desc(&p.tmQ16); tma_prefetch_desc(&p.tmDO64);
     tma_prefetch_desc(&p.tmDO16); tma_prefetch_desc(&p.tmK); tma_prefetch_desc(&p.tmV);
-    for (int i = 0; i < kBwStages; ++i) { mbar_init(&sm.st_full[i], 1); mbar_init(&sm.st_empty[i], 1); }
+    for (int i = 0; i < kBwStages; ++i) { mbar_init(&sm.st_full[i], 1); mbar_init(&sm.st_empty[i], FOLD ? 3 : 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&sm.kv_full[i], 1); mbar_init(&sm.kv_empty[i], 1);
+      mbar_init(&sm.kv_full[i], 1); mbar_init(&sm.kv_empty[i], FOLD ? 3 : 1);
+      mbar_init(&sm.tail_done[i], 2);
       mbar_init(&sm.s_full[i], 1); mbar_init(&sm.chunk_done[i], kBwEwThreads); mbar_init(&sm.bufs_free[i], 1);
     }
     mbar_init(sm.akv_full, 1); mbar_init(sm.akv_free, kBwEpThreads);
@@ -543,8 +562,8 @@ __global__ void __launch_bounds__(bw_threads(EW), 1) attn_bwd_tc_kernel(const __
         }
       }
     }
-  } else {
-    // =============================== epilogue (warps 10-13) ===============================
+  } else if (warp < 2 + EW + 4) {
+    // =============================== epilogue (4 warps) ===============================
     // dK_j / dV_j after each key tile, dQ after each head; off the elementwise warps' critical path: the MMA
     // issuer needs the accumulators back only one (dK/dV) or two (dQ) chunks into the next tile / head.
     const int quarter = warp & 3;
@@ -575,9 +594,18 @@ __global__ void __launch_bounds__(bw_threads(EW), 1) attn_bwd_tc_kernel(const __
       for (int T = 0; T < kBwMaxQTiles; ++T)
 #pragma unroll
         for (int t = 0; t < kBwTailMax; ++t)
-          dsc[T][t] = (T < p.n_qt && t < p.tail_k && T * 128 + rit < p.Sq)
+          dsc[T][t] = (!FOLD && T < p.n_qt && t < p.tail_k && T * 128 + rit < p.Sq)
                           ? __ldg(p.ds_col + (static_cast<long long>(head) * p.tail_k + t) * p.sq_pad + T * 128 + rit)
                           : 0.f;
+      if constexpr (FOLD) {
+        if (p.tail_k > 0) {      // the tail warps wrote this head's column into the CTA's scratch (plain loads: same SM)
+          mbar_wait(&sm.tail_done[head_it & 1], (head_it >> 1) & 1);
+          const float* col = p.fold_ws + (static_cast<long long>(blockIdx.x) * 2 + (head_it & 1)) * p.sq_pad;
+#pragma unroll
+          for (int T = 0; T < kBwMaxQTiles; ++T)
+            if (T < p.n_qt && T * 128 + rit < p.Sq) dsc[T][0] = *reinterpret_cast<const volatile float*>(col + T * 128 + rit);
+        }
+      }
       mbar_wait(sm.dq_full, head_it & 1);
       tc_fence_after();
 #pragma unroll
@@ -615,6 +643,114 @@ __global__ void __launch_bounds__(bw_threads(EW), 1) attn_bwd_tc_kernel(const __
     }
   }
 
+  else if constexpr (FOLD) {
+    // =============================== tail warps (2) ===============================
+    const int tw = warp - (2 + EW + 4);                  // 0 / 1
+    const float sc = p.scale * kBwLog2e;
+    const int kt = p.n_kt * 128, qt = p.n_qt * 128;      // the tail key / the tail query (tail_k, tail_q <= 1)
+    float* ws_cta = p.fold_ws + static_cast<long long>(gridDim.x) * 2 * p.sq_pad + static_cast<long long>(blockIdx.x) * 192;
+    int g = 0, kvt = 0, head_it = 0;
+    for (int head = blockIdx.x; head < n_heads; head += gridDim.x, ++head_it) {
+      const int b = head / p.H, h = head % p.H;
+      const int kvl = p.kv_len ? min(p.kv_len[b], p.Skv) : p.Skv;
+      // lane l owns head dims 2l, 2l+1 of the tail key's K / V rows and of the tail query's Q / dO rows
+      float2 Kt = make_float2(0.f, 0.f), Vt = Kt, Qt = Kt, dOt = Kt;
+      float l2t = INFINITY, dlt = 0.f;
+      if (p.tail_k > 0) {
+        Kt = bw_ld_bf2(p.k + (static_cast<long long>(b) * p.Skv + kt) * p.ldkv + h * 64 + 2 * lane);
+        Vt = bw_ld_bf2(p.v_g + (static_cast<long long>(b) * p.Skv + kt) * p.ldkv + h * 64 + 2 * lane);
+      }
+      if (p.tail_q > 0) {
+        Qt = bw_ld_bf2(p.q_g + (static_cast<long long>(b) * p.Sq + qt) * p.ldq_g + h * 64 + 2 * lane);
+        dOt = bw_ld_bf2(p.do_g + (static_cast<long long>(b) * p.Sq + qt) * p.lddo_g + h * 64 + 2 * lane);
+        l2t = p.lse2[static_cast<long long>(head) * p.sq_pad + qt];
+        dlt = p.delta_s[static_cast<long long>(head) * p.sq_pad + qt];
+      }
+      const bool kt_ok = kt < kvl;
+      float2 accV = make_float2(0.f, 0.f), accK = accV, accQ = accV;
+      float* col = p.fold_ws + (static_cast<long long>(blockIdx.x) * 2 + (head_it & 1)) * p.sq_pad;
+      for (int j = 0; j < p.n_kt; ++j, ++kvt) {
+        const int slot = kvt & 1;
+        for (int i = 0; i < p.n_chunks; ++i, ++g) {
+          const int st = g % kBwStages;
+          const int nq = min(64, p.sq_pad - 64 * i);
+          mbar_wait(&sm.st_full[st], (g / kBwStages) & 1);
+          if (j == 0 && p.tail_k > 0) {
+            // tail key column against this chunk's queries: this warp's 32 rows, one at a time, all lanes on one row
+            const uint8_t* sq = sm.q0 + st * 8192;
+            const uint8_t* sdo = sm.do0 + st * 8192;
+            const float* st_lse = sm.stats + st * 128;
+            const float* st_dl = st_lse + 64;
+            float my_ds = 0.f;
+            for (int rr = 0; rr < 32; ++rr) {
+              const int r = 32 * tw + rr;
+              if (r >= nq) break;                                    // warp-uniform
+              const uint32_t off = sw128(r, lane >> 2) + (lane & 3) * 4;
+              const float2 qv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sq + off));
+              const float2 dv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sdo + off));
+              const float s = bw_warp_sum(qv.x * Kt.x + qv.y * Kt.y), dp = bw_warp_sum(dv.x * Vt.x + dv.y * Vt.y);
+              const int q = 64 * i + r;
+              const float pr = (kt_ok && (!p.causal || kt <= q)) ? ex2_approx(fmaf(s, sc, -st_lse[r])) : 0.f;
+              const float ds = pr * fmaf(dp, p.scale, -st_dl[r]);
+              accV.x = fmaf(pr, dv.x, accV.x); accV.y = fmaf(pr, dv.y, accV.y);
+              accK.x = fmaf(ds, qv.x, accK.x); accK.y = fmaf(ds, qv.y, accK.y);
+              if (lane == rr) my_ds = ds;
+            }
+            if (32 * tw + lane < nq) col[64 * i + 32 * tw + lane] = my_ds;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.st_empty[st]);
+        }
+        if (p.tail_q > 0) {
+          // tail query row against this tile's keys: this warp's 64 keys
+          mbar_wait(&sm.kv_full[slot], (kvt >> 1) & 1);
+          const uint8_t* sk = sm.k0 + slot * 16384;
+          const uint8_t* sv = sm.v0 + slot * 16384;
+          const int klim = p.causal ? min(kvl, qt + 1) : kvl;
+          for (int kk = 0; kk < 64; ++kk) {
+            const int r = 64 * tw + kk, key = 128 * j + r;
+            if (key >= klim) break;                                  // warp-uniform (keys ascend)
+            const uint32_t off = sw128(r, lane >> 2) + (lane & 3) * 4;
+            const float2 kv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sk + off));
+            const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sv + off));
+            const float s = bw_warp_sum(kv.x * Qt.x + kv.y * Qt.y), dp = bw_warp_sum(vv.x * dOt.x + vv.y * dOt.y);
+            const float ds = ex2_approx(fmaf(s, sc, -l2t)) * fmaf(dp, p.scale, -dlt);
+            accQ.x = fmaf(ds, kv.x, accQ.x); accQ.y = fmaf(ds, kv.y, accQ.y);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.kv_empty[slot]);
+        if (j == 0 && lane == 0) mbar_arrive(&sm.tail_done[head_it & 1]);   // release: the column is published
+      }
+      // corner (tail query x tail key) for dQ[qt]: recomputed by warp 0
+      if (tw == 0 && p.tail_q > 0 && p.tail_k > 0) {
+        const float s = bw_warp_sum(Qt.x * Kt.x + Qt.y * Kt.y), dp = bw_warp_sum(dOt.x * Vt.x + dOt.y * Vt.y);
+        const float pr = (kt_ok && (!p.causal || kt <= qt)) ? ex2_approx(fmaf(s, sc, -l2t)) : 0.f;
+        const float ds = pr * fmaf(dp, p.scale, -dlt);
+        accQ.x = fmaf(ds, Kt.x, accQ.x); accQ.y = fmaf(ds, Kt.y, accQ.y);
+      }
+      // the two warps' partial sums meet in the CTA's global scratch; warp 0 stores the three 64-wide rows
+      if (tw == 1) {
+        ws_cta[2 * lane] = accV.x; ws_cta[2 * lane + 1] = accV.y;
+        ws_cta[64 + 2 * lane] = accK.x; ws_cta[64 + 2 * lane + 1] = accK.y;
+        ws_cta[128 + 2 * lane] = accQ.x; ws_cta[128 + 2 * lane + 1] = accQ.y;
+      }
+      named_bar_sync(3, 64);
+      if (tw == 0) {
+        const volatile float* wv = ws_cta;
+        if (p.tail_k > 0) {
+          const long long o = (static_cast<long long>(b) * p.Skv + kt) * p.lddkv + h * 64 + 2 * lane;
+          *reinterpret_cast<uint32_t*>(p.dv + o) = pack2_bf16(accV.x + wv[2 * lane], accV.y + wv[2 * lane + 1]);
+          *reinterpret_cast<uint32_t*>(p.dk + o) = pack2_bf16(accK.x + wv[64 + 2 * lane], accK.y + wv[64 + 2 * lane + 1]);
+        }
+        if (p.tail_q > 0)
+          *reinterpret_cast<uint32_t*>(p.dq + (static_cast<long long>(b) * p.Sq + qt) * p.lddq + h * 64 + 2 * lane) =
+              pack2_bf16(accQ.x + wv[128 + 2 * lane], accQ.y + wv[128 + 2 * lane + 1]);
+      }
+      named_bar_sync(3, 64);            // the scratch is rewritten by warp 1 for the next head
+    }
+  }
+
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -629,7 +765,8 @@ long long attn_bwd_ws_floats(int B, int Sq, int Skv, int H) {
   const long long sq_pad = (Sq + 15) / 16 * 16;
   const int rem = Skv % 128;
   const int tail_k = (Skv > 128 && rem > 0 && rem <= kBwTailMax) ? rem : 0;
-  return static_cast<long long>(B) * H * sq_pad * (2 + tail_k);
+  // + the per-CTA scratch of the FOLD variant (2 x sq_pad + 192 floats per SM; small, always included)
+  return static_cast<long long>(B) * H * sq_pad * (2 + tail_k) + static_cast<long long>(num_sms()) * (2 * sq_pad + 192);
 }
 
 int attn_bwd_tc_try(const __nv_bfloat16* q, long long ldq, const __nv_bfloat16* k, const __nv_bfloat16* v,
@@ -657,15 +794,25 @@ int attn_bwd_tc_try(const __nv_bfloat16* q, long long ldq, const __nv_bfloat16* 
   float* lse2 = ws;
   float* delta_s = ws + bh * sq_pad;
   float* ds_col = ws + 2 * bh * sq_pad;
+  float* fold_ws = ds_col + bh * tail_k * sq_pad;
+  // opt-in: tail column / row inside the main kernel (see the FOLD note above the kernel); one tail at most
+  static int fold_env = -1;
+  if (fold_env < 0) {
+    const char* e = getenv("UNIIR_ATTN_BWD_FOLD");
+    fold_env = (e && atoi(e) != 0);
+  }
+  const bool fold = fold_env && (tail_k > 0 || tail_q > 0) && tail_k <= 1 && tail_q <= 1;
 
   pp.q = q; pp.k = k; pp.v = v; pp.out = out; pp.dout = dout;
   pp.ldq = ldq; pp.ldkv = ldkv; pp.ldo = ldo; pp.lddo = lddo;
   pp.lse = lse; pp.kv_len = kv_len; pp.lse2 = lse2; pp.delta_s = delta_s; pp.ds_col = ds_col;
   pp.dq = dq; pp.dk = dk; pp.dv = dv; pp.lddq = lddq; pp.lddkv = lddkv;
   pp.B = B; pp.H = H; pp.Sq = Sq; pp.Skv = Skv; pp.causal = causal; pp.sq_pad = sq_pad;
-  pp.n_kt = n_kt; pp.tail_k = tail_k; pp.n_qt = n_qt; pp.tail_q = tail_q; pp.scale = scale;
+  pp.n_kt = n_kt; pp.tail_k = fold ? 0 : tail_k; pp.n_qt = n_qt; pp.tail_q = fold ? 0 : tail_q; pp.scale = scale;
+  // (fold: the prep kernel only writes delta and the base-2 LSE)
 
   p.lse2 = lse2; p.delta_s = delta_s; p.ds_col = ds_col; p.k = k; p.ldkv = ldkv;
+  p.fold_ws = fold_ws; p.v_g = v; p.q_g = q; p.do_g = dout; p.ldq_g = ldq; p.lddo_g = lddo;
   p.dq = dq; p.dk = dk; p.dv = dv; p.lddq = lddq; p.lddkv = lddkv; p.kv_len = kv_len;
   p.B = B; p.H = H; p.Sq = Sq; p.Skv = Skv; p.causal = causal; p.sq_pad = sq_pad;
   p.n_chunks = (sq_pad + 63) / 64; p.n_kt = n_kt; p.tail_k = tail_k; p.n_qt = n_qt; p.tail_q = tail_q;
@@ -687,12 +834,14 @@ int attn_bwd_tc_try(const __nv_bfloat16* q, long long ldq, const __nv_bfloat16* 
     ew16 = (e && atoi(e) == 16);
     UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwSmemBytes));
     UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwSmemBytes));
+    UNIIR_CUDA_OK((cudaFuncSetAttribute(attn_bwd_tc_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwSmemBytes)));
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   attn_bwd_prep_kernel<<<dim3(H, B), kPrepThreads, 0, st>>>(pp);
   const int heads = B * H;
   const int grid = heads < num_sms() ? heads : num_sms();
-  if (ew16) attn_bwd_tc_kernel<16><<<grid, bw_threads(16), kBwSmemBytes, st>>>(p);
+  if (fold) attn_bwd_tc_kernel<8, true><<<grid, bw_threads(8, true), kBwSmemBytes, st>>>(p);
+  else if (ew16) attn_bwd_tc_kernel<16><<<grid, bw_threads(16), kBwSmemBytes, st>>>(p);
   else attn_bwd_tc_kernel<8><<<grid, bw_threads(8), kBwSmemBytes, st>>>(p);
   count_launch(2);
   UNIIR_CUDA_OK(cudaGetLastError());
