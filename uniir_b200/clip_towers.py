@@ -165,7 +165,8 @@ class CLIPEncoder:
     def __init__(self, params: FlatParamModule, dims: CLIPDims, mb: int, dev, train: bool):
         self.P, self.d, self.mb, self.dev, self.train = params, dims, mb, dev, train
         d = dims
-        mem0 = torch.cuda.memory_allocated(dev)
+        on_gpu = torch.device(dev).type == "cuda"       # (CPU only in the host-logic tests, which swap the kernels out)
+        mem0 = torch.cuda.memory_allocated(dev) if on_gpu else 0
         bf = dict(device=dev, dtype=torch.bfloat16)
         f32 = dict(device=dev, dtype=torch.float32)
         self.vis = Tower(params, "visual.transformer", d.v_width, d.v_layers, d.v_heads, d.v_tokens, False,
@@ -204,7 +205,7 @@ class CLIPEncoder:
             self.d_v = torch.zeros(mb, d.embed_dim, **bf)
         self._graphs = {}
         self._side = None
-        self.bytes_allocated = torch.cuda.memory_allocated(dev) - mem0   # what one more encoder like this costs
+        self.bytes_allocated = (torch.cuda.memory_allocated(dev) - mem0) if on_gpu else 0   # what one more encoder like this costs
 
     def refresh_weights(self):
         d = self.d
