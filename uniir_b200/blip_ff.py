@@ -198,6 +198,64 @@ class BLIPEncoder:
             self.att_len = None
             self.ids = None
 
+    # ---- CUDA-graph front-end (opt-in: BLIPFeatureFusion.use_cuda_graphs).  The eager step issues 120-150 k kernel
+    # launches per 2048-pair batch; captured, a micro-batch is one graph launch.  Static I/O buffers, first call eager
+    # (kernel attributes, allocator warm-up), second call captures, later calls replay -- as CLIPEncoder._run. ----
+    def _static_io(self):
+        if getattr(self, "in_ids", None) is None:
+            dev, d, mb, S = self.dev, self.d, self.mb, self.S
+            self.in_ids = torch.zeros(mb, S, device=dev, dtype=torch.int32)
+            self.in_len = torch.ones(mb, device=dev, dtype=torch.int32)
+            self.in_img = torch.zeros(mb, 3, d.image_size, d.image_size, device=dev, dtype=torch.float32)
+            self.in_mt = torch.ones(mb, device=dev, dtype=torch.int64)
+            self.in_mv = torch.ones(mb, device=dev, dtype=torch.int64)
+            self.in_demb = torch.zeros_like(self.emb)
+            self._graphs = {}
+
+    def run(self, ids, att_len, img, mt=None, mv=None, d_emb=None, use_graph=False):
+        """forward (d_emb None: no activations kept) or forward-with-activations + backward (d_emb given), eagerly or
+        through a captured CUDA graph over the static I/O buffers.  Returns the embedding buffer."""
+        if not use_graph:
+            out = self.forward(ids, att_len, img, save=d_emb is not None, mt=mt, mv=mv)
+            if d_emb is not None:
+                self.backward(d_emb)
+            return out
+        self._static_io()
+        self.in_ids.copy_(ids, non_blocking=True); self.in_len.copy_(att_len, non_blocking=True)
+        self.in_img.copy_(img, non_blocking=True)
+        if mt is not None:
+            self.in_mt.copy_(mt, non_blocking=True); self.in_mv.copy_(mv, non_blocking=True)
+        sf = self.mode == "sf"
+        if d_emb is None:
+            key = "fwd"
+            body = lambda: self.forward(self.in_ids, self.in_len, self.in_img, save=False,
+                                        mt=self.in_mt if sf else None, mv=self.in_mv if sf else None)
+        else:
+            key = "fwdbwd"
+            self.in_demb.copy_(d_emb, non_blocking=True)
+
+            def body():
+                self.forward(self.in_ids, self.in_len, self.in_img, save=True, mt=self.in_mt if sf else None,
+                             mv=self.in_mv if sf else None)
+                self.backward(self.in_demb)
+        st = self._graphs.get(key, 0)
+        if st == 0:
+            body()
+            self._graphs[key] = 1
+        elif st == 1:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = L.launch_count()
+            with torch.cuda.graph(g):
+                body()
+            self._graphs[key] = (g, L.launch_count() - n0)
+            g.replay()                         # capture does not execute
+            ops.add_graph_launches(self._graphs[key][1])
+        else:
+            st[0].replay()
+            ops.add_graph_launches(st[1])
+        return self.emb
+
     def _fused(self, first, rows, cols, bufs=None):
         """[rows, cols] view starting at parameter `first` (adjacent parameters, see blip_param_specs)."""
         decay, off, n, shape = self.P._index[first]
@@ -428,6 +486,7 @@ class BLIPFeatureFusion(nn.Module):
         self._enc = {}
         self._train_state = None
         self.train_micro_batch = 64
+        self.use_cuda_graphs = False     # opt-in (BLIPEncoder.run): not yet confirmed on hardware
 
     # ---- reference surface -------------------------------------------------------------
     def get_img_preprocess_fn(self):
@@ -503,9 +562,9 @@ class BLIPFeatureFusion(nn.Module):
                 im_c = torch.cat([im_c, im_c.new_zeros(pad, *im_c.shape[1:])])
                 if mt is not None:
                     mt_c = torch.cat([mt_c, mt_c.new_zeros(pad)]); mv_c = torch.cat([mv_c, mv_c.new_zeros(pad)])
-            out[s:e] = enc.forward(i_c.contiguous(), l_c.contiguous(), im_c.contiguous(),
-                                   mt=None if mt_c is None else mt_c.contiguous(),
-                                   mv=None if mv_c is None else mv_c.contiguous())[:e - s]
+            out[s:e] = enc.run(i_c.contiguous(), l_c.contiguous(), im_c.contiguous(),
+                               mt=None if mt_c is None else mt_c.contiguous(),
+                               mv=None if mv_c is None else mv_c.contiguous(), use_graph=self.use_cuda_graphs)[:e - s]
         return out
 
     def forward(self, batch, alpha=None, encode_mbeir_batch=False):
@@ -617,8 +676,8 @@ class BLIPFeatureFusion(nn.Module):
         P.refresh_shadow()
         for s in range(0, n, mb):
             e = s + mb
-            enc.forward(st["ids"][s:e].contiguous(), st["lens"][s:e].contiguous(), st["img"][s:e].contiguous(), save=True,
-                        mt=None if st["mt"] is None else st["mt"][s:e].contiguous(),
-                        mv=None if st["mv"] is None else st["mv"][s:e].contiguous())
-            enc.backward(st["d_emb"][s:e].contiguous())
+            enc.run(st["ids"][s:e].contiguous(), st["lens"][s:e].contiguous(), st["img"][s:e].contiguous(),
+                    mt=None if st["mt"] is None else st["mt"][s:e].contiguous(),
+                    mv=None if st["mv"] is None else st["mv"][s:e].contiguous(), d_emb=st["d_emb"][s:e].contiguous(),
+                    use_graph=self.use_cuda_graphs)
         self._train_state = None

@@ -3,7 +3,7 @@ SURVEY.md 8f-3) on the B200-native kernels -- ENCODE PATH (``encode_multimodal_i
 encode_mbeir_batch=True)`` / ``encode_mbeir_batch``: embedding extraction and retrieval with CLIP_FF checkpoints).
 
 STATUS: written and compiled in a session that had no GPU time left; parity against the oracle is asserted by
-tests/test_zz_clip_ff_gpu.py, which is marked xfail(strict=False) until it has been seen green on a B200.
+tests/test_zz_unconfirmed_gpu.py, which is marked xfail(strict=False) until it has been seen green on a B200.
 Training (``compute_inbatch_contrastive_loss``) raises NotImplementedError: the backward of the T5 stack (RMS-norm
 backward, the bias gradient of the attention) is not built.
 
