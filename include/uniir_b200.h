@@ -132,6 +132,12 @@ int uniir_rmsnorm_fwd(const float* x, int64_t ldx, const float* gamma, float eps
 /* out[b, :] = mean over the S token rows of x[b, :, :] (x fp32 [B, S, D] contiguous): the mean pooling that ends
  * CLIPFeatureFusion.encode_multimodal_input (clip_ff.py:185-192). */
 int uniir_token_mean(const float* x, int32_t B, int32_t S, int32_t D, float* out, void* stream);
+/* Backward of uniir_rmsnorm_fwd (rstd recomputed from x; x, dy, dx fp32 [rows, D] contiguous):
+ * dx (+)= rstd * (gamma o dy - x^ * mean(gamma o dy o x^)), dgamma += sum over rows of dy o x^. */
+int uniir_rmsnorm_bwd(const float* dy, const float* x, const float* gamma, float eps, int64_t rows, int32_t D, float* dx,
+                      int32_t dx_accumulate, float* dgamma, void* stream);
+/* Backward of uniir_token_mean: dx[b, s, :] = d_out[b, :] / S. */
+int uniir_token_mean_bwd(const float* d_out, int32_t B, int32_t S, int32_t D, float* dx, void* stream);
 /* visual.conv1 (stride = kernel = patch, no bias; clip_ff.py:36) as im2col:
  * img fp32 [B,3,H,W] -> bf16 [B*(H/P)^2, Kpad], k = c*P*P + py*P + px, zero padded. */
 int uniir_patch_im2col(const float* img, int32_t B, int32_t H, int32_t W, int32_t P, int32_t Kpad,
@@ -208,6 +214,12 @@ int uniir_attn_set_trace(void* device_buf_3x256_int64);
 int uniir_attn_fwd_bias(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, int32_t B, int32_t Sq,
                         int32_t Skv, int32_t H, float scale, const float* bias, void* out, int64_t ldo, float* lse,
                         void* stream);
+/* Backward of uniir_attn_fwd_bias; dbias fp32 [H, Sq, Skv] += the gradient of the bias (sum over the batch of
+ * P o (dP - delta); zero it first).  mma.sync kernels.  delta_ws: B * H * Sq floats. */
+int uniir_attn_bwd_bias(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const void* out,
+                        int64_t ldo, const void* dout, int64_t lddo, const float* lse, int32_t B, int32_t Sq, int32_t Skv,
+                        int32_t H, float scale, const float* bias, float* dbias, float* delta_ws, void* dq, int64_t lddq,
+                        void* dk, void* dv, int64_t lddkv, void* stream);
 /* Backward workspace (fp32 elements, 16-byte aligned): delta = rowsum(dO o O), the base-2 LSE and the dS of
  * the key columns beyond the last full 128-key tile, each padded to 16 rows per head. */
 int64_t uniir_attn_bwd_workspace_floats(int32_t B, int32_t Sq, int32_t Skv, int32_t H);

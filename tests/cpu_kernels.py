@@ -161,6 +161,31 @@ def install(monkeypatch):
         out.view(-1, D).copy_(xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + eps) * gamma)
         return out
 
+    def rmsnorm_bwd(dy, x, gamma, eps, dx, dgamma, accumulate=True):
+        D = gamma.numel()
+        xr, dyr = x.reshape(-1, D).float(), dy.reshape(-1, D).float()
+        rstd = torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + eps)
+        xh = xr * rstd
+        g = dyr * gamma
+        d = rstd * (g - xh * (g * xh).mean(-1, keepdim=True))
+        dxv = dx.view(-1, D)
+        dxv.copy_(dxv + d if accumulate else d)
+        dgamma.add_((dyr * xh).sum(0))
+
+    def token_mean_bwd(d_out, S, out):
+        B, D = d_out.shape
+        out.view(B, S, D).copy_((d_out / S)[:, None, :].expand(B, S, D))
+        return out
+
+    def attn_bwd_bias(q, k, v, out, dout, lse, B, Sq, Skv, H, bias, dbias, dq, dk, dv, scale=1.0, delta=None):
+        qf, kf, vf = (t.float().detach().clone().requires_grad_(True) for t in (q, k, v))
+        bf = bias.detach().clone().requires_grad_(True)
+        s = _scores(qf, kf, B, Sq, Skv, H, scale, False, None, bf)
+        y = (s.softmax(-1) @ _split(vf, B, Skv, H)).transpose(1, 2).reshape(B * Sq, H * 64)
+        y.backward(dout.float())
+        dq.copy_(qf.grad); dk.copy_(kf.grad); dv.copy_(vf.grad)
+        dbias.add_(bf.grad)
+
     def token_mean(x, out=None):
         y = x.mean(1)
         return y if out is None else out.copy_(y)
@@ -223,6 +248,7 @@ def install(monkeypatch):
     fns = dict(gemm=gemm, wgrad=wgrad, colsum_accum=colsum_accum, layernorm_fwd=layernorm_fwd, layernorm_bwd=layernorm_bwd,
                attn_fwd=attn_fwd, attn_fwd_ex=attn_fwd_ex, attn_fwd_bias=attn_fwd_bias, attn_bwd=attn_bwd,
                attn_bwd_ex=attn_bwd_ex, attn_bwd_ws_floats=attn_bwd_ws_floats, rmsnorm_fwd=rmsnorm_fwd,
+               rmsnorm_bwd=rmsnorm_bwd, token_mean_bwd=token_mean_bwd, attn_bwd_bias=attn_bwd_bias,
                token_mean=token_mean, patch_im2col=patch_im2col, vision_embed_fwd=vision_embed_fwd,
                vision_embed_bwd=vision_embed_bwd, text_embed_fwd=text_embed_fwd, text_embed_bwd=text_embed_bwd,
                score_fuse_fwd=score_fuse_fwd, score_fuse_bwd=score_fuse_bwd, pad_cast_bf16=pad_cast_bf16,

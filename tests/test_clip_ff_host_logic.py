@@ -45,3 +45,50 @@ def test_clip_ff_encoder_sequencing_reproduces_the_oracle(monkeypatch):
         t_ref, v_ref = orc.encode_text(ids.long()), orc.encode_image(img)
     assert F.cosine_similarity(enc.t_feat.flatten(1), t_ref.flatten(1), dim=-1).min() > 1 - 1e-3
     assert F.cosine_similarity(enc.v_feat.flatten(1), v_ref.flatten(1), dim=-1).min() > 1 - 1e-3
+
+
+def test_clip_ff_encoder_backward_sequencing_reproduces_the_oracle_gradients(monkeypatch):
+    """forward(save=True) + the hand-written backward (T5 stack: RMS-norm backward, attention backward with the bias
+    gradient scattered into the bucket embedding, ReLU FFN; un-pooled towers) against the oracle's autograd."""
+    cpu_kernels.install(monkeypatch)
+    from uniir_b200.clip_ff import CLIPFFEncoder, clip_ff_param_specs, t5_heads
+    from uniir_b200.params import CLIP_CONFIGS, FlatParamModule
+    name = "tiny-test"
+    torch.manual_seed(13)
+    orc = CLIPFeatureFusionOracle(name).eval()
+    with torch.no_grad():
+        for n, p in orc.t5_layers.named_parameters():
+            p.normal_(0.0, 0.08) if "layer_norm" not in n else p.normal_(1.0, 0.1)
+    d = CLIP_CONFIGS[name]
+    root = torch.nn.Module()
+    P = FlatParamModule(clip_ff_param_specs(d, t5_heads(name)), "cpu", root=root)
+    root.load_state_dict(orc.state_dict(), strict=True)
+    P.refresh_shadow(force=True)
+    P.ensure_grad()
+    mb = 3
+    enc = CLIPFFEncoder(P, d, t5_heads(name), mb, "cpu", train=True)
+    enc.refresh_weights()
+    g = torch.Generator().manual_seed(14)
+    ids = torch.zeros(mb, d.context, dtype=torch.int32)
+    for i in range(mb):
+        n = int(torch.randint(1, d.context - 2, (1,), generator=g))
+        ids[i, 0] = d.vocab - 2; ids[i, 1:1 + n] = torch.randint(1, d.vocab - 2, (n,), generator=g).int(); ids[i, 1 + n] = d.vocab - 1
+    img = torch.randn(mb, 3, d.image_size, d.image_size, generator=g)
+    d_emb = torch.randn(mb, d.embed_dim, generator=g)
+    ref = orc.encode_multimodal_input(ids.long(), img)
+    ref.backward(d_emb)
+    out = enc.forward(ids, img, save=True).clone()
+    assert F.cosine_similarity(out, ref.detach(), dim=-1).min().item() > 1 - 1e-3
+    enc.backward(d_emb)
+    worst = (1.0, "")
+    for n_, p_o in orc.named_parameters():
+        if n_ == "clip_model.logit_scale":
+            continue
+        gm = P.g(n_).flatten().double()
+        if p_o.grad is None:
+            assert gm.abs().max().item() == 0, n_
+            continue
+        a = p_o.grad.flatten().double()
+        cos = (torch.dot(a, gm) / (a.norm() * gm.norm() + 1e-30)).item()
+        worst = min(worst, (cos, n_))
+    assert worst[0] > 0.999, worst

@@ -70,9 +70,6 @@ def test_clip_ff_encode_matches_oracle_and_api_contract():
     emb, idl = m({"txt_batched": ids, "image_batched": img, "txt_mask_batched": one, "image_mask_batched": one,
                   "did_list": list(range(10, 10 + B))}, encode_mbeir_batch=True)
     assert emb.shape == (B, d.embed_dim) and idl == list(range(10, 10 + B))
-    with pytest.raises(NotImplementedError):
-        m({"txt_batched": ids, "image_batched": img, "txt_mask_batched": one, "image_mask_batched": one,
-           "index_mapping": {"query": [[0]], "pos_cand": [[1]]}})
 
 
 def test_blip_step_under_cuda_graphs_equals_eager():
@@ -107,3 +104,75 @@ def test_blip_step_under_cuda_graphs_equals_eager():
         assert abs(a - b_) < 1e-5 * max(1.0, abs(a))
     for n, ga in res[False][1].items():
         assert (ga - res[True][1][n]).norm() <= 2e-3 * (ga.norm() + 1e-12), n
+
+
+def test_new_backward_kernels_against_torch():
+    from uniir_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    # RMS norm backward (rstd recomputed), accumulate and overwrite
+    x = torch.randn(333, 768, generator=g) * 1.5; w = torch.randn(768, generator=g); dy = torch.randn(333, 768, generator=g)
+    xr = x.clone().requires_grad_(True); wr = w.clone().requires_grad_(True)
+    (xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-6) * wr).backward(dy)
+    dx = torch.full((333, 768), 0.5, device=dev); dg = torch.zeros(768, device=dev)
+    ops.rmsnorm_bwd(dy.to(dev), x.to(dev), w.to(dev), 1e-6, dx, dg, accumulate=True)
+    assert (dx.cpu() - 0.5 - xr.grad).abs().max() < 1e-4 and (dg.cpu() - wr.grad).abs().max() < 1e-3 * wr.grad.abs().max()
+    ops.rmsnorm_bwd(dy.to(dev), x.to(dev), w.to(dev), 1e-6, dx, dg, accumulate=False)
+    assert (dx.cpu() - xr.grad).abs().max() < 1e-4
+    # token mean backward
+    d = torch.randn(5, 768, generator=g)
+    o = ops.token_mean_bwd(d.to(dev), 334, torch.empty(5, 334, 768, device=dev))
+    assert (o.cpu() - (d / 334)[:, None, :].expand(5, 334, 768)).abs().max() < 1e-7
+    # attention backward with a score bias (T5: scale 1), incl. the bias gradient summed over the batch
+    B, S, H = 3, 94, 2
+    D = H * 64
+    qkv = (torch.randn(B * S, 3 * D, generator=g) * 0.3).bfloat16()
+    bias = torch.randn(H, S, S, generator=g)
+    dout = torch.randn(B * S, D, generator=g).bfloat16()
+    qd = qkv.to(dev)
+    lse = torch.empty(B, H, S, device=dev)
+    out = ops.attn_fwd_bias(qd[:, :D], qd[:, D:2 * D], qd[:, 2 * D:], B, S, S, H, bias.to(dev), scale=1.0, lse=lse)
+    dqkv = torch.zeros(B * S, 3 * D, device=dev, dtype=torch.bfloat16); dbias = torch.zeros(H, S, S, device=dev)
+    ops.attn_bwd_bias(qd[:, :D], qd[:, D:2 * D], qd[:, 2 * D:], out, dout.to(dev), lse, B, S, S, H, bias.to(dev), dbias,
+                      dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], scale=1.0)
+    xq = qkv.float().requires_grad_(True); br = bias.clone().requires_grad_(True)
+    q, k, v = xq.view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ((q @ k.transpose(-1, -2) + br).softmax(-1) @ v).transpose(1, 2).reshape(B * S, D).backward(dout.float())
+    rel = lambda a, b: ((a.float().cpu() - b).norm() / b.norm()).item()
+    assert rel(dqkv, xq.grad) < 1.2e-2 and rel(dbias, br.grad) < 1.2e-2
+
+
+def test_clip_ff_training_step_matches_oracle():
+    from oracle.clip_ff_oracle import CLIPFeatureFusionOracle
+    from uniir_b200.clip_ff import CLIPFeatureFusion
+    from uniir_b200.engine import FlatAdamW, train_step
+    torch.manual_seed(21)
+    orc = CLIPFeatureFusionOracle("tiny-test")
+    with torch.no_grad():
+        for n, p in orc.t5_layers.named_parameters():
+            p.normal_(0.0, 0.08) if "layer_norm" not in n else p.normal_(1.0, 0.1)
+    m = CLIPFeatureFusion("tiny-test", device=dev, micro_batch=8)
+    m.train_micro_batch = 8
+    m.load_state_dict(orc.state_dict(), strict=True)
+    d = orc.clip_model.dims
+    g = torch.Generator().manual_seed(22)
+    bs = 8
+    ids = torch.zeros(2 * bs, d.context, dtype=torch.long)
+    for i in range(2 * bs):
+        n = int(torch.randint(1, d.context - 2, (1,), generator=g))
+        ids[i, 0] = d.vocab - 2; ids[i, 1:1 + n] = torch.randint(1, d.vocab - 2, (n,), generator=g); ids[i, 1 + n] = d.vocab - 1
+    img = torch.randn(2 * bs, 3, d.image_size, d.image_size, generator=g)
+    one = torch.ones(2 * bs, dtype=torch.long)
+    b = dict(txt_batched=ids, image_batched=img, txt_mask_batched=one, image_mask_batched=one,
+             index_mapping={"query": [[2 * i] for i in range(bs)], "pos_cand": [[2 * i + 1] for i in range(bs)]})
+    ref = orc(b)
+    ref["loss"].backward()
+    opt = FlatAdamW(m._flat, lr=1e-4)
+    loss, acc = train_step(m, {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in b.items()}, opt, do_step=False)
+    torch.cuda.synchronize()
+    assert abs(loss.item() - ref["loss"].item()) < 2e-2 * max(1.0, abs(ref["loss"].item()))
+    worst = (1.0, "")
+    for n_, p_o in orc.named_parameters():
+        a, c = p_o.grad.flatten().double(), m._flat.g(n_).cpu().flatten().double()
+        if a.numel() > 1:
+            worst = min(worst, ((torch.dot(a, c) / (a.norm() * c.norm() + 1e-30)).item(), n_))
+    assert worst[0] > 0.995, worst

@@ -96,7 +96,8 @@ struct AttnParams {
   long long ldq, ldkv, ldo;
   int Sq, Skv;
   const int* kv_len;         // optional [B]: keys >= kv_len[b] are masked (BERT padding mask)
-  const float* bias;         // optional fp32 [H, Sq, Skv] added to scale * QK^T (T5 relative-position bias; forward only)
+  const float* bias;         // optional fp32 [H, Sq, Skv] added to scale * QK^T (T5 relative-position bias)
+  float* dbias;              // backward with bias: fp32 [H, Sq, Skv] += sum over the batch of dS (atomics)
   __nv_bfloat16 *dq, *dk, *dv;     // backward outputs: dq rows stride lddq; dk/dv rows stride lddkv
   long long lddq, lddkv, lddo;     // lddo: row stride of dout
   __nv_bfloat16* out;        // [B*S, D]
@@ -295,6 +296,9 @@ __global__ void attn_delta_kernel(const AttnParams p) {
 }
 
 // backward dQ: K, V resident; per warp 16 query rows (Q and dO tiles private).
+// BIAS (separate instantiation, the tower path compiles as before): scores get p.bias[h, q, key] / scale before the
+// exponential, and dS = P o (dP - delta) -- the gradient of the bias -- is accumulated over the batch into p.dbias.
+template <bool BIAS>
 __global__ void __launch_bounds__(kAttnThreads, 2) attn_bwd_dq_kernel(const AttnParams p, int spad) {
   extern __shared__ __align__(128) uint8_t sm[];
   const uint32_t sK = s_u32(sm), sV = sK + spad * 128, sW = sV + spad * 128;
@@ -354,6 +358,20 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_bwd_dq_kernel(const Attn
           }
         }
       }
+      if constexpr (BIAS) {
+        const float inv_scale = 1.f / p.scale;
+        const float* bh = p.bias + static_cast<long long>(h) * p.Sq * p.Skv;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int key = k0 + j * 8 + (lane & 3) * 2 + (e & 1);
+            const int qr = (e < 2) ? r0 : r1;
+            if (j < nt && key < p.Skv && qr < p.Sq)
+              s[j][e] = fmaf(__ldg(bh + static_cast<long long>(qr) * p.Skv + key), inv_scale, s[j][e]);
+          }
+        }
+      }
       const bool need_mask = nt < 8 || k0 + kBlk > kvl || q0 + 16 > p.Sq || (p.causal && k0 + kBlk - 1 > q0);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -375,6 +393,18 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_bwd_dq_kernel(const Attn
       for (int j = 0; j < 8; ++j) {
         s[j][0] *= dpv[j][0] - dl0; s[j][1] *= dpv[j][1] - dl0;
         s[j][2] *= dpv[j][2] - dl1; s[j][3] *= dpv[j][3] - dl1;
+      }
+      if constexpr (BIAS) {
+        float* gh = p.dbias + static_cast<long long>(h) * p.Sq * p.Skv;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int key = k0 + j * 8 + (lane & 3) * 2 + (e & 1);
+            const int qr = (e < 2) ? r0 : r1;
+            if (j < nt && key < p.Skv && qr < p.Sq) atomicAdd(gh + static_cast<long long>(qr) * p.Skv + key, s[j][e]);
+          }
+        }
       }
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
@@ -404,6 +434,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_bwd_dq_kernel(const Attn
 }
 
 // backward dK/dV: Q, dO, LSE, delta resident; per warp 16 keys (K and V tiles private).
+// BIAS: as in the dQ kernel (scores only; the bias gradient is accumulated there).
+template <bool BIAS>
 __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dkv_kernel(const AttnParams p, int spad) {
   extern __shared__ __align__(128) uint8_t sm[];
   const uint32_t sQ = s_u32(sm), sDO = sQ + spad * 128, sW = sDO + spad * 128;
@@ -470,6 +502,20 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dkv_kernel(const AttnPa
             frag_b_nk(bDO, j, kk, bb);
             mma_bf16(dpt[j], va[kk], bb[0], bb[1]);
             mma_bf16(dpt[j + 1], va[kk], bb[2], bb[3]);
+          }
+        }
+      }
+      if constexpr (BIAS) {
+        const float inv_scale = 1.f / p.scale;
+        const float* bh = p.bias + static_cast<long long>(h) * p.Sq * p.Skv;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int q = q0 + j * 8 + (lane & 3) * 2 + (e & 1);
+            const int key = (e < 2) ? key0 : key1;
+            if (j < nt && key < p.Skv && q < p.Sq)
+              st[j][e] = fmaf(__ldg(bh + static_cast<long long>(q) * p.Skv + key), inv_scale, st[j][e]);
           }
         }
       }
@@ -544,8 +590,10 @@ static int attn_set_smem() {
     const int mx = 227 * 1024;
     UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     done = true;
   }
   return UNIIR_OK;
@@ -639,16 +687,23 @@ extern "C" int64_t uniir_attn_bwd_workspace_floats(int32_t B, int32_t Sq, int32_
 
 static int attn_bwd_launch(AttnParams& p, void* stream) {
   // tcgen05 backward (attention_bwd_tc.cu) when enabled and the shape fits; > 0 means "not applicable"
-  const int tc = attn_bwd_tc_try(p.q, p.ldq, p.k, p.v, p.ldkv, p.out, p.ldo, p.dout, p.lddo, p.lse, p.B, p.Sq, p.Skv,
-                                 p.H, p.causal, p.kv_len, p.delta, p.dq, p.lddq, p.dk, p.dv, p.lddkv, p.scale, stream);
-  if (tc <= 0) return tc;
+  if (!p.bias) {     // the tcgen05 kernel takes no score bias
+    const int tc = attn_bwd_tc_try(p.q, p.ldq, p.k, p.v, p.ldkv, p.out, p.ldo, p.dout, p.lddo, p.lse, p.B, p.Sq, p.Skv,
+                                   p.H, p.causal, p.kv_len, p.delta, p.dq, p.lddq, p.dk, p.dv, p.lddkv, p.scale, stream);
+    if (tc <= 0) return tc;
+  }
   UNIIR_CHECK_ARG(p.Sq <= 768 && p.Skv <= 768, "uniir_attn_bwd: sequence length exceeds the head-resident limit of 768");
   if (int rc = attn_set_smem()) return rc;
   const int spad_kv = (p.Skv + 15) / 16 * 16, spad_q = (p.Sq + 15) / 16 * 16;
   const long long warps = 1LL * p.B * p.Sq * p.H;
   attn_delta_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, ST(stream)>>>(p);
-  attn_bwd_dq_kernel<<<dim3(p.H, p.B), kAttnThreads, attn_smem(spad_kv, true), ST(stream)>>>(p, spad_kv);
-  attn_bwd_dkv_kernel<<<dim3(p.H, p.B), kAttnThreads, attn_smem(spad_q, true), ST(stream)>>>(p, spad_q);
+  if (p.bias) {
+    attn_bwd_dq_kernel<true><<<dim3(p.H, p.B), kAttnThreads, attn_smem(spad_kv, true), ST(stream)>>>(p, spad_kv);
+    attn_bwd_dkv_kernel<true><<<dim3(p.H, p.B), kAttnThreads, attn_smem(spad_q, true), ST(stream)>>>(p, spad_q);
+  } else {
+    attn_bwd_dq_kernel<false><<<dim3(p.H, p.B), kAttnThreads, attn_smem(spad_kv, true), ST(stream)>>>(p, spad_kv);
+    attn_bwd_dkv_kernel<false><<<dim3(p.H, p.B), kAttnThreads, attn_smem(spad_q, true), ST(stream)>>>(p, spad_q);
+  }
   count_launch(3);
   UNIIR_CUDA_OK(cudaGetLastError());
   return UNIIR_OK;
@@ -702,5 +757,32 @@ extern "C" int uniir_attn_bwd_ex(const void* q, int64_t ldq, const void* k, cons
   p.dq = static_cast<__nv_bfloat16*>(dq); p.dk = static_cast<__nv_bfloat16*>(dk); p.dv = static_cast<__nv_bfloat16*>(dv);
   p.lddq = lddq; p.lddkv = lddkv;
   p.B = B; p.S = Sq; p.Sq = Sq; p.Skv = Skv; p.H = H; p.D = H * kHD; p.causal = causal; p.scale = 0.125f;
+  return attn_bwd_launch(p, stream);
+}
+
+
+extern "C" int uniir_attn_bwd_bias(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const void* out,
+                                   int64_t ldo, const void* dout, int64_t lddo, const float* lse, int32_t B, int32_t Sq,
+                                   int32_t Skv, int32_t H, float scale, const float* bias, float* dbias, float* delta_ws,
+                                   void* dq, int64_t lddq, void* dk, void* dv, int64_t lddkv, void* stream) {
+  UNIIR_CHECK_ARG(q && k && v && out && dout && lse && delta_ws && dq && dk && dv && bias && dbias && B > 0 && Sq > 0 &&
+                  Skv > 0 && H > 0 && scale > 0.f, "uniir_attn_bwd_bias: bad args");
+  UNIIR_CHECK_ARG(ldq % 8 == 0 && ldkv % 8 == 0 && lddo % 8 == 0 && ldo % 2 == 0 && lddq % 2 == 0 && lddkv % 2 == 0,
+                  "uniir_attn_bwd_bias: strides must keep row alignment");
+  AttnParams p{};
+  p.q = static_cast<const __nv_bfloat16*>(q);
+  p.k = static_cast<const __nv_bfloat16*>(k);
+  p.v = static_cast<const __nv_bfloat16*>(v);
+  p.ldq = ldq; p.ldkv = ldkv;
+  p.out = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(out));
+  p.ldo = ldo;
+  p.dout = static_cast<const __nv_bfloat16*>(dout);
+  p.lddo = lddo;
+  p.lse = const_cast<float*>(lse);
+  p.delta = delta_ws;
+  p.bias = bias; p.dbias = dbias;
+  p.dq = static_cast<__nv_bfloat16*>(dq); p.dk = static_cast<__nv_bfloat16*>(dk); p.dv = static_cast<__nv_bfloat16*>(dv);
+  p.lddq = lddq; p.lddkv = lddkv;
+  p.B = B; p.S = Sq; p.Sq = Sq; p.Skv = Skv; p.H = H; p.D = H * kHD; p.causal = 0; p.scale = scale;
   return attn_bwd_launch(p, stream);
 }

@@ -379,6 +379,88 @@ layernorm_bwd_warp_kernel(const void* __restrict__ dy, long long lddy,
   }
 }
 
+// T5LayerNorm backward (y = x * rstd * gamma, rstd = rsqrt(mean(x^2) + eps), recomputed from x -- nothing is saved):
+//   g = dy o gamma,  x^ = x * rstd,  dx (+)= rstd * (g - x^ * mean(g o x^)),  dgamma += sum_rows dy o x^.
+// Same structure as the LayerNorm backward above (warp per row, per-CTA column reduction, one atomic per column).
+template <int NV>
+__global__ void __launch_bounds__(kLnWarpsBwd * 32)
+rmsnorm_bwd_warp_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                        float eps, int D, long long rows, int rows_per_cta, float* __restrict__ dx, int dx_accumulate,
+                        float* __restrict__ dgamma) {
+  __shared__ float4 red[kLnWarpsBwd][NV * 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float4 dg[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) dg[i] = make_float4(0, 0, 0, 0);
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  const long long r1 = min(rows, r0 + rows_per_cta);
+  for (long long r = r0 + w; r < r1; r += kLnWarpsBwd) {
+    float4 xh[NV], d[NV], old[NV];
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + i * 32) * 4;
+      xh[i] = d[i] = old[i] = make_float4(0, 0, 0, 0);
+      if (c < D) {
+        xh[i] = __ldcs(reinterpret_cast<const float4*>(x + r * D + c));
+        d[i] = __ldcs(reinterpret_cast<const float4*>(dy + r * D + c));
+        if (dx_accumulate) old[i] = *reinterpret_cast<const float4*>(dx + r * D + c);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) q += (xh[i].x * xh[i].x + xh[i].y * xh[i].y) + (xh[i].z * xh[i].z + xh[i].w * xh[i].w);
+    const float rs = rsqrtf(warp_sum(q) / D + eps);
+    float s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + i * 32) * 4;
+      if (c < D) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        xh[i] = make_float4(xh[i].x * rs, xh[i].y * rs, xh[i].z * rs, xh[i].w * rs);
+        dg[i].x += d[i].x * xh[i].x; dg[i].y += d[i].y * xh[i].y;
+        dg[i].z += d[i].z * xh[i].z; dg[i].w += d[i].w * xh[i].w;
+        d[i] = make_float4(d[i].x * g.x, d[i].y * g.y, d[i].z * g.z, d[i].w * g.w);   // from here on: gamma o dy
+        s2 += (d[i].x * xh[i].x + d[i].y * xh[i].y) + (d[i].z * xh[i].z + d[i].w * xh[i].w);
+      }
+    }
+    const float m2 = warp_sum(s2) / D;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + i * 32) * 4;
+      if (c < D) {
+        float4 o;
+        o.x = rs * (d[i].x - xh[i].x * m2) + old[i].x;
+        o.y = rs * (d[i].y - xh[i].y * m2) + old[i].y;
+        o.z = rs * (d[i].z - xh[i].z * m2) + old[i].z;
+        o.w = rs * (d[i].w - xh[i].w * m2) + old[i].w;
+        *reinterpret_cast<float4*>(dx + r * D + c) = o;
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) red[w][lane + i * 32] = dg[i];
+  __syncthreads();
+  const float* rf = reinterpret_cast<const float*>(&red[0][0]);
+  for (int col = threadIdx.x; col < D; col += kLnWarpsBwd * 32) {
+    float t = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < kLnWarpsBwd; ++ww) t += rf[(ww * NV * 32 + (col >> 2)) * 4 + (col & 3)];
+    atomicAdd(dgamma + col, t);
+  }
+}
+
+// dx[b, s, c..c+3] = d[b, c..c+3] / S: backward of token_mean_kernel
+__global__ void token_mean_bwd_kernel(const float* __restrict__ d, int S, int D, float* __restrict__ dx) {
+  const int b = blockIdx.y, c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c >= D) return;
+  const float inv = 1.f / S;
+  float4 v = *reinterpret_cast<const float4*>(d + static_cast<long long>(b) * D + c);
+  v = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+  float* o = dx + static_cast<long long>(b) * S * D + c;
+  for (int s = 0; s < S; ++s) *reinterpret_cast<float4*>(o + static_cast<long long>(s) * D) = v;
+}
+
 // ---------------------------------------------------------------------------------
 // im2col for the stride=patch conv: img fp32 [B,3,H,W] -> bf16 [B*g*g, Kpad],
 // k = c*P*P + py*P + px (conv weight [out, c, py, px] flattened), zero padded to Kpad.
@@ -733,6 +815,34 @@ extern "C" int uniir_rmsnorm_fwd(const float* x, int64_t ldx, const float* gamma
   if (nv <= 1) RMS_FWD_W(1); else if (nv <= 2) RMS_FWD_W(2); else if (nv <= 4) RMS_FWD_W(4);
   else if (nv <= 6) RMS_FWD_W(6); else RMS_FWD_W(8);
 #undef RMS_FWD_W
+  count_launch();
+  UNIIR_CUDA_OK(cudaGetLastError());
+  return UNIIR_OK;
+}
+
+extern "C" int uniir_rmsnorm_bwd(const float* dy, const float* x, const float* gamma, float eps, int64_t rows, int32_t D,
+                                 float* dx, int32_t dx_accumulate, float* dgamma, void* stream) {
+  UNIIR_CHECK_ARG(dy && x && gamma && dx && dgamma && D > 0 && D % 4 == 0 && D <= 1024,
+                  "uniir_rmsnorm_bwd: bad args (D must be a multiple of 4, at most 1024)");
+  if (rows == 0) return UNIIR_OK;
+  long long ctas = 2LL * num_sms();
+  long long rpc = (rows + ctas - 1) / ctas;
+  rpc = (rpc + kLnWarpsBwd - 1) / kLnWarpsBwd * kLnWarpsBwd;
+  const unsigned grid = static_cast<unsigned>((rows + rpc - 1) / rpc);
+  const int nv = (D + 127) / 128;
+#define RMS_BWD_W(V) rmsnorm_bwd_warp_kernel<V><<<grid, kLnWarpsBwd * 32, 0, ST(stream)>>>(dy, x, gamma, eps, D, rows, (int)rpc, dx, dx_accumulate, dgamma)
+  if (nv <= 1) RMS_BWD_W(1); else if (nv <= 2) RMS_BWD_W(2); else if (nv <= 4) RMS_BWD_W(4);
+  else if (nv <= 6) RMS_BWD_W(6); else RMS_BWD_W(8);
+#undef RMS_BWD_W
+  count_launch();
+  UNIIR_CUDA_OK(cudaGetLastError());
+  return UNIIR_OK;
+}
+
+extern "C" int uniir_token_mean_bwd(const float* d_out, int32_t B, int32_t S, int32_t D, float* dx, void* stream) {
+  UNIIR_CHECK_ARG(d_out && dx && B > 0 && S > 0 && D > 0 && D % 4 == 0 && B <= 65535, "uniir_token_mean_bwd: bad args");
+  const int threads = 128;
+  token_mean_bwd_kernel<<<dim3((D / 4 + threads - 1) / threads, B), threads, 0, ST(stream)>>>(d_out, S, D, dx);
   count_launch();
   UNIIR_CUDA_OK(cudaGetLastError());
   return UNIIR_OK;

@@ -91,7 +91,7 @@ def train_step(model, batch, optimizer: FlatAdamW, scheduler=None, accumulation_
     loss, acc = loss.clone(), acc.clone()
     model._loss_backward(batch, None)
     if do_step:
-        allreduce_grads(model.clip_model)
+        allreduce_grads(optimizer.P)          # the flat parameter set being optimised (CLIP_SF: model.clip_model)
         optimizer.step(grad_scale=1.0 / accumulation_steps)
         if scheduler is not None:
             scheduler.step()

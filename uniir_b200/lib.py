@@ -77,6 +77,10 @@ _SIGS = {
     "uniir_attn_fwd_bias": (C.c_int, [VP, I64, VP, VP, I64, I32, I32, I32, I32, C.c_float, VP, VP, I64, VP, VP]),
     "uniir_rmsnorm_fwd": (C.c_int, [VP, I64, VP, C.c_float, I64, I32, VP, I64, I32, VP]),
     "uniir_token_mean": (C.c_int, [VP, I32, I32, I32, VP, VP]),
+    "uniir_rmsnorm_bwd": (C.c_int, [VP, VP, VP, C.c_float, I64, I32, VP, I32, VP, VP]),
+    "uniir_token_mean_bwd": (C.c_int, [VP, I32, I32, I32, VP, VP]),
+    "uniir_attn_bwd_bias": (C.c_int, [VP, I64, VP, VP, I64, VP, I64, VP, I64, VP, I32, I32, I32, I32, C.c_float, VP, VP, VP,
+                                      VP, I64, VP, VP, I64, VP]),
     "uniir_attn_set_mode": (C.c_int, [I32]),
     "uniir_attn_bwd_workspace_floats": (C.c_int64, [I32, I32, I32, I32]),
     "uniir_attn_set_trace": (C.c_int, [VP]),

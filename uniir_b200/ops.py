@@ -225,6 +225,23 @@ def token_mean(x, out=None):
     return out
 
 
+def rmsnorm_bwd(dy, x, gamma, eps, dx, dgamma, accumulate=True):
+    """Backward of rmsnorm_fwd: dx (+)= d x, dgamma += d gamma; dy / x / dx fp32 [rows, D] contiguous."""
+    D = gamma.numel()
+    rows = x.numel() // D
+    assert dy.dtype == x.dtype == dx.dtype == torch.float32 and dy.is_contiguous() and x.is_contiguous() and dx.is_contiguous()
+    L.check(L.load().uniir_rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), eps, rows, D, dx.data_ptr(),
+                                       int(accumulate), dgamma.data_ptr(), _stream()), "uniir_rmsnorm_bwd")
+
+
+def token_mean_bwd(d_out, S, out):
+    """out fp32 [B, S, D] <- d_out[B, D] / S broadcast over the tokens."""
+    B, D = d_out.shape
+    assert d_out.dtype == torch.float32 and d_out.is_contiguous() and out.is_contiguous() and out.numel() == B * S * D
+    L.check(L.load().uniir_token_mean_bwd(d_out.data_ptr(), B, S, D, out.data_ptr(), _stream()), "uniir_token_mean_bwd")
+    return out
+
+
 def patch_im2col(img, P, Kpad, out=None):
     B, C3, H, W = img.shape
     assert C3 == 3 and img.dtype == torch.float32 and img.is_contiguous()
@@ -392,6 +409,19 @@ def attn_fwd_bias(q, k, v, B, Sq, Skv, H, bias, scale=1.0, out=None, lse=None):
                                          float(scale), bias.data_ptr(), out.data_ptr(), out.stride(0), _ptr(lse), _stream()),
             "uniir_attn_fwd_bias")
     return out
+
+
+def attn_bwd_bias(q, k, v, out, dout, lse, B, Sq, Skv, H, bias, dbias, dq, dk, dv, scale=1.0, delta=None):
+    """Backward of attn_fwd_bias; dbias fp32 [H, Sq, Skv] += gradient of the bias (zero it first)."""
+    if delta is None:
+        delta = torch.empty(B * H * Sq, device=q.device, dtype=torch.float32)
+    assert dk.stride(0) == dv.stride(0) and k.stride(0) == v.stride(0)
+    assert bias.shape == dbias.shape == (H, Sq, Skv) and dbias.dtype == torch.float32 and dbias.is_contiguous()
+    L.check(L.load().uniir_attn_bwd_bias(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), out.data_ptr(),
+                                         out.stride(0), dout.data_ptr(), dout.stride(0), lse.data_ptr(), B, Sq, Skv, H,
+                                         float(scale), bias.data_ptr(), dbias.data_ptr(), delta.data_ptr(), dq.data_ptr(),
+                                         dq.stride(0), dk.data_ptr(), dv.data_ptr(), dk.stride(0), _stream()),
+            "uniir_attn_bwd_bias")
 
 
 def attn_bwd(qkv, out, dout, lse, B, S, H, causal, dqkv=None, delta=None):
