@@ -44,7 +44,9 @@ def clip_ff_param_specs(d: CLIPDims, heads: int, layers: int = 2):
     q / k / v weights of a block are adjacent, so the fused [3 * inner, d_model] projection is a plain view."""
     specs = [("clip_model." + n, s, dc, std) for n, s, dc, std in clip_param_specs(d) if n != "text_projection"]
     D, inner = d.embed_dim, heads * T5_DKV
-    add = lambda n, shape, std: specs.append((n, tuple(shape), len(shape) >= 2 and "layer_norm" not in n, std))
+    # every t5 parameter is in the reference's weight-decay-0.2 group, norms and bias table included
+    # (clip_featurefusion/train.py:200-206: the no-decay rule applies only to names without "t5")
+    add = lambda n, shape, std: specs.append((n, tuple(shape), True, std))
     for i in range(layers):
         a, f = f"t5_layers.block.{i}.layer.0", f"t5_layers.block.{i}.layer.1"
         for nm in ("q", "k", "v"):
