@@ -242,6 +242,19 @@ def install(monkeypatch):
     def cast_bf16(src, out=None):
         return src.bfloat16() if out is None else out.copy_(src)
 
+    def adamw_step(p, g, m, v, p16, lr, betas, eps, wd, step, grad_scale=1.0):
+        # rowops.cu::adamw_kernel: decoupled decay, bias correction, bf16 shadow refresh, gradient zeroed
+        b1, b2 = betas
+        gr = g * grad_scale
+        p.mul_(1.0 - lr * wd)
+        m.mul_(b1).add_(gr, alpha=1 - b1)
+        v.mul_(b2).addcmul_(gr, gr, value=1 - b2)
+        bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
+        p.sub_((lr / bc1) * m / (v.sqrt() / bc2 ** 0.5 + eps))
+        g.zero_()
+        if p16 is not None:
+            p16.copy_(p)
+
     def tanh_bwd(dy, y, out):
         out.copy_(dy * (1 - y * y))
 
@@ -252,6 +265,6 @@ def install(monkeypatch):
                token_mean=token_mean, patch_im2col=patch_im2col, vision_embed_fwd=vision_embed_fwd,
                vision_embed_bwd=vision_embed_bwd, text_embed_fwd=text_embed_fwd, text_embed_bwd=text_embed_bwd,
                score_fuse_fwd=score_fuse_fwd, score_fuse_bwd=score_fuse_bwd, pad_cast_bf16=pad_cast_bf16,
-               unpad_accum=unpad_accum, cast_bf16=cast_bf16, tanh_bwd=tanh_bwd)
+               unpad_accum=unpad_accum, cast_bf16=cast_bf16, tanh_bwd=tanh_bwd, adamw_step=adamw_step)
     for name, fn in fns.items():
         monkeypatch.setattr(ops, name, fn)

@@ -92,3 +92,37 @@ def test_clip_ff_encoder_backward_sequencing_reproduces_the_oracle_gradients(mon
         cos = (torch.dot(a, gm) / (a.norm() * gm.norm() + 1e-30)).item()
         worst = min(worst, (cos, n_))
     assert worst[0] > 0.999, worst
+
+
+def test_fused_adamw_parameter_groups_equal_the_reference_optimizer(monkeypatch):
+    """FlatAdamW with a per-parameter learning-rate multiplier (sub-ranges of the flat segments) against torch.optim.AdamW
+    with the reference's three CLIP_FF groups (clip_featurefusion/train.py:49-63, 200-206); and without the multiplier
+    against the two CLIP_SF groups (clip_scorefusion/train.py:52-61)."""
+    cpu_kernels.install(monkeypatch)
+    from uniir_b200.clip_ff import clip_ff_param_specs, t5_heads
+    from uniir_b200.engine import FlatAdamW
+    from uniir_b200.params import CLIP_CONFIGS, FlatParamModule
+    d = CLIP_CONFIGS["tiny-test"]
+    for use_scale in (True, False):
+        root = torch.nn.Module()
+        P = FlatParamModule(clip_ff_param_specs(d, t5_heads("tiny-test")), "cpu", seed=3, root=root)
+        ref = {n: p.detach().clone().requires_grad_(True) for n, p in root.named_parameters()}
+        excl = lambda n, p: (p.ndim < 2 or any(s in n for s in ("bn", "ln", "bias", "logit_scale"))) and "t5" not in n
+        groups = [{"params": [p for n, p in ref.items() if excl(n, p)], "weight_decay": 0.0},
+                  {"params": [p for n, p in ref.items() if not excl(n, p) and "t5" not in n], "weight_decay": 0.2},
+                  {"params": [p for n, p in ref.items() if "t5" in n], "weight_decay": 0.2, "lr": 5e-4 if use_scale else 1e-5}]
+        topt = torch.optim.AdamW(groups, lr=1e-5, betas=(0.9, 0.98), eps=1e-6)
+        opt = FlatAdamW(P, lr=1e-5, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.2,
+                        lr_scale=(lambda n: 50.0 if n.startswith("t5_layers.") else 1.0) if use_scale else None)
+        if use_scale:
+            assert sum(len(r) for r in opt._ranges.values()) <= 4      # a handful of launches, not one per parameter
+        g = torch.Generator().manual_seed(4)
+        for step in range(3):
+            for n, p in ref.items():
+                gr = torch.randn(p.shape, generator=g) * 0.1
+                p.grad = gr.clone()
+                P.g(n).copy_(gr)
+            topt.step(); opt.step()
+        for n, p in ref.items():
+            assert torch.allclose(P.w(n), p.detach(), atol=1e-7, rtol=1e-5), n
+            assert P.g(n).abs().max().item() == 0                       # the fused step zeroes the gradients

@@ -301,6 +301,14 @@ class CLIPFeatureFusion(nn.Module):
         self._nce = None
         self._train_state = None
 
+    def build_optimizer(self, learning_rate=1e-5, t5_learning_rate=5e-4, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.2):
+        """The reference's three AdamW groups (clip_featurefusion/train.py:49-63, 200-206) on the fused optimizer: CLIP
+        gains / biases without decay, the other CLIP parameters and every T5 parameter with 0.2, T5 at its own rate."""
+        from .engine import FlatAdamW
+        scale = t5_learning_rate / learning_rate
+        return FlatAdamW(self._flat, lr=learning_rate, betas=betas, eps=eps, weight_decay=weight_decay,
+                         lr_scale=lambda name: scale if name.startswith("t5_layers.") else 1.0)
+
     # ---- reference surface ---------------------------------------------------------
     def get_img_preprocess_fn(self):
         from .preprocess import clip_image_preprocess

@@ -21,7 +21,12 @@ class FlatAdamW:
     """AdamW over FlatParamModule's two flat segments; state_dict mirrors torch's layout keys
     loosely (step / exp_avg / exp_avg_sq per segment)."""
 
-    def __init__(self, flat_params, lr=1e-5, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.2):
+    def __init__(self, flat_params, lr=1e-5, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.2, lr_scale=None):
+        """lr_scale: optional callable(parameter name) -> multiplier of the learning rate for that parameter.  The
+        reference trains the T5 fusion layers of CLIP_FF at ``t5_learning_rate`` (5e-4) and the CLIP towers at
+        ``learning_rate`` (1e-5) (clip_featurefusion/train.py:49-63, inbatch.yaml:48-49); a scheduler scales both, as
+        torch's does.  Adjacent parameters with the same multiplier share one kernel launch over their sub-range
+        of the flat segment; without lr_scale each segment is one launch, as before."""
         self.P = flat_params
         self.P.ensure_grad()
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
@@ -29,14 +34,32 @@ class FlatAdamW:
         self.v = {k: torch.zeros_like(v) for k, v in self.P.flat.items()}
         self.step_count = 0
         self.param_groups = [{"lr": lr}]  # MetricLogger reads optimizer.param_groups[0]["lr"]
+        self._ranges = None
+        if lr_scale is not None:
+            A = self.P.ALIGN
+            self._ranges = {k: [] for k in self.P.flat}
+            for name, *_ in self.P._specs:                      # allocation order within each segment
+                seg, off, n, _ = self.P._index[name]
+                hi, sc = off + (n + A - 1) // A * A, float(lr_scale(name))
+                r = self._ranges[seg]
+                if r and r[-1][2] == sc and r[-1][1] == off:
+                    r[-1][1] = hi
+                else:
+                    r.append([off, hi, sc])
 
     def step(self, grad_scale=1.0):
         self.step_count += 1
         lr = self.param_groups[0]["lr"]
         for decay in (True, False):
-            ops.adamw_step(self.P.flat[decay], self.P.grad[decay], self.m[decay], self.v[decay],
-                           self.P.flat16[decay], lr, self.betas, self.eps, self.wd if decay else 0.0,
-                           self.step_count, grad_scale)
+            wd = self.wd if decay else 0.0
+            if self._ranges is None:
+                ops.adamw_step(self.P.flat[decay], self.P.grad[decay], self.m[decay], self.v[decay],
+                               self.P.flat16[decay], lr, self.betas, self.eps, wd, self.step_count, grad_scale)
+                continue
+            for lo, hi, sc in self._ranges[decay]:
+                ops.adamw_step(self.P.flat[decay][lo:hi], self.P.grad[decay][lo:hi], self.m[decay][lo:hi],
+                               self.v[decay][lo:hi], self.P.flat16[decay][lo:hi], lr * sc, self.betas, self.eps, wd,
+                               self.step_count, grad_scale)
         self.P.mark_shadow_fresh()
 
     def zero_grad(self, set_to_none=False):
