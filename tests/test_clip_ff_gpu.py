@@ -1,14 +1,12 @@
 """GPU parity of the CLIP_FF encode path (uniir_b200/clip_ff.py) against the oracle, whose T5 stack is
 pinned against transformers' T5Stack (tests/test_oracle_clip_ff.py).
 
-These tests were written in a session that had no GPU time left: the kernels they exercise (uniir_rmsnorm_fwd,
-uniir_attn_fwd_bias, the ReLU epilogue, uniir_token_mean) compile for sm_100a but have not run on hardware yet.
-They are therefore xfail(strict=False) -- XPASS means the path is confirmed and the marker can go -- and the file
-sorts last so that it cannot mask any confirmed test."""
+All five passed on the driver's B200 at the end of round 1 (GPUTEST_r01: 5 xpassed) and again in round 2
+(gpurun_out/r2c1_tests.log), so the round-1 xfail marker is gone: a CLIP_FF regression now fails the suite."""
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="CLIP_FF kernels not yet confirmed on a B200")]
+pytestmark = pytest.mark.gpu
 dev = "cuda"
 
 

@@ -165,6 +165,38 @@ def test_vit_b32_batch4_matches_oracle():
     _check_against_oracle("ViT-B/32", 4, 8, 0.995)
 
 
+@pytest.mark.parametrize("masks", ["mixed", "ones"])
+def test_vit_l14_dims_match_oracle(masks):
+    """The headline configuration's architecture (BASELINE configs[1], ViT-L/14: 24 x 1024 vision, 12 x 768 text,
+    257 / 77 tokens, embed 768) at 2 pairs: embeddings within 1e-3 cosine, loss, every parameter gradient."""
+    orc, mine = _pair("ViT-L/14", 4)
+    b = _batch(orc.clip_model.dims, 2)
+    if masks == "ones":
+        b["txt_mask_batched"] = torch.ones(4, dtype=torch.long); b["image_mask_batched"] = torch.ones(4, dtype=torch.long)
+    ref = orc(b)
+    ref["loss"].backward()
+    with torch.no_grad():
+        emb_o = orc.encode_multimodal_input(b["txt_batched"], b["image_batched"], b["txt_mask_batched"], b["image_mask_batched"])
+    gb = _cuda(b)
+    emb_m = mine.encode_multimodal_input(gb["txt_batched"], gb["image_batched"], gb["txt_mask_batched"], gb["image_mask_batched"]).cpu()
+    cos = torch.nn.functional.cosine_similarity(emb_m, emb_o, dim=-1)
+    assert cos.min().item() > 1 - COS_TOL, cos.min().item()
+    mine.micro_batch = 8 if masks == "mixed" else 4     # mixed masks: compacted towers; ones: fused two-tower pass
+    out = mine(gb)
+    assert abs(out["loss"].item() - ref["loss"].item()) < LOSS_RTOL * max(1.0, abs(ref["loss"].item()))
+    out["loss"].backward()
+    worst, worst_name = 1.0, None
+    for n_, p_o in orc.named_parameters():
+        gm = mine.get_parameter(n_).grad
+        assert gm is not None, n_
+        a, c = p_o.grad.flatten().double(), gm.cpu().flatten().double()
+        if a.numel() > 1 and a.norm() > 0:
+            cs = (torch.dot(a, c) / (a.norm() * c.norm() + 1e-30)).item()
+            if cs < worst:
+                worst, worst_name = cs, n_
+    assert worst > 0.99, (worst, worst_name)
+
+
 def test_golden_vectors():
     from uniir_b200.clip_sf import CLIPScoreFusion
     g = np.load(os.path.join(GOLDEN, "clip_tiny.npz"))
@@ -313,3 +345,20 @@ def test_hard_negative_branch_matches_oracle():
         if a.numel() > 1:
             worst = min(worst, (torch.dot(a, c) / (a.norm() * c.norm() + 1e-30)).item())
     assert worst > 0.99, worst
+
+
+def test_hard_negative_kernel_matches_reference_golden():
+    """tests/golden/infonce.npz `hn_*`: produced by the reference's own clip_sf.py:105-131 (scripts/make_golden.py
+    asserts the oracle agrees) -- loss, accuracy and d_emb of the fused hard-negative kernel."""
+    from uniir_b200 import ops
+    g = np.load(os.path.join(GOLDEN, "infonce.npz"))
+    emb = torch.from_numpy(g["hn_emb"]).cuda()
+    bs = emb.shape[0] // 4
+    base = torch.arange(bs, device="cuda", dtype=torch.int32) * 4
+    n_idx = torch.stack([base + 2, base + 3], dim=1).contiguous()
+    ls = torch.tensor(np.log(100.0), device="cuda", dtype=torch.float32)
+    dls = torch.zeros((), device="cuda")
+    loss, acc, d_emb = ops.hardneg_loss(emb, base, base + 1, n_idx, int(g["hn_in_batch_neg_num"]), ls, dls)
+    assert abs(loss.item() - float(g["hn_loss"])) < 1e-4 and abs(acc.item() - float(g["hn_acc"])) < 1e-6
+    ref = torch.from_numpy(g["hn_g"])
+    assert ((d_emb.cpu() - ref).norm() / ref.norm()).item() < 1e-4

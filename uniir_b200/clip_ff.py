@@ -2,11 +2,12 @@
 SURVEY.md 8f-3) on the B200-native kernels: the encode path (``encode_multimodal_input``, ``forward(batch,
 encode_mbeir_batch=True)`` / ``encode_mbeir_batch``) and the in-batch contrastive training step.
 
-STATUS: written and compiled in a session that had no GPU time left.  The HOST logic (kernel sequencing of the forward
-and of the hand-written backward) is verified on CPU against the oracle's autograd with every kernel wrapper replaced
-by its torch contract (tests/test_clip_ff_host_logic.py); the new kernels (RMS norm fwd/bwd, attention with score bias
-fwd/bwd + bias gradient, ReLU epilogue, token mean fwd/bwd) compile for sm_100a and are asserted against torch by
-tests/test_zz_unconfirmed_gpu.py, which is xfail(strict=False) until it has been seen green on a B200.
+STATUS: the host logic (kernel sequencing of the forward and of the hand-written backward) is verified on CPU against
+the oracle's autograd with every kernel wrapper replaced by its torch contract (tests/test_clip_ff_host_logic.py); the
+kernels (RMS norm fwd/bwd, attention with score bias fwd/bwd + bias gradient, ReLU epilogue, token mean fwd/bwd),
+the encode path and the training step are asserted against torch / the oracle on the GPU by tests/test_clip_ff_gpu.py
+(green on a B200 since the end of round 1); the oracle is pinned to the reference's own class
+(tests/test_oracle_clip_ref.py).
 Training: ``engine.train_step(model, batch, FlatAdamW(model._flat))`` (gradient-cached, like CLIP_SF).
 
 Arithmetic (restated in oracle/clip_ff_oracle.py, whose T5 stack is pinned against transformers' own ``T5Stack``):

@@ -40,6 +40,7 @@ struct TileSched {
     w.m_blk = first_m + r % rows;
     w.n_begin = r / rows;
     w.n_end = w.n_begin + 1;
+    w.rot = 0;
     const int per = (kb_total + split_k - 1) / split_k;
     w.kb_begin = ks * per;
     w.kb_end = min(kb_total, w.kb_begin + per);

@@ -32,6 +32,12 @@ constexpr int num_threads(int ne) { return 64 + 32 * ne; }
 struct WorkItem {
   int m_blk, n_begin, n_end, kb_begin, kb_end;
   int tag, aux;  // scheduler-defined (retrieval: state slot, chunk index / last-chunk flag)
+  int rot;       // the item's tiles are visited in the cyclic order n_begin + (i + rot) % (n_end - n_begin)
+  // i-th tile of the item in visiting order (0 <= rot < n_end - n_begin)
+  __device__ __forceinline__ int tile_at(int i) const {
+    const int n = n_begin + i + rot;
+    return n >= n_end ? n - (n_end - n_begin) : n;
+  }
 };
 
 template <int BN>
@@ -103,7 +109,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
       WorkItem w;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         if (!sched.get(item, w)) continue;
-        for (int n = w.n_begin; n < w.n_end; ++n) {
+        for (int ti = 0; ti < w.n_end - w.n_begin; ++ti) {
+          const int n = w.tile_at(ti);
           for (int kb = w.kb_begin; kb < w.kb_end; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = ring + stage * S::kStageBytes;
@@ -139,7 +146,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
       WorkItem w;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         if (!sched.get(item, w)) continue;
-        for (int n = w.n_begin; n < w.n_end; ++n) {
+        for (int ti = 0; ti < w.n_end - w.n_begin; ++ti) {
           mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + acc * BN;
@@ -179,7 +186,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA, const CUtensor
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       if (!sched.get(item, w)) continue;
       epi.item_begin(w, row);
-      for (int n = w.n_begin; n < w.n_end; ++n) {
+      for (int ti = 0; ti < w.n_end - w.n_begin; ++ti) {
+        const int n = w.tile_at(ti);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         epi.tile(w, n, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN, row, col_half);
@@ -230,7 +238,8 @@ struct GemmSmem2 {
 template <int BN, bool A_MN, bool B_MN, int NE, class Sched, class Epi>
 __device__ __forceinline__ void gemm_body_2cta(const CUtensorMap* tmA, const CUtensorMap* tmB,
                                                uint32_t idesc, const Sched& sched, Epi& epi,
-                                               uint8_t* smem /*1024-aligned*/) {
+                                               uint8_t* smem /*1024-aligned*/,
+                                               int l2_hint_a = kL2None, int l2_hint_b = kL2None) {
   using S = GemmSmem2<BN>;
   constexpr int kStages = S::kStages;
   uint8_t* ring = smem;
@@ -272,9 +281,11 @@ __device__ __forceinline__ void gemm_body_2cta(const CUtensorMap* tmA, const CUt
       int stage = 0;
       uint32_t phase = 0;
       WorkItem w;
+      const uint64_t pol_a = make_l2_policy(l2_hint_a), pol_b = make_l2_policy(l2_hint_b);
       for (int item = pair; item < n_items; item += n_pairs) {
         if (!sched.get(item, w)) continue;
-        for (int n = w.n_begin; n < w.n_end; ++n) {
+        for (int ti = 0; ti < w.n_end - w.n_begin; ++ti) {
+          const int n = w.tile_at(ti);
           for (int kb = w.kb_begin; kb < w.kb_end; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = ring + stage * S::kStageBytes;
@@ -284,13 +295,15 @@ __device__ __forceinline__ void gemm_body_2cta(const CUtensorMap* tmA, const CUt
             const int a_row = w.m_blk * 2 * kBM + rank * kBM;
             const int b_row = n * BN + rank * (BN / 2);
             if constexpr (!A_MN) {
-              tma_load_2d_2sm(sa, tmA, fb, kb * kBK, a_row);
+              if (l2_hint_a) tma_load_2d_2sm_hint(sa, tmA, fb, kb * kBK, a_row, pol_a);
+              else tma_load_2d_2sm(sa, tmA, fb, kb * kBK, a_row);
             } else {
 #pragma unroll
               for (int g = 0; g < kBM / 64; ++g) tma_load_2d_2sm(sa + g * (kBK * 128), tmA, fb, a_row + g * 64, kb * kBK);
             }
             if constexpr (!B_MN) {
-              tma_load_2d_2sm(sb, tmB, fb, kb * kBK, b_row);
+              if (l2_hint_b) tma_load_2d_2sm_hint(sb, tmB, fb, kb * kBK, b_row, pol_b);
+              else tma_load_2d_2sm(sb, tmB, fb, kb * kBK, b_row);
             } else {
 #pragma unroll
               for (int g = 0; g < BN / 128; ++g) tma_load_2d_2sm(sb + g * (kBK * 128), tmB, fb, b_row + g * 64, kb * kBK);
@@ -310,7 +323,7 @@ __device__ __forceinline__ void gemm_body_2cta(const CUtensorMap* tmA, const CUt
       WorkItem w;
       for (int item = pair; item < n_items; item += n_pairs) {
         if (!sched.get(item, w)) continue;
-        for (int n = w.n_begin; n < w.n_end; ++n) {
+        for (int ti = 0; ti < w.n_end - w.n_begin; ++ti) {
           mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + acc * BN;
@@ -350,7 +363,8 @@ __device__ __forceinline__ void gemm_body_2cta(const CUtensorMap* tmA, const CUt
       w.m_blk = w.m_blk * 2 + static_cast<int>(rank);   // this CTA's 128-row block
       w.tag = w.tag * 2 + static_cast<int>(rank);
       epi.item_begin(w, row);
-      for (int n = w.n_begin; n < w.n_end; ++n) {
+      for (int ti = 0; ti < w.n_end - w.n_begin; ++ti) {
+        const int n = w.tile_at(ti);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         epi.tile(w, n, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN, row, col_half);

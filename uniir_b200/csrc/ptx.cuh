@@ -234,6 +234,23 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 eviction-priority policies for hinted TMA loads (0 = no hint)
+enum : int { kL2None = 0, kL2EvictNormal = 1, kL2EvictFirst = 2, kL2EvictLast = 3 };
+__device__ __forceinline__ uint64_t make_l2_policy(int kind) {
+  uint64_t pol = 0;
+  if (kind == kL2EvictFirst) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else if (kind == kL2EvictLast) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else if (kind == kL2EvictNormal) asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_2d_2sm_hint(void* smem_dst, const CUtensorMap* m, uint32_t mbar_cluster_addr,
+                                                     int32_t c0, int32_t c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "n"(kCols)
