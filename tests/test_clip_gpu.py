@@ -168,11 +168,12 @@ def test_vit_b32_batch4_matches_oracle():
 @pytest.mark.parametrize("masks", ["mixed", "ones"])
 def test_vit_l14_dims_match_oracle(masks):
     """The headline configuration's architecture (BASELINE configs[1], ViT-L/14: 24 x 1024 vision, 12 x 768 text,
-    257 / 77 tokens, embed 768) at 2 pairs: embeddings within 1e-3 cosine, loss, every parameter gradient."""
-    orc, mine = _pair("ViT-L/14", 4)
-    b = _batch(orc.clip_model.dims, 2)
+    257 / 77 tokens, embed 768) at 4 pairs (the training micro-batch is a multiple of 8 items): embeddings within
+    1e-3 cosine, loss, every parameter gradient."""
+    orc, mine = _pair("ViT-L/14", 8)
+    b = _batch(orc.clip_model.dims, 4)
     if masks == "ones":
-        b["txt_mask_batched"] = torch.ones(4, dtype=torch.long); b["image_mask_batched"] = torch.ones(4, dtype=torch.long)
+        b["txt_mask_batched"] = torch.ones(8, dtype=torch.long); b["image_mask_batched"] = torch.ones(8, dtype=torch.long)
     ref = orc(b)
     ref["loss"].backward()
     with torch.no_grad():
@@ -181,8 +182,7 @@ def test_vit_l14_dims_match_oracle(masks):
     emb_m = mine.encode_multimodal_input(gb["txt_batched"], gb["image_batched"], gb["txt_mask_batched"], gb["image_mask_batched"]).cpu()
     cos = torch.nn.functional.cosine_similarity(emb_m, emb_o, dim=-1)
     assert cos.min().item() > 1 - COS_TOL, cos.min().item()
-    mine.micro_batch = 8 if masks == "mixed" else 4     # mixed masks: compacted towers; ones: fused two-tower pass
-    out = mine(gb)
+    out = mine(gb)                                      # mixed masks: compacted towers; ones: fused two-tower pass
     assert abs(out["loss"].item() - ref["loss"].item()) < LOSS_RTOL * max(1.0, abs(ref["loss"].item()))
     out["loss"].backward()
     worst, worst_name = 1.0, None

@@ -133,3 +133,60 @@ def _sharded_search(rank, world):
 def test_sharded_search_exchange_matches_unsharded_oracle():
     for rank, (same, err) in _run(_sharded_search):
         assert same and err < 1e-6
+
+
+class _FakeEmbedModel:
+    """CPU stand-in with the model's embed API, so the embedder's gather logic can run under gloo."""
+
+    def __call__(self, batch, encode_mbeir_batch=False):
+        ids = batch["did_list"]
+        return torch.tensor([[float(i), float(i) * 0.5, 1.0, -2.0] for i in ids]), ids
+
+
+def _ragged_gather(rank, world):
+    from uniir_b200.mbeir_embedder import _gather_ragged, generate_embeds_and_ids_for_dataset_with_gather
+    n = 5 if rank == 0 else 3                                 # the reference's dist.gather breaks on unequal sizes
+    x = torch.arange(n * 2, dtype=torch.float32).view(n, 2) + 100 * rank
+    parts = _gather_ragged(x, 0)
+    ok = [p.shape[0] for p in parts] == [5, 3] and torch.equal(parts[rank], x)
+    base = 10 if rank == 0 else 50
+    loader = [{"did_list": [base + i for i in range(s, min(n, s + 2))]} for s in range(0, n, 2)]
+    emb, ids = generate_embeds_and_ids_for_dataset_with_gather(_FakeEmbedModel(), loader, "cpu")
+    if rank == 0:
+        want = [10, 11, 12, 13, 14, 50, 51, 52]
+        return ok and ids == want and emb.dtype == np.float16 and emb.shape == (8, 4) and emb[:, 0].tolist() == [float(i) for i in want]
+    return ok and emb is None and ids == [50, 51, 52]
+
+
+def test_embedder_gather_handles_ragged_rank_shards():
+    for rank, ok in _run(_ragged_gather):
+        assert ok, rank
+
+
+def _shard_handoff(rank, world):
+    """embedder -> retriever without the rank-0 funnel: each rank saves its rows, a link-style index points at them,
+    each rank loads exactly its own shard file again."""
+    from uniir_b200 import mbeir_embedder as me, mbeir_retriever as mr
+    from uniir_b200.dist_utils import shard_range
+    root = os.environ["UNIIR_TEST_TMP"]
+    e_path, i_path = me.embed_paths(root, "embed", "X/", "cand_pool", "union")
+    n = 4 if rank == 0 else 3
+    emb = (torch.arange(n * 8, dtype=torch.float32).view(n, 8) + 1000 * rank).half()
+    ids = torch.arange(n, dtype=torch.int64) + 100 * rank
+    me.save_rank_shards(e_path, i_path, emb, ids)
+    dist.barrier()
+    if rank == 0:
+        assert me._concat_rank_shards(e_path, i_path, world) == 7
+        mr.write_index_link(os.path.join(root, "u.index"), e_path, i_path)
+    dist.barrier()
+    full = np.load(e_path)
+    lo, hi = shard_range(7, world, rank)
+    e, i = mr.read_index_rows(os.path.join(root, "u.index"), lo, hi)
+    return bool(full.shape == (7, 8) and np.array_equal(e, emb.numpy()) and np.array_equal(i, ids.numpy()) and
+                mr.index_shape(os.path.join(root, "u.index")) == (7, 8))
+
+
+def test_rank_shard_handoff_embedder_to_retriever(tmp_path):
+    os.environ["UNIIR_TEST_TMP"] = str(tmp_path)
+    for rank, ok in _run(_shard_handoff):
+        assert ok, rank

@@ -95,3 +95,75 @@ def test_image_preprocess_contract():
     t = clip_image_preprocess(224)(Image.new("RGB", (320, 240), (0, 0, 0)))
     assert t.shape == (3, 224, 224) and t.dtype == torch.float32
     assert torch.allclose(t[:, 0, 0], torch.tensor([-0.48145466 / 0.26862954, -0.4578275 / 0.26130258, -0.40821073 / 0.27577711]), atol=1e-5)
+
+
+def test_flat_adamw_state_dict_is_torch_adamw_layout_of_the_reference_groups():
+    """Reference checkpoints carry `optimizer.state_dict()` of torch.optim.AdamW over two groups built with the
+    conditions of clip_scorefusion/train.py:195-199 (train.py:52-61, 64-79).  FlatAdamW must write that layout (a torch
+    optimizer built the reference's way loads it and finds every tensor in the right slot) and read it back."""
+    import torch
+    from oracle.clip_oracle import CLIPScoreFusionOracle
+    from uniir_b200.engine import FlatAdamW
+    from uniir_b200.params import CLIP_CONFIGS, FlatParamModule, clip_param_specs
+    torch.manual_seed(0)
+    P = FlatParamModule(clip_param_specs(CLIP_CONFIGS["tiny-test"]), "cpu")
+    opt = FlatAdamW(P, lr=3e-5)
+    for k in opt.m:
+        opt.m[k].normal_(); opt.v[k].uniform_()
+    opt.step_count = 3
+    sd = opt.state_dict()
+    # the reference's grouping, verbatim conditions, on a model with the reference's parameter names / order
+    ref_model = CLIPScoreFusionOracle("tiny-test")
+    exclude = lambda n, p: p.ndim < 2 or any(sub in n for sub in ["bn", "ln", "bias", "logit_scale"])
+    named = list(ref_model.named_parameters())
+    gain_or_bias = [p for n, p in named if exclude(n, p) and p.requires_grad]
+    rest = [p for n, p in named if not exclude(n, p) and p.requires_grad]
+    topt = torch.optim.AdamW([{"params": gain_or_bias, "weight_decay": 0.0}, {"params": rest, "weight_decay": 0.2}],
+                             lr=1e-5, betas=(0.9, 0.98), eps=1.0e-6)
+    topt.load_state_dict(sd)                                   # shapes / group sizes must fit
+    assert topt.param_groups[0]["weight_decay"] == 0.0 and topt.param_groups[1]["weight_decay"] == 0.2
+    assert topt.param_groups[0]["lr"] == 3e-5
+    names0 = [n[len("clip_model."):] for n, p in named if exclude(n, p)]
+    names1 = [n[len("clip_model."):] for n, p in named if not exclude(n, p)]
+    for p, n in list(zip(gain_or_bias, names0)) + list(zip(rest, names1)):
+        st = topt.state[p]
+        assert float(st["step"]) == 3.0
+        assert torch.equal(st["exp_avg"], P._view(opt.m, n)) and torch.equal(st["exp_avg_sq"], P._view(opt.v, n)), n
+    # and back: a state dict written by torch loads into a fresh FlatAdamW
+    opt2 = FlatAdamW(FlatParamModule(clip_param_specs(CLIP_CONFIGS["tiny-test"]), "cpu"), lr=1e-5)
+    opt2.load_state_dict(topt.state_dict())
+    assert opt2.step_count == 3 and opt2.param_groups[0]["lr"] == 3e-5
+    for n, *_ in P._specs:      # (the alignment padding between parameters carries no state)
+        assert torch.equal(opt2.P._view(opt2.m, n), P._view(opt.m, n)) and torch.equal(opt2.P._view(opt2.v, n), P._view(opt.v, n)), n
+    # no step taken yet: empty state, like torch
+    assert FlatAdamW(P, lr=1e-5).state_dict()["state"] == {}
+
+
+def test_bpe_pretokenizer_unicode_classes():
+    """clip.tokenize splits on \\p{L}+ | \\p{N} | [^\\s\\p{L}\\p{N}]+ : non-ASCII letters stay in one word, every
+    digit is its own token (the ASCII-only classes split accented / CJK text differently)."""
+    from uniir_b200.preprocess import bpe_pretokenizer
+    pat, fallback = bpe_pretokenizer(), bpe_pretokenizer(force_stdlib=True)
+    cases = {"café über straße": ["café", "über", "straße"], "東京タワー 2023年": ["東京タワー", "2", "0", "2", "3", "年"],
+             "it's a dog's life!!": ["it", "'s", "a", "dog", "'s", "life", "!!"], "x_y 42": ["x", "_", "y", "4", "2"],
+             "<|startoftext|>abc<|endoftext|>": ["<|startoftext|>", "abc", "<|endoftext|>"]}
+    for text, want in cases.items():
+        assert pat.findall(text) == want, text
+        assert fallback.findall(text) == want, text
+
+
+def test_clip_image_preprocess_matches_torchvision_arithmetic():
+    tv = pytest.importorskip("torchvision.transforms")
+    import numpy as np
+    import torch
+    from PIL import Image
+    from uniir_b200.preprocess import CLIP_MEAN, CLIP_STD, clip_image_preprocess
+    ref = tv.Compose([tv.Resize(224, interpolation=tv.InterpolationMode.BICUBIC), tv.CenterCrop(224),
+                      lambda im: im.convert("RGB"), tv.ToTensor(), tv.Normalize(CLIP_MEAN, CLIP_STD)])
+    mine = clip_image_preprocess(224)
+    rng = np.random.default_rng(0)
+    for w, h in ((640, 427), (333, 500), (224, 224), (225, 300), (301, 226), (1000, 227)):
+        img = Image.fromarray(rng.integers(0, 255, (h, w, 3), dtype=np.uint8))
+        a, b = mine(img), ref(img)
+        assert a.shape == b.shape == (3, 224, 224)
+        assert torch.allclose(a, b, atol=1e-6), (w, h, (a - b).abs().max())

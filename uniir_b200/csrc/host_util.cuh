@@ -15,6 +15,14 @@ void set_error(const char* fmt, ...);  // api.cu
 int num_sms();                         // api.cu (cached, current device)
 extern std::atomic<int64_t> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+// true the first time it is called with this mask on the current device: function attributes
+// (cudaFuncSetAttribute) are per device, and one process may drive several GPUs (single-process retrieval)
+inline bool first_on_device(std::atomic<uint64_t>& mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  const uint64_t bit = 1ull << dev;
+  return (mask.fetch_or(bit, std::memory_order_relaxed) & bit) == 0;
+}
 
 #define UNIIR_CHECK_ARG(cond, ...)              \
   do {                                          \

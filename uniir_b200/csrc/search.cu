@@ -32,6 +32,7 @@ constexpr float kNegInf = -INFINITY;
 constexpr float kFaissNeg = -3.4028234663852886e38f;
 
 constexpr int kDefaultTilesPerChunk = 64;   // 64 x 256 candidates x 1536 B = 25 MB: L2-resident per wave
+constexpr int kDefaultTilesPerChunkTs = 512; // 64 k candidates per chunk in 128-candidate tiles (queries-on-chip kernel)
 
 struct SearchParams {
   long long Q, N;
@@ -134,13 +135,14 @@ __device__ __forceinline__ void warp_bitonic_desc(float (&key)[R], IdxT (&idx)[R
   }
 }
 
-struct SearchEpilogue {
+template <int BN>
+struct SearchEpilogueT {
   const SearchParams& p;
-  float* invc_s;  // [2][256] in shared memory
+  float* invc_s;  // [2][BN] in shared memory
   float thr;
   int cnt;
   int tcount;
-  __device__ SearchEpilogue(const SearchParams& p_, float* s) : p(p_), invc_s(s), thr(kNegInf), cnt(0), tcount(0) {}
+  __device__ SearchEpilogueT(const SearchParams& p_, float* s) : p(p_), invc_s(s), thr(kNegInf), cnt(0), tcount(0) {}
 
   long long slot_row0;  // first state row of the current (split, query tile) slot
 
@@ -233,20 +235,27 @@ struct SearchEpilogue {
     __syncwarp();
   }
 
-  __device__ __forceinline__ void tile(const WorkItem& w, int n_blk, uint32_t tmem_acc, int row, int /*col_half*/) {
-    float* invc = invc_s + (tcount & 1) * kSearchBN;
-    ++tcount;
-    const long long col_base = static_cast<long long>(n_blk) * kSearchBN;
+  // `staged`: the tile's BN inverse candidate norms already sit in shared memory (the caller prefetched them a
+  // tile ahead); otherwise they are fetched here and published to the four epilogue warps with a named barrier.
+  __device__ __forceinline__ void tile(const WorkItem& w, int n_blk, uint32_t tmem_acc, int row, int /*col_half*/,
+                                       const float* staged = nullptr) {
+    const float* invc = staged;
+    const long long col_base = static_cast<long long>(n_blk) * BN;
+    if (staged == nullptr) {
+      float* buf = invc_s + (tcount & 1) * BN;
+      ++tcount;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const long long c = col_base + row + h * kBM;
-      invc[row + h * kBM] = (c < p.N) ? p.c_inv[c] : 0.f;
+      for (int i = row; i < BN; i += kBM) {
+        const long long c = col_base + i;
+        buf[i] = (c < p.N) ? p.c_inv[c] : 0.f;
+      }
+      named_bar_sync(1, 128);
+      invc = buf;
     }
-    named_bar_sync(1, 128);
-    const bool tail = col_base + kSearchBN > p.N;
+    const bool tail = col_base + BN > p.N;
     const long long wsb = ws_base(row);
 #pragma unroll 1
-    for (int c = 0; c < kSearchBN / 32; ++c) {
+    for (int c = 0; c < BN / 32; ++c) {
       uint32_t r[32];
       tmem_ld_32x32b_x32(tmem_acc + c * 32, r);
       tmem_ld_wait();
@@ -306,6 +315,8 @@ struct SearchEpilogue {
   }
 };
 
+using SearchEpilogue = SearchEpilogueT<kSearchBN>;
+
 __global__ void __launch_bounds__(num_threads(4), 1)
 ip_topk_kernel(const __grid_constant__ GemmTensorMaps maps, const SearchParams p,
                const SearchSched sched, const uint32_t idesc) {
@@ -328,6 +339,285 @@ ip_topk_kernel_2cta(const __grid_constant__ GemmTensorMaps maps, const SearchPar
   float* invc_s = reinterpret_cast<float*>(smem + SM::kRingBytes + SM::kBarBytes);
   SearchEpilogue epi(p, invc_s);
   gemm_body_2cta<kSearchBN, false, false, 4>(&maps.a, &maps.b, idesc, sched, epi, smem, hint_a, hint_b);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Queries resident on the SM (default).  ncu on the kernels above (profiles/search_l2_diagnosis_r02.txt): they
+// stream BOTH operands from L2 for every 256 x 256 tile, 64 B/clk/SM at full tensor rate = 8.5 TB/s chip-wide
+// measured -- the L2 -> SM throughput cap -- and 1.0 PFLOP/s whatever the SM clock.  Here a CTA pair keeps its 256
+// query rows (128 per CTA) on chip for a whole work item and streams only the candidates:
+//   * k-blocks 0-7 of the queries (K = 512) sit in TENSOR MEMORY -- 256 columns, two fp16 per 32-bit column,
+//     lane = row -- and enter `tcgen05.mma` as the A operand from TMEM;
+//   * k-blocks 8-11 (K = 256, 64 KB per CTA) sit in SHARED MEMORY, loaded once per item by TMA, and enter as an
+//     ordinary shared-memory A operand;
+//   * the other 256 TMEM columns are two 128-column accumulators: the tile is 256 queries x 128 candidates,
+//     double-buffered against the epilogue.  (All 384 query columns in TMEM leave room for 64-candidate tiles
+//     only; that version was correct but issue-bound: a 256 x 64 x 16 MMA lasts 32 clocks and the single issuing
+//     thread needs ~40 for the descriptor arithmetic -- 52 % tensor pipe, ncu r2c5.)
+// L2 -> SM bytes per FLOP halve (256 FLOP/B); the ring holds nothing but candidates (9 stages x 16 KB per CTA).
+//   warp 0   : TMA producer (both CTAs): per item the shared-memory part of its queries, then its 64 rows of each
+//              128-candidate tile, 2 k-blocks (16 KB) per stage
+//   warp 1   : MMA issuer (leader CTA): per k-block 4 x tcgen05.mma.cta_group::2 (M 256, N 128, K 16)
+//   warps 2-5: per item, copy k-blocks 0-7 of this CTA's 128 query rows global -> registers -> TMEM
+//              (tcgen05.st); then the top-k epilogue on 128-column tiles
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kTsBN = 128;                // candidates per tile
+constexpr int kTsStageKb = 2;             // k-blocks per smem stage
+constexpr int kTsStages = 9;
+constexpr int kTsKbBytes = (kTsBN / 2) * kBK * 2;              // 8 KB: this CTA's 64 rows of one k-block
+constexpr int kTsStageBytes = kTsStageKb * kTsKbBytes;         // 16 KB
+constexpr int kTsRingBytes = kTsStages * kTsStageBytes;        // 144 KB
+constexpr int kTsTmemKb = 8;              // query k-blocks held in TMEM (8 x 32 = 256 columns)
+constexpr int kTsSmemKb = 4;              // query k-blocks held in shared memory
+constexpr int kTsMaxKb = kTsTmemKb + kTsSmemKb;                // 12 x 64 = 768
+constexpr int kTsAKbBytes = kBM * kBK * 2;                     // 16 KB: this CTA's 128 rows of one k-block
+constexpr int kTsASmemBytes = kTsSmemKb * kTsAKbBytes;         // 64 KB
+constexpr int kTsACols = kTsTmemKb * (kBK / 2);                // 256
+constexpr int kTsBarBytes = ((2 * kTsStages + 6) * 8 + 8 + 127) / 128 * 128;
+constexpr int kTsInvBytes = 4 * 2 * kTsBN * static_cast<int>(sizeof(float));   // per epilogue warp: two tiles of 1/||c||
+constexpr int kTsSmemBytes = kTsRingBytes + kTsASmemBytes + kTsBarBytes + kTsInvBytes + 1024;
+static_assert(kTsACols + 2 * kTsBN == 512, "TMEM budget: queries + two accumulators");
+static_assert(kTsSmemBytes <= 232448, "shared memory budget");
+using SearchEpilogueTs = SearchEpilogueT<kTsBN>;
+
+// One 128-candidate tile's MMAs.  kFull: d = 768 (12 k-blocks, 6 full stages): everything but the stage slot is a
+// compile-time constant, so each MMA costs the issuing thread two adds.
+template <bool kFull>
+__device__ __forceinline__ void ts_issue_tile(uint32_t tmem_d, uint32_t tmem_a, uint64_t adesc0, uint64_t bdesc0,
+                                              uint32_t idesc, int kb_total, uint64_t* full_bar, uint64_t* empty_bar,
+                                              int& stage, uint32_t& phase) {
+  if constexpr (kFull) {
+#pragma unroll
+    for (int s6 = 0; s6 < kTsMaxKb / kTsStageKb; ++s6) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint64_t bd = bdesc0 + static_cast<uint64_t>(stage * (kTsStageBytes >> 4));
+#pragma unroll
+      for (int j = 0; j < kTsStageKb; ++j) {
+        const int kb = s6 * kTsStageKb + j;
+#pragma unroll
+        for (int k = 0; k < kBK / kUmmaK; ++k) {
+          const uint64_t db = bd + static_cast<uint64_t>((j * kTsKbBytes + k * 32) >> 4);
+          if (kb < kTsTmemKb)
+            umma_f16_ts_2sm(tmem_d, tmem_a + kb * (kBK / 2) + k * (kUmmaK / 2), db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          else
+            umma_f16_2sm(tmem_d, adesc0 + static_cast<uint64_t>(((kb - kTsTmemKb) * kTsAKbBytes + k * 32) >> 4), db, idesc, 1u);
+        }
+      }
+      umma_commit_2sm(&empty_bar[stage], 0x3);
+      if (++stage == kTsStages) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    for (int kb0 = 0; kb0 < kb_total; kb0 += kTsStageKb) {
+      const int nkb = min(kTsStageKb, kb_total - kb0);
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint64_t bd = bdesc0 + static_cast<uint64_t>(stage * (kTsStageBytes >> 4));
+      for (int j = 0; j < nkb; ++j) {
+        const int kb = kb0 + j;
+#pragma unroll
+        for (int k = 0; k < kBK / kUmmaK; ++k) {
+          const uint64_t db = bd + static_cast<uint64_t>((j * kTsKbBytes + k * 32) >> 4);
+          if (kb < kTsTmemKb)
+            umma_f16_ts_2sm(tmem_d, tmem_a + kb * (kBK / 2) + k * (kUmmaK / 2), db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          else
+            umma_f16_2sm(tmem_d, adesc0 + static_cast<uint64_t>(((kb - kTsTmemKb) * kTsAKbBytes + k * 32) >> 4), db, idesc, 1u);
+        }
+      }
+      umma_commit_2sm(&empty_bar[stage], 0x3);
+      if (++stage == kTsStages) { stage = 0; phase ^= 1; }
+    }
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(num_threads(4), 1)
+ip_topk_kernel_ts(const __grid_constant__ GemmTensorMaps maps, const __half* __restrict__ q, const int d,
+                  const SearchParams p, const SearchSched sched, const uint32_t idesc) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem_1024(smem_raw);
+  uint8_t* ring = smem;
+  uint8_t* a_smem = smem + kTsRingBytes;                      // query k-blocks 8..11, K-major 128B-swizzled
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kTsRingBytes + kTsASmemBytes);
+  uint64_t* empty_bar = full_bar + kTsStages;
+  uint64_t* tfull_bar = empty_bar + kTsStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* afull_bar = tempty_bar + 2;
+  uint64_t* aempty_bar = afull_bar + 1;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aempty_bar + 1);
+  float* invc_s = reinterpret_cast<float*>(smem + kTsRingBytes + kTsASmemBytes + kTsBarBytes);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp_idx == 0 && elect_one()) {
+    tma_prefetch_desc(&maps.a);
+    tma_prefetch_desc(&maps.b);
+    for (int i = 0; i < kTsStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 2 * 4);     // one arrival per epilogue warp of both CTAs
+    }
+    mbar_init(afull_bar, 2 * 128 + 1);      // TMEM part: every epilogue thread of both CTAs; smem part: the leader's expect_tx
+    mbar_init(aempty_bar, 1);               // the item's last MMA has retired: the shared-memory queries may be replaced
+    fence_barrier_init();
+  }
+  if (warp_idx == 1) tmem_alloc_2sm<512>(tmem_ptr_smem);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_a = tmem_base;                  // columns [0, 256)
+  const uint32_t tmem_d0 = tmem_base + kTsACols;      // two 128-column accumulators
+
+  const int n_items = sched.num_items();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int kb_total = sched.kb_total;
+  const int kb_tmem = min(kb_total, kTsTmemKb), kb_smem = kb_total - kb_tmem;
+
+  if (warp_idx == 0) {
+    // ============================ TMA producer (both CTAs) ============================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0, a_phase = 0;
+      const uint32_t af = mapa_cluster(smem_u32(afull_bar), 0);
+      WorkItem w;
+      for (int item = pair; item < n_items; item += n_pairs) {
+        if (!sched.get(item, w)) continue;
+        if (w.n_begin >= w.n_end) continue;
+        // this item's shared-memory query k-blocks (the previous item's MMAs must have let go of the buffer)
+        if (kb_smem > 0) mbar_wait(aempty_bar, a_phase ^ 1);
+        a_phase ^= 1;
+        if (leader) mbar_arrive_expect_tx(afull_bar, 2 * kb_smem * kTsAKbBytes);
+        const int a_row = (w.m_blk * 2 + static_cast<int>(rank)) * kBM;
+        for (int j = 0; j < kb_smem; ++j) tma_load_2d_2sm(a_smem + j * kTsAKbBytes, &maps.a, af, (kTsTmemKb + j) * kBK, a_row);
+        for (int ti = 0; ti < w.n_end - w.n_begin; ++ti) {
+          const int b_row = w.tile_at(ti) * kTsBN + static_cast<int>(rank) * (kTsBN / 2);
+          for (int kb0 = 0; kb0 < kb_total; kb0 += kTsStageKb) {
+            const int nkb = min(kTsStageKb, kb_total - kb0);
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            const uint32_t fb = mapa_cluster(smem_u32(&full_bar[stage]), 0);
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * nkb * kTsKbBytes);
+            uint8_t* sb = ring + stage * kTsStageBytes;
+            for (int j = 0; j < nkb; ++j) tma_load_2d_2sm(sb + j * kTsKbBytes, &maps.b, fb, (kb0 + j) * kBK, b_row);
+            if (++stage == kTsStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ============================ MMA issuer (leader only) ============================
+    if (leader && elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0, a_phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(ring), 16, 1024);
+      const uint64_t adesc0 = make_smem_desc(smem_u32(a_smem), 16, 1024);
+      const bool full_k = kb_total == kTsMaxKb;
+      WorkItem w;
+      for (int item = pair; item < n_items; item += n_pairs) {
+        if (!sched.get(item, w)) continue;
+        if (w.n_begin >= w.n_end) continue;   // an empty split: nothing to multiply (the epilogue pads its result)
+        mbar_wait(afull_bar, a_phase);        // this item's queries are on chip in both CTAs
+        a_phase ^= 1;
+        tc_fence_after();
+        for (int ti = 0; ti < w.n_end - w.n_begin; ++ti) {
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_d0 + acc * kTsBN;
+          if (full_k) ts_issue_tile<true>(tmem_d, tmem_a, adesc0, bdesc0, idesc, kb_total, full_bar, empty_bar, stage, phase);
+          else ts_issue_tile<false>(tmem_d, tmem_a, adesc0, bdesc0, idesc, kb_total, full_bar, empty_bar, stage, phase);
+          umma_commit_2sm(&tfull_bar[acc], 0x3);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+        if (kb_smem > 0) umma_commit_2sm(aempty_bar, 0x3);
+      }
+    }
+  } else {
+    // ============================ query loader + epilogue (both CTAs) ================================
+    SearchEpilogueTs epi(p, invc_s);
+    const int quarter = warp_idx & 3;
+    const int row = quarter * 32 + lane_id();
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t te0 = mapa_cluster(smem_u32(&tempty_bar[0]), 0), te1 = mapa_cluster(smem_u32(&tempty_bar[1]), 0);
+    const uint32_t af = mapa_cluster(smem_u32(afull_bar), 0);
+    float* winv_base = invc_s + (warp_idx - 2) * 2 * kTsBN;
+    int inv_buf = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    WorkItem w;
+    for (int item = pair; item < n_items; item += n_pairs) {
+      if (!sched.get(item, w)) continue;
+      w.m_blk = w.m_blk * 2 + static_cast<int>(rank);
+      w.tag = w.tag * 2 + static_cast<int>(rank);
+      // Every MMA that read the previous item's queries has retired: this thread consumed that item's last
+      // accumulator, and the commit that published it covers all earlier MMAs of the issuer.
+      if (w.n_begin < w.n_end) {
+        const long long qrow = static_cast<long long>(w.m_blk) * kBM + row;
+        const uint4* src = reinterpret_cast<const uint4*>(q + qrow * d);
+        const bool live = qrow < p.Q;
+        for (int c = 0; c < kb_tmem; ++c) {        // 64 fp16 = 128 B = 32 TMEM columns per step
+          uint32_t r[32];
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            const int e = c * kBK + v * 8;          // first element of this 16-byte piece
+            uint4 u = make_uint4(0u, 0u, 0u, 0u);   // rows beyond Q and columns beyond d are zero
+            if (live && e < d) u = __ldg(src + c * 8 + v);
+            r[v * 4 + 0] = u.x; r[v * 4 + 1] = u.y; r[v * 4 + 2] = u.z; r[v * 4 + 3] = u.w;
+          }
+          tmem_st_32x32b_x32(tmem_a + lane_base + c * (kBK / 2), r);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive_cluster(af);
+      }
+      epi.item_begin(w, row);
+      // 1/||c|| of a tile: fetched one tile ahead into registers, parked in this warp's own slice of shared memory
+      // before the accumulator is waited for, so neither a global-load latency nor a cross-warp barrier sits
+      // between "accumulator ready" and "accumulator released"
+      const int n_tiles_item = w.n_end - w.n_begin;
+      float nx[kTsBN / 32];
+      auto fetch_inv = [&](int n_blk) {
+#pragma unroll
+        for (int t = 0; t < kTsBN / 32; ++t) {
+          const long long c0 = static_cast<long long>(n_blk) * kTsBN + t * 32 + lane_id();
+          nx[t] = (c0 < p.N) ? __ldg(p.c_inv + c0) : 0.f;
+        }
+      };
+      if (n_tiles_item > 0) fetch_inv(w.tile_at(0));
+      for (int ti = 0; ti < n_tiles_item; ++ti) {
+        const int n = w.tile_at(ti);
+        float* winv = winv_base + (inv_buf & 1) * kTsBN;
+        ++inv_buf;
+#pragma unroll
+        for (int t = 0; t < kTsBN / 32; ++t) winv[t * 32 + lane_id()] = nx[t];
+        __syncwarp();
+        if (ti + 1 < n_tiles_item) fetch_inv(w.tile_at(ti + 1));
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        epi.tile(w, n, tmem_d0 + lane_base + acc * kTsBN, row, 0, winv);
+        tc_fence_before();
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive_cluster(acc ? te1 : te0);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      epi.item_end(w, row);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm<512>(tmem_base);
+  }
 }
 
 // ---------------------------------------------------------------------------------
@@ -417,13 +707,27 @@ __global__ void topk_merge_kernel(const float* __restrict__ in_s, const void* __
   }
 }
 
+// Kernel family: 2 = queries in TMEM (CTA pairs, 64-candidate tiles; needs d <= 768), 1 = CTA pairs streaming both
+// operands (256-candidate tiles), 0 = single CTAs.  UNIIR_SEARCH_MODE overrides; UNIIR_SEARCH_2CTA=0 is the round-1
+// spelling of mode 0.
+static int search_mode(int d) {
+  int m = 2;
+  if (const char* e = getenv("UNIIR_SEARCH_MODE")) m = atoi(e);
+  if (const char* e = getenv("UNIIR_SEARCH_2CTA")) { if (atoi(e) == 0) m = 0; }
+  if (m == 2 && d > kTsMaxKb * kBK) m = 1;
+  return m < 0 ? 0 : (m > 2 ? 2 : m);
+}
 static bool search_pairs() {
   const char* e = getenv("UNIIR_SEARCH_2CTA");
-  return !(e && atoi(e) == 0);
+  if (e && atoi(e) == 0) return false;
+  if (const char* m = getenv("UNIIR_SEARCH_MODE")) return atoi(m) != 0;
+  return true;
 }
 
-// n_qtiles is the number of 128-row state slots per split (padded to an even count in pair mode)
-static void plan_splits(long long Q, long long N, int* splits, int* tiles_per_split, int* n_tiles,
+// n_qtiles is the number of 128-row state slots per split (padded to an even count in pair mode).  The number of
+// splits does not depend on the kernel family (the plan call does not know d): it is sized on 256-candidate tiles;
+// tiles_per_split / n_tiles are in tiles of `bn` candidates.
+static void plan_splits(long long Q, long long N, int bn, int* splits, int* tiles_per_split, int* n_tiles,
                         int* n_qtiles) {
   const int sms = num_sms();
   const bool pairs = search_pairs();
@@ -431,17 +735,18 @@ static void plan_splits(long long Q, long long N, int* splits, int* tiles_per_sp
   if (pairs) nq = (nq + 1) / 2 * 2;
   const int units = pairs ? nq / 2 : nq;          // schedulable units per chunk and split
   const int workers = pairs ? sms / 2 : sms;
-  const int nt = static_cast<int>((N + kSearchBN - 1) / kSearchBN);
+  const int nt256 = static_cast<int>((N + kSearchBN - 1) / kSearchBN);
   // Enough independent (split, unit) slots to keep every SM busy; one split when the query set
   // alone provides them.  Each split needs a few tiles to be worth its ramp-up.
   int s = 1;
   if (units < workers) {
     s = (workers + units - 1) / units;
     if (s > 32) s = 32;
-    while (s > 1 && (nt + s - 1) / s < 8) --s;
+    while (s > 1 && (nt256 + s - 1) / s < 8) --s;
   }
+  const int nt = static_cast<int>((N + bn - 1) / bn);
   *splits = s;
-  *tiles_per_split = (nt + s - 1) / s;
+  *tiles_per_split = ((nt256 + s - 1) / s) * (kSearchBN / bn);   // split boundaries do not move with the tile width
   *n_tiles = nt;
   *n_qtiles = nq;
 }
@@ -478,7 +783,7 @@ extern "C" int uniir_ip_topk_plan(int64_t Q, int64_t N, int32_t k, int32_t* spli
   UNIIR_CHECK_ARG(Q > 0 && N > 0 && k > 0 && k <= kMaxK && splits && workspace_bytes,
                   "uniir_ip_topk_plan: bad args (k must be in [1,%d])", kMaxK);
   int s, tps, nt, nq;
-  plan_splits(Q, N, &s, &tps, &nt, &nq);
+  plan_splits(Q, N, kSearchBN, &s, &tps, &nt, &nq);
   *splits = s;
   *workspace_bytes = search_ws_bytes(s, nq);
   return UNIIR_OK;
@@ -494,8 +799,10 @@ extern "C" int uniir_ip_topk(const void* q, const float* q_inv, const void* c, c
   UNIIR_CHECK_ARG(Q > 0 && N > 0 && N < (1LL << 31) && d > 0 && d % 8 == 0,
                   "uniir_ip_topk: bad shape Q=%lld N=%lld d=%d", (long long)Q, (long long)N, d);
   UNIIR_CHECK_ARG(k > 0 && k <= kMaxK, "uniir_ip_topk: k must be in [1,%d]", kMaxK);
+  const int mode = search_mode(d);
+  const int bn = mode == 2 ? kTsBN : kSearchBN;
   int s, tps, nt, nq;
-  plan_splits(Q, N, &s, &tps, &nt, &nq);
+  plan_splits(Q, N, bn, &s, &tps, &nt, &nq);
   UNIIR_CHECK_ARG(splits == s, "uniir_ip_topk: splits=%d does not match uniir_ip_topk_plan (%d)",
                   splits, s);
   const int sms = num_sms();
@@ -507,7 +814,7 @@ extern "C" int uniir_ip_topk(const void* q, const float* q_inv, const void* c, c
   GemmTensorMaps maps;
   int rc = make_tmap_2d(&maps.a, q, UNIIR_F16, d, Q, d, kBK, kBM);
   if (rc) return rc;
-  rc = make_tmap_2d(&maps.b, c, UNIIR_F16, d, N, d, kBK, pairs ? kSearchBN / 2 : kSearchBN);
+  rc = make_tmap_2d(&maps.b, c, UNIIR_F16, d, N, d, kBK, mode == 2 ? kTsBN / 2 : (pairs ? kSearchBN / 2 : kSearchBN));
   if (rc) return rc;
 
   SearchParams p;
@@ -516,7 +823,7 @@ extern "C" int uniir_ip_topk(const void* q, const float* q_inv, const void* c, c
   p.q_inv = q_inv; p.c_inv = c_inv;
   p.part_scores = part_scores; p.part_idx = part_idx;
   const size_t rows = static_cast<size_t>(s) * nq * kBM;
-  int tpc = kDefaultTilesPerChunk;
+  int tpc = mode == 2 ? kDefaultTilesPerChunkTs : kDefaultTilesPerChunk;
   if (const char* e = getenv("UNIIR_SEARCH_TPC")) { const int v = atoi(e); if (v >= 1) tpc = v; }
   p.n_chunks = (tps + tpc - 1) / tpc;
   p.ws_scores = static_cast<float*>(workspace);
@@ -532,14 +839,21 @@ extern "C" int uniir_ip_topk(const void* q, const float* q_inv, const void* c, c
   const long long items = 1LL * units * s * p.n_chunks;
   UNIIR_CHECK_ARG(items < (1LL << 31), "uniir_ip_topk: too many work items");
 
-  if (pairs) {
+  if (mode == 2) {
+    static std::atomic<uint64_t> attr_ts{0};
+    if (first_on_device(attr_ts))
+      UNIIR_CUDA_OK(cudaFuncSetAttribute(ip_topk_kernel_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes));
+    int npairs = sms / 2;
+    if (items < npairs) npairs = static_cast<int>(items);
+    sched.n_workers = stagger ? npairs : 0;
+    const uint32_t idesc = make_idesc_f16(false, false, false, 2 * kBM, kTsBN);
+    ip_topk_kernel_ts<<<2 * npairs, num_threads(4), kTsSmemBytes, stream>>>(maps, static_cast<const __half*>(q), d, p, sched, idesc);
+  } else if (pairs) {
     using SM = GemmSmem2<kSearchBN>;
     const int smem_bytes = SM::kRingBytes + SM::kBarBytes + 2 * kSearchBN * sizeof(float) + 1024;
-    static bool attr2 = false;
-    if (!attr2) {
+    static std::atomic<uint64_t> attr2{0};
+    if (first_on_device(attr2))
       UNIIR_CUDA_OK(cudaFuncSetAttribute(ip_topk_kernel_2cta, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-      attr2 = true;
-    }
     int npairs = sms / 2;
     if (items < npairs) npairs = static_cast<int>(items);
     const uint32_t idesc = make_idesc_f16(false, false, false, 2 * kBM, kSearchBN);
@@ -550,11 +864,9 @@ extern "C" int uniir_ip_topk(const void* q, const float* q_inv, const void* c, c
   } else {
     using SM = GemmSmem<kSearchBN>;
     const int smem_bytes = SM::kRingBytes + SM::kBarBytes + 2 * kSearchBN * sizeof(float) + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<uint64_t> attr_set{0};
+    if (first_on_device(attr_set))
       UNIIR_CUDA_OK(cudaFuncSetAttribute(ip_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-      attr_set = true;
-    }
     const int grid = items < sms ? static_cast<int>(items) : sms;
     sched.n_workers = stagger ? grid : 0;
     const uint32_t idesc = make_idesc_f16(false, false, false, kBM, kSearchBN);

@@ -18,8 +18,11 @@ from . import ops
 
 
 class FlatAdamW:
-    """AdamW over FlatParamModule's two flat segments; state_dict mirrors torch's layout keys
-    loosely (step / exp_avg / exp_avg_sq per segment)."""
+    """AdamW over FlatParamModule's two flat segments.  ``state_dict()`` / ``load_state_dict()`` speak
+    ``torch.optim.AdamW``'s layout for the reference's two parameter groups (clip_scorefusion/train.py:52-61:
+    group 0 = gains / biases / logit_scale without weight decay, group 1 = the rest with it, each in
+    ``named_parameters()`` order), so the ``optimizer`` entry of a reference checkpoint (train.py:64-79) resumes here
+    and a checkpoint written here resumes in the reference (train.py:204-211)."""
 
     def __init__(self, flat_params, lr=1e-5, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.2, lr_scale=None):
         """lr_scale: optional callable(parameter name) -> multiplier of the learning rate for that parameter.  The
@@ -66,16 +69,58 @@ class FlatAdamW:
         for g in self.P.grad.values():
             g.zero_()
 
+    def _group_names(self):
+        """Parameter names of the reference's two groups, in the order torch numbers them."""
+        trainable = [(n, decay) for n, _, decay, _ in self.P._specs if self.P._root.get_parameter(n).requires_grad]
+        return [n for n, decay in trainable if not decay], [n for n, decay in trainable if decay]
+
     def state_dict(self):
-        return {"step": self.step_count, "exp_avg": self.m, "exp_avg_sq": self.v,
-                "param_groups": self.param_groups}
+        if self._ranges is not None:     # per-parameter lr multipliers (CLIP_FF): flat layout, not the reference's groups
+            return {"uniir_flat": True, "step": self.step_count, "exp_avg": self.m, "exp_avg_sq": self.v,
+                    "param_groups": self.param_groups}
+        groups = self._group_names()
+        lr = self.param_groups[0]["lr"]
+        proto = torch.optim.AdamW([torch.nn.Parameter(torch.zeros(1))], lr=lr, betas=self.betas, eps=self.eps).state_dict()
+        state, param_groups, idx = {}, [], 0
+        for names, wd in zip(groups, (0.0, self.wd)):
+            ids = list(range(idx, idx + len(names)))
+            for n in names:
+                if self.step_count > 0:
+                    state[idx] = {"step": torch.tensor(float(self.step_count)),
+                                  "exp_avg": self.P._view(self.m, n).clone(), "exp_avg_sq": self.P._view(self.v, n).clone()}
+                idx += 1
+            g = dict(proto["param_groups"][0])
+            g.update(lr=lr, betas=tuple(self.betas), eps=self.eps, weight_decay=wd, params=ids)
+            if "initial_lr" in self.param_groups[0]:
+                g["initial_lr"] = self.param_groups[0]["initial_lr"]
+            param_groups.append(g)
+        return {"state": state, "param_groups": param_groups}
 
     def load_state_dict(self, sd):
-        self.step_count = sd["step"]
-        for k in self.m:
-            self.m[k].copy_(sd["exp_avg"][k])
-            self.v[k].copy_(sd["exp_avg_sq"][k])
+        if "state" not in sd:            # flat layout (round 1 / lr-multiplier runs)
+            self.step_count = sd["step"]
+            for k in self.m:
+                self.m[k].copy_(sd["exp_avg"][k])
+                self.v[k].copy_(sd["exp_avg_sq"][k])
+            self.param_groups[0]["lr"] = sd["param_groups"][0]["lr"]
+            return
+        groups = self._group_names()
+        assert len(sd["param_groups"]) == 2 and [len(g["params"]) for g in sd["param_groups"]] == [len(g) for g in groups], \
+            "optimizer state does not have the reference's two parameter groups (train.py:52-61)"
+        steps = set()
+        for g, names in zip(sd["param_groups"], groups):
+            for pid, n in zip(g["params"], names):
+                st = sd["state"].get(pid)
+                if st is None:
+                    continue
+                self.P._view(self.m, n).copy_(st["exp_avg"].to(self.m[True].device, torch.float32).view(self.P._index[n][3]))
+                self.P._view(self.v, n).copy_(st["exp_avg_sq"].to(self.v[True].device, torch.float32).view(self.P._index[n][3]))
+                steps.add(int(float(st["step"])))
+        assert len(steps) <= 1, "parameters with different step counts cannot share the fused AdamW step"
+        self.step_count = steps.pop() if steps else 0
         self.param_groups[0]["lr"] = sd["param_groups"][0]["lr"]
+        if "initial_lr" in sd["param_groups"][0]:
+            self.param_groups[0]["initial_lr"] = sd["param_groups"][0]["initial_lr"]
 
 
 class CosineLR:
@@ -161,6 +206,33 @@ def train_one_epoch(model, data_loader, optimizer, epoch, gpu_id, scheduler, glo
     stats = {"loss": torch.stack(losses).mean().item() if losses else 0.0,
              "inbatch_accuracy": torch.stack(accs).mean().item() if accs else 0.0,
              "lr": optimizer.param_groups[0]["lr"]}
+    if dist.is_available() and dist.is_initialized():
+        t = torch.tensor([stats["loss"], stats["inbatch_accuracy"]], device=gpu_id, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.AVG)
+        stats["loss"], stats["inbatch_accuracy"] = t[0].item(), t[1].item()
+    print("Averaged stats:", stats)
+    return stats
+
+
+@torch.no_grad()
+def eval_engine(model, data_loader, gpu_id, config):
+    """In-batch validation (uniir_clip/engine.py:59-84): mean loss / in-batch accuracy over the loader, averaged
+    over ranks.  No gradients, no activations kept; one host sync at the end instead of two per batch."""
+    model.eval()
+    inner = model.module if hasattr(model, "module") else model
+    print_freq = config.evaluator.print_freq
+    losses, accs = [], []
+    for i, batch in enumerate(data_loader):
+        for key in batch:
+            if isinstance(batch[key], torch.Tensor):
+                batch[key] = batch[key].to(gpu_id, non_blocking=True)
+        out = inner(batch)
+        losses.append(out["loss"].detach())
+        accs.append(out["accuracy"].detach())
+        if (i + 1) % print_freq == 0:
+            print(f"Test: [{i + 1}/{len(data_loader)}] loss: {losses[-1].item():.4f} inbatch_accuracy: {accs[-1].item():.4f}")
+    stats = {"loss": torch.stack(losses).mean().item() if losses else 0.0,
+             "inbatch_accuracy": torch.stack(accs).mean().item() if accs else 0.0}
     if dist.is_available() and dist.is_initialized():
         t = torch.tensor([stats["loss"], stats["inbatch_accuracy"]], device=gpu_id, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.AVG)

@@ -11,12 +11,13 @@ Differences: no DDP wrapper around an inference model, ids gathered as an int64 
 ``gather_object`` of python lists, uniqueness checked with ``torch.unique`` on the device; and
 ``generate_local_embeds_and_ids`` + ``save_rank_shards`` / ``load_rank_shard`` hand each rank's rows to the
 retrieval stage directly (no rank-0 funnel of the 8.6 GB matrix).
-The M-BEIR dataset / collator classes are the reference's own (``data.mbeir_dataset``): the loader is
-outside the hot path, so ``main`` imports them from the reference tree on PYTHONPATH.
+``generate_embeds_for_config`` / ``main`` / ``cli`` are the reference CLI body (mbeir_embedder.py:195-527) over this
+package's own M-BEIR dataset / collator classes (``mbeir_dataset.py``): the reference tree is not needed at run time.
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import os
 
 import numpy as np
@@ -166,34 +167,190 @@ def build_model_from_config(config):
     return model
 
 
+def _concat_rank_shards(embed_path, ids_path, world):
+    """Rank 0: stitch the per-rank shard files into the reference's single .npy pair on the HOST (streamed through
+    a memory map; nothing is funnelled through a GPU or a collective), keeping the reference's global uniqueness
+    check (mbeir_embedder.py:103-108)."""
+    parts = [shard_paths(embed_path, ids_path, r, world) for r in range(world)]
+    embs = [np.load(e, mmap_mode="r") for e, _ in parts]
+    ids = np.concatenate([np.load(i) for _, i in parts]) if parts else np.zeros((0,), np.int64)
+    n, d = sum(e.shape[0] for e in embs), embs[0].shape[1]
+    assert len(ids) == n
+    assert len(np.unique(ids)) == n, "Hashed IDs should be unique"
+    os.makedirs(os.path.dirname(embed_path), exist_ok=True)
+    out = np.lib.format.open_memmap(embed_path, mode="w+", dtype=np.float16, shape=(n, d))
+    at = 0
+    for e in embs:
+        out[at:at + e.shape[0]] = e
+        at += e.shape[0]
+    out.flush()
+    del out
+    np.save(ids_path, ids.astype(np.int64, copy=False))
+    return n
+
+
+def _splits_to_embed(config):
+    """(split, split_dir, dataset names, candidate-pool names) per enabled block of embed_config
+    (mbeir_embedder.py:212-240)."""
+    embed_config, data_config = config.embed_config, config.data_config
+    splits = []
+    for split_name in ("train", "val", "test"):
+        ds_cfg = getattr(embed_config, f"{split_name}_datasets_config", None)
+        if ds_cfg and ds_cfg.enable_embed:
+            names, pools = ds_cfg.datasets_name, ds_cfg.correspond_cand_pools_name
+            assert len(names) == len(pools), "Mismatch between datasets and candidate pools."
+            splits.append((split_name, getattr(data_config, f"{split_name}_dir_name"), names, pools))
+    pool_cfg = embed_config.cand_pools_config
+    if pool_cfg and pool_cfg.enable_embed:
+        pools = pool_cfg.cand_pools_name_to_embed
+        splits.append(("cand_pool", data_config.cand_pool_dir_name, [None] * len(pools), pools))
+    return splits
+
+
+@torch.no_grad()
+def generate_embeds_for_config(model, img_preprocess_fn, tokenizer, config):
+    """Embeds every configured query split and candidate pool (mbeir_embedder.py:195-461).  Each rank embeds its
+    contiguous row block (ContiguousDistributedSampler) and writes it as a shard file next to the target; rank 0
+    then stitches the shards into the reference's ``mbeir_{name}_{split}_{embed,ids}.npy`` pair on the host.  The
+    shard files stay: ``mbeir_retriever.search_index`` under ``torch.distributed.run`` loads them straight into the
+    row-sharded index (no rank-0 funnel).  The union pool is the concatenation of the single pools'
+    files (mbeir_embedder.py:388-461)."""
+    from torch.utils.data import DataLoader
+    from .mbeir_dataset import (MBEIRCandidatePoolCollator, MBEIRCandidatePoolDataset, MBEIRMainCollator,
+                                MBEIRMainDataset, Mode)
+    uniir_dir, mbeir_data_dir = config.uniir_dir, config.mbeir_data_dir
+    embed_config, data_config = config.embed_config, config.data_config
+    embed_dir_name, expt = embed_config.embed_dir_name, config.experiment.path_suffix
+    cand_pool_dir = data_config.cand_pool_dir_name
+    image_size = tuple(map(int, str(data_config.image_size).split(",")))
+    main, W, r = du.rank() == 0, du.world(), du.rank()
+    device = config.dist_config.gpu_id
+    splits = _splits_to_embed(config)
+    if main:
+        print("-" * 30)
+        for split_name, split_dir, names, pools in splits:
+            what = f"Candidate pools to embed: {pools}" if split_name == "cand_pool" else f"Datasets to embed: {names}"
+            print(f"Split: {split_name}, Split dir: {split_dir}, {what}")
+            print("-" * 30)
+    for split_name, split_dir, names, pools in splits:
+        for dataset_name, cand_pool_name in zip(names, pools):
+            cand_pool_name = cand_pool_name.lower()
+            if split_name == "cand_pool":
+                cand_path = os.path.join(cand_pool_dir, f"mbeir_{cand_pool_name}_{split_name}.jsonl")
+                if main:
+                    print(f"\nEmbedder Log: Generating embeddings for {cand_path}...")
+                dataset = MBEIRCandidatePoolDataset(mbeir_data_dir=mbeir_data_dir, cand_pool_data_path=cand_path,
+                                                    img_preprocess_fn=img_preprocess_fn, print_config=main)
+                collator = MBEIRCandidatePoolCollator(tokenizer=tokenizer, image_size=image_size)
+                mid_name = cand_pool_name
+            else:
+                dataset_name = dataset_name.lower()
+                query_path = os.path.join(split_dir, f"mbeir_{dataset_name}_{split_name}.jsonl")
+                cand_path = os.path.join(cand_pool_dir, f"mbeir_{cand_pool_name}_cand_pool.jsonl")
+                if main:
+                    print(f"\nEmbedder Log: Generating embeddings for {query_path} with {cand_path}...")
+                dataset = MBEIRMainDataset(mbeir_data_dir=mbeir_data_dir, query_data_path=query_path,
+                                           cand_pool_path=cand_path, query_instruct_path=data_config.query_instruct_path,
+                                           img_preprocess_fn=img_preprocess_fn, mode=Mode.EVAL,
+                                           enable_query_instruct=data_config.enable_query_instruct,
+                                           shuffle_cand=data_config.shuffle_cand, print_config=main)
+                collator = MBEIRMainCollator(tokenizer=tokenizer, image_size=image_size, mode=Mode.EVAL)
+                mid_name = dataset_name
+            sampler = du.ContiguousDistributedSampler(dataset, num_replicas=W, rank=r)   # dataset is in sorted order
+            loader = DataLoader(dataset, batch_size=config.dataloader_config.batch_size,
+                                num_workers=config.dataloader_config.num_workers, pin_memory=True, sampler=sampler,
+                                shuffle=False, collate_fn=collator, drop_last=False)
+            if du.is_on():
+                dist.barrier()
+            embed_path, ids_path = embed_paths(uniir_dir, embed_dir_name, expt, split_name, mid_name)
+            emb, ids = generate_local_embeds_and_ids(model, loader, device)
+            if W > 1:
+                save_rank_shards(embed_path, ids_path, emb, ids)
+                dist.barrier()                                   # every shard is on disk
+                if main:
+                    n = _concat_rank_shards(embed_path, ids_path, W)
+            else:
+                assert torch.unique(ids).numel() == ids.numel(), "Hashed IDs should be unique"
+                save_embeddings(embed_path, ids_path, emb.cpu().numpy(), ids.cpu().numpy())
+                n = ids.numel()
+            if main:
+                print(f"Embedder Log: Embedding list length: {n}")
+                print(f"Embedder Log: Saved embeddings to {embed_path}.")
+                print(f"Embedder Log: Saved ids to {ids_path}.")
+            if du.is_on():
+                dist.barrier()
+            del emb, ids, loader, dataset, collator, sampler
+            gc.collect()
+            torch.cuda.empty_cache()
+        if split_name == "cand_pool" and embed_config.cand_pools_config.embed_union_pool:
+            if main:   # the union (global) pool is the concatenation of the single pools' saved files
+                print("\nEmbedder Log: Generating embeddings for union pool...")
+                all_e, all_i = [], []
+                for cand_pool_name in pools:
+                    e_path, i_path = embed_paths(uniir_dir, embed_dir_name, expt, split_name, cand_pool_name.lower())
+                    all_e.append(np.load(e_path))
+                    all_i.append(np.load(i_path))
+                    print(f"Embedder Log: Concatenating embeddings from {e_path} and ids from {i_path}.")
+                all_e, all_i = np.concatenate(all_e, axis=0), np.concatenate(all_i, axis=0)
+                assert len(all_e) == len(all_i), "Mismatch between embeddings and IDs length."
+                e_path, i_path = embed_paths(uniir_dir, embed_dir_name, expt, split_name, "union")
+                save_embeddings(e_path, i_path, all_e, all_i)
+                print(f"Embedder Log: Saved embeddings to {e_path}.")
+                print(f"Embedder Log: Saved ids to {i_path}.")
+                del all_e, all_i
+                gc.collect()
+            if du.is_on():
+                dist.barrier()
+
+
 def main(config):
-    """mbeir_embedder.py:464-495: build model, check the duck-typed API, embed every configured split."""
+    """mbeir_embedder.py:464-495: seed, build the model, check the duck-typed API, embed every configured split.
+    No DDP wrapper: an inference-only model has nothing to all-reduce."""
+    import random
+    seed = config.seed + du.rank()
+    random.seed(seed); np.random.seed(seed); torch.manual_seed(seed)
     model = build_model_from_config(config)
     model.eval()
-    for attr in ("encode_mbeir_batch", "get_img_preprocess_fn", "get_tokenizer"):
-        assert callable(getattr(model, attr, None)), f"The provided model does not have a callable '{attr}' method."
-    try:
-        from data.mbeir_data_utils import build_mbeir_dataset_from_config  # reference src/ on PYTHONPATH
-    except ImportError as e:
-        raise ImportError("the M-BEIR dataset/collator classes are the reference's own (src/data); add the "
-                          "reference's src/ to PYTHONPATH to run the embedder CLI") from e
-    raise NotImplementedError("dataset wiring is delegated to the reference's generate_embeds_for_config; call "
-                              "generate_embeds_and_ids_for_dataset_with_gather with its DataLoader (INTEGRATION.md)")
+    if not callable(getattr(model, "encode_mbeir_batch", None)):
+        raise AttributeError("The provided model does not have a callable 'encode' method.")
+    if not callable(getattr(model, "get_img_preprocess_fn", None)):
+        raise AttributeError("The provided model does not have an 'img_preprocess_fn' attribute.")
+    if not callable(getattr(model, "get_tokenizer", None)):
+        raise AttributeError("The provided model does not have a 'tokenizer' attribute.")
+    print(f"Model is set up on GPU {config.dist_config.gpu_id}.")
+    generate_embeds_for_config(model=model, img_preprocess_fn=model.get_img_preprocess_fn(),
+                               tokenizer=model.get_tokenizer(), config=config)
 
 
-def parse_arguments():
+def parse_arguments(argv=None):
     p = argparse.ArgumentParser(description="Generate Embeddings for MBEIR")
     p.add_argument("--uniir_dir", type=str, default="/data/UniIR")
     p.add_argument("--mbeir_data_dir", type=str, default="/data/UniIR/mbeir_data")
     p.add_argument("--config_path", default="config.yaml", help="Path to the config file.")
-    return p.parse_args()
+    return p.parse_args(argv)
 
 
-if __name__ == "__main__":
+def cli(argv=None):
+    """`python -m [torch.distributed.run --nproc_per_node=N -m] uniir_b200.mbeir_embedder --config_path ...`
+    (mbeir_embedder.py:506-527)."""
     from . import config as cfg
-    args = parse_arguments()
+    args = parse_arguments(argv)
     config = cfg.load(args.config_path)
     config.uniir_dir = args.uniir_dir
     config.mbeir_data_dir = args.mbeir_data_dir
-    du.init_distributed_mode(config.dist_config)
-    main(config)
+    args.dist_url = config.dist_config.dist_url
+    du.init_distributed_mode(args)
+    config.dist_config.gpu_id = args.gpu
+    config.dist_config.distributed_mode = args.distributed
+    if du.rank() == 0:
+        import yaml
+        print(yaml.safe_dump(config.to_dict(), sort_keys=False))
+    try:
+        main(config)
+    finally:
+        if config.dist_config.distributed_mode:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    cli()

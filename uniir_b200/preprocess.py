@@ -5,6 +5,9 @@
 The BPE vocabulary file ships with the openai/CLIP package, which is not vendored in the
 reference and not available offline; point UNIIR_CLIP_BPE at ``bpe_simple_vocab_16e6.txt.gz``
 to tokenise real text.  Synthetic token ids (bench / tests) do not need it.
+Known deviation: upstream ``clip.tokenize`` first runs ``ftfy.fix_text`` (mojibake repair); ftfy is not
+installable here, so text is only HTML-unescaped and whitespace-normalised -- well-formed UTF-8 text tokenises
+identically, text with encoding damage does not.
 """
 from __future__ import annotations
 
@@ -28,11 +31,16 @@ def clip_image_preprocess(size=224):
 
     def fn(img):
         from PIL import Image
+        # torchvision arithmetic: Resize(size) keeps the short side at `size` and truncates the long one
+        # (int(size * long / short)); CenterCrop rounds half the margin (int(round((h - size) / 2.0)))
         w, h = img.size
-        s = size / min(w, h)
-        nw, nh = max(size, round(w * s)), max(size, round(h * s))
-        img = img.resize((nw, nh), Image.BICUBIC)
-        left, top = (nw - size) // 2, (nh - size) // 2
+        if w <= h:
+            nw, nh = size, int(size * h / w)
+        else:
+            nw, nh = int(size * w / h), size
+        if (nw, nh) != (w, h):
+            img = img.resize((nw, nh), Image.BICUBIC)
+        left, top = int(round((nw - size) / 2.0)), int(round((nh - size) / 2.0))
         img = img.crop((left, top, left + size, top + size)).convert("RGB")
         t = torch.from_numpy(np.asarray(img, dtype=np.uint8).copy()).permute(2, 0, 1).float() / 255.0
         return (t - mean) / std
@@ -54,6 +62,24 @@ def _bytes_to_unicode():
     return dict(zip(bs, [chr(c) for c in cs]))
 
 
+_SPECIALS = r"<\|startoftext\|>|<\|endoftext\|>|'s|'t|'re|'ve|'m|'ll|'d|"
+
+
+def bpe_pretokenizer(force_stdlib=False):
+    """Upstream pattern: ...|[\\p{L}]+|[\\p{N}]|[^\\s\\p{L}\\p{N}]+ (case-insensitive) -- Unicode letters / numbers, not
+    ASCII ranges: accented and CJK text (WebQA, OVEN, InfoSeek, EDIS) must split the way the checkpoints saw it.
+    Uses the `regex` module when importable; otherwise stdlib `re` with the closest classes it has
+    ([^\\W\\d_] = letters, \\d = decimal digits; the other \\p{N} characters such as superscripts and vulgar
+    fractions are then grouped with the punctuation run -- tests/test_host_logic.py quantifies it)."""
+    if not force_stdlib:
+        try:
+            import regex
+            return regex.compile(_SPECIALS + r"[\p{L}]+|[\p{N}]|[^\s\p{L}\p{N}]+", regex.IGNORECASE)
+        except ImportError:
+            pass
+    return re.compile(_SPECIALS + r"[^\W\d_]+|\d|(?:[^\s\w]|_)+", re.IGNORECASE)
+
+
 class _BPE:
     """Byte-pair encoder over the published CLIP merges file (same algorithm as GPT-2's)."""
 
@@ -69,8 +95,7 @@ class _BPE:
         self.ranks = dict(zip(merges, range(len(merges))))
         self.b2u = b2u
         self.cache = {}
-        self.pat = re.compile(r"<\|startoftext\|>|<\|endoftext\|>|'s|'t|'re|'ve|'m|'ll|'d|[a-zA-Z]+|[0-9]|[^\sa-zA-Z0-9]+",
-                              re.IGNORECASE)
+        self.pat = bpe_pretokenizer()
 
     def _bpe(self, token):
         if token in self.cache:
@@ -98,7 +123,7 @@ class _BPE:
         text = html.unescape(html.unescape(text)).strip()
         text = re.sub(r"\s+", " ", text).strip().lower()
         ids = []
-        for tok in re.findall(self.pat, text):
+        for tok in self.pat.findall(text):
             tok = "".join(self.b2u[b] for b in tok.encode("utf-8"))
             ids.extend(self.enc[t] for t in self._bpe(tok))
         return ids

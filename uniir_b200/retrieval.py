@@ -125,3 +125,53 @@ class ShardedFlatIPIndex:
 
     def _merge(self, ps, pi, k):
         return ops.topk_merge(ps, pi, k)
+
+
+class MultiGPUFlatIPIndex:
+    """ONE process driving every visible GPU, the way the reference's FAISS stage does
+    (`faiss.index_cpu_to_all_gpus(..., co.shard=True)`, mbeir_retriever.py:96-100, 202-206): the candidate rows are
+    split into contiguous blocks, one `FlatIPIndex` per device; a search copies the queries to every device, runs the
+    fused kernel on each (the launches are asynchronous, so the devices work concurrently), brings the [Q,k] partial
+    lists to device 0 and merges them there.  With one visible GPU this is a plain FlatIPIndex."""
+
+    def __init__(self, dim, devices=None):
+        L.load()
+        if devices is None:
+            devices = list(range(torch.cuda.device_count()))
+        if not devices:
+            raise L.UniirError("MultiGPUFlatIPIndex needs at least one CUDA device (no CPU fallback)")
+        self.dim = dim
+        self.devices = [torch.device("cuda", int(i)) if not isinstance(i, torch.device) else i for i in devices]
+        self.shards = [FlatIPIndex(dim, d) for d in self.devices]
+
+    @property
+    def ntotal(self):
+        return sum(s.ntotal for s in self.shards)
+
+    def add_with_ids(self, emb, ids):
+        n = len(ids)
+        W = len(self.shards)
+        for r, sh in enumerate(self.shards):
+            lo, hi = shard_range(n, W, r)
+            if hi > lo:
+                with torch.cuda.device(sh.device):
+                    sh.add_with_ids(emb[lo:hi], ids[lo:hi])
+
+    def search(self, q, k):
+        q = torch.as_tensor(q)
+        parts = []
+        for sh in self.shards:                      # launch everywhere first ...
+            if sh.ntotal == 0:
+                continue
+            with torch.cuda.device(sh.device):
+                parts.append(sh.search_device(q.to(sh.device, torch.float16, non_blocking=True), k))
+        d0 = self.devices[0]
+        if not parts:
+            return self.shards[0].search(q, k)
+        with torch.cuda.device(d0):                 # ... then gather (the copies wait for each device's stream)
+            for sh in self.shards:
+                torch.cuda.synchronize(sh.device)
+            ps = torch.stack([s.to(d0) for s, _ in parts], dim=1).contiguous()      # [Q, W, k]
+            pi = torch.stack([i.to(d0) for _, i in parts], dim=1).contiguous()
+            s, i = ops.topk_merge(ps, pi, k) if len(parts) > 1 else parts[0]
+            return s.cpu().numpy(), i.cpu().numpy()
