@@ -34,12 +34,48 @@ SEARCH_Q, SEARCH_N, SEARCH_D, SEARCH_K = 190_000, 5_600_000, 768, 50
 
 
 def load_peaks():
+    """Roofline denominators: the driver-written MEASURED_PEAKS.json (copy bandwidth, cuBLAS bf16 8192^3 burst =
+    best of 10 for a kernel timed alone, sustained = back to back for 4 s for a kernel timed inside a long step);
+    else the fallback of /opt/skills/guides/B200_PROFILING.md."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
         return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"],
-                "bf16_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
+                "bf16_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "MEASURED_PEAKS.json"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "B200_PROFILING.md fallback"}
+
+
+def _fp16_peaks():
+    """The kernel computes in fp16, MEASURED_PEAKS.json holds bf16: cuBLAS fp16 8192^3 measured on this pool with
+    scripts/peak_fp16.py (profiles/peak_fp16_r02.json) is reported beside the roofline for reference."""
+    p = os.path.join(ROOT, "profiles", "peak_fp16_r02.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
+def gemm_roofline(sink_timed, iso_ms, iso_fl, peaks, step_ms, step_alg_tflops, traffic):
+    """Roofline record of the tcgen05 GEMM family of one step.
+      achieved / frac            : sum(algorithmic FLOPs) / sum(durations) of every GEMM launch, each timed IN ITS PLACE
+                                   in the step (CUDA events around the launch, real predecessors / L2 state) -> against
+                                   the SUSTAINED peak (kernel inside a long step);
+      isolated_*                 : the same launches timed alone, back to back on warm operands -> against the BURST peak;
+      frac_step_algorithmic      : the whole step's algorithmic FLOP/s against the sustained peak (what the step, not
+                                   the kernel, achieves: re-forward, attention, LayerNorm, optimizer are all in it)."""
+    fl = sum(2.0 * c["M"] * c["N"] * c["K"] for c in sink_timed)
+    ms = sum(c["events"][0].elapsed_time(c["events"][1]) for c in sink_timed)
+    ach = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+    iso = iso_fl / (iso_ms * 1e-3) / 1e12 if iso_ms > 0 else 0.0
+    return {"bound": "tensor", "kernel": "uniir::gemm_epi_kernel (tcgen05.mma kind::f16, TMA-fed, TMEM accum)",
+            "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
+            "peak_src": f"{peaks['src']}: sustained bf16 (launches timed in place inside the step)",
+            "timing": "CUDA events around every GEMM launch of one eagerly executed micro-batch pass (embedding pass + "
+                      "re-forward + backward), scaled by the micro-batches per step",
+            "isolated_achieved": iso, "isolated_peak": peaks["bf16_burst"], "isolated_frac": iso / peaks["bf16_burst"],
+            "isolated_note": "same launches timed alone (5 back-to-back launches on warm operands) against the burst peak",
+            "gemm_share_of_step": None, "traffic": traffic, "step_algorithmic_tflops": step_alg_tflops,
+            "frac_step_algorithmic": step_alg_tflops / peaks["bf16_sustained"]}
 
 
 class ClockSampler:
@@ -193,10 +229,38 @@ def cpu_search_reference(steps, warmup, queries=1024, cands=500_000):
                       f"linearly to N={SEARCH_N}"}, dt
 
 
+def cpu_embed_reference(steps, warmup, items=8):
+    """configs[3] on the host cores: the oracle's embed path (both towers + score fusion, fp32) on `items` items."""
+    from oracle.clip_oracle import CLIPScoreFusionOracle
+    cores = _cpu_threads()
+    torch.manual_seed(2023)
+    model = CLIPScoreFusionOracle(MODEL).eval()
+    b = synth_batch(model.clip_model.dims, items // 2, 2023, torch.device("cpu"))
+    b.pop("index_mapping"); b["did_list"] = list(range(items))
+    b["txt_batched"] = b["txt_batched"].long()
+
+    def step():
+        with torch.no_grad():
+            emb, _ = model(b, encode_mbeir_batch=True)
+            return emb.half()
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": items / dt, "unit": "items/s", "cores": cores, "kind": "port",
+            "sample": f"oracle CLIP_SF {MODEL} fp32 encode_mbeir_batch, {items} items/step (of the 5.6M-candidate pool), {steps} timed steps"}, dt
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
-    if args.workload == "search":
+    if args.workload == "embed":
+        cb, dt = cpu_embed_reference(args.steps, args.warmup)
+        metric, unit, cfg = "embedded_items_per_sec", "items/s", {"workload": f"embedding extraction, CLIP_SF {MODEL} (BASELINE configs[3])"}
+    elif args.workload == "search":
         cb, dt = cpu_search_reference(args.steps, args.warmup)
         metric, unit, cfg = "queries_per_sec_top50", "queries/s", {"workload": "dense_retrieval_190k_x_5.6M_d768_fp16_top50"}
     elif args.workload == "blip":
@@ -270,39 +334,36 @@ def run_train(args, rank, world, dev, peaks):
            "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e}
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM), timed live with CUDA events -----
-    # The step replays CUDA graphs, which cannot be event-timed per kernel.  So: trace every GEMM
-    # launch of one micro-batch (embed pass + forward/backward pass), time each distinct
-    # (shape, operand majors, epilogue) with CUDA events over back-to-back launches, and weight by
-    # its launch count.  achieved = sum(algorithmic FLOPs) / sum(durations).
+    # The step replays CUDA graphs, which cannot be event-timed per kernel.  So one micro-batch pass (embedding pass
+    # + re-forward + backward: every kernel of the step in its real order) runs eagerly with a pair of CUDA events
+    # around each GEMM launch; the same launches are additionally timed alone for the burst-peak comparison.
     from collections import Counter
     enc = model._enc[(model._train_mb, True)]
     sink = []
-    ops.set_gemm_profiler(sink)
+    ops.set_gemm_profiler(sink, events=True)
     enc._body_embed()
     enc._body_fwdbwd()
     ops.set_gemm_profiler(None)
+    torch.cuda.synchronize()
     for gbuf in model.clip_model.grad.values():
         gbuf.zero_()
-    torch.cuda.synchronize()
-    keyf = lambda c: tuple(sorted((k, str(v)) for k, v in c.items()))
+    keyf = lambda c: tuple(sorted((k, str(v)) for k, v in c.items() if k != "events"))
     uniq, counts = {}, Counter()
     for c in sink:
         uniq[keyf(c)] = c
         counts[keyf(c)] += 1
     n_mb = (2 * pairs) // model._train_mb
-    g_ms = g_fl = 0.0
+    iso_ms = iso_fl = 0.0
     for k_, c in uniq.items():
         t = ops.time_gemm_config(c, iters=5, device=dev)
-        g_ms += t * counts[k_] * n_mb
-        g_fl += 2.0 * c["M"] * c["N"] * c["K"] * counts[k_] * n_mb
-    prof = sink * n_mb
-    achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
-    roof = {"bound": "tensor", "kernel": "uniir::gemm_epi_kernel (tcgen05.mma kind::f16, TMA-fed, TMEM accum)",
-            "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-            "frac": achieved / peaks["bf16_sustained"], "peak_src": f"{peaks['src']} sustained bf16 (kernel timed inside a long step)",
-            "launches": len(prof), "distinct_configs": len(uniq), "gemm_share_of_step": g_ms / ms if ms else None,
-            "traffic": _ncu_traffic("gemm"),
-            "step_algorithmic_tflops": FLOPS_PER_PAIR * GB / world / (ms / 1e3) / 1e12}
+        iso_ms += t * counts[k_]
+        iso_fl += 2.0 * c["M"] * c["N"] * c["K"] * counts[k_]
+    roof = gemm_roofline(sink, iso_ms, iso_fl, peaks, ms, FLOPS_PER_PAIR * GB / world / (ms / 1e3) / 1e12, _ncu_traffic("gemm"))
+    in_place_ms = sum(c["events"][0].elapsed_time(c["events"][1]) for c in sink)
+    n_fwd_only = getattr(model, "_n_retained", 0)
+    # per step: every micro-batch runs the embedding pass; the re-forward + backward pass runs for all of them (the
+    # retained ones skip only the re-forward, which this estimate ignores: it is an upper bound of the GEMM share)
+    roof.update(launches=len(sink) * n_mb, distinct_configs=len(uniq), gemm_share_of_step=in_place_ms * n_mb / ms if ms else None)
     out = {"metric": "contrastive_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -325,14 +386,21 @@ def run_train(args, rank, world, dev, peaks):
     return out
 
 
-def _ncu_traffic(key):
+def _ncu_traffic(key, rows=None):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu captures
+    (profiles/roofline_traffic.json, written by scripts/make_traffic_json.py from the `ncu` CSVs beside it).  The
+    retrieval entry is keyed by the candidate rows of the launch (5.6M / 2.8M / 1.4M / 0.7M = the 1/2/4/8-GPU shards);
+    a size that was not captured reports null rather than another size's number."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p)).get(key)
-        except Exception:
-            return None
-    return None
+    if not os.path.exists(p):
+        return None
+    try:
+        v = json.load(open(p)).get(key)
+    except Exception:
+        return None
+    if isinstance(v, dict):
+        return v.get(str(rows))
+    return v
 
 
 # ----------------------------------------------------------------------------------------
@@ -394,11 +462,13 @@ def run_search(args, rank, world, dev, peaks, steps=None, warmup=None):
     kms = e0.elapsed_time(e1)
     fl = 2.0 * Q * (hi - lo) * d
     achieved = fl / (kms * 1e-3) / 1e12
-    roof = {"bound": "tensor", "kernel": "uniir::ip_topk_kernel (fp16 tcgen05 GEMM + fused top-k epilogue)",
+    roof = {"bound": "tensor", "kernel": "uniir::ip_topk_kernel_ts (fp16 tcgen05 GEMM, queries resident in TMEM + smem, "
+                                         "candidates TMA-streamed, fused top-k epilogue)",
             "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_burst"],
-            "peak_src": f"{peaks['src']} burst bf16/fp16 (kernel timed alone)", "kernel_ms": kms,
-            "algorithmic_flops_per_launch": fl, "traffic": _ncu_traffic("search"),
-            "min_bytes_per_launch": (hi - lo) * d * 2 + Q * d * 2 + Q * k * 8 * splits}
+            "peak_src": f"{peaks['src']}: burst bf16 (kernel timed alone)", "kernel_ms": kms,
+            "algorithmic_flops_per_launch": fl, "traffic": _ncu_traffic("search", hi - lo),
+            "min_bytes_per_launch": (hi - lo) * d * 2 + Q * d * 2 + Q * k * 8 * splits,
+            "fp16_cublas_peaks_this_pool": _fp16_peaks()}
     out = {"metric": "queries_per_sec_top50", "value": value, "unit": "queries/s", "n_gpus": world, "steps": steps,
            "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "f16", "data": "synthetic",
@@ -533,26 +603,25 @@ def run_train_blip(args, rank, world, dev, peaks):
     ms_e2e = timed(e2e_step, 1, world)
 
     sink = []
-    ops.set_gemm_profiler(sink)
+    graphs_on, model.use_cuda_graphs = model.use_cuda_graphs, False
+    ops.set_gemm_profiler(sink, events=True)     # one whole step executed eagerly: every GEMM launch, in place
     step()
     ops.set_gemm_profiler(None)
+    model.use_cuda_graphs = graphs_on
     torch.cuda.synchronize()
-    keyf = lambda c: tuple(sorted((k, str(v)) for k, v in c.items()))
+    keyf = lambda c: tuple(sorted((k, str(v)) for k, v in c.items() if k != "events"))
     uniq, counts = {}, Counter()
     for c in sink:
         uniq[keyf(c)] = c
         counts[keyf(c)] += 1
-    g_ms = g_fl = 0.0
+    iso_ms = iso_fl = 0.0
     for k_, c in uniq.items():
         t = ops.time_gemm_config(c, iters=5, device=dev)
-        g_ms += t * counts[k_]
-        g_fl += 2.0 * c["M"] * c["N"] * c["K"] * counts[k_]
-    achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
-    roof = {"bound": "tensor", "kernel": "uniir::gemm_epi_kernel (tcgen05.mma kind::f16, TMA-fed, TMEM accum)",
-            "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
-            "peak_src": f"{peaks['src']} sustained bf16 (kernel timed inside a long step)", "launches": len(sink),
-            "distinct_configs": len(uniq), "gemm_share_of_step": g_ms / ms if ms else None, "traffic": None,
-            "step_algorithmic_tflops": flops_per_pair * BLIP_GLOBAL_BATCH / world / (ms / 1e3) / 1e12}
+        iso_ms += t * counts[k_]
+        iso_fl += 2.0 * c["M"] * c["N"] * c["K"] * counts[k_]
+    roof = gemm_roofline(sink, iso_ms, iso_fl, peaks, ms, flops_per_pair * BLIP_GLOBAL_BATCH / world / (ms / 1e3) / 1e12, None)
+    roof.update(launches=len(sink), distinct_configs=len(uniq),
+                gemm_share_of_step=sum(c["events"][0].elapsed_time(c["events"][1]) for c in sink) / ms if ms else None)
     out = {"metric": "contrastive_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "bf16", "data": "synthetic",
@@ -642,24 +711,37 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
+    cpu_ok = rank == 0 and not args.no_cpu_baseline and world == 1
+    CPU_STEPS, CPU_WARM = 3, 1          # cpu_baseline: 3 timed steps after 1 warm-up, each a bounded sample of the workload
     if args.workload == "embed":
         out = run_embed(args, rank, world, dev, peaks)
+        if cpu_ok:
+            out["cpu_baseline"], _ = cpu_embed_reference(CPU_STEPS, CPU_WARM)
     elif args.workload == "blip":
         out = run_train_blip(args, rank, world, dev, peaks)
-        if rank == 0 and not args.no_cpu_baseline and world == 1:
-            out["cpu_baseline"], _ = cpu_blip_reference(1, 1, sf=args.blip_model == "sf")
+        if cpu_ok:
+            out["cpu_baseline"], _ = cpu_blip_reference(CPU_STEPS, CPU_WARM, sf=args.blip_model == "sf")
     elif args.workload == "search":
         out = run_search(args, rank, world, dev, peaks)
-        if rank == 0 and not args.no_cpu_baseline and world == 1:
-            out["cpu_baseline"], _ = cpu_search_reference(1, 1)
+        if cpu_ok:
+            out["cpu_baseline"], _ = cpu_search_reference(CPU_STEPS, CPU_WARM)
     else:
         out = run_train(args, rank, world, dev, peaks)
         if not args.no_extra:
-            out["extra"] = {"retrieval": run_search(args, rank, world, dev, peaks, steps=2, warmup=3)}
-        if rank == 0 and not args.no_cpu_baseline and world == 1:
-            out["cpu_baseline"], _ = cpu_train_reference(1, 1)
+            # the other GPU configurations of BASELINE.json on the same line, each with its own roofline / e2e /
+            # cpu_baseline: configs[4] retrieval, configs[2] BLIP_FF training, configs[3] embedding extraction
+            import copy
+            ex = out["extra"] = {}
+            ex["retrieval"] = run_search(args, rank, world, dev, peaks, steps=2, warmup=3)
+            a2 = copy.copy(args); a2.steps, a2.warmup = 2, 3
+            ex["blip"] = run_train_blip(a2, rank, world, dev, peaks)
+            ex["embed"] = run_embed(a2, rank, world, dev, peaks)
+        if cpu_ok:
+            out["cpu_baseline"], _ = cpu_train_reference(CPU_STEPS, CPU_WARM)
             if "extra" in out:
-                out["extra"]["retrieval"]["cpu_baseline"], _ = cpu_search_reference(1, 1)
+                out["extra"]["retrieval"]["cpu_baseline"], _ = cpu_search_reference(CPU_STEPS, CPU_WARM)
+                out["extra"]["blip"]["cpu_baseline"], _ = cpu_blip_reference(CPU_STEPS, CPU_WARM)
+                out["extra"]["embed"]["cpu_baseline"], _ = cpu_embed_reference(CPU_STEPS, CPU_WARM)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

@@ -222,7 +222,9 @@ class BLIPBertOracle(nn.Module):
 class BLIPFeatureFusionOracle(nn.Module):
     """Reference BLIPFeatureFusion restated: encode path (blip_ff.py:82-116, 259-287), momentum encoders
     and queues (:41-63), contrastive loss with momentum distillation (:118-257), EMA (:289-292) and queue
-    update (:295-310).  Hard-negative variant of the loss is not restated (default hard_neg_num: 0)."""
+    update (:295-310), including the hard-negative variant (:126-131, 160-171, 208-218, 233-246: the negatives'
+    momentum features -- NOT normalised in the reference -- and ids replace the first bs*neg_num queue columns; a
+    coin flip decides whether the positives or each query's first negative are enqueued)."""
 
     def __init__(self, size="large", embed_dim=None, queue_size=57600, momentum=0.995, dims=None, gather_fn=None):
         super().__init__()
@@ -280,7 +282,10 @@ class BLIPFeatureFusionOracle(nn.Module):
         ids, att, img = t["input_ids"], t["attention_mask"], batch["image_batched"]
         pc_idx = torch.tensor(batch["p_did_list"]).view(-1, 1)
         im = batch["index_mapping"]
-        assert "neg_cand_list" not in im, "hard-negative variant not restated"
+        hard = "neg_cand_list" in im
+        if hard:
+            nc_idx = torch.tensor(batch["nc_dids_list"]).view(-1, 1)          # [bs * neg_num, 1]
+            hard_n = nc_idx.size(0)
         with torch.no_grad():
             self.temp.clamp_(0.001, 0.5)
         mt, mv = batch.get("txt_mask_batched"), batch.get("image_mask_batched")   # ignored by FF, applied by SF
@@ -288,7 +293,10 @@ class BLIPFeatureFusionOracle(nn.Module):
         qi = torch.tensor(im["query"]).flatten()
         pi = torch.tensor(im["pos_cand"]).flatten()
         q, pc = F.normalize(emb[qi], dim=-1), F.normalize(emb[pi], dim=-1)
-        idx_all = torch.cat([pc_idx.t(), self.idx_queue.clone()], dim=1)
+        if hard:
+            idx_all = torch.cat([pc_idx.t(), nc_idx.t(), self.idx_queue.clone()[:, hard_n:]], dim=1)
+        else:
+            idx_all = torch.cat([pc_idx.t(), self.idx_queue.clone()], dim=1)
         pos = torch.eq(pc_idx, idx_all).float()
         sim_targets = pos / pos.sum(1, keepdim=True)
         with torch.no_grad():
@@ -296,13 +304,20 @@ class BLIPFeatureFusionOracle(nn.Module):
             emb_m = self.encode_multimodal_input(ids, att, img, mt, mv, use_momentum=True)
             q_m, pc_m = F.normalize(emb_m[qi], dim=-1), F.normalize(emb_m[pi], dim=-1)
             q_all = torch.cat([q_m.t(), self.query_queue.clone()], dim=1)
-            pc_all = torch.cat([pc_m.t(), self.cand_queue.clone()], dim=1)
+            if hard:
+                nc_m = emb_m[torch.tensor(im["neg_cand_list"])]                # [bs, neg_num, E], un-normalised (:196)
+                pc_all = torch.cat([pc_m.t(), nc_m.view(hard_n, -1).t(), self.cand_queue.clone()[:, hard_n:]], dim=1)
+            else:
+                pc_all = torch.cat([pc_m.t(), self.cand_queue.clone()], dim=1)
             t_q2pc = alpha * F.softmax(q_m @ pc_all / self.temp, dim=1) + (1 - alpha) * sim_targets
             t_pc2q = alpha * F.softmax(pc_m @ q_all / self.temp, dim=1) + (1 - alpha) * sim_targets
         s_q2pc = q @ pc_all / self.temp
         s_pc2q = pc @ q_all / self.temp
         loss = (-(F.log_softmax(s_q2pc, dim=1) * t_q2pc).sum(1).mean() - (F.log_softmax(s_pc2q, dim=1) * t_pc2q).sum(1).mean()) / 2
-        self._dequeue_and_enqueue(q_m, pc_m, pc_idx)
+        if hard and not bool(torch.rand(1) < 0.5):                             # :233-244
+            self._dequeue_and_enqueue(q_m, nc_m[:, 0, :].contiguous(), nc_idx.view(q.size(0), -1)[:, 0].contiguous())
+        else:
+            self._dequeue_and_enqueue(q_m, pc_m, pc_idx)
         acc = pos.gather(1, s_q2pc.max(1)[1].unsqueeze(1)).squeeze().mean()
         return {"loss": loss, "accuracy": acc}
 

@@ -1,0 +1,92 @@
+"""The embed -> index -> retrieval CLI under `torch.distributed.run` on N GPUs against the same pipeline in one
+process: per-rank shard files from the embedder, a link-style index that points at them (no 8.6 GB copy, no rank-0
+funnel), row-sharded search with one query all-gather + one all-to-all, rank 0 writing the results.
+
+    python scripts/cli_e2e_multigpu.py [N]        (gpurun --gpus N; default N = all visible GPUs)
+
+Prints one JSON line; exit code 0 iff the N-rank run files / TSV / embeddings agree with the single-process ones."""
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import torch
+
+import synth_mbeir as sm
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else torch.cuda.device_count()
+tmp = tempfile.mkdtemp(prefix="uniir_e2e_")
+data_root = os.path.join(tmp, "mbeir_data")
+sm.make_tree(data_root, n_queries=67, n_cands=80, seed=0)
+env = dict(os.environ, UNIIR_CLIP_BPE="word-hash", PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+SUFFIX = "CLIP_SF/Tiny/Instruct/InBatch/"
+
+
+def run(cmd, **kw):
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, **kw)
+    if r.returncode != 0:
+        print(r.stdout[-3000:], r.stderr[-3000:])
+        raise SystemExit(f"FAILED: {' '.join(cmd)}")
+    return r
+
+
+def pipeline(uniir, world, link):
+    cfgs = sm.write_configs(os.path.join(uniir, "cfg"), link_index=link)
+    ckpt = os.path.join(uniir, "checkpoint", SUFFIX, "clip_sf_tiny.pth")
+    os.makedirs(os.path.dirname(ckpt), exist_ok=True)
+    shutil.copy(os.path.join(tmp, "w.pth"), ckpt)
+    common = ["--uniir_dir", uniir, "--mbeir_data_dir", data_root]
+    launch = [sys.executable] if world == 1 else [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                                    f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                                                    "--master-port", "29611"]
+    run(launch + ["-m", "uniir_b200.mbeir_embedder", "--config_path", cfgs["embed"]] + common)
+    run([sys.executable, "-m", "uniir_b200.mbeir_retriever", "--config_path", cfgs["index"], "--enable_create_index"] + common)
+    run(launch + ["-m", "uniir_b200.mbeir_retriever", "--config_path", cfgs["retrieval"], "--enable_retrieval"] + common)
+
+
+from uniir_b200.clip_sf import CLIPScoreFusion
+torch.save({"model": CLIPScoreFusion("tiny-test", device="cuda:0", seed=3).state_dict()}, os.path.join(tmp, "w.pth"))
+one, many = os.path.join(tmp, "one"), os.path.join(tmp, "many")
+pipeline(one, 1, link=False)
+pipeline(many, N, link=True)
+
+res = {"gpus": N, "ok": True, "checks": {}}
+names = [n for n, *_ in sm.DATASETS]
+for name in names + ["union"]:
+    a = np.load(os.path.join(one, "embed", SUFFIX, "cand_pool", f"mbeir_{name}_cand_pool_embed.npy")).astype(np.float32)
+    b = np.load(os.path.join(many, "embed", SUFFIX, "cand_pool", f"mbeir_{name}_cand_pool_embed.npy")).astype(np.float32)
+    ia = np.load(os.path.join(one, "embed", SUFFIX, "cand_pool", f"mbeir_{name}_cand_pool_ids.npy"))
+    ib = np.load(os.path.join(many, "embed", SUFFIX, "cand_pool", f"mbeir_{name}_cand_pool_ids.npy"))
+    same_ids = bool(np.array_equal(ia, ib))
+    err = float(np.abs(a - b).max())
+    res["checks"][f"embed_{name}"] = {"ids_equal": same_ids, "max_abs_diff": err}
+    res["ok"] &= same_ids and err < 2e-2
+shards = [f for f in os.listdir(os.path.join(many, "embed", SUFFIX, "cand_pool")) if ".rank" in f]
+res["checks"]["rank_shard_files"] = len(shards)
+res["ok"] &= len(shards) == 2 * N * len(names)          # embed + ids per rank per pool
+idx = os.path.join(many, "index", SUFFIX, "cand_pool", "mbeir_union_cand_pool.index")
+res["checks"]["link_index_bytes"] = os.path.getsize(idx)
+res["ok"] &= os.path.getsize(idx) < 4096                   # a pointer, not a copy of the embeddings
+run_a = os.path.join(one, "retrieval_results", SUFFIX, "run_files")
+run_b = os.path.join(many, "retrieval_results", SUFFIX, "run_files")
+for f in sorted(os.listdir(run_a)):
+    la = [l.split() for l in open(os.path.join(run_a, f))]
+    lb = [l.split() for l in open(os.path.join(run_b, f))]
+    same = len(la) == len(lb) and np.mean([x[:4] == y[:4] for x, y in zip(la, lb)]) if la else 0.0
+    res["checks"][f] = float(same)
+    res["ok"] &= same >= 0.98            # bf16 towers, different batch composition per rank: near-ties may swap
+tsv = lambda d: open(os.path.join(d, "retrieval_results", SUFFIX, "final_tsv", os.listdir(os.path.join(d, "retrieval_results", SUFFIX, "final_tsv"))[0])).read().splitlines()
+ta, tb = tsv(one), tsv(many)
+diff = max(abs(float(x.split("\t")[6]) - float(y.split("\t")[6])) for x, y in zip(ta[1:], tb[1:]))
+res["checks"]["tsv_rows"] = len(tb) - 1
+res["checks"]["tsv_max_recall_diff"] = diff
+res["ok"] &= len(ta) == len(tb) and diff <= 0.031
+print(json.dumps(res))
+shutil.rmtree(tmp, ignore_errors=True)
+sys.exit(0 if res["ok"] else 1)

@@ -76,22 +76,9 @@ def make_tree(root, n_queries=67, n_cands=80, seed=0):
 
 
 def word_hash_tokenizer(context_length=77, vocab=512):
-    """list[str] -> int32 [B, context_length]: [SOT, 1 + crc32(word) % (vocab - 3) ..., EOT, 0 ...], truncated like
-    clip.tokenize(truncate=True); EOT is the largest id so the text tower pools at it."""
-    sot, eot = vocab - 2, vocab - 1
-
-    def tok(txts):
-        if isinstance(txts, str):
-            txts = [txts]
-        out = torch.zeros(len(txts), context_length, dtype=torch.int32)
-        for i, t in enumerate(txts):
-            ids = [sot] + [1 + zlib.crc32(w.encode()) % (vocab - 3) for w in t.lower().split()] + [eot]
-            if len(ids) > context_length:
-                ids = ids[:context_length]
-                ids[-1] = eot
-            out[i, :len(ids)] = torch.tensor(ids, dtype=torch.int32)
-        return out
-    return tok
+    """The product's own stand-in tokenizer (uniir_b200.preprocess.word_hash_tokenizer, UNIIR_CLIP_BPE=word-hash)."""
+    from uniir_b200.preprocess import word_hash_tokenizer as wh
+    return wh(context_length, vocab)
 
 
 COMMON_YAML = '''

@@ -190,3 +190,57 @@ def test_cross_attention_backward_kernel():
     r2 = ((q3 @ k3.transpose(-1, -2) * 0.125 + mask).softmax(-1) @ v3).transpose(1, 2).reshape(B * S, D)
     r2.backward(do.float())
     assert rel(dqkv, x.grad) < 1.2e-2
+
+
+def test_blip_ff_hard_negative_variant_matches_oracle():
+    """blip_ff.py:126-131,160-171,208-218,233-246 (oracle pinned to the real reference class in
+    tests/test_oracle_blip.py): the negatives' ids / un-normalised momentum features replace the first queue columns;
+    a coin flip (host RNG, same seed on both sides) enqueues the positives or each query's first negative."""
+    from oracle.blip_oracle import BLIPFeatureFusionOracle
+    from uniir_b200.blip_ff import BLIPFeatureFusion
+    from test_oracle_blip import _inputs
+    torch.manual_seed(5)
+    orc = BLIPFeatureFusionOracle("tiny-test", embed_dim=64, queue_size=32).eval()
+    with torch.no_grad():
+        for n_, p_ in orc.named_parameters():
+            if p_.ndim >= 2 and "_m." not in n_:
+                p_.mul_(4.0)
+    orc.copy_params()
+    m = BLIPFeatureFusion(vit="tiny-test", image_size=64, embed_dim=64, queue_size=32, micro_batch=8)
+    m.train_micro_batch = 8
+    m.load_state_dict(orc.state_dict(), strict=False)
+    d = orc.dims
+    flips = set()
+    for step, seed in enumerate((102, 103)):            # rand(1) < 0.5 is True for 102, False for 103
+        ids, att, img = _inputs(d, 16, 24, 60 + step)   # 4 pairs x [query, pos, neg, neg]
+        b = dict(txt_batched={"input_ids": ids, "attention_mask": att}, image_batched=img, txt_mask_batched=None,
+                 image_mask_batched=None, p_did_list=[5, 6, 5, 7 + step], nc_dids_list=[[20, 21], [22, 6], [24, 25], [26, 27 + step]],
+                 index_mapping={"query": [[4 * i] for i in range(4)], "pos_cand": [[4 * i + 1] for i in range(4)],
+                                "neg_cand_list": [[4 * i + 2, 4 * i + 3] for i in range(4)]})
+        orc.zero_grad()
+        torch.manual_seed(seed); ref = orc.compute_contrastive_loss(b, alpha=0.3); ref["loss"].backward()
+        if m._online.grad is not None:
+            for gbuf in m._online.grad.values():
+                gbuf.zero_()
+        torch.manual_seed(seed); out = m.compute_contrastive_loss(b, alpha=0.3)
+        m.backward_contrastive()
+        torch.manual_seed(seed); flips.add(bool(torch.rand(1) < 0.5))
+        torch.cuda.synchronize()
+        assert abs(out["loss"].item() - ref["loss"].item()) < 2e-2 * max(1.0, abs(ref["loss"].item())), (out["loss"].item(), ref["loss"].item())
+        assert abs(out["accuracy"].item() - ref["accuracy"].item()) <= 1.0 / 4 + 1e-6
+        worst = (1.0, "")
+        for n_, p_o in orc.named_parameters():
+            if p_o.grad is None or n_.endswith("self.key.bias") or p_o.grad.numel() == 1:
+                continue
+            a, c = p_o.grad.flatten().double(), m._online.g(n_).cpu().flatten().double()
+            worst = min(worst, ((torch.dot(a, c) / (a.norm() * c.norm() + 1e-30)).item(), n_))
+        assert worst[0] > 0.995, worst
+        assert torch.equal(m.idx_queue.cpu(), orc.idx_queue) and int(m.new_ptr_queue) == int(orc.new_ptr_queue)
+        live = orc.idx_queue[0] != -100
+        assert torch.nn.functional.cosine_similarity(m.cand_queue.cpu().t()[live], orc.cand_queue.t()[live], dim=-1).min() > 1 - 1e-3
+        with torch.no_grad():
+            for n_, p_o in orc.named_parameters():
+                if p_o.grad is not None:
+                    p_o -= 1e-2 * p_o.grad
+                    m.get_parameter(n_).copy_(p_o)
+    assert flips == {True, False}

@@ -71,8 +71,8 @@ def test_clip_ff_encode_matches_oracle_and_api_contract():
 
 
 def test_blip_step_under_cuda_graphs_equals_eager():
-    """BLIPEncoder.run(use_graph=True) (opt-in, BLIPFeatureFusion.use_cuda_graphs): eager, capture and replay must give
-    the eager path's loss and gradients.  Written without GPU time left, hence in this xfail-guarded file."""
+    """BLIPEncoder.run(use_graph=True) (BLIPFeatureFusion.use_cuda_graphs, the default): eager, capture and replay must
+    give the eager path's loss and gradients."""
     from oracle.blip_oracle import BLIPFeatureFusionOracle
     from uniir_b200.blip_ff import BLIPFeatureFusion
     from test_oracle_blip import _inputs

@@ -106,6 +106,45 @@ def test_training_loss_matches_reference_class(tmp_path):
 
 
 @pytest.mark.skipif(not ref_blip_shim.available(), reason="reference tree not present (GPU box): golden vectors cover it")
+def test_hard_negative_variant_matches_reference_class(tmp_path):
+    """blip_ff.py:126-131,160-171,208-218,233-246: negatives in place of the first queue columns, un-normalised
+    negative momentum features, the coin flip between enqueueing positives and first negatives (same torch seed on
+    both sides) -- three steps so that both outcomes of the flip and a non-trivial queue are covered."""
+    import types
+    from oracle.blip_oracle import BLIPDims
+    bf = ref_blip_shim.load_blip_ff()
+    cfg = dict(json.load(open("/root/reference/src/models/uniir_blip/backbone/configs/med_config.json")))
+    cfg.update(hidden_size=64, intermediate_size=256, num_attention_heads=1, num_hidden_layers=2, vocab_size=600,
+               max_position_embeddings=128, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    p = tmp_path / "med.json"; p.write_text(json.dumps(cfg))
+    torch.manual_seed(0)
+    ref = bf.BLIPFeatureFusion(med_config=str(p), image_size=64, vit="base", embed_dim=64, queue_size=16, config=None).eval()
+    d = BLIPDims(image_size=64, patch=16, v_width=768, v_layers=12, v_heads=12, t_width=64, t_layers=2, t_heads=1,
+                 t_inter=256, vocab=600, max_pos=128)
+    orc = BLIPFeatureFusionOracle(dims=d, embed_dim=64, queue_size=16).eval()
+    orc.load_state_dict(ref.state_dict(), strict=False)
+    flips = set()
+    for step in range(3):
+        ids, att, img = _inputs(d, 16, 20, 30 + step)          # 4 pairs x [query, pos, neg, neg]
+        mk = lambda: dict(image_batched=img, txt_mask_batched=None, image_mask_batched=None, p_did_list=[7, 8, 7, 9 + step],
+                          nc_dids_list=[[20, 21], [22, 8], [24, 25], [26, 27 + step]],
+                          index_mapping={"query": [[4 * i] for i in range(4)], "pos_cand": [[4 * i + 1] for i in range(4)],
+                                         "neg_cand_list": [[4 * i + 2, 4 * i + 3] for i in range(4)]})
+        br = mk(); br["txt_batched"] = types.SimpleNamespace(input_ids=ids, attention_mask=att)
+        bo = mk(); bo["txt_batched"] = {"input_ids": ids, "attention_mask": att}
+        ref.zero_grad(); orc.zero_grad()
+        torch.manual_seed(102 + step); o_r = ref.compute_contrastive_loss(br, alpha=0.3); o_r["loss"].backward()
+        torch.manual_seed(102 + step); o_o = orc.compute_contrastive_loss(bo, alpha=0.3); o_o["loss"].backward()
+        torch.manual_seed(102 + step); flips.add(bool(torch.rand(1) < 0.5))
+        assert abs(o_r["loss"].item() - o_o["loss"].item()) < 1e-5 and abs(o_r["accuracy"].item() - o_o["accuracy"].item()) < 1e-6
+        for n in ("temp", "text_encoder.pooler.dense.weight", "visual_encoder.blocks.3.attn.qkv.weight"):
+            assert torch.allclose(ref.get_parameter(n).grad, orc.get_parameter(n).grad, atol=1e-6, rtol=1e-4), n
+        assert torch.equal(ref.idx_queue, orc.idx_queue) and torch.equal(ref.new_ptr_queue, orc.new_ptr_queue)
+        assert torch.allclose(ref.cand_queue, orc.cand_queue, atol=1e-6) and torch.allclose(ref.query_queue, orc.query_queue, atol=1e-6)
+    assert flips == {True, False}
+
+
+@pytest.mark.skipif(not ref_blip_shim.available(), reason="reference tree not present (GPU box): golden vectors cover it")
 def test_blip_sf_restatement_matches_reference_class(tmp_path):
     """The REAL reference BLIPScoreFusion (blip_sf.py) vs the oracle restatement: state-dict keys, masked
     score-fusion embeddings (online and momentum), and two consecutive training steps (loss, accuracy, gradients

@@ -198,7 +198,7 @@ class BLIPEncoder:
             self.att_len = None
             self.ids = None
 
-    # ---- CUDA-graph front-end (opt-in: BLIPFeatureFusion.use_cuda_graphs).  The eager step issues 120-150 k kernel
+    # ---- CUDA-graph front-end (BLIPFeatureFusion.use_cuda_graphs, default on).  The eager step issues 120-150 k kernel
     # launches per 2048-pair batch; captured, a micro-batch is one graph launch.  Static I/O buffers, first call eager
     # (kernel attributes, allocator warm-up), second call captures, later calls replay -- as CLIPEncoder._run. ----
     def _static_io(self):
@@ -486,7 +486,7 @@ class BLIPFeatureFusion(nn.Module):
         self._enc = {}
         self._train_state = None
         self.train_micro_batch = 64
-        self.use_cuda_graphs = False     # opt-in (BLIPEncoder.run): not yet confirmed on hardware
+        self.use_cuda_graphs = True      # BLIPEncoder.run: one graph launch per micro-batch instead of ~2400 kernel launches
 
     # ---- reference surface -------------------------------------------------------------
     def get_img_preprocess_fn(self):
@@ -583,9 +583,22 @@ class BLIPFeatureFusion(nn.Module):
 
     # ---- training: momentum distillation + queue (blip_ff.py:118-257) ---------------------------
     def compute_contrastive_loss(self, batch, alpha):
-        """Reference-compatible entry: returns {"loss", "accuracy"}; gradients are produced by
-        ``backward_contrastive`` (the fused engine path, uniir_b200.engine.train_step_blip)."""
-        loss, acc = self._loss_forward(batch, alpha)
+        """Reference-compatible entry: returns {"loss", "accuracy"}.  With autograd enabled the loss is a graph node
+        whose ``.backward()`` (the reference loop's ``scaler.scale(loss).backward()``, uniir_blip/engine.py:45) runs
+        ``backward_contrastive`` and fills ``p.grad`` of the online parameters; the fused engine path
+        (``engine.train_step_blip`` / ``blip_engine.train_one_epoch``) calls the two halves directly."""
+        if torch.is_grad_enabled() and self.training:
+            from .autograd_bridge import bridged_loss
+
+            def bwd(g_loss):
+                self.backward_contrastive()
+                g = float(g_loss)
+                if g != 1.0:
+                    for buf in self._online.grad.values():
+                        buf.mul_(g)
+            loss, acc = bridged_loss(self._online, lambda: self._loss_forward(batch, alpha), bwd)
+        else:
+            loss, acc = self._loss_forward(batch, alpha)
         return {"loss": loss, "accuracy": acc}
 
     @torch.no_grad()
@@ -611,8 +624,7 @@ class BLIPFeatureFusion(nn.Module):
     @torch.no_grad()
     def _loss_forward(self, batch, alpha):
         im = batch["index_mapping"]
-        if "neg_cand_list" in im:
-            raise NotImplementedError("BLIP_FF hard-negative variant (blip_ff.py:127-131,160-171) is not built")
+        hard = "neg_cand_list" in im                                      # blip_ff.py:126-131
         dev, E = self.device_, self._out_dim
         P = self._online
         P.w("temp").clamp_(0.001, 0.5)                                   # blip_ff.py:132-133
@@ -636,8 +648,18 @@ class BLIPFeatureFusion(nn.Module):
         L.check(lib.uniir_infonce_normalize(emb_m.data_ptr(), q_idx.data_ptr(), p_idx.data_ptr(), bs, E, qm.data_ptr(),
                                             pm.data_ptr(), tmpn.data_ptr(), tmpn.data_ptr(), ops._stream()), "normalize")
         q_all = torch.cat([qm.t(), self.query_queue], dim=1).contiguous()     # [E, bs+Qz]  (data movement only)
-        pc_all = torch.cat([pm.t(), self.cand_queue], dim=1).contiguous()
-        id_all = torch.cat([pc_ids, self.idx_queue[0]]).contiguous()
+        if hard:
+            # blip_ff.py:160-171, 208-218: the negatives' ids and (un-normalised, :196) momentum features take the place
+            # of the first bs*neg_num queue columns
+            n_rows = torch.tensor(im["neg_cand_list"], dtype=torch.int64).to(dev)         # [bs, neg_num]
+            nc_ids = torch.as_tensor(batch["nc_dids_list"]).to(dev, torch.int64).reshape(bs, -1)
+            hard_n = nc_ids.numel()
+            nc_m = emb_m[n_rows.flatten()]                                                  # [bs*neg_num, E]
+            pc_all = torch.cat([pm.t(), nc_m.t(), self.cand_queue[:, hard_n:]], dim=1).contiguous()
+            id_all = torch.cat([pc_ids, nc_ids.flatten(), self.idx_queue[0, hard_n:]]).contiguous()
+        else:
+            pc_all = torch.cat([pm.t(), self.cand_queue], dim=1).contiguous()
+            id_all = torch.cat([pc_ids, self.idx_queue[0]]).contiguous()
         temp = P.w("temp")
         S1, S1m = ops.sgemm_temp(qn, pc_all, True, temp), ops.sgemm_temp(qm, pc_all, True, temp)
         S2, S2m = ops.sgemm_temp(pn, q_all, True, temp), ops.sgemm_temp(pm, q_all, True, temp)
@@ -653,7 +675,10 @@ class BLIPFeatureFusion(nn.Module):
         L.check(lib.uniir_infonce_normalize_bwd(q_idx.data_ptr(), p_idx.data_ptr(), qn.data_ptr(), pn.data_ptr(),
                                                 qnorm.data_ptr(), pnorm.data_ptr(), d_qn.data_ptr(), d_pn.data_ptr(), bs, E,
                                                 d_emb.data_ptr(), ops._stream()), "normalize_bwd")
-        self._dequeue_and_enqueue(qm, pm, pc_ids)                         # blip_ff.py:247
+        if hard and not bool(torch.rand(1) < 0.5):                        # blip_ff.py:233-244: coin flip (host RNG, like the reference)
+            self._dequeue_and_enqueue(qm, nc_m.view(bs, -1, E)[:, 0, :].contiguous(), nc_ids[:, 0].contiguous())
+        else:
+            self._dequeue_and_enqueue(qm, pm, pc_ids)                     # blip_ff.py:247
         self._train_state = dict(ids=ids, lens=lens, img=img, d_emb=d_emb, d_temp=acc_l[3].clone(), mt=mt, mv=mv)
         return loss.clone(), acc.clone()
 

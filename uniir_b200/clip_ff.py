@@ -317,7 +317,7 @@ class CLIPFeatureFusion(nn.Module):
 
     def get_tokenizer(self):
         from .preprocess import clip_tokenizer
-        return clip_tokenizer(context_length=77)
+        return clip_tokenizer(context_length=77, vocab=self.dims.vocab)
 
     def get_logit_scale(self):
         return self.get_parameter("clip_model.logit_scale").exp()
@@ -359,8 +359,13 @@ class CLIPFeatureFusion(nn.Module):
     # keeping activations, the loss kernels give dLoss/d(embedding), phase C re-runs each micro-batch with saved
     # activations and backpropagates.  Driven by engine.train_step(model, batch, FlatAdamW(model._flat)). ----
     def compute_inbatch_contrastive_loss(self, batch):
-        """Reference-compatible entry: {"loss", "accuracy"} (0-d tensors); the gradients are produced by
-        ``_loss_backward`` (engine.train_step), not by autograd."""
+        """Reference-compatible entry: {"loss", "accuracy"} (0-d tensors).  With autograd enabled the loss is a graph
+        node whose ``.backward()`` runs ``_loss_backward`` and fills ``p.grad`` (the reference loop,
+        uniir_clip/engine.py:26-45); ``engine.train_step`` calls the two halves directly."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .autograd_bridge import bridged_loss
+            loss, acc = bridged_loss(self._flat, lambda: self._loss_forward(batch), lambda g: self._loss_backward(batch, g))
+            return {"loss": loss, "accuracy": acc}
         loss, acc = self._loss_forward(batch)
         return {"loss": loss.clone(), "accuracy": acc.clone()}
 

@@ -95,7 +95,7 @@ class CLIPScoreFusion(nn.Module):
 
     def get_tokenizer(self):
         from .preprocess import clip_tokenizer
-        return clip_tokenizer(context_length=77)
+        return clip_tokenizer(context_length=77, vocab=self.dims.vocab)
 
     def get_logit_scale(self):
         return self.clip_model.logit_scale.exp()

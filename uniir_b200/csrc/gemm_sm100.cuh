@@ -369,7 +369,7 @@ __device__ __forceinline__ void gemm_body_2cta(const CUtensorMap* tmA, const CUt
         tc_fence_after();
         epi.tile(w, n, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN, row, col_half);
         tc_fence_before();
-        mbar_arrive_cluster(acc ? te1 : te0);
+        mbar_arrive_remote(acc ? te1 : te0);   // accumulator release: no global-memory ordering involved
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }

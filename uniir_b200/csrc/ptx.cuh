@@ -224,6 +224,13 @@ __device__ __forceinline__ uint32_t mapa_cluster(uint32_t local_smem_addr, uint3
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Same arrival with the default (.release.cta) semantics: what a consumer needs to hand a TMEM / smem buffer back to
+// a producer in the peer CTA once its own tcgen05.ld's are fenced (tcgen05.fence::before_thread_sync).  The
+// .release.cluster form above compiles to MEMBAR.ALL.GPU + ERRBAR in front of every arrival -- 16 % of all warp
+// samples of the retrieval kernel sat there (ncu r2c6), on the accumulator-release critical path.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // 2-SM TMA load: data lands in THIS CTA's smem, the transaction bytes are credited to the
 // mbarrier at `mbar_cluster_addr` (the leader CTA's barrier)
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t mbar_cluster_addr,

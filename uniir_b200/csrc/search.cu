@@ -32,7 +32,7 @@ constexpr float kNegInf = -INFINITY;
 constexpr float kFaissNeg = -3.4028234663852886e38f;
 
 constexpr int kDefaultTilesPerChunk = 64;   // 64 x 256 candidates x 1536 B = 25 MB: L2-resident per wave
-constexpr int kDefaultTilesPerChunkTs = 512; // 64 k candidates per chunk in 128-candidate tiles (queries-on-chip kernel)
+constexpr int kDefaultTilesPerChunkTs = 128; // 16 k candidates (25 MB) per chunk in 128-candidate tiles: L2-resident across the ~10 query rounds; same-box sweeps r2c9 / r2c10
 
 struct SearchParams {
   long long Q, N;
@@ -237,6 +237,7 @@ struct SearchEpilogueT {
 
   // `staged`: the tile's BN inverse candidate norms already sit in shared memory (the caller prefetched them a
   // tile ahead); otherwise they are fetched here and published to the four epilogue warps with a named barrier.
+  template <bool kPipe = true>
   __device__ __forceinline__ void tile(const WorkItem& w, int n_blk, uint32_t tmem_acc, int row, int /*col_half*/,
                                        const float* staged = nullptr) {
     const float* invc = staged;
@@ -254,11 +255,8 @@ struct SearchEpilogueT {
     }
     const bool tail = col_base + BN > p.N;
     const long long wsb = ws_base(row);
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_acc + c * 32, r);
-      tmem_ld_wait();
+    // one 32-column chunk of this row: scale, reject against the row's k-th best, keep the rare survivors
+    auto chunk = [&](int c, const uint32_t (&r)[32]) {
       float s[32];
       float m = kNegInf;
 #pragma unroll
@@ -298,6 +296,30 @@ struct SearchEpilogueT {
       }
       const uint32_t need = __ballot_sync(0xffffffffu, cnt > kCap - 32);
       if (need) compact(need, row, false, w);
+    };
+    // two register buffers: the TMEM load of the next chunk is in flight while this one is processed
+    static_assert((BN / 32) % 2 == 0, "chunks are processed in pairs");
+    if constexpr (kPipe) {
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32b_x32(tmem_acc, ra);
+      tmem_ld_wait();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; c += 2) {
+        tmem_ld_32x32b_x32(tmem_acc + (c + 1) * 32, rb);
+        chunk(c, ra);
+        tmem_ld_wait();
+        if (c + 2 < BN / 32) tmem_ld_32x32b_x32(tmem_acc + (c + 2) * 32, ra);
+        chunk(c + 1, rb);
+        tmem_ld_wait();
+      }
+    } else {
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_acc + c * 32, r);
+        tmem_ld_wait();
+        chunk(c, r);
+      }
     }
   }
 
@@ -431,6 +453,7 @@ __device__ __forceinline__ void ts_issue_tile(uint32_t tmem_d, uint32_t tmem_a, 
   }
 }
 
+template <bool kPipe>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(num_threads(4), 1)
 ip_topk_kernel_ts(const __grid_constant__ GemmTensorMaps maps, const __half* __restrict__ q, const int d,
                   const SearchParams p, const SearchSched sched, const uint32_t idesc) {
@@ -489,15 +512,25 @@ ip_topk_kernel_ts(const __grid_constant__ GemmTensorMaps maps, const __half* __r
       for (int item = pair; item < n_items; item += n_pairs) {
         if (!sched.get(item, w)) continue;
         if (w.n_begin >= w.n_end) continue;
-        // this item's shared-memory query k-blocks (the previous item's MMAs must have let go of the buffer)
-        if (kb_smem > 0) mbar_wait(aempty_bar, a_phase ^ 1);
-        a_phase ^= 1;
-        if (leader) mbar_arrive_expect_tx(afull_bar, 2 * kb_smem * kTsAKbBytes);
+        // The candidate ring does not depend on the queries: the first ring-full of this item's stages is issued
+        // while the previous item is still draining; only then wait until its MMAs have let go of the
+        // shared-memory query buffer and load this item's query k-blocks 8..11.
         const int a_row = (w.m_blk * 2 + static_cast<int>(rank)) * kBM;
-        for (int j = 0; j < kb_smem; ++j) tma_load_2d_2sm(a_smem + j * kTsAKbBytes, &maps.a, af, (kTsTmemKb + j) * kBK, a_row);
+        const int stages_per_tile = (kb_total + kTsStageKb - 1) / kTsStageKb;
+        const int n_stage_loads = (w.n_end - w.n_begin) * stages_per_tile;
+        const int a_after = min(kTsStages, n_stage_loads);      // query load goes in after this many stage loads
+        auto load_queries = [&]() {
+          if (kb_smem > 0) mbar_wait(aempty_bar, a_phase ^ 1);
+          a_phase ^= 1;
+          if (leader) mbar_arrive_expect_tx(afull_bar, 2 * kb_smem * kTsAKbBytes);
+          for (int j = 0; j < kb_smem; ++j) tma_load_2d_2sm(a_smem + j * kTsAKbBytes, &maps.a, af, (kTsTmemKb + j) * kBK, a_row);
+        };
+        int issued = 0;
         for (int ti = 0; ti < w.n_end - w.n_begin; ++ti) {
           const int b_row = w.tile_at(ti) * kTsBN + static_cast<int>(rank) * (kTsBN / 2);
           for (int kb0 = 0; kb0 < kb_total; kb0 += kTsStageKb) {
+            if (issued == a_after) load_queries();
+            ++issued;
             const int nkb = min(kTsStageKb, kb_total - kb0);
             mbar_wait(&empty_bar[stage], phase ^ 1);
             const uint32_t fb = mapa_cluster(smem_u32(&full_bar[stage]), 0);
@@ -507,6 +540,7 @@ ip_topk_kernel_ts(const __grid_constant__ GemmTensorMaps maps, const __half* __r
             if (++stage == kTsStages) { stage = 0; phase ^= 1; }
           }
         }
+        if (issued <= a_after) load_queries();
       }
     }
   } else if (warp_idx == 1) {
@@ -593,6 +627,19 @@ ip_topk_kernel_ts(const __grid_constant__ GemmTensorMaps maps, const __half* __r
       if (n_tiles_item > 0) fetch_inv(w.tile_at(0));
       for (int ti = 0; ti < n_tiles_item; ++ti) {
         const int n = w.tile_at(ti);
+        if (ti == n_tiles_item - 16 || (n_tiles_item < 16 && ti == 0)) {
+          // shortly before the item ends: pull the NEXT item's query row into L2, so that the row-per-thread loads
+          // that refill tensor memory at the item boundary (nothing else runs then) hit L2 instead of DRAM
+          WorkItem w2;
+          const int nxt = item + n_pairs;
+          if (nxt < n_items && sched.get(nxt, w2)) {
+            const long long qrow2 = static_cast<long long>(w2.m_blk * 2 + static_cast<int>(rank)) * kBM + row;
+            if (qrow2 < p.Q) {
+              const char* base = reinterpret_cast<const char*>(q + qrow2 * d);
+              for (int b = 0; b < d * 2; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + b));
+            }
+          }
+        }
         float* winv = winv_base + (inv_buf & 1) * kTsBN;
         ++inv_buf;
 #pragma unroll
@@ -601,10 +648,10 @@ ip_topk_kernel_ts(const __grid_constant__ GemmTensorMaps maps, const __half* __r
         if (ti + 1 < n_tiles_item) fetch_inv(w.tile_at(ti + 1));
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
-        epi.tile(w, n, tmem_d0 + lane_base + acc * kTsBN, row, 0, winv);
+        epi.template tile<kPipe>(w, n, tmem_d0 + lane_base + acc * kTsBN, row, 0, winv);
         tc_fence_before();
         __syncwarp();
-        if (lane_id() == 0) mbar_arrive_cluster(acc ? te1 : te0);
+        if (lane_id() == 0) mbar_arrive_remote(acc ? te1 : te0);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -841,13 +888,20 @@ extern "C" int uniir_ip_topk(const void* q, const float* q_inv, const void* c, c
 
   if (mode == 2) {
     static std::atomic<uint64_t> attr_ts{0};
-    if (first_on_device(attr_ts))
-      UNIIR_CUDA_OK(cudaFuncSetAttribute(ip_topk_kernel_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes));
+    if (first_on_device(attr_ts)) {
+      UNIIR_CUDA_OK(cudaFuncSetAttribute(ip_topk_kernel_ts<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes));
+      UNIIR_CUDA_OK(cudaFuncSetAttribute(ip_topk_kernel_ts<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes));
+    }
+    // Epilogue with double-buffered TMEM loads: measured SLOWER on the same box (1107 vs 1177 TFLOP/s at 512-tile
+    // chunks, gpurun_out/r2c8_modes_full.txt; 183 vs 138 registers, twice the epilogue code) -> opt-in only.
+    bool pipe = false;
+    if (const char* e = getenv("UNIIR_SEARCH_EPIPIPE")) pipe = atoi(e) != 0;
     int npairs = sms / 2;
     if (items < npairs) npairs = static_cast<int>(items);
     sched.n_workers = stagger ? npairs : 0;
     const uint32_t idesc = make_idesc_f16(false, false, false, 2 * kBM, kTsBN);
-    ip_topk_kernel_ts<<<2 * npairs, num_threads(4), kTsSmemBytes, stream>>>(maps, static_cast<const __half*>(q), d, p, sched, idesc);
+    if (pipe) ip_topk_kernel_ts<true><<<2 * npairs, num_threads(4), kTsSmemBytes, stream>>>(maps, static_cast<const __half*>(q), d, p, sched, idesc);
+    else ip_topk_kernel_ts<false><<<2 * npairs, num_threads(4), kTsSmemBytes, stream>>>(maps, static_cast<const __half*>(q), d, p, sched, idesc);
   } else if (pairs) {
     using SM = GemmSmem2<kSearchBN>;
     const int smem_bytes = SM::kRingBytes + SM::kBarBytes + 2 * kSearchBN * sizeof(float) + 1024;

@@ -26,6 +26,7 @@ def _ptr(t):
 
 
 _GEMM_PROF = None
+_GEMM_EVENTS = False
 _GRAPH_LAUNCHES = 0
 
 
@@ -39,10 +40,14 @@ def add_graph_launches(n):
     _GRAPH_LAUNCHES += n
 
 
-def set_gemm_profiler(sink):
-    """sink: list that receives one descriptor dict per GEMM launch (shape + epilogue flags), or None."""
-    global _GEMM_PROF
+def set_gemm_profiler(sink, events=False):
+    """sink: list that receives one descriptor dict per GEMM launch (shape + epilogue flags), or None.
+    events=True: every launch is also bracketed by two CUDA events on the launching stream (entry["events"]); after
+    a synchronize, `e0.elapsed_time(e1)` is that launch's duration IN ITS PLACE in the step -- same predecessor
+    kernels, same L2 contents -- which is what a roofline against the sustained peak has to be measured on."""
+    global _GEMM_PROF, _GEMM_EVENTS
     _GEMM_PROF = sink
+    _GEMM_EVENTS = bool(events) and sink is not None
 
 
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=None, act=L.ACT_NONE,
@@ -87,6 +92,13 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=None, a
                                residual=None if residual is None else residual.dtype,
                                aux=aux_out is not None, ags=act_grad_src is not None,
                                accumulate=bool(accumulate), split_k=split_k))
+        if _GEMM_EVENTS:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            L.check(L.load().uniir_gemm_epi(C.byref(d), _stream()), "uniir_gemm_epi")
+            e1.record()
+            _GEMM_PROF[-1]["events"] = (e0, e1)
+            return out
     L.check(L.load().uniir_gemm_epi(C.byref(d), _stream()), "uniir_gemm_epi")
     return out
 

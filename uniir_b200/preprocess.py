@@ -129,8 +129,31 @@ class _BPE:
         return ids
 
 
-def clip_tokenizer(context_length=77):
+def word_hash_tokenizer(context_length=77, vocab=49408):
+    """NOT the CLIP vocabulary: [SOT, 1 + crc32(word) % (vocab - 3) ..., EOT, 0 ...] per whitespace-separated word,
+    truncated like clip.tokenize(truncate=True).  For pipeline runs where the BPE merges file is unavailable (no
+    network): synthetic data, smoke tests, the end-to-end CLI tests.  Selected with UNIIR_CLIP_BPE=word-hash."""
+    import zlib
+    sot, eot = vocab - 2, vocab - 1
+
+    def tok(txts):
+        if isinstance(txts, str):
+            txts = [txts]
+        out = torch.zeros(len(txts), context_length, dtype=torch.int32)
+        for i, t in enumerate(txts):
+            ids = [sot] + [1 + zlib.crc32(w.encode()) % (vocab - 3) for w in t.lower().split()] + [eot]
+            if len(ids) > context_length:
+                ids = ids[:context_length]
+                ids[-1] = eot
+            out[i, :len(ids)] = torch.tensor(ids, dtype=torch.int32)
+        return out
+    return tok
+
+
+def clip_tokenizer(context_length=77, vocab=49408):
     state = {}
+    if os.environ.get("UNIIR_CLIP_BPE") == "word-hash":
+        return word_hash_tokenizer(context_length, vocab)
 
     def tokenizer_wrapper(txt):
         if isinstance(txt, str):
