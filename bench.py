@@ -516,7 +516,7 @@ def run_embed(args, rank, world, dev, peaks):
     e2e_step()
     ms_e2e = timed(e2e_step, max(1, min(2, args.steps)), world)
     items = B * world
-    alg = 175.33e9 * items / (ms / 1e3) / 1e12
+    alg = 175.33e9 * B / (ms / 1e3) / 1e12          # per GPU
     return {"metric": "embedded_items_per_sec", "value": items / (ms / 1e3), "unit": "items/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -525,7 +525,7 @@ def run_embed(args, rank, world, dev, peaks):
             "clocks": clocks, "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": alg, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": alg / peaks["bf16_sustained"], "traffic": None,
-                         "note": "whole forward (175.33 GFLOP/item algorithmic) against measured sustained bf16"},
+                         "note": "whole forward (175.33 GFLOP/item algorithmic), per GPU, against measured sustained bf16"},
             "e2e": {"value": items / (ms_e2e / 1e3), "unit": "items/s", "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in hb.values() if torch.is_tensor(v)) * world,
                     "d2h_bytes_per_step": B * 768 * 2 * world, "ms_per_step": ms_e2e}}
 

@@ -14,7 +14,7 @@ for s in range(0, N, 1 << 20):
     e = min(N, s + (1 << 20)); c[s:e] = torch.randn(e - s, d, generator=g, device="cuda").half()
 q = torch.randn(Q, d, generator=g, device="cuda").half()
 qi, ci = ops.row_inv_norm(q), ops.row_inv_norm(c)
-KEYS = ("UNIIR_SEARCH_MODE", "UNIIR_SEARCH_TPC", "UNIIR_SEARCH_ROT", "UNIIR_SEARCH_2CTA", "UNIIR_SEARCH_HINT", "UNIIR_SEARCH_EPIPIPE")
+KEYS = ("UNIIR_SEARCH_MODE", "UNIIR_SEARCH_TPC", "UNIIR_SEARCH_ROT", "UNIIR_SEARCH_2CTA", "UNIIR_SEARCH_HINT", "UNIIR_SEARCH_EPIPIPE", "UNIIR_SEARCH_SELECT")
 times = [[] for _ in cfgs]
 ref = None
 for r in range(reps + 1):

@@ -5,7 +5,7 @@ subprocess (a device trap kills the CUDA context, the next shape still runs).  P
     python scripts/check_attn_bwd.py one B S H causal [Skv]
 
 Variants are selected by environment (read once by the library): UNIIR_ATTN_BWD_EW=16 (16 elementwise warps),
-UNIIR_ATTN_BWD_FOLD=1 (tail column / row inside the main kernel -- not yet run on hardware: run this script first).
+UNIIR_ATTN_BWD_FOLD=1 (tail column / row inside the main kernel: correct on hardware, 2.2x slower, opt-in only).
 """
 import os
 import subprocess

@@ -23,7 +23,9 @@ import synth_mbeir as sm
 N = int(sys.argv[1]) if len(sys.argv) > 1 else torch.cuda.device_count()
 tmp = tempfile.mkdtemp(prefix="uniir_e2e_")
 data_root = os.path.join(tmp, "mbeir_data")
-sm.make_tree(data_root, n_queries=67, n_cands=80, seed=0)
+# one instruction per task: the reference seeds each rank with config.seed + rank (mbeir_embedder.py:466), so with
+# several prompts per task the N-rank run would draw different query texts than the single-process run
+sm.make_tree(data_root, n_queries=67, n_cands=80, seed=0, n_prompts=1)
 env = dict(os.environ, UNIIR_CLIP_BPE="word-hash", PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
 SUFFIX = "CLIP_SF/Tiny/Instruct/InBatch/"
 
@@ -87,6 +89,7 @@ diff = max(abs(float(x.split("\t")[6]) - float(y.split("\t")[6])) for x, y in zi
 res["checks"]["tsv_rows"] = len(tb) - 1
 res["checks"]["tsv_max_recall_diff"] = diff
 res["ok"] &= len(ta) == len(tb) and diff <= 0.031
-print(json.dumps(res))
+res["ok"] = bool(res["ok"])
+print(json.dumps(res, default=lambda o: o.item() if hasattr(o, "item") else str(o)))
 shutil.rmtree(tmp, ignore_errors=True)
 sys.exit(0 if res["ok"] else 1)

@@ -27,15 +27,17 @@ def _image(path, rng, size=72):
     Image.fromarray(base).resize((size + 24, size), Image.NEAREST).save(path, "JPEG", quality=90)
 
 
-def make_tree(root, n_queries=67, n_cands=80, seed=0):
-    """Writes the tree under `root` (= mbeir_data_dir).  Returns {dataset: (queries, candidates)}."""
+def make_tree(root, n_queries=67, n_cands=80, seed=0, n_prompts=2):
+    """Writes the tree under `root` (= mbeir_data_dir).  Returns {dataset: (queries, candidates)}.
+    n_prompts=1: one instruction per task, so the query text does not depend on the per-rank RNG stream."""
     rng = np.random.default_rng(seed)
     out = {}
     os.makedirs(os.path.join(root, "instructions"), exist_ok=True)
     with open(os.path.join(root, "instructions", "query_instructions.tsv"), "w") as f:
         f.write("query_modality\tcand_modality\ttask\tdataset_id\tprompt_1\tprompt_2\tprompt_3\tprompt_4\n")
         for name, ds, qm, cm, task in DATASETS:
-            f.write(f"{qm}\t{cm}\t{task}\t{ds}\tFind me a matching {cm} for this {qm}\tretrieve the {cm}\t\t\n")
+            second = f"retrieve the {cm}" if n_prompts > 1 else ""
+            f.write(f"{qm}\t{cm}\t{task}\t{ds}\tFind me a matching {cm} for this {qm}\t{second}\t\t\n")
     for name, ds, qm, cm, task in DATASETS:
         cands, queries = [], []
         for j in range(1, n_cands + 1):

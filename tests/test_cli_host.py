@@ -67,8 +67,9 @@ def test_index_file_roundtrip_without_gpu(tmp_path):
     ids = np.arange(5, dtype=np.int64) * 10_000_000
     p = str(tmp_path / "x" / "mbeir_union_cand_pool.index")
     write_index(p, emb, ids)
-    with np.load(p) as z:
-        assert (z["embeddings"] == emb).all() and (z["ids"] == ids).all() and z["embeddings"].dtype == np.float16
+    from uniir_b200.mbeir_retriever import index_shape, read_index_rows
+    e, i = read_index_rows(p)
+    assert index_shape(p) == (5, 8) and (e == emb).all() and (i == ids).all() and e.dtype == np.float16
 
 
 def _ref_select(retrieved, pos, neg, num_hard_negs):
@@ -131,8 +132,8 @@ def test_run_hard_negative_mining_end_to_end_with_injected_search(tmp_path):
 
     def np_search(query_embed_path, cand_index_path, batch_size=10, num_cand_to_retrieve=10):
         qq = np.load(query_embed_path).astype(np.float32)
-        with np.load(cand_index_path) as z:
-            cc, ids = z["embeddings"].astype(np.float32), z["ids"]
+        cc, ids = mr.read_index_rows(cand_index_path)
+        cc, ids = np.asarray(cc, dtype=np.float32), np.asarray(ids)
         qq /= np.linalg.norm(qq, axis=1, keepdims=True); cc /= np.linalg.norm(cc, axis=1, keepdims=True)
         sc = qq @ cc.T
         order = np.argsort(-sc, axis=1)[:, :num_cand_to_retrieve]

@@ -76,7 +76,7 @@ def _worker(rank, world, port, out_dir):
                "acc_ref": (logits[rank * BS:(rank + 1) * BS].argmax(1) == tgt[rank * BS:(rank + 1) * BS]).float().mean().item()}
         worst = 1.0
         for n_, p_o in orc.named_parameters():
-            a, c = p_o.grad.flatten().double(), mine.clip_model.g(n_).cpu().flatten().double()
+            a, c = p_o.grad.flatten().double(), mine.clip_model.g(n_[len("clip_model."):]).cpu().flatten().double()
             if a.numel() > 1:
                 worst = min(worst, (torch.dot(a, c) / (a.norm() * c.norm() + 1e-30)).item())
             else:

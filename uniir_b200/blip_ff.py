@@ -5,8 +5,14 @@ blip_ff.py:11-332) on the B200-native kernels, and the
 Built: constructor / state-dict layout (online + momentum encoders, queues, temp: reference checkpoints load
 with a plain ``load_state_dict``), ``encode_multimodal_input``, ``forward(batch, encode_mbeir_batch=True)`` /
 ``encode_mbeir_batch``, and the momentum-distillation training step (``compute_contrastive_loss`` +
-``backward_contrastive``, driven by ``engine.train_step_blip``): EMA, queue, soft-label cross-entropy, gradient
-caching.  Not built: the hard-negative variant of the loss (blip_ff.py:127-131,160-171).
+``backward_contrastive``, driven by ``engine.train_step_blip`` / ``blip_engine.train_one_epoch``, or through
+autograd via ``autograd_bridge``): EMA, queue, soft-label cross-entropy, gradient caching, and the hard-negative variant
+of the loss (blip_ff.py:126-131,160-171,208-218,233-246).
+
+DELIBERATE DEVIATION: no dropout.  The reference trains this model in ``model.train()`` with BERT
+``hidden_dropout_prob`` / ``attention_probs_dropout_prob`` = 0.1 (med_config.json) and DropPath 0.1 in the large ViT;
+the hand-written forward / backward here applies neither, so training regularises differently (parity is stated and
+tested in eval mode).
 
 Arithmetic (vendored reference code, restated in oracle/blip_oracle.py and pinned against the shimmed
 reference modules): ViT-L/16 with biased patch-embed, pre-LN blocks (eps 1e-6), exact GELU, final norm, all

@@ -16,6 +16,8 @@ Arithmetic (restated in oracle/clip_ff_oracle.py, whose T5 stack is pinned again
   fusion  cat([text, image]) -> 2-layer T5 encoder (RMS norm, q/k/v/o without bias, unscaled scores + relative-
           position bias, ReLU FFN 768 -> 2048 -> 768) -> final RMS norm -> mean over the 334 tokens (:161-192);
           ``txt_mask`` / ``img_mask`` are accepted and ignored, exactly like the reference (:173-176).
+DELIBERATE DEVIATION: no dropout -- the reference's T5Stack trains with ``dropout_rate`` 0.1 (T5Config default); the
+hand-written T5 forward / backward here applies none (parity is stated and tested in eval mode).
 Kernels: the CLIP towers of clip_towers.py (tcgen05 GEMMs, tcgen05 / mma.sync attention, LayerNorm), plus
 ``uniir_rmsnorm_fwd``, ``uniir_attn_fwd_bias`` (S = 334 > the tcgen05 forward's window: mma.sync kernel with the bias
 added in score units), the ReLU GEMM epilogue and ``uniir_token_mean``.

@@ -340,8 +340,9 @@ __device__ __forceinline__ void bw_store32(__nv_bfloat16* dst, const uint32_t (&
                        pack2_bf16(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
 }
 
-// FOLD (opt-in, UNIIR_ATTN_BWD_FOLD=1; NOT yet run on hardware -- written after this round's GPU time was spent, the
-// default instantiation <8, false> is unchanged): two more warps compute the tail key column and the tail query
+// FOLD (opt-in diagnostic, UNIIR_ATTN_BWD_FOLD=1; run on a B200 in round 2: correct on every shape of
+// scripts/check_attn_bwd.py but 2.2x SLOWER than the default <8, false> + prep kernel -- 849 vs 382 us on the
+// ViT-L/14 shape -- so it is not the default): two more warps compute the tail key column and the tail query
 // row (257 = 2 x 128 + 1) from the operands already in shared memory, in registers, instead of the prep kernel's
 // second pass over Q / K / V / dO in HBM.  Only tail_k <= 1 and tail_q <= 1.
 template <int EW, bool FOLD = false>

@@ -20,13 +20,16 @@
 #include <float.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "gemm_sm100.cuh"
 #include "host_util.cuh"
 
 namespace uniir {
 
 constexpr int kSearchBN = 256;
-constexpr int kCap = 128;      // per-row candidate buffer (entries)
+constexpr int kCap = 128;      // per-row candidate buffer (entries) of the streaming kernels
+constexpr int kCapMax = 256;   // ... of the deferred-compaction experiment; the workspace is sized for it
 constexpr int kMaxK = 64;
 constexpr float kNegInf = -INFINITY;
 constexpr float kFaissNeg = -3.4028234663852886e38f;
@@ -135,7 +138,7 @@ __device__ __forceinline__ void warp_bitonic_desc(float (&key)[R], IdxT (&idx)[R
   }
 }
 
-template <int BN>
+template <int BN, int CAP = kCap, bool kSelect = false>
 struct SearchEpilogueT {
   const SearchParams& p;
   float* invc_s;  // [2][BN] in shared memory
@@ -146,7 +149,7 @@ struct SearchEpilogueT {
 
   long long slot_row0;  // first state row of the current (split, query tile) slot
 
-  __device__ __forceinline__ long long ws_base(int row) const { return (slot_row0 + row) * kCap; }
+  __device__ __forceinline__ long long ws_base(int row) const { return (slot_row0 + row) * CAP; }
 
   // Pick up the running top-k state of this query tile from whoever processed the previous chunk.
   __device__ __forceinline__ void item_begin(const WorkItem& w, int row) {
@@ -183,20 +186,70 @@ struct SearchEpilogueT {
       mask &= mask - 1;
       const long long base = ws_base(row0 + L);
       const int cntL = __shfl_sync(0xffffffffu, cnt, L);
-      float key[4];
-      int idx[4];
+      constexpr int R = CAP / 32;
+      float key[R];
+      int idx[R];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
+      for (int r = 0; r < R; ++r) {
         const int e = r * 32 + lane;
         const bool ok = e < cntL;
         // L2 loads: earlier chunks of this row were written by other SMs (L1 is not coherent)
         key[r] = ok ? __ldcg(p.ws_scores + base + e) : kNegInf;
         idx[r] = ok ? __ldcg(p.ws_idx + base + e) : 0x7fffffff;
       }
-      warp_bitonic_desc<4, int>(key, idx);
+      if constexpr (kSelect) {
+        // Mid-scan compaction by SELECTION: the exact k-th best value by an MSB-first radix select over the
+        // order-preserving integer image of the scores (32 rounds of R ballots), then every entry >= it is kept, in
+        // any order (the final compaction sorts).  ~3x cheaper than the bitonic sort of the same buffer and
+        // independent of its size, which is what makes a 256-entry buffer (5.7 instead of 13 compactions per row at
+        // k = 50) pay.  Ties beyond k stay (a superset of the exact top-k); a buffer that is mostly ties falls back
+        // to the sort so that it always shrinks.
+        if (!final && cntL >= p.k) {
+          uint32_t u[R];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const uint32_t b = __float_as_uint(key[r]);
+            u[r] = (r * 32 + lane < cntL) ? ((b & 0x80000000u) ? ~b : (b | 0x80000000u)) : 0u;
+          }
+          uint32_t prefix = 0;
+          int remaining = p.k;
+#pragma unroll 1
+          for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t trial = prefix | (1u << bit);
+            const uint32_t hi = 0xffffffffu << bit;
+            int c = 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) c += __popc(__ballot_sync(0xffffffffu, (u[r] & hi) == trial));
+            if (c >= remaining) prefix = trial; else remaining -= c;
+          }
+          int ge = 0;
+#pragma unroll
+          for (int r = 0; r < R; ++r) ge += __popc(__ballot_sync(0xffffffffu, u[r] >= prefix));
+          if (ge <= CAP / 2) {
+            int at = 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              const bool keep_it = u[r] >= prefix;
+              const uint32_t m = __ballot_sync(0xffffffffu, keep_it);
+              if (keep_it) {
+                const int pos = at + __popc(m & ((1u << lane) - 1u));
+                p.ws_scores[base + pos] = key[r];
+                p.ws_idx[base + pos] = idx[r];
+              }
+              at += __popc(m);
+            }
+            if (lane == L) {
+              cnt = ge;
+              thr = __uint_as_float((prefix & 0x80000000u) ? (prefix ^ 0x80000000u) : ~prefix);
+            }
+            continue;
+          }
+        }
+      }
+      warp_bitonic_desc<R, int>(key, idx);
       const int keep = min(cntL, p.k);
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
+      for (int r = 0; r < (kMaxK + 31) / 32; ++r) {
         const int e = r * 32 + lane;
         if (e < keep) {
           p.ws_scores[base + e] = key[r];
@@ -207,7 +260,7 @@ struct SearchEpilogueT {
       const int kr = (p.k - 1) >> 5, kl = (p.k - 1) & 31;
       float kth = kNegInf;
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
+      for (int r = 0; r < (kMaxK + 31) / 32; ++r) {
         const float v = __shfl_sync(0xffffffffu, key[r], kl);
         if (r == kr) kth = v;
       }
@@ -222,7 +275,7 @@ struct SearchEpilogueT {
           const long long ob = (q * p.splits + split) * p.k;
           const float qi = p.q_inv[q];
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
+          for (int r = 0; r < (kMaxK + 31) / 32; ++r) {
             const int e = r * 32 + lane;
             if (e < p.k) {
               p.part_scores[ob + e] = (e < keep) ? key[r] * qi : kFaissNeg;
@@ -237,7 +290,9 @@ struct SearchEpilogueT {
 
   // `staged`: the tile's BN inverse candidate norms already sit in shared memory (the caller prefetched them a
   // tile ahead); otherwise they are fetched here and published to the four epilogue warps with a named barrier.
-  template <bool kPipe = true>
+  // kDefer (experiment, off): the row buffer has room for a whole tile (cnt <= CAP - BN on entry), nothing is
+  // compacted inside the tile; the caller releases the accumulator first and then calls compact_deferred().
+  template <bool kPipe = true, bool kDefer = false>
   __device__ __forceinline__ void tile(const WorkItem& w, int n_blk, uint32_t tmem_acc, int row, int /*col_half*/,
                                        const float* staged = nullptr) {
     const float* invc = staged;
@@ -294,8 +349,10 @@ struct SearchEpilogueT {
           }
         }
       }
-      const uint32_t need = __ballot_sync(0xffffffffu, cnt > kCap - 32);
-      if (need) compact(need, row, false, w);
+      if constexpr (!kDefer) {
+        const uint32_t need = __ballot_sync(0xffffffffu, cnt > CAP - 32);
+        if (need) compact(need, row, false, w);
+      }
     };
     // two register buffers: the TMEM load of the next chunk is in flight while this one is processed
     static_assert((BN / 32) % 2 == 0, "chunks are processed in pairs");
@@ -321,6 +378,11 @@ struct SearchEpilogueT {
         chunk(c, r);
       }
     }
+  }
+
+  __device__ __forceinline__ void compact_deferred(const WorkItem& w, int row) {
+    const uint32_t need = __ballot_sync(0xffffffffu, cnt > CAP - BN);
+    if (need) compact(need, row, false, w);
   }
 
   __device__ __forceinline__ void item_end(const WorkItem& w, int row) {
@@ -401,7 +463,16 @@ constexpr int kTsInvBytes = 4 * 2 * kTsBN * static_cast<int>(sizeof(float));   /
 constexpr int kTsSmemBytes = kTsRingBytes + kTsASmemBytes + kTsBarBytes + kTsInvBytes + 1024;
 static_assert(kTsACols + 2 * kTsBN == 512, "TMEM budget: queries + two accumulators");
 static_assert(kTsSmemBytes <= 232448, "shared memory budget");
-using SearchEpilogueTs = SearchEpilogueT<kTsBN>;
+// Row buffers: 128 entries, compacted inside the tile when they fill.  The alternative -- 256-entry buffers that
+// always have room for a whole tile, compacted AFTER the accumulator is released (tile<.., kDefer = true> +
+// compact_deferred) -- was measured slower (k = 50, 0.7 M / 2.8 M / 5.6 M rows: 216 / 684 / 1331 ms against
+// 196 / 646 / 1309 ms; gpurun r2c13 vs r2c14): a bitonic sort of 256 costs 2.6x one of 128 and the double-buffered
+// accumulator does not hide it.  k = 1 runs the same launches in 158 / 585 / 1200 ms: the remaining cost of the
+// top-k is the sort-based compaction itself (~13 per row at k = 50); a selection-based one is the next step.
+constexpr bool kTsDeferCompaction = false;
+// Row buffers of the queries-on-chip kernel: 256 entries, compacted in the tile by selection (see compact()).
+using SearchEpilogueTs = SearchEpilogueT<kTsBN, kCapMax, true>;
+using SearchEpilogueTsSort = SearchEpilogueT<kTsBN, kCap, false>;     // UNIIR_SEARCH_SELECT=0: 128 entries, bitonic sort
 
 // One 128-candidate tile's MMAs.  kFull: d = 768 (12 k-blocks, 6 full stages): everything but the stage slot is a
 // compile-time constant, so each MMA costs the issuing thread two adds.
@@ -453,7 +524,7 @@ __device__ __forceinline__ void ts_issue_tile(uint32_t tmem_d, uint32_t tmem_a, 
   }
 }
 
-template <bool kPipe>
+template <bool kPipe, bool kSel = true>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(num_threads(4), 1)
 ip_topk_kernel_ts(const __grid_constant__ GemmTensorMaps maps, const __half* __restrict__ q, const int d,
                   const SearchParams p, const SearchSched sched, const uint32_t idesc) {
@@ -575,7 +646,7 @@ ip_topk_kernel_ts(const __grid_constant__ GemmTensorMaps maps, const __half* __r
     }
   } else {
     // ============================ query loader + epilogue (both CTAs) ================================
-    SearchEpilogueTs epi(p, invc_s);
+    typename std::conditional<kSel, SearchEpilogueTs, SearchEpilogueTsSort>::type epi(p, invc_s);
     const int quarter = warp_idx & 3;
     const int row = quarter * 32 + lane_id();
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
@@ -648,10 +719,11 @@ ip_topk_kernel_ts(const __grid_constant__ GemmTensorMaps maps, const __half* __r
         if (ti + 1 < n_tiles_item) fetch_inv(w.tile_at(ti + 1));
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
-        epi.template tile<kPipe>(w, n, tmem_d0 + lane_base + acc * kTsBN, row, 0, winv);
+        epi.template tile<kPipe, kTsDeferCompaction>(w, n, tmem_d0 + lane_base + acc * kTsBN, row, 0, winv);
         tc_fence_before();
         __syncwarp();
         if (lane_id() == 0) mbar_arrive_remote(acc ? te1 : te0);
+        if constexpr (kTsDeferCompaction) epi.compact_deferred(w, row);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -800,7 +872,7 @@ static void plan_splits(long long Q, long long N, int bn, int* splits, int* tile
 
 static size_t search_ws_bytes(int splits, int nq) {
   const size_t rows = static_cast<size_t>(splits) * nq * kBM;
-  return rows * kCap * (sizeof(float) + sizeof(int)) + rows * (sizeof(float) + sizeof(int)) +
+  return rows * kCapMax * (sizeof(float) + sizeof(int)) + rows * (sizeof(float) + sizeof(int)) +
          static_cast<size_t>(splits) * nq * sizeof(int) + 256;
 }
 
@@ -874,8 +946,8 @@ extern "C" int uniir_ip_topk(const void* q, const float* q_inv, const void* c, c
   if (const char* e = getenv("UNIIR_SEARCH_TPC")) { const int v = atoi(e); if (v >= 1) tpc = v; }
   p.n_chunks = (tps + tpc - 1) / tpc;
   p.ws_scores = static_cast<float*>(workspace);
-  p.ws_idx = reinterpret_cast<int*>(p.ws_scores + rows * kCap);
-  p.g_thr = reinterpret_cast<float*>(p.ws_idx + rows * kCap);
+  p.ws_idx = reinterpret_cast<int*>(p.ws_scores + rows * kCapMax);
+  p.g_thr = reinterpret_cast<float*>(p.ws_idx + rows * kCapMax);
   p.g_cnt = reinterpret_cast<int*>(p.g_thr + rows);
   p.done = p.g_cnt + rows;
   UNIIR_CUDA_OK(cudaMemsetAsync(p.done, 0, static_cast<size_t>(s) * nq * sizeof(int), stream));
@@ -889,9 +961,12 @@ extern "C" int uniir_ip_topk(const void* q, const float* q_inv, const void* c, c
   if (mode == 2) {
     static std::atomic<uint64_t> attr_ts{0};
     if (first_on_device(attr_ts)) {
-      UNIIR_CUDA_OK(cudaFuncSetAttribute(ip_topk_kernel_ts<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes));
-      UNIIR_CUDA_OK(cudaFuncSetAttribute(ip_topk_kernel_ts<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes));
+      UNIIR_CUDA_OK(cudaFuncSetAttribute(ip_topk_kernel_ts<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes));
+      UNIIR_CUDA_OK(cudaFuncSetAttribute(ip_topk_kernel_ts<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes));
+      UNIIR_CUDA_OK(cudaFuncSetAttribute(ip_topk_kernel_ts<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes));
     }
+    bool select = true;    // UNIIR_SEARCH_SELECT=0: the round-2a epilogue (128-entry buffers compacted by a bitonic sort)
+    if (const char* e = getenv("UNIIR_SEARCH_SELECT")) select = atoi(e) != 0;
     // Epilogue with double-buffered TMEM loads: measured SLOWER on the same box (1107 vs 1177 TFLOP/s at 512-tile
     // chunks, gpurun_out/r2c8_modes_full.txt; 183 vs 138 registers, twice the epilogue code) -> opt-in only.
     bool pipe = false;
@@ -900,8 +975,9 @@ extern "C" int uniir_ip_topk(const void* q, const float* q_inv, const void* c, c
     if (items < npairs) npairs = static_cast<int>(items);
     sched.n_workers = stagger ? npairs : 0;
     const uint32_t idesc = make_idesc_f16(false, false, false, 2 * kBM, kTsBN);
-    if (pipe) ip_topk_kernel_ts<true><<<2 * npairs, num_threads(4), kTsSmemBytes, stream>>>(maps, static_cast<const __half*>(q), d, p, sched, idesc);
-    else ip_topk_kernel_ts<false><<<2 * npairs, num_threads(4), kTsSmemBytes, stream>>>(maps, static_cast<const __half*>(q), d, p, sched, idesc);
+    if (!select) ip_topk_kernel_ts<false, false><<<2 * npairs, num_threads(4), kTsSmemBytes, stream>>>(maps, static_cast<const __half*>(q), d, p, sched, idesc);
+    else if (pipe) ip_topk_kernel_ts<true, true><<<2 * npairs, num_threads(4), kTsSmemBytes, stream>>>(maps, static_cast<const __half*>(q), d, p, sched, idesc);
+    else ip_topk_kernel_ts<false, true><<<2 * npairs, num_threads(4), kTsSmemBytes, stream>>>(maps, static_cast<const __half*>(q), d, p, sched, idesc);
   } else if (pairs) {
     using SM = GemmSmem2<kSearchBN>;
     const int smem_bytes = SM::kRingBytes + SM::kBarBytes + 2 * kSearchBN * sizeof(float) + 1024;
