@@ -152,3 +152,32 @@ def test_run_hard_negative_mining_end_to_end_with_injected_search(tmp_path):
         want = _ref_select([mr.unhash_did(x) for x in I[i]], entries[i]["pos_cand_list"], entries[i]["neg_cand_list"], 3)
         assert e["qid"] == entries[i]["qid"] and e["neg_cand_list"] == entries[i]["neg_cand_list"] + want
         assert len(want) == 3 and not set(want) & set(entries[i]["pos_cand_list"])
+
+
+def test_fp32_queries_are_cast_exactly_or_warned_about():
+    """search_index_with_batch takes fp32 and the kernel computes on fp16 -- exact for embeddings
+    that were stored as fp16 (every reference call site), a visible warning otherwise."""
+    import warnings
+    from uniir_b200.mbeir_retriever import _as_fp16_queries
+    q16 = np.random.default_rng(0).standard_normal((4, 8)).astype(np.float16)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        out = _as_fp16_queries(q16.astype(np.float32))          # fp16-representable: silent and exact
+    assert out.dtype == np.float16 and np.array_equal(out, q16)
+    with pytest.warns(UserWarning, match="not exactly representable"):
+        _as_fp16_queries(q16.astype(np.float32) + np.float32(1e-4))
+
+
+def test_word_hash_tokenizer_is_selected_by_env(monkeypatch):
+    import torch
+    from uniir_b200 import preprocess
+    monkeypatch.setenv("UNIIR_CLIP_BPE", "word-hash")
+    tok = preprocess.clip_tokenizer(context_length=77, vocab=512)
+    t = tok(["A dog.", "a dog. " + "word " * 100, ""])
+    assert t.shape == (3, 77) and t.dtype == torch.int32
+    assert t[0, 0] == 510 and t[0].max() == 511 and int((t[0] != 0).sum()) == 4       # SOT a dog. EOT
+    assert torch.equal(t[0, :3], t[1, :3]) and t[1, 76] == 511 and (t[1] != 0).all()   # truncated, EOT kept last
+    assert t[2, 0] == 510 and t[2, 1] == 511 and t[2, 2:].sum() == 0
+    monkeypatch.delenv("UNIIR_CLIP_BPE")
+    with pytest.raises(FileNotFoundError):
+        preprocess.clip_tokenizer()(["needs the BPE file"])

@@ -463,12 +463,12 @@ constexpr int kTsInvBytes = 4 * 2 * kTsBN * static_cast<int>(sizeof(float));   /
 constexpr int kTsSmemBytes = kTsRingBytes + kTsASmemBytes + kTsBarBytes + kTsInvBytes + 1024;
 static_assert(kTsACols + 2 * kTsBN == 512, "TMEM budget: queries + two accumulators");
 static_assert(kTsSmemBytes <= 232448, "shared memory budget");
-// Row buffers: 128 entries, compacted inside the tile when they fill.  The alternative -- 256-entry buffers that
-// always have room for a whole tile, compacted AFTER the accumulator is released (tile<.., kDefer = true> +
-// compact_deferred) -- was measured slower (k = 50, 0.7 M / 2.8 M / 5.6 M rows: 216 / 684 / 1331 ms against
-// 196 / 646 / 1309 ms; gpurun r2c13 vs r2c14): a bitonic sort of 256 costs 2.6x one of 128 and the double-buffered
-// accumulator does not hide it.  k = 1 runs the same launches in 158 / 585 / 1200 ms: the remaining cost of the
-// top-k is the sort-based compaction itself (~13 per row at k = 50); a selection-based one is the next step.
+// Row buffers and their compaction (k = 50; same launch with k = 1: 1173 / 159 ms at 5.6 M / 0.7 M rows):
+//   128 entries, bitonic sort in the tile (round-2a)                         1259 / 193 ms   (same box, r2c16)
+//   256 entries, exact radix SELECT in the tile (default)                    1241 / 185 ms
+//   256 entries, bitonic sort AFTER the accumulator release (kDefer)         slower than 128-in-tile (r2c14): a sort
+//                                                                            of 256 costs 2.6x one of 128 and the
+//                                                                            double-buffered accumulator does not hide it
 constexpr bool kTsDeferCompaction = false;
 // Row buffers of the queries-on-chip kernel: 256 entries, compacted in the tile by selection (see compact()).
 using SearchEpilogueTs = SearchEpilogueT<kTsBN, kCapMax, true>;
