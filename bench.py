@@ -732,10 +732,13 @@ def main():
             # cpu_baseline: configs[4] retrieval, configs[2] BLIP_FF training, configs[3] embedding extraction
             import copy
             ex = out["extra"] = {}
-            ex["retrieval"] = run_search(args, rank, world, dev, peaks, steps=2, warmup=3)
+            # (the sharded search and the extraction step get faster with N: more steps keep the timed region long
+            # enough for the 200 ms clock sampler)
+            ex["retrieval"] = run_search(args, rank, world, dev, peaks, steps=2 * world, warmup=3)
             a2 = copy.copy(args); a2.steps, a2.warmup = 2, 3
             ex["blip"] = run_train_blip(a2, rank, world, dev, peaks)
-            ex["embed"] = run_embed(a2, rank, world, dev, peaks)
+            a3 = copy.copy(args); a3.steps, a3.warmup = 8, 3
+            ex["embed"] = run_embed(a3, rank, world, dev, peaks)
         if cpu_ok:
             out["cpu_baseline"], _ = cpu_train_reference(CPU_STEPS, CPU_WARM)
             if "extra" in out:

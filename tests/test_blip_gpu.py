@@ -244,3 +244,23 @@ def test_blip_ff_hard_negative_variant_matches_oracle():
                     p_o -= 1e-2 * p_o.grad
                     m.get_parameter(n_).copy_(p_o)
     assert flips == {True, False}
+
+
+def test_med_config_file_is_read_and_checked(tmp_path):
+    """The reference builds its BERT from med_config.json (blip_ff.py:34-36); a file that disagrees with the built-in
+    dimensions must be refused, not ignored."""
+    import json
+    from uniir_b200.blip_ff import BLIP_CONFIGS, BLIPFeatureFusion
+    d = BLIP_CONFIGS["tiny-test"]
+    good = dict(hidden_size=d.t_width, num_hidden_layers=d.t_layers, num_attention_heads=d.t_heads,
+                intermediate_size=d.t_inter, vocab_size=d.vocab, max_position_embeddings=d.max_pos, hidden_act="gelu",
+                layer_norm_eps=1e-12, hidden_dropout_prob=0.1)
+    p = tmp_path / "med.json"
+    p.write_text(json.dumps(good))
+    BLIPFeatureFusion(med_config=str(p), vit="tiny-test", image_size=64, embed_dim=64, queue_size=16)
+    p.write_text(json.dumps(dict(good, num_hidden_layers=d.t_layers + 1)))
+    with pytest.raises(ValueError, match="does not match"):
+        BLIPFeatureFusion(med_config=str(p), vit="tiny-test", image_size=64, embed_dim=64, queue_size=16)
+    p.write_text(json.dumps(dict(good, hidden_act="relu")))
+    with pytest.raises(ValueError, match="hidden_act"):
+        BLIPFeatureFusion(med_config=str(p), vit="tiny-test", image_size=64, embed_dim=64, queue_size=16)

@@ -22,7 +22,9 @@ GELU FFN, then pooler tanh(W h[:,0] + b) (backbone/med.py:52-98,101-232,330-396,
 """
 from __future__ import annotations
 
+import json
 import math
+import os
 from dataclasses import dataclass
 
 import torch
@@ -467,6 +469,19 @@ class BLIPFeatureFusion(nn.Module):
             d = BLIPDims(**{**d.__dict__, "image_size": image_size})
         if isinstance(med_config, dict):   # the reference reads a BertConfig json; a dict is accepted for tests
             d = BLIPDims(**{**d.__dict__, **med_config})
+        elif isinstance(med_config, str) and os.path.isfile(med_config):
+            # The reference builds its BERT from this BertConfig json (blip_ff.py:34-36).  The kernels here are laid out
+            # for the dimensions of BLIPDims: read the file and refuse a configuration they would silently ignore.
+            with open(med_config) as f:
+                mc = json.load(f)
+            want = {"hidden_size": d.t_width, "num_hidden_layers": d.t_layers, "num_attention_heads": d.t_heads,
+                    "intermediate_size": d.t_inter, "vocab_size": d.vocab, "max_position_embeddings": d.max_pos}
+            bad = {k: (mc[k], v) for k, v in want.items() if k in mc and mc[k] != v}
+            if bad:
+                raise ValueError(f"med_config {med_config} does not match the built-in BERT dimensions "
+                                 f"(file value, built-in value): {bad}; pass the overrides as a dict")
+            if mc.get("hidden_act", "gelu") != "gelu" or abs(mc.get("layer_norm_eps", 1e-12) - 1e-12) > 1e-15:
+                raise ValueError("med_config: only hidden_act='gelu' and layer_norm_eps=1e-12 are implemented")
         self.dims, self.device_, self.micro_batch = d, dev, micro_batch
         self.image_size, self.queue_size, self.momentum, self.embed_dim, self.config = image_size, queue_size, momentum, embed_dim, config
         # online + momentum encoders as two flat parameter sets with identical layouts (EMA = one kernel)
