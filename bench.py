@@ -71,7 +71,7 @@ def gemm_roofline(sink_timed, iso_ms, iso_fl, peaks, step_ms, step_alg_tflops, t
             "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
             "peak_src": f"{peaks['src']}: sustained bf16 (launches timed in place inside the step)",
             "timing": "CUDA events around every GEMM launch of one eagerly executed micro-batch pass (embedding pass + "
-                      "re-forward + backward), scaled by the micro-batches per step",
+                      "re-forward + backward; both towers on one stream for this pass), scaled by the micro-batches per step",
             "isolated_achieved": iso, "isolated_peak": peaks["bf16_burst"], "isolated_frac": iso / peaks["bf16_burst"],
             "isolated_note": "same launches timed alone (5 back-to-back launches on warm operands) against the burst peak",
             "gemm_share_of_step": None, "traffic": traffic, "step_algorithmic_tflops": step_alg_tflops,
@@ -259,21 +259,26 @@ def run_reference(args, rank):
         return
     if args.workload == "embed":
         cb, dt = cpu_embed_reference(args.steps, args.warmup)
-        metric, unit, cfg = "embedded_items_per_sec", "items/s", {"workload": f"embedding extraction, CLIP_SF {MODEL} (BASELINE configs[3])"}
+        metric, unit = "embedded_items_per_sec", "items/s"
+        cfg = {"workload": f"embedding extraction, CLIP_SF {MODEL}, batch 2048/GPU (BASELINE configs[3] shape)",
+               "sampled": "8 items per step on the host cores"}
     elif args.workload == "search":
         cb, dt = cpu_search_reference(args.steps, args.warmup)
-        metric, unit, cfg = "queries_per_sec_top50", "queries/s", {"workload": "dense_retrieval_190k_x_5.6M_d768_fp16_top50"}
+        metric, unit = "queries_per_sec_top50", "queries/s"
+        cfg = {"workload": f"dense retrieval {SEARCH_Q} queries x {SEARCH_N} candidates, d={SEARCH_D} fp16, top-{SEARCH_K} (BASELINE configs[4])",
+               "sampled": "1024 queries x 500000 candidates per step, scaled linearly"}
     elif args.workload == "blip":
         cb, dt = cpu_blip_reference(args.steps, args.warmup, sf=args.blip_model == "sf")
         metric, unit = "contrastive_pairs_per_sec", "pairs/s"
-        cfg = {"workload": ("BLIP_SF" if args.blip_model == "sf" else "BLIP_FF")
-               + " ViT-L/16 + BERT-base momentum-distillation training step (BASELINE configs[2])",
-               "global_batch": BLIP_GLOBAL_BATCH}
+        cfg = {"workload": ("BLIP_SF ViT-L/16 + text-mode BERT-base momentum-distillation training step (SURVEY 8f-3; BASELINE configs[2] shape)"
+                            if args.blip_model == "sf" else
+                            "BLIP_FF ViT-L/16 + BERT-base momentum-distillation training step (BASELINE configs[2])"),
+               "global_batch": BLIP_GLOBAL_BATCH, "sampled": "2 pairs per step on the host cores"}
     else:
         cb, dt = cpu_train_reference(args.steps, args.warmup)
         metric, unit = "contrastive_pairs_per_sec", "pairs/s"
-        cfg = {"workload": f"CLIP_SF {MODEL} in-batch contrastive training step, global batch {GLOBAL_BATCH}",
-               "global_batch": GLOBAL_BATCH}
+        cfg = {"workload": f"CLIP_SF {MODEL} in-batch contrastive training step (BASELINE configs[1])",
+               "model": f"CLIP_SF {MODEL}", "global_batch": GLOBAL_BATCH, "sampled": "4 pairs per step on the host cores"}
     print(json.dumps({"impl": "reference", "metric": metric, "value": cb["value"], "unit": unit,
                       "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
                       "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -340,10 +345,12 @@ def run_train(args, rank, world, dev, peaks):
     from collections import Counter
     enc = model._enc[(model._train_mb, True)]
     sink = []
+    enc.serial_towers = True          # one stream: a timed GEMM does not share the SMs with the other tower's kernels
     ops.set_gemm_profiler(sink, events=True)
     enc._body_embed()
     enc._body_fwdbwd()
     ops.set_gemm_profiler(None)
+    enc.serial_towers = False
     torch.cuda.synchronize()
     for gbuf in model.clip_model.grad.values():
         gbuf.zero_()
@@ -520,8 +527,8 @@ def run_embed(args, rank, world, dev, peaks):
     return {"metric": "embedded_items_per_sec", "value": items / (ms / 1e3), "unit": "items/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"embedding extraction, CLIP_SF {MODEL}, batch {B}/GPU (BASELINE configs[3] shape; "
-                                   f"5.6M items = {5.6e6 / (items / (ms / 1e3)):.0f} s at this rate)", "micro_batch_items": 256},
+            "config": {"workload": f"embedding extraction, CLIP_SF {MODEL}, batch {B}/GPU (BASELINE configs[3] shape)",
+                       "note": f"5.6M items = {5.6e6 / (items / (ms / 1e3)):.0f} s at this rate", "micro_batch_items": 256},
             "clocks": clocks, "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": alg, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": alg / peaks["bf16_sustained"], "traffic": None,

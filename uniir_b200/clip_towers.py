@@ -215,15 +215,22 @@ class CLIPEncoder:
     # ---- the two towers are independent until score fusion: the text tower runs on a side
     # stream (fork/join with events; captured as parallel branches of the CUDA graph) so its
     # small GEMMs fill the SMs the vision kernels leave idle ------------------------------------
+    serial_towers = False   # diagnostics (bench roofline pass): run the text tower on the main stream too, so that a
+    #                         kernel timed with events in its place in the step is not sharing the SMs with the other tower
+
     def _fork(self):
-        if self._side is None:
-            self._side = torch.cuda.Stream(device=self.dev)
         main = torch.cuda.current_stream()
+        if self.serial_towers:
+            self._side = main
+            return main
+        if self._side is None or self._side is main:
+            self._side = torch.cuda.Stream(device=self.dev)
         self._side.wait_stream(main)
         return main
 
     def _join(self, main):
-        main.wait_stream(self._side)
+        if self._side is not main:
+            main.wait_stream(self._side)
 
     def _vision_fwd(self, img, save):
         P, d, mb = self.P, self.d, self.mb
