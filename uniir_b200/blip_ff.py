@@ -23,7 +23,6 @@ GELU FFN, then pooler tanh(W h[:,0] + b) (backbone/med.py:52-98,101-232,330-396,
 from __future__ import annotations
 
 import json
-import math
 import os
 from dataclasses import dataclass
 
