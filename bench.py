@@ -578,6 +578,9 @@ def run_train_blip(args, rank, world, dev, peaks):
     model = (BLIPScoreFusion if sf else BLIPFeatureFusion)(vit="large", image_size=224, embed_dim=768, queue_size=57344,
                                                            device=dev, micro_batch=256)
     model.train_micro_batch = args.blip_micro_batch
+    model.train()                       # as uniir_blip/engine.py:16: dropout 0.1 / 0.1 in the BERT, DropPath 0.1 in the ViT-L
+    if args.blip_no_dropout:
+        model.set_dropout(0.0, 0.0, 0.0)
     opt = FlatAdamW(model._online, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05)
     batch = synth_blip_batch(model.dims, pairs, 2023 + rank, dev)
     state = {}
@@ -637,7 +640,10 @@ def run_train_blip(args, rank, world, dev, peaks):
                       "model": "BLIP_SF large" if sf else "BLIP_FF large", "global_batch": BLIP_GLOBAL_BATCH, "pairs_per_gpu": pairs, "queue_size": 57344,
                       "seq_len": "197 vision tokens + 100 text tokens per item, 2 items per pair", "micro_batch_items": model.train_micro_batch,
                       "parallelism": f"dp{world}", "grad_cache": "embedding-level (1 extra online forward + momentum forward, not credited)",
-                      "l2": "inputs+weights+activations per step >> 126 MB L2 (no flush needed)"},
+                      "l2": "inputs+weights+activations per step >> 126 MB L2 (no flush needed)",
+                      "dropout": (f"train mode as the reference: hidden {model.hidden_dropout_prob} / attention "
+                                  f"{model.attention_probs_dropout_prob} in the BERT stack, DropPath {model.drop_path_rate} in the ViT "
+                                  "(online and momentum encoders; counter-based masks regenerated in the re-forward)")},
            "clocks": clocks, "gpu_launches": launches, "roofline": roof,
            "e2e": {"value": BLIP_GLOBAL_BATCH / (ms_e2e / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": h2d * world,
                    "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e},
@@ -686,6 +692,7 @@ def main():
     ap.add_argument("--workload", default="train", choices=["train", "search", "embed", "blip"])
     ap.add_argument("--blip-micro-batch", type=int, default=64)
     ap.add_argument("--blip-model", default="ff", choices=["ff", "sf"], help="--workload blip: BLIP_FF (configs[2]) or BLIP_SF")
+    ap.add_argument("--blip-no-dropout", action="store_true", help="--workload blip: train step without the reference's dropout / DropPath (A/B only)")
     ap.add_argument("--micro-batch", type=int, default=128, help="encoder items per micro-batch")
     ap.add_argument("--no-extra", action="store_true", help="skip the attached retrieval measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -72,6 +72,9 @@ typedef struct uniir_gemm_desc {
   float alpha;
   int32_t accumulate;               /* out += value (out_dtype must be F32) */
   int32_t split_k;                  /* >1: split contraction, atomic fp32 accumulate */
+  const float* row_scale;           /* optional fp32 [ceil(M / row_scale_rows)]: (alpha*AB + bias) is multiplied by   */
+  int32_t row_scale_rows;           /* row_scale[row / row_scale_rows] after the activation and before the residual   */
+                                    /* is added: per-item DropPath of a residual branch (vit.py:151-152, timm)        */
 } uniir_gemm_desc;
 int uniir_gemm_epi(const uniir_gemm_desc* d, void* stream);
 
@@ -280,6 +283,50 @@ int uniir_sgemm_temp(const float* A, const float* B, int32_t b_kn, int32_t M, in
 int uniir_blip_softce(float* S, const float* Sm, const int64_t* pc_id, const int64_t* id_all, int32_t bs, int32_t n,
                       float alpha, float gscale, const float* temp, float* loss_sum, float* acc_sum, float* d_temp,
                       void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Dropout / stochastic depth of the reference's training arms: BERT "MED" hidden dropout and attention-probability
+ * dropout (uniir_blip/backbone/med.py:63,97 embeddings; :123,217 attention probabilities; :240,244 and :321,325 the
+ * dense outputs; config hidden_dropout_prob = attention_probs_dropout_prob = 0.1), timm DropPath of the ViT-L blocks
+ * (backbone/vit.py:136,151-152,217; blip.py:253 drop_path_rate 0.1) and the T5 fusion stack of CLIP_FF
+ * (clip_ff.py:82-98, T5Config dropout_rate 0.1).  torch draws these masks from its stateful Philox stream; here a
+ * mask is a pure function of (ctx[0] = seed of the step, site, element index within the WHOLE batch):
+ *     keep = mix32(idx ^ mix32(seed + site * 0x9E3779B1)) >= floor(p * 2^32)
+ * with mix32 the 32-bit finaliser x^=x>>16; x*=0x7feb352d; x^=x>>15; x*=0x846ca68b; x^=x>>16 and
+ * idx = ctx[1] * per_item + i (mod 2^32), ctx[1] = index of this micro-batch's first item in the batch.  Nothing is
+ * saved: the gradient-cache re-forward and the backward regenerate the same bits under any micro-batch tiling, and
+ * a captured CUDA graph replays with a new seed because ctx (uint32[2]) is device memory.
+ * ---------------------------------------------------------------------------------- */
+/* out[i] = (keep(i) ? x[i] / (1 - p) : 0) + (residual ? residual[i] : 0), i < n; x / out fp32 or bf16 (UNIIR_F32 /
+ * UNIIR_BF16), residual fp32; out may alias x or residual.  Forward: the dense output before the residual + LayerNorm;
+ * backward: the same call on the gradient (no residual). */
+int uniir_dropout(const void* x, int32_t x_dtype, const float* residual, void* out, int32_t out_dtype, int64_t n,
+                  const uint32_t* ctx, uint32_t site, int64_t per_item, float p, void* stream);
+/* keep[i] (uint8, 1 = kept) of the same mask: what the tests and an external checker read. */
+int uniir_dropout_mask(const uint32_t* ctx, uint32_t site, int64_t per_item, int64_t n, float p, uint8_t* keep,
+                       void* stream);
+/* DropPath: scales[s * mb + b] = keep ? 1 / (1 - p_sites[s]) : 0 for site site_base + s and batch item ctx[1] + b
+ * (one draw per sample and residual branch, timm scale_by_keep).  p_sites: device fp32 [n_sites]. */
+int uniir_droppath_scales(const uint32_t* ctx, uint32_t site_base, int32_t n_sites, int32_t mb, const float* p_sites,
+                          float* scales, void* stream);
+/* x[r, :] *= scales[r / rows_per_scale], bf16 in place: the branch gradient under DropPath. */
+int uniir_row_scale(void* x_bf16, int64_t rows, int32_t cols, int64_t ld, const float* scales, int32_t rows_per_scale,
+                    void* stream);
+/* softmax(scale * QK^T [+ bias] [key-padding / causal mask]) with dropout on the probabilities, then V: element
+ * (b, h, q, key) of the batch-wide [items, H, Sq, Skv] tensor is element ((ctx[1] + b) * H + h) * Sq * Skv + q * Skv + key
+ * of site `site`.  Addressing as uniir_attn_fwd_ex; bias (fp32 [H, Sq, Skv]) may be NULL; lse is that of the undropped
+ * softmax.  mma.sync head-resident kernels (Skv <= 768). */
+int uniir_attn_fwd_drop(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, int32_t B, int32_t Sq,
+                        int32_t Skv, int32_t H, int32_t causal, const int32_t* kv_len, float scale, const float* bias,
+                        void* out, int64_t ldo, float* lse, const uint32_t* drop_ctx, uint32_t site, float p_drop,
+                        void* stream);
+/* Backward of uniir_attn_fwd_drop with the same (ctx, site, p); dbias as uniir_attn_bwd_bias (NULL iff bias is NULL);
+ * delta_ws: B * H * Sq floats. */
+int uniir_attn_bwd_drop(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const void* out,
+                        int64_t ldo, const void* dout, int64_t lddo, const float* lse, int32_t B, int32_t Sq, int32_t Skv,
+                        int32_t H, int32_t causal, const int32_t* kv_len, float scale, const float* bias, float* dbias,
+                        float* delta_ws, void* dq, int64_t lddq, void* dk, void* dv, int64_t lddkv,
+                        const uint32_t* drop_ctx, uint32_t site, float p_drop, void* stream);
 
 #ifdef __cplusplus
 }

@@ -45,6 +45,22 @@ class BLIPDims:
         return (self.image_size // self.patch) ** 2 + 1
 
 
+# Dropout sites of the reference in train mode: med.py:97 (embeddings, after the LayerNorm), :217 (attention
+# probabilities, self and cross), :244 and :325 (dense outputs, before the residual + LayerNorm), vit.py:151-152 (timm
+# DropPath on both residual branches; rate linspace(0, 0.1, depth)[layer] for ViT-L, 0 for ViT-B: blip.py:241,253).
+# The restatement is the eval-mode arithmetic (identity at every site) unless a test installs DROPOUT, a callable
+# (tag, kind, layer, x) -> x with tag "" / "_m" (online / momentum encoders) and kind one of "emb", "self_probs",
+# "self_out", "cross_probs", "cross_out", "ffn_out", "path_attn", "path_mlp": the masks then come from the caller
+# (the reference's own come from torch's RNG stream; tests/test_oracle_blip.py pins the SITES against the reference's
+# modules by handing both the same masks).
+DROPOUT = None
+_CTX = {"tag": "", "layer": 0}
+
+
+def _drop(kind, x):
+    return x if DROPOUT is None else DROPOUT(_CTX["tag"], kind, _CTX["layer"], x)
+
+
 BLIP_CONFIGS = {
     "large": BLIPDims(),                                                       # blip.py:247-253
     "base": BLIPDims(v_width=768, v_layers=12, v_heads=12),                    # blip.py:235-245
@@ -86,8 +102,8 @@ class _VitBlock(nn.Module):
         self.mlp = _VitMlp(dim)
 
     def forward(self, x):
-        x = x + self.attn(self.norm1(x))
-        return x + self.mlp(self.norm2(x))
+        x = x + _drop("path_attn", self.attn(self.norm1(x)))
+        return x + _drop("path_mlp", self.mlp(self.norm2(x)))
 
 
 class _PatchEmbed(nn.Module):
@@ -108,7 +124,8 @@ class BLIPViTOracle(nn.Module):
     def forward(self, img):
         x = self.patch_embed.proj(img).flatten(2).transpose(1, 2)
         x = torch.cat([self.cls_token.expand(x.shape[0], -1, -1), x], 1) + self.pos_embed[:, :x.shape[1] + 1]
-        for b in self.blocks:
+        for i, b in enumerate(self.blocks):
+            _CTX["layer"] = i
             x = b(x)
         return self.norm(x)
 
@@ -121,7 +138,7 @@ class _SelfAttn(nn.Module):
         self.key = nn.Linear(kv_width, hidden)
         self.value = nn.Linear(kv_width, hidden)
 
-    def forward(self, h, kv, add_mask):
+    def forward(self, h, kv, add_mask, kind="self"):
         B, S, D = h.shape
         H = self.heads
         sp = lambda t: t.view(B, -1, H, D // H).permute(0, 2, 1, 3)
@@ -129,7 +146,7 @@ class _SelfAttn(nn.Module):
         s = q @ k.transpose(-1, -2) / math.sqrt(D // H)
         if add_mask is not None:
             s = s + add_mask
-        return (s.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(B, S, D)
+        return (_drop(kind + "_probs", s.softmax(-1)) @ v).permute(0, 2, 1, 3).reshape(B, S, D)
 
 
 class _AttnOut(nn.Module):
@@ -138,8 +155,8 @@ class _AttnOut(nn.Module):
         self.dense = nn.Linear(hidden, hidden)
         self.LayerNorm = nn.LayerNorm(hidden, eps=1e-12)
 
-    def forward(self, ctx, inp):
-        return self.LayerNorm(self.dense(ctx) + inp)
+    def forward(self, ctx, inp, kind="self"):
+        return self.LayerNorm(_drop(kind + "_out", self.dense(ctx)) + inp)
 
 
 class _BertAttention(nn.Module):
@@ -148,8 +165,8 @@ class _BertAttention(nn.Module):
         self.self = _SelfAttn(hidden, heads, kv_width)
         self.output = _AttnOut(hidden)
 
-    def forward(self, h, kv, mask):
-        return self.output(self.self(h, kv, mask), h)
+    def forward(self, h, kv, mask, kind="self"):
+        return self.output(self.self(h, kv, mask, kind), h, kind)
 
 
 class _Dense(nn.Module):
@@ -176,8 +193,8 @@ class _BertLayer(nn.Module):
     def forward(self, h, mask, enc, enc_mask):
         a = self.attention(h, h, mask)
         if enc is not None:          # mode="multimodal"; mode="text" skips the cross-attention (med.py:368-383)
-            a = self.crossattention(a, enc, enc_mask)
-        return self.output.LayerNorm(self.output.dense(F.gelu(self.intermediate.dense(a))) + a)
+            a = self.crossattention(a, enc, enc_mask, "cross")
+        return self.output.LayerNorm(_drop("ffn_out", self.output.dense(F.gelu(self.intermediate.dense(a)))) + a)
 
 
 class _Embeddings(nn.Module):
@@ -190,7 +207,7 @@ class _Embeddings(nn.Module):
 
     def forward(self, ids):
         S = ids.shape[1]
-        return self.LayerNorm(self.word_embeddings(ids) + self.position_embeddings(self.position_ids[:, :S]))
+        return _drop("emb", self.LayerNorm(self.word_embeddings(ids) + self.position_embeddings(self.position_ids[:, :S])))
 
 
 class _Encoder(nn.Module):
@@ -210,8 +227,10 @@ class BLIPBertOracle(nn.Module):
     def hidden(self, input_ids, attention_mask, encoder_hidden_states=None):
         """last_hidden_state; encoder_hidden_states=None is the reference's mode="text" (no cross-attention)."""
         mask = (1.0 - attention_mask[:, None, None, :].float()) * -10000.0        # med.py:687-688
+        _CTX["layer"] = 0
         h = self.embeddings(input_ids.long())
-        for lyr in self.encoder.layer:
+        for i, lyr in enumerate(self.encoder.layer):
+            _CTX["layer"] = i
             h = lyr(h, mask, encoder_hidden_states, None)   # image mask is all ones (blip_ff.py:107)
         return h
 
@@ -275,6 +294,7 @@ class BLIPFeatureFusionOracle(nn.Module):
 
     def encode_multimodal_input(self, input_ids, attention_mask, image, txt_mask=None, img_mask=None, use_momentum=False):
         v, t = (self.visual_encoder_m, self.text_encoder_m) if use_momentum else (self.visual_encoder, self.text_encoder)
+        _CTX["tag"] = "_m" if use_momentum else ""
         return t(input_ids, attention_mask, v(image.float()))
 
     def compute_contrastive_loss(self, batch, alpha):
@@ -374,6 +394,7 @@ class BLIPScoreFusionOracle(BLIPFeatureFusionOracle):
     def encode_multimodal_input(self, input_ids, attention_mask, image, txt_mask=None, img_mask=None, use_momentum=False):
         v, vp, t, tp = ((self.visual_encoder_m, self.vision_proj_m, self.text_encoder_m, self.text_proj_m) if use_momentum
                         else (self.visual_encoder, self.vision_proj, self.text_encoder, self.text_proj))
+        _CTX["tag"] = "_m" if use_momentum else ""
         txt = tp(t.hidden(input_ids, attention_mask)[:, 0, :]) * txt_mask.unsqueeze(-1)        # blip_sf.py:97-121,168
         img = vp(v(image.float())[:, 0, :]) * img_mask.unsqueeze(-1)                           # :123-143,169
         return img + txt                                                                       # :145-156

@@ -8,6 +8,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+# BertConfig overrides that switch the train-mode dropout off, as the reference pin tests do (tests/test_oracle_blip.py):
+# the oracle and the golden vectors are the deterministic (eval-mode) arithmetic
+NO_DROP = {"hidden_dropout_prob": 0.0, "attention_probs_dropout_prob": 0.0}
 
 
 def pytest_configure(config):

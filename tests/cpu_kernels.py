@@ -31,13 +31,45 @@ def _act_grad(x, act, L):
     return torch.ones_like(x)
 
 
+# ---- counter-based dropout masks (include/uniir_b200.h, csrc/dropout.cuh), restated with int64 arithmetic ------------
+_M32 = 0xFFFFFFFF
+
+
+def mix32(x):
+    x = x & _M32
+    x = x ^ (x >> 16); x = (x * 0x7feb352d) & _M32
+    x = x ^ (x >> 15); x = (x * 0x846ca68b) & _M32
+    return x ^ (x >> 16)
+
+
+def drop_thresh(p):
+    import numpy as np
+    t = float(np.float32(p)) * 4294967296.0
+    return 0xFFFFFFFF if t >= 4294967295.0 else max(0, int(t))
+
+
+def drop_scale(p):
+    import numpy as np
+    return float(np.float32(1.0) / (np.float32(1.0) - np.float32(p)))
+
+
+def keep_mask(seed, site, idx, p):
+    """idx: int64 tensor of element indices within the whole batch (taken mod 2^32) -> bool keep."""
+    key = mix32(torch.tensor((int(seed) + int(site) * 0x9E3779B1) & _M32, dtype=torch.int64))
+    return mix32((idx & _M32) ^ key) >= drop_thresh(p)
+
+
+def _ctx(ctx):
+    return int(ctx[0]) & _M32, int(ctx[1]) & _M32
+
+
 def install(monkeypatch):
     from uniir_b200 import lib as L
     from uniir_b200 import ops
 
     def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=None, act=L.ACT_NONE, residual=None,
-             aux_out=None, act_grad_src=None, alpha=1.0, accumulate=False, split_k=1):
-        # epilogue order of gemm_kernel.cuh: scale / bias / (aux copy) / act | act-grad / residual / accumulate / store
+             aux_out=None, act_grad_src=None, alpha=1.0, accumulate=False, split_k=1, row_scale=None, row_scale_rows=1):
+        # epilogue order of gemm_kernel.cuh: scale / bias / (aux copy) / act | act-grad / row scale / residual / accumulate / store
         A = a.float().t() if a_mn else a.float()
         Bm = b.float() if b_mn else b.float().t()
         y = alpha * (A @ Bm)
@@ -49,6 +81,8 @@ def install(monkeypatch):
             y = y * _act_grad(act_grad_src.float(), act, L)
         else:
             y = _act(y, act, L)
+        if row_scale is not None:
+            y = y * row_scale[torch.arange(y.shape[0]) // row_scale_rows][:, None]
         if residual is not None:
             y = y + residual.float()
         if out is None:
@@ -111,9 +145,21 @@ def install(monkeypatch):
             s = s.masked_fill(torch.arange(Skv)[None, None, None, :] >= kv_len.long()[:, None, None, None], float("-inf"))
         return s
 
-    def _attn_fwd(q, k, v, B, Sq, Skv, H, scale, causal, kv_len, out, lse, bias=None):
+    def _prob_mask(drop, B, Sq, Skv, H):
+        """mask / (1 - p) over [B, H, Sq, Skv]: element ((item0 + b) * H + h) * Sq * Skv + q * Skv + key of `site`."""
+        if drop is None:
+            return None
+        ctx, site, p = drop
+        seed, item0 = _ctx(ctx)
+        idx = torch.arange(B * H * Sq * Skv, dtype=torch.int64) + item0 * H * Sq * Skv
+        return keep_mask(seed, site, idx, p).view(B, H, Sq, Skv).float() * drop_scale(p)
+
+    def _attn_fwd(q, k, v, B, Sq, Skv, H, scale, causal, kv_len, out, lse, bias=None, drop=None):
         s = _scores(q, k, B, Sq, Skv, H, scale, causal, kv_len, bias)
-        y = (s.softmax(-1) @ _split(v, B, Skv, H)).transpose(1, 2).reshape(B * Sq, H * 64)
+        pr = s.softmax(-1)
+        if drop is not None:
+            pr = pr * _prob_mask(drop, B, Sq, Skv, H)
+        y = (pr @ _split(v, B, Skv, H)).transpose(1, 2).reshape(B * Sq, H * 64)
         if out is None:
             out = torch.empty(B * Sq, H * 64, dtype=torch.bfloat16)
         out.copy_(y)
@@ -121,10 +167,13 @@ def install(monkeypatch):
             lse.copy_(torch.logsumexp(s, -1))
         return out
 
-    def _attn_bwd(q, k, v, dout, B, Sq, Skv, H, scale, causal, kv_len):
+    def _attn_bwd(q, k, v, dout, B, Sq, Skv, H, scale, causal, kv_len, drop=None):
         qf, kf, vf = (t.float().detach().clone().requires_grad_(True) for t in (q, k, v))
         s = _scores(qf, kf, B, Sq, Skv, H, scale, causal, kv_len)
-        y = (s.softmax(-1) @ _split(vf, B, Skv, H)).transpose(1, 2).reshape(B * Sq, H * 64)
+        pr = s.softmax(-1)
+        if drop is not None:
+            pr = pr * _prob_mask(drop, B, Sq, Skv, H)
+        y = (pr @ _split(vf, B, Skv, H)).transpose(1, 2).reshape(B * Sq, H * 64)
         y.backward(dout.float())
         return qf.grad, kf.grad, vf.grad
 
@@ -134,11 +183,11 @@ def install(monkeypatch):
             lse = torch.empty(B, H, S)
         return _attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B, S, S, H, 0.125, causal, None, out, lse), lse
 
-    def attn_fwd_ex(q, k, v, B, Sq, Skv, H, *, causal=False, kv_len=None, out=None, lse=None):
-        return _attn_fwd(q, k, v, B, Sq, Skv, H, 0.125, causal, kv_len, out, lse)
+    def attn_fwd_ex(q, k, v, B, Sq, Skv, H, *, causal=False, kv_len=None, out=None, lse=None, drop=None):
+        return _attn_fwd(q, k, v, B, Sq, Skv, H, 0.125, causal, kv_len, out, lse, drop=drop)
 
-    def attn_fwd_bias(q, k, v, B, Sq, Skv, H, bias, scale=1.0, out=None, lse=None):
-        return _attn_fwd(q, k, v, B, Sq, Skv, H, scale, False, None, out, lse, bias)
+    def attn_fwd_bias(q, k, v, B, Sq, Skv, H, bias, scale=1.0, out=None, lse=None, drop=None):
+        return _attn_fwd(q, k, v, B, Sq, Skv, H, scale, False, None, out, lse, bias, drop=drop)
 
     def attn_bwd(qkv, out, dout, lse, B, S, H, causal, dqkv=None, delta=None):
         D = H * 64
@@ -148,8 +197,8 @@ def install(monkeypatch):
         dqkv[:, :D] = dq.to(dqkv.dtype); dqkv[:, D:2 * D] = dk.to(dqkv.dtype); dqkv[:, 2 * D:] = dv.to(dqkv.dtype)
         return dqkv
 
-    def attn_bwd_ex(q, k, v, out, dout, lse, B, Sq, Skv, H, dq, dk, dv, *, causal=False, kv_len=None, delta=None):
-        a, b_, c = _attn_bwd(q, k, v, dout, B, Sq, Skv, H, 0.125, causal, kv_len)
+    def attn_bwd_ex(q, k, v, out, dout, lse, B, Sq, Skv, H, dq, dk, dv, *, causal=False, kv_len=None, delta=None, drop=None):
+        a, b_, c = _attn_bwd(q, k, v, dout, B, Sq, Skv, H, 0.125, causal, kv_len, drop=drop)
         dq.copy_(a); dk.copy_(b_); dv.copy_(c)
 
     def attn_bwd_ws_floats(B, Sq, Skv, H):
@@ -177,11 +226,14 @@ def install(monkeypatch):
         out.view(B, S, D).copy_((d_out / S)[:, None, :].expand(B, S, D))
         return out
 
-    def attn_bwd_bias(q, k, v, out, dout, lse, B, Sq, Skv, H, bias, dbias, dq, dk, dv, scale=1.0, delta=None):
+    def attn_bwd_bias(q, k, v, out, dout, lse, B, Sq, Skv, H, bias, dbias, dq, dk, dv, scale=1.0, delta=None, drop=None):
         qf, kf, vf = (t.float().detach().clone().requires_grad_(True) for t in (q, k, v))
         bf = bias.detach().clone().requires_grad_(True)
         s = _scores(qf, kf, B, Sq, Skv, H, scale, False, None, bf)
-        y = (s.softmax(-1) @ _split(vf, B, Skv, H)).transpose(1, 2).reshape(B * Sq, H * 64)
+        pr = s.softmax(-1)
+        if drop is not None:
+            pr = pr * _prob_mask(drop, B, Sq, Skv, H)
+        y = (pr @ _split(vf, B, Skv, H)).transpose(1, 2).reshape(B * Sq, H * 64)
         y.backward(dout.float())
         dq.copy_(qf.grad); dk.copy_(kf.grad); dv.copy_(vf.grad)
         dbias.add_(bf.grad)
@@ -258,6 +310,36 @@ def install(monkeypatch):
     def tanh_bwd(dy, y, out):
         out.copy_(dy * (1 - y * y))
 
+    def drop_ctx(device):
+        return torch.zeros(2, dtype=torch.int32)
+
+    def dropout(x, ctx, site, per_item, p, *, residual=None, out=None):
+        out = x if out is None else out
+        seed, item0 = _ctx(ctx)
+        idx = torch.arange(x.numel(), dtype=torch.int64) + item0 * per_item
+        y = torch.where(keep_mask(seed, site, idx, p).view(x.shape), x.float() * drop_scale(p), torch.zeros(()))
+        if residual is not None:
+            y = y + residual.view(x.shape)
+        out.copy_(y.view(out.shape))
+        return out
+
+    def dropout_mask(ctx, site, per_item, n, p):
+        seed, item0 = _ctx(ctx)
+        return keep_mask(seed, site, torch.arange(n, dtype=torch.int64) + item0 * per_item, p).to(torch.uint8)
+
+    def droppath_scales(ctx, site_base, p_sites, mb, out=None):
+        seed, item0 = _ctx(ctx)
+        rows = []
+        for s_, p in enumerate(p_sites.tolist()):
+            keep = keep_mask(seed, site_base + s_, torch.arange(mb, dtype=torch.int64) + item0, p)
+            rows.append(keep.float() * drop_scale(p))
+        y = torch.stack(rows)
+        return y if out is None else out.copy_(y)
+
+    def row_scale(x, scales, rows_per_scale):
+        x.copy_(x.float() * scales[torch.arange(x.shape[0]) // rows_per_scale][:, None])
+        return x
+
     fns = dict(gemm=gemm, wgrad=wgrad, colsum_accum=colsum_accum, layernorm_fwd=layernorm_fwd, layernorm_bwd=layernorm_bwd,
                attn_fwd=attn_fwd, attn_fwd_ex=attn_fwd_ex, attn_fwd_bias=attn_fwd_bias, attn_bwd=attn_bwd,
                attn_bwd_ex=attn_bwd_ex, attn_bwd_ws_floats=attn_bwd_ws_floats, rmsnorm_fwd=rmsnorm_fwd,
@@ -265,6 +347,8 @@ def install(monkeypatch):
                token_mean=token_mean, patch_im2col=patch_im2col, vision_embed_fwd=vision_embed_fwd,
                vision_embed_bwd=vision_embed_bwd, text_embed_fwd=text_embed_fwd, text_embed_bwd=text_embed_bwd,
                score_fuse_fwd=score_fuse_fwd, score_fuse_bwd=score_fuse_bwd, pad_cast_bf16=pad_cast_bf16,
-               unpad_accum=unpad_accum, cast_bf16=cast_bf16, tanh_bwd=tanh_bwd, adamw_step=adamw_step)
+               unpad_accum=unpad_accum, cast_bf16=cast_bf16, tanh_bwd=tanh_bwd, adamw_step=adamw_step,
+               drop_ctx=drop_ctx, dropout=dropout, dropout_mask=dropout_mask, droppath_scales=droppath_scales,
+               row_scale=row_scale)
     for name, fn in fns.items():
         monkeypatch.setattr(ops, name, fn)

@@ -41,11 +41,26 @@ def load():
             return self.proj(x).flatten(2).transpose(1, 2)
 
     class DropPath(nn.Module):
-        def __init__(self, p=0.0):
+        """timm.models.layers.DropPath (timm is a third-party dependency of the reference, not in this image; the
+        reference's env pins timm 0.4.12), restated from its published source: per-sample stochastic depth,
+        `x.div(keep_prob) * floor(keep_prob + rand(B, 1, ..))`, identity in eval mode or at drop_prob 0.
+        `mask_fn` (class attribute, None = torch's RNG) lets a test supply the per-sample keep decisions."""
+        mask_fn = None
+
+        def __init__(self, drop_prob=0.0):
             super().__init__()
+            self.drop_prob = drop_prob
 
         def forward(self, x):
-            return x
+            if self.drop_prob == 0.0 or not self.training:
+                return x
+            keep_prob = 1 - self.drop_prob
+            shape = (x.shape[0],) + (1,) * (x.ndim - 1)
+            if DropPath.mask_fn is not None:
+                random_tensor = DropPath.mask_fn(shape, self.drop_prob).to(x.dtype)
+            else:
+                random_tensor = (keep_prob + torch.rand(shape, dtype=x.dtype, device=x.device)).floor_()
+            return x.div(keep_prob) * random_tensor
 
     if "timm" not in sys.modules:
         stub("timm"); stub("timm.models")

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN
+from conftest import GOLDEN, NO_DROP
 
 pytestmark = pytest.mark.gpu
 COS_TOL = 1e-3
@@ -23,7 +23,7 @@ def test_blip_ff_golden_and_oracle():
     from uniir_b200.blip_ff import BLIPFeatureFusion
     g = np.load(os.path.join(GOLDEN, "blip_tiny.npz"))
     sd = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w:")}
-    m = BLIPFeatureFusion(vit="tiny-test", image_size=64, embed_dim=64, queue_size=64, micro_batch=4)
+    m = BLIPFeatureFusion(med_config=NO_DROP, vit="tiny-test", image_size=64, embed_dim=64, queue_size=64, micro_batch=4)
     _load_oracle_weights(m, sd)
     txt = {"input_ids": torch.from_numpy(g["ids"]).cuda(), "attention_mask": torch.from_numpy(g["att"]).cuda()}
     emb = m.encode_multimodal_input(txt, torch.from_numpy(g["img"]).cuda(), None, None).cpu()   # 6 items, mb 4: ragged tail
@@ -46,7 +46,7 @@ def test_blip_ff_golden_and_oracle():
 
 def test_blip_ff_api_contract():
     from uniir_b200.blip_ff import BLIPFeatureFusion
-    m = BLIPFeatureFusion(vit="tiny-test", image_size=64, embed_dim=64, queue_size=128)
+    m = BLIPFeatureFusion(med_config=NO_DROP, vit="tiny-test", image_size=64, embed_dim=64, queue_size=128)
     d = m.dims
     from test_oracle_blip import _inputs
     ids, att, img = _inputs(d, 3, 16, 1)
@@ -106,7 +106,7 @@ def test_blip_ff_training_step_matches_oracle():
             if p_.ndim >= 2 and "_m." not in n_:
                 p_.mul_(4.0)
     orc.copy_params()
-    m = BLIPFeatureFusion(vit="tiny-test", image_size=64, embed_dim=64, queue_size=16, micro_batch=8)
+    m = BLIPFeatureFusion(med_config=NO_DROP, vit="tiny-test", image_size=64, embed_dim=64, queue_size=16, micro_batch=8)
     m.train_micro_batch = 8
     missing, unexpected = m.load_state_dict(orc.state_dict(), strict=False)
     assert not unexpected and not missing, (missing, unexpected)
@@ -206,7 +206,7 @@ def test_blip_ff_hard_negative_variant_matches_oracle():
             if p_.ndim >= 2 and "_m." not in n_:
                 p_.mul_(4.0)
     orc.copy_params()
-    m = BLIPFeatureFusion(vit="tiny-test", image_size=64, embed_dim=64, queue_size=32, micro_batch=8)
+    m = BLIPFeatureFusion(med_config=NO_DROP, vit="tiny-test", image_size=64, embed_dim=64, queue_size=32, micro_batch=8)
     m.train_micro_batch = 8
     m.load_state_dict(orc.state_dict(), strict=False)
     d = orc.dims

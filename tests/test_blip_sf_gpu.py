@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN
+from conftest import GOLDEN, NO_DROP
 
 pytestmark = pytest.mark.gpu
 COS_TOL = 1e-3
@@ -18,7 +18,7 @@ def test_blip_sf_golden_oracle_and_api():
     from test_oracle_blip import _inputs
     g = np.load(os.path.join(GOLDEN, "blip_sf_tiny.npz"))
     sd = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w:")}
-    m = BLIPScoreFusion(vit="tiny-test", image_size=64, embed_dim=64, queue_size=64, micro_batch=4)
+    m = BLIPScoreFusion(med_config=NO_DROP, vit="tiny-test", image_size=64, embed_dim=64, queue_size=64, micro_batch=4)
     missing, unexpected = m.load_state_dict(sd, strict=False)
     assert not unexpected and all(("_m." in k) or k in ("query_queue", "cand_queue", "idx_queue", "new_ptr_queue", "temp") for k in missing), (missing, unexpected)
     txt = {"input_ids": torch.from_numpy(g["ids"]).cuda(), "attention_mask": torch.from_numpy(g["att"]).cuda()}
@@ -69,7 +69,7 @@ def test_blip_sf_training_step_matches_oracle_and_keeps_frozen_layers():
             if p_.ndim >= 2 and "_m." not in n_ and "_m" != n_.split(".")[0][-2:]:
                 p_.mul_(4.0)
     orc.copy_params()
-    m = BLIPScoreFusion(vit="tiny-test", image_size=64, embed_dim=64, queue_size=16, micro_batch=8)
+    m = BLIPScoreFusion(med_config=NO_DROP, vit="tiny-test", image_size=64, embed_dim=64, queue_size=16, micro_batch=8)
     m.train_micro_batch = 8
     missing, unexpected = m.load_state_dict(orc.state_dict(), strict=False)
     assert not unexpected and not missing, (missing, unexpected)

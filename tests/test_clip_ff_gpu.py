@@ -6,6 +6,8 @@ All five passed on the driver's B200 at the end of round 1 (GPUTEST_r01: 5 xpass
 import pytest
 import torch
 
+from conftest import NO_DROP
+
 pytestmark = pytest.mark.gpu
 dev = "cuda"
 
@@ -80,7 +82,7 @@ def test_blip_step_under_cuda_graphs_equals_eager():
     orc = BLIPFeatureFusionOracle("tiny-test", embed_dim=64, queue_size=16).eval()
     res = {}
     for use in (False, True):
-        m = BLIPFeatureFusion(vit="tiny-test", image_size=64, embed_dim=64, queue_size=16, micro_batch=8)
+        m = BLIPFeatureFusion(med_config=NO_DROP, vit="tiny-test", image_size=64, embed_dim=64, queue_size=16, micro_batch=8)
         m.train_micro_batch = 8
         m.use_cuda_graphs = use
         m.load_state_dict(orc.state_dict(), strict=False)

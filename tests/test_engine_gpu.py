@@ -9,6 +9,8 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import NO_DROP
+
 pytestmark = pytest.mark.gpu
 
 
@@ -87,7 +89,7 @@ def test_blip_train_one_epoch_alpha_ramp_and_eval_engine_restores_state():
     assert blip_engine.epoch_alpha(cfg, 1, 0, 4) == 0.4
     res = {}
     for how in ("epoch", "manual"):
-        m = BLIPFeatureFusion(vit="tiny-test", image_size=64, embed_dim=64, queue_size=32, micro_batch=8, seed=11)
+        m = BLIPFeatureFusion(med_config=NO_DROP, vit="tiny-test", image_size=64, embed_dim=64, queue_size=32, micro_batch=8, seed=11)
         m.train_micro_batch = 8
         opt = FlatAdamW(m._online, lr=1e-3, weight_decay=0.05)
         sched = CosineLR(opt, T_max=8)
@@ -158,7 +160,7 @@ def test_blip_autograd_bridge_fills_param_grads_like_the_fused_path():
     from uniir_b200.blip_ff import BLIPFeatureFusion
     res = {}
     for how in ("bridge", "fused"):
-        m = BLIPFeatureFusion(vit="tiny-test", image_size=64, embed_dim=64, queue_size=32, micro_batch=8, seed=13)
+        m = BLIPFeatureFusion(med_config=NO_DROP, vit="tiny-test", image_size=64, embed_dim=64, queue_size=32, micro_batch=8, seed=13)
         m.train_micro_batch = 8
         b = _blip_batches(m.dims, 1, seed0=90)[0]
         if how == "bridge":

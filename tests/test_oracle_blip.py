@@ -52,6 +52,79 @@ def test_restatement_matches_reference_modules(tmp_path):
     assert torch.allclose(e_orc, e_ref, atol=1e-5, rtol=1e-4), (e_orc - e_ref).abs().max()
 
 
+class _SeqMasks:
+    """Keep decisions handed out in call order (call i draws from a generator seeded base + i): the reference's
+    nn.Dropout / DropPath modules and the oracle's hook see the same bits iff they sit at the same sites."""
+
+    def __init__(self, base):
+        self.base, self.i = base, 0
+
+    def keep(self, shape, p):
+        g = torch.Generator().manual_seed(self.base + self.i)
+        self.i += 1
+        return (torch.rand(shape, generator=g) >= p).float()
+
+
+@pytest.mark.skipif(not ref_blip_shim.available(), reason="reference tree not present (GPU box)")
+def test_dropout_sites_match_reference_modules_in_train_mode(tmp_path, monkeypatch):
+    """Train mode: med.py:97,217,244,325 (hidden / attention-probability dropout 0.1) and vit.py:151-152 (DropPath,
+    linspace(0, 0.3, depth) here).  The reference modules and the oracle get the same keep decisions in call order;
+    outputs and gradients agree only if every dropout of the reference has its hook at the same place in the oracle."""
+    import oracle.blip_oracle as bo
+    vit, med = ref_blip_shim.load()
+    import sys
+    DropPath = sys.modules["timm.models.layers"].DropPath
+    d = BLIP_CONFIGS["tiny-test"]
+    torch.manual_seed(0)
+    orc = BLIPFeatureFusionOracle("tiny-test").train()
+    from functools import partial
+    rate = 0.3
+    rv = vit.VisionTransformer(img_size=d.image_size, patch_size=d.patch, embed_dim=d.v_width, depth=d.v_layers,
+                               num_heads=d.v_heads, mlp_ratio=4, qkv_bias=True, drop_path_rate=rate,
+                               norm_layer=partial(torch.nn.LayerNorm, eps=1e-6)).train()
+    cfg = dict(json.load(open("/root/reference/src/models/uniir_blip/backbone/configs/med_config.json")))
+    assert cfg["hidden_dropout_prob"] == 0.1 and cfg["attention_probs_dropout_prob"] == 0.1
+    cfg.update(hidden_size=d.t_width, intermediate_size=d.t_inter, num_attention_heads=d.t_heads,
+               num_hidden_layers=d.t_layers, vocab_size=d.vocab, max_position_embeddings=d.max_pos, encoder_width=d.v_width)
+    p = tmp_path / "med.json"; p.write_text(json.dumps(cfg))
+    rb = med.BertModel(config=med.BertConfig.from_json_file(str(p)), add_pooling_layer=True).train()
+    rv.load_state_dict(orc.visual_encoder.state_dict(), strict=True)
+    rb.load_state_dict(orc.text_encoder.state_dict(), strict=False)
+    ids, att, img = _inputs(d, 4, 20, 1)
+    # ---- reference: nn.Dropout and DropPath draw from the sequence
+    seq = _SeqMasks(1000)
+    monkeypatch.setattr(torch.nn.Dropout, "forward",
+                        lambda self, x: x if (not self.training or self.p == 0) else x * seq.keep(x.shape, self.p) / (1 - self.p))
+    monkeypatch.setattr(DropPath, "mask_fn", staticmethod(lambda shape, p: seq.keep(shape, p)))
+    v_ref = rv(img)
+    e_ref = rb(ids, attention_mask=att, encoder_hidden_states=v_ref,
+               encoder_attention_mask=torch.ones(v_ref.shape[:-1], dtype=torch.long), return_dict=True).pooler_output
+    calls_ref = seq.i
+    e_ref.square().sum().backward()
+    # ---- oracle: the hook draws from a fresh copy of the same sequence
+    seq2 = _SeqMasks(1000)
+    dpr = torch.linspace(0, rate, d.v_layers).tolist()
+
+    def hook(tag, kind, layer, x):
+        if kind.startswith("path"):
+            pl = dpr[layer]
+            if pl == 0.0:
+                return x                                   # nn.Identity in the reference (vit.py:136): no draw
+            return x / (1 - pl) * seq2.keep((x.shape[0],) + (1,) * (x.ndim - 1), pl)
+        return x * seq2.keep(x.shape, 0.1) / (1 - 0.1)
+    monkeypatch.setattr(bo, "DROPOUT", hook)
+    e_orc = orc.encode_multimodal_input(ids, att, img)
+    assert seq2.i == calls_ref == 2 * (d.v_layers - 1) + 1 + 5 * d.t_layers
+    e_orc.square().sum().backward()
+    assert torch.allclose(e_orc, e_ref, atol=1e-5, rtol=1e-4), (e_orc - e_ref).abs().max()
+    for n, pr in rb.named_parameters():
+        if n in ("embeddings.word_embeddings.weight", "encoder.layer.0.attention.self.key.weight",
+                 "encoder.layer.1.crossattention.output.dense.bias", "encoder.layer.0.output.dense.weight", "pooler.dense.weight"):
+            assert torch.allclose(pr.grad, orc.text_encoder.get_parameter(n).grad, atol=1e-6, rtol=1e-4), n
+    for n in ("blocks.0.attn.qkv.weight", "blocks.1.mlp.fc2.bias", "cls_token"):
+        assert torch.allclose(rv.get_parameter(n).grad, orc.visual_encoder.get_parameter(n).grad, atol=1e-6, rtol=1e-4), n
+
+
 def test_param_count_of_blip_ff_large_online_encoder():
     m = BLIPFeatureFusionOracle("large", queue_size=64)
     n = sum(p.numel() for k, p in m.named_parameters() if k.startswith(("visual_encoder.", "text_encoder.")))

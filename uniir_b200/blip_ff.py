@@ -27,6 +27,7 @@ import os
 from dataclasses import dataclass
 
 import torch
+import torch.distributed as dist
 from torch import nn
 
 from . import lib as L
@@ -163,6 +164,9 @@ class BLIPEncoder:
         self.patch = torch.empty(mb * d.grid ** 2, d.v_width, **bf)
         self.img_tok = torch.empty(Tv, d.v_width, **bf)
         T, H = mb * S, d.t_width
+        self.dctx = None         # dropout (set_dropout): ops.drop_ctx buffer {seed, first item}; _drop: on for this run
+        self.p_h = self.p_a = 0.0
+        self._drop = False
         self.h = torch.empty(T, H, **f32)
         self.tmp = torch.empty(T, H, **f32)
         self.hb = torch.empty(T, H, **bf)
@@ -205,6 +209,18 @@ class BLIPEncoder:
             self.att_len = None
             self.ids = None
 
+    # ---- dropout of the reference's train mode.  Sites: 0 = embeddings (med.py:97); 1 + 5 i + {0: self-attention
+    # probabilities, 1: self-attention output, 2: cross-attention probabilities, 3: cross-attention output, 4: FFN output}
+    # of BERT layer i (med.py:217,244,325); 4096 + 2 l + {0, 1}: DropPath of ViT block l (vit.py:151-152).  The masks are
+    # functions of (seed, site, element index in the whole batch): see include/uniir_b200.h. ----
+    def set_dropout(self, p_hidden, p_attn, drop_path_rate):
+        self.p_h, self.p_a = float(p_hidden), float(p_attn)
+        self.dctx = ops.drop_ctx(self.dev)
+        self.vis.set_drop_path(float(drop_path_rate), self.dctx)
+
+    def _site(self, layer, k):
+        return 1 + 5 * layer + k
+
     # ---- CUDA-graph front-end (BLIPFeatureFusion.use_cuda_graphs, default on).  The eager step issues 120-150 k kernel
     # launches per 2048-pair batch; captured, a micro-batch is one graph launch.  Static I/O buffers, first call eager
     # (kernel attributes, allocator warm-up), second call captures, later calls replay -- as CLIPEncoder._run. ----
@@ -219,9 +235,15 @@ class BLIPEncoder:
             self.in_demb = torch.zeros_like(self.emb)
             self._graphs = {}
 
-    def run(self, ids, att_len, img, mt=None, mv=None, d_emb=None, use_graph=False):
+    def run(self, ids, att_len, img, mt=None, mv=None, d_emb=None, use_graph=False, drop_seed=None, item0=0):
         """forward (d_emb None: no activations kept) or forward-with-activations + backward (d_emb given), eagerly or
-        through a captured CUDA graph over the static I/O buffers.  Returns the embedding buffer."""
+        through a captured CUDA graph over the static I/O buffers.  Returns the embedding buffer.
+        drop_seed (int, needs set_dropout): run with the train-mode dropout masks of that seed; item0 = index of this
+        micro-batch's first item in the batch (the masks are indexed by batch position, not micro-batch position)."""
+        self._drop = drop_seed is not None and self.dctx is not None
+        self.vis.dp_on = self._drop and self.vis.dp is not None
+        if self._drop:
+            self.dctx.copy_(torch.tensor([int(drop_seed) & 0x7FFFFFFF, int(item0)], dtype=torch.int32), non_blocking=True)
         if not use_graph:
             out = self.forward(ids, att_len, img, save=d_emb is not None, mt=mt, mv=mv)
             if d_emb is not None:
@@ -234,11 +256,11 @@ class BLIPEncoder:
             self.in_mt.copy_(mt, non_blocking=True); self.in_mv.copy_(mv, non_blocking=True)
         sf = self.mode == "sf"
         if d_emb is None:
-            key = "fwd"
+            key = "fwd+drop" if self._drop else "fwd"
             body = lambda: self.forward(self.in_ids, self.in_len, self.in_img, save=False,
                                         mt=self.in_mt if sf else None, mv=self.in_mv if sf else None)
         else:
-            key = "fwdbwd"
+            key = "fwdbwd+drop" if self._drop else "fwdbwd"
             self.in_demb.copy_(d_emb, non_blocking=True)
 
             def body():
@@ -297,11 +319,16 @@ class BLIPEncoder:
             ops.gemm(self.v_pool, w16(f"vision_proj{self.sfx}.weight"), bias=w(f"vision_proj{self.sfx}.bias"), out=self.v_emb)
         # ---------------- BERT ----------------
         H, nh = d.t_width, d.t_heads
+        ctx, per = self.dctx, S * H
+        dh = self._drop and self.p_h > 0           # hidden dropout / attention-probability dropout on for this run
+        da = self._drop and self.p_a > 0
         e_pre = self.emb_pre if save else self.tmp
         ops.text_embed_fwd(ids, w(f"{t}.embeddings.word_embeddings.weight"),
                            w(f"{t}.embeddings.position_embeddings.weight")[:S], out=e_pre.view(mb, S, H))
         ops.layernorm_fwd(e_pre, w(f"{t}.embeddings.LayerNorm.weight"), w(f"{t}.embeddings.LayerNorm.bias"), 1e-12,
                           out=self.h, stats=((self.me, self.re) if save else None))
+        if dh:
+            ops.dropout(self.h, ctx, 0, per, self.p_h)                                        # med.py:97
         if save:
             self.att_len, self.ids = att_len, ids
         for i in range(d.t_layers):
@@ -314,10 +341,12 @@ class BLIPEncoder:
             ops.gemm(hb_in, self._fused(f"{l}.attention.self.query.weight", 3 * H, H),
                      bias=self._fused1(f"{l}.attention.self.query.bias", 3 * H), out=qkv)
             ops.attn_fwd_ex(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], mb, S, S, nh, kv_len=att_len, out=ctx1,
-                            lse=(a.lse1 if save else None))
+                            lse=(a.lse1 if save else None), drop=((ctx, self._site(i, 0), self.p_a) if da else None))
             t1 = a.t1 if save else self.tmp
             ops.gemm(ctx1, w16(f"{l}.attention.output.dense.weight"), bias=w(f"{l}.attention.output.dense.bias"),
-                     residual=self.h, out=t1)
+                     residual=(None if dh else self.h), out=t1)
+            if dh:     # med.py:244: dropout on the dense output, then the residual
+                ops.dropout(t1, ctx, self._site(i, 1), per, self.p_h, residual=self.h)
             ops.layernorm_fwd(t1, w(f"{l}.attention.output.LayerNorm.weight"), w(f"{l}.attention.output.LayerNorm.bias"),
                               1e-12, out=self.h, stats=((a.m1, a.r1) if save else None))
             h1b = a.h1b if save else self.hb
@@ -328,10 +357,13 @@ class BLIPEncoder:
                 ops.gemm(h1b, w16(f"{l}.crossattention.self.query.weight"), bias=w(f"{l}.crossattention.self.query.bias"), out=q2)
                 ops.gemm(self.img_tok, self._fused(f"{l}.crossattention.self.key.weight", 2 * H, d.v_width),
                          bias=self._fused1(f"{l}.crossattention.self.key.bias", 2 * H), out=kv2)
-                ops.attn_fwd_ex(q2, kv2[:, :H], kv2[:, H:], mb, S, d.v_tokens, nh, out=ctx2, lse=(a.lse2 if save else None))
+                ops.attn_fwd_ex(q2, kv2[:, :H], kv2[:, H:], mb, S, d.v_tokens, nh, out=ctx2, lse=(a.lse2 if save else None),
+                                drop=((ctx, self._site(i, 2), self.p_a) if da else None))
                 t2 = a.t2 if save else self.tmp
                 ops.gemm(ctx2, w16(f"{l}.crossattention.output.dense.weight"), bias=w(f"{l}.crossattention.output.dense.bias"),
-                         residual=self.h, out=t2)
+                         residual=(None if dh else self.h), out=t2)
+                if dh:
+                    ops.dropout(t2, ctx, self._site(i, 3), per, self.p_h, residual=self.h)
                 ops.layernorm_fwd(t2, w(f"{l}.crossattention.output.LayerNorm.weight"),
                                   w(f"{l}.crossattention.output.LayerNorm.bias"), 1e-12, out=self.h,
                                   stats=((a.m2, a.r2) if save else None))
@@ -344,7 +376,10 @@ class BLIPEncoder:
             ops.gemm(h2b, w16(f"{l}.intermediate.dense.weight"), bias=w(f"{l}.intermediate.dense.bias"), act=L.ACT_GELU,
                      aux_out=pre, out=act)
             t3 = a.t3 if save else self.tmp
-            ops.gemm(act, w16(f"{l}.output.dense.weight"), bias=w(f"{l}.output.dense.bias"), residual=self.h, out=t3)
+            ops.gemm(act, w16(f"{l}.output.dense.weight"), bias=w(f"{l}.output.dense.bias"), residual=(None if dh else self.h),
+                     out=t3)
+            if dh:     # med.py:325
+                ops.dropout(t3, ctx, self._site(i, 4), per, self.p_h, residual=self.h)
             ops.layernorm_fwd(t3, w(f"{l}.output.LayerNorm.weight"), w(f"{l}.output.LayerNorm.bias"), 1e-12, out=self.h,
                               stats=((a.m3, a.r3) if save else None))
         ops.cast_bf16(self.h, out=self.hb)
@@ -367,6 +402,21 @@ class BLIPEncoder:
         H, nh, Sv = d.t_width, d.t_heads, d.v_tokens
         G = P.grad
         ff = self.mode == "ff"
+        ctx, per = self.dctx, S * H
+        dh = self._drop and self.p_h > 0
+        da = self._drop and self.p_a > 0
+
+        def dense_out_bwd(t_saved, m, r, ln, dense_bias, site):
+            """Backward of LN(dropout(dense(.)) + residual): self.dt = gradient of the pre-LN sum (it is also the residual
+            gradient), self.dtb = bf16 gradient of the dense output, bias gradient accumulated."""
+            if not dh:
+                ops.layernorm_bwd(self.dh, t_saved, m, r, w(f"{ln}.weight"), self.dt, g(f"{ln}.weight"), g(f"{ln}.bias"),
+                                  accumulate=False, dx_bf16=self.dtb, dcolsum=g(dense_bias))
+                return
+            ops.layernorm_bwd(self.dh, t_saved, m, r, w(f"{ln}.weight"), self.dt, g(f"{ln}.weight"), g(f"{ln}.bias"),
+                              accumulate=False)
+            ops.dropout(self.dt, ctx, site, per, self.p_h, out=self.dtb)
+            ops.colsum_accum(self.dtb, g(dense_bias))
         if ff:
             # ---- pooler: emb = tanh(W h[:,0] + b)
             ops.tanh_bwd(d_emb, self.emb, self.dz)
@@ -386,9 +436,7 @@ class BLIPEncoder:
             l = f"{t}.encoder.layer.{i}"
             a = self.acts[i]
             # ---- FFN: h3 = LN(dense2(gelu(dense1(h2))) + h2)
-            ops.layernorm_bwd(self.dh, a.t3, a.m3, a.r3, w(f"{l}.output.LayerNorm.weight"), self.dt,
-                              g(f"{l}.output.LayerNorm.weight"), g(f"{l}.output.LayerNorm.bias"), accumulate=False, dx_bf16=self.dtb,
-                              dcolsum=g(f"{l}.output.dense.bias"))
+            dense_out_bwd(a.t3, a.m3, a.r3, f"{l}.output.LayerNorm", f"{l}.output.dense.bias", self._site(i, 4))
             ops.wgrad(self.dtb, a.act, g(f"{l}.output.dense.weight"))
             ops.gemm(self.dtb, w16(f"{l}.output.dense.weight"), b_mn=True, act=L.ACT_GELU, act_grad_src=a.pre, out=self.d_pre)
             ops.wgrad(self.d_pre, a.h2b, g(f"{l}.intermediate.dense.weight"))
@@ -396,14 +444,13 @@ class BLIPEncoder:
             ops.gemm(self.d_pre, w16(f"{l}.intermediate.dense.weight"), b_mn=True, residual=self.dt, out=self.dh)
             # ---- cross-attention: h2 = LN(dense(attn(q(h1), kv(img))) + h1)   (mode "sf": absent, dh passes through)
             if ff:
-                ops.layernorm_bwd(self.dh, a.t2, a.m2, a.r2, w(f"{l}.crossattention.output.LayerNorm.weight"), self.dt,
-                                  g(f"{l}.crossattention.output.LayerNorm.weight"), g(f"{l}.crossattention.output.LayerNorm.bias"),
-                                  accumulate=False, dx_bf16=self.dtb,
-                                  dcolsum=g(f"{l}.crossattention.output.dense.bias"))
+                dense_out_bwd(a.t2, a.m2, a.r2, f"{l}.crossattention.output.LayerNorm", f"{l}.crossattention.output.dense.bias",
+                              self._site(i, 3))
                 ops.wgrad(self.dtb, a.ctx2, g(f"{l}.crossattention.output.dense.weight"))
                 ops.gemm(self.dtb, w16(f"{l}.crossattention.output.dense.weight"), b_mn=True, out=self.d_ctx)
                 ops.attn_bwd_ex(a.q2, a.kv2[:, :H], a.kv2[:, H:], a.ctx2, self.d_ctx, a.lse2, mb, S, Sv, nh,
-                                self.dq2, self.dkv2[:, :H], self.dkv2[:, H:], delta=self.delta)
+                                self.dq2, self.dkv2[:, :H], self.dkv2[:, H:], delta=self.delta,
+                                drop=((ctx, self._site(i, 2), self.p_a) if da else None))
                 ops.wgrad(self.dq2, a.h1b, g(f"{l}.crossattention.self.query.weight"))
                 ops.colsum_accum(self.dq2, g(f"{l}.crossattention.self.query.bias"))
                 ops.gemm(self.dq2, w16(f"{l}.crossattention.self.query.weight"), b_mn=True, residual=self.dt, out=self.dh)
@@ -412,18 +459,18 @@ class BLIPEncoder:
                 ops.gemm(self.dkv2, self._fused(f"{l}.crossattention.self.key.weight", 2 * H, d.v_width), b_mn=True,
                          out=self.d_img, accumulate=True)
             # ---- self-attention: h1 = LN(dense(attn(qkv(h_in))) + h_in)
-            ops.layernorm_bwd(self.dh, a.t1, a.m1, a.r1, w(f"{l}.attention.output.LayerNorm.weight"), self.dt,
-                              g(f"{l}.attention.output.LayerNorm.weight"), g(f"{l}.attention.output.LayerNorm.bias"),
-                              accumulate=False, dx_bf16=self.dtb,
-                              dcolsum=g(f"{l}.attention.output.dense.bias"))
+            dense_out_bwd(a.t1, a.m1, a.r1, f"{l}.attention.output.LayerNorm", f"{l}.attention.output.dense.bias", self._site(i, 1))
             ops.wgrad(self.dtb, a.ctx1, g(f"{l}.attention.output.dense.weight"))
             ops.gemm(self.dtb, w16(f"{l}.attention.output.dense.weight"), b_mn=True, out=self.d_ctx)
             ops.attn_bwd_ex(a.qkv[:, :H], a.qkv[:, H:2 * H], a.qkv[:, 2 * H:], a.ctx1, self.d_ctx, a.lse1, mb, S, S, nh,
-                            self.dqkv[:, :H], self.dqkv[:, H:2 * H], self.dqkv[:, 2 * H:], kv_len=self.att_len, delta=self.delta)
+                            self.dqkv[:, :H], self.dqkv[:, H:2 * H], self.dqkv[:, 2 * H:], kv_len=self.att_len, delta=self.delta,
+                            drop=((ctx, self._site(i, 0), self.p_a) if da else None))
             ops.wgrad(self.dqkv, a.hb_in, self._fused(f"{l}.attention.self.query.weight", 3 * H, H, G))
             ops.colsum_accum(self.dqkv, self._fused1(f"{l}.attention.self.query.bias", 3 * H, G))
             ops.gemm(self.dqkv, self._fused(f"{l}.attention.self.query.weight", 3 * H, H), b_mn=True, residual=self.dt, out=self.dh)
-        # ---- embeddings: h0 = LN(word[ids] + pos)
+        # ---- embeddings: h0 = dropout(LN(word[ids] + pos))
+        if dh:
+            ops.dropout(self.dh, ctx, 0, per, self.p_h)
         ops.layernorm_bwd(self.dh, self.emb_pre, self.me, self.re, w(f"{t}.embeddings.LayerNorm.weight"), self.dt,
                           g(f"{t}.embeddings.LayerNorm.weight"), g(f"{t}.embeddings.LayerNorm.bias"), accumulate=False)
         ops.text_embed_bwd(self.dt.view(mb, S, H), self.ids, g(f"{t}.embeddings.word_embeddings.weight"),
@@ -432,7 +479,7 @@ class BLIPEncoder:
             # ---- ViT: img_tok = LN_final(blocks(patch-embed(img)))
             ops.layernorm_bwd(self.d_img, self.vis.x_out, self.vn_m, self.vn_r, w(f"{v}.norm.weight"), self.vis.dx,
                               g(f"{v}.norm.weight"), g(f"{v}.norm.bias"), accumulate=False, dx_bf16=self.vis.dxb,
-                              dcolsum=self.vis.top_bias_grad())
+                              dcolsum=(None if self.vis.dp_on else self.vis.top_bias_grad()))
         else:
             # ---- ViT: v_emb = vision_proj(LN_final(x_out)[class-token rows])
             ops.wgrad(self.d_v, self.v_pool, g(f"vision_proj{self.sfx}.weight"))
@@ -442,8 +489,8 @@ class BLIPEncoder:
             self.vis.dxb.zero_()
             ops.layernorm_bwd(self.d_vpool, self.vis.x_out, self.vn_m[:mb], self.vn_r[:mb], w(f"{v}.norm.weight"), self.vis.dx,
                               g(f"{v}.norm.weight"), g(f"{v}.norm.bias"), row_index=self.cls_rows, accumulate=False,
-                              dx_bf16=self.vis.dxb, dcolsum=self.vis.top_bias_grad())
-        self.vis.backward(top_bias_done=True)
+                              dx_bf16=self.vis.dxb, dcolsum=(None if self.vis.dp_on else self.vis.top_bias_grad()))
+        self.vis.backward(top_bias_done=not self.vis.dp_on)
         ops.vision_embed_bwd(self.vis.dx.view(mb, Sv, d.v_width), mb, Sv, d.v_width, self.d_patch,
                              g(f"{v}.cls_token").view(-1), g(f"{v}.pos_embed").view(Sv, d.v_width))
         ops.wgrad(self.d_patch, self.col, g(f"{v}.patch_embed.proj.weight").view(d.v_width, -1))
@@ -452,6 +499,10 @@ class BLIPEncoder:
 
 class BLIPFeatureFusion(nn.Module):
     MODE = "ff"     # BLIPScoreFusion (blip_sf.py) overrides: same loss / queues / EMA, different encoder head
+    # Train-mode regularisation of the reference: BertConfig hidden_dropout_prob / attention_probs_dropout_prob (0.1 in
+    # backbone/configs/med_config.json) and timm DropPath in the ViT (blip.py:241,253: rate 0.1 for "large", 0 for "base").
+    # Active whenever the module is in train mode, like nn.Dropout; `model.eval()` or `set_dropout(0, 0, 0)` turn it off.
+    DROP_PATH_RATE = {"large": 0.1}
 
     def __init__(self, med_config="backbone/configs/med_config.json", image_size=224, vit="base", vit_grad_ckpt=False,
                  vit_ckpt_layer=0, embed_dim=768, queue_size=57600, momentum=0.995, config=None, device="cuda",
@@ -466,7 +517,11 @@ class BLIPFeatureFusion(nn.Module):
         d = BLIP_CONFIGS[vit]
         if image_size != d.image_size:
             d = BLIPDims(**{**d.__dict__, "image_size": image_size})
+        p_hidden = p_attn = 0.1            # backbone/configs/med_config.json:5,7
         if isinstance(med_config, dict):   # the reference reads a BertConfig json; a dict is accepted for tests
+            med_config = dict(med_config)
+            p_hidden = med_config.pop("hidden_dropout_prob", p_hidden)
+            p_attn = med_config.pop("attention_probs_dropout_prob", p_attn)
             d = BLIPDims(**{**d.__dict__, **med_config})
         elif isinstance(med_config, str) and os.path.isfile(med_config):
             # The reference builds its BERT from this BertConfig json (blip_ff.py:34-36).  The kernels here are laid out
@@ -481,6 +536,8 @@ class BLIPFeatureFusion(nn.Module):
                                  f"(file value, built-in value): {bad}; pass the overrides as a dict")
             if mc.get("hidden_act", "gelu") != "gelu" or abs(mc.get("layer_norm_eps", 1e-12) - 1e-12) > 1e-15:
                 raise ValueError("med_config: only hidden_act='gelu' and layer_norm_eps=1e-12 are implemented")
+            p_hidden = mc.get("hidden_dropout_prob", p_hidden)
+            p_attn = mc.get("attention_probs_dropout_prob", p_attn)
         self.dims, self.device_, self.micro_batch = d, dev, micro_batch
         self.image_size, self.queue_size, self.momentum, self.embed_dim, self.config = image_size, queue_size, momentum, embed_dim, config
         # online + momentum encoders as two flat parameter sets with identical layouts (EMA = one kernel)
@@ -505,6 +562,10 @@ class BLIPFeatureFusion(nn.Module):
         self.register_buffer("new_ptr_queue", torch.zeros(1, dtype=torch.long, device=dev))
         self._enc = {}
         self._train_state = None
+        self.hidden_dropout_prob, self.attention_probs_dropout_prob = float(p_hidden), float(p_attn)
+        self.drop_path_rate = float(self.DROP_PATH_RATE.get(vit, 0.0))
+        self._drop_gen = None            # host generator of the per-step mask seeds (seeded with seed + rank, lazily)
+        self._drop_seed0 = seed
         self.train_micro_batch = 64
         self.use_cuda_graphs = True      # BLIPEncoder.run: one graph launch per micro-batch instead of ~2400 kernel launches
 
@@ -529,7 +590,25 @@ class BLIPFeatureFusion(nn.Module):
             self._enc = {k: v for k, v in self._enc.items() if (k[2], k[3]) != (momentum, train)}
             self._enc[key] = BLIPEncoder(self._mom if momentum else self._online, self.dims, mb, S, self.device_,
                                          "_m" if momentum else "", train=train, mode=self.MODE, embed_dim=self.embed_dim)
-        return self._enc[key]
+        enc = self._enc[key]
+        probs = (self.hidden_dropout_prob, self.attention_probs_dropout_prob, self.drop_path_rate)
+        if getattr(enc, "_drop_probs", None) != probs:
+            enc.set_dropout(*probs)
+            enc._drop_probs = probs
+        return enc
+
+    def set_dropout(self, hidden=0.0, attention=0.0, drop_path=0.0):
+        """Override the train-mode dropout probabilities (the reference's come from med_config / create_vit)."""
+        self.hidden_dropout_prob, self.attention_probs_dropout_prob, self.drop_path_rate = float(hidden), float(attention), float(drop_path)
+
+    def _dropout_active(self):
+        return self.training and (self.hidden_dropout_prob > 0 or self.attention_probs_dropout_prob > 0 or self.drop_path_rate > 0)
+
+    def _next_drop_seed(self):
+        if self._drop_gen is None:
+            rank = dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+            self._drop_gen = torch.Generator(device="cpu").manual_seed(self._drop_seed0 * 1000003 + rank)   # seed + rank, as train.py
+        return int(torch.randint(0, 2 ** 31 - 1, (1,), generator=self._drop_gen))
 
     def _masks(self, txt_mask, img_mask, n):
         """Modality masks as int64 [n] device tensors (score fusion); None for feature fusion, which ignores them."""
@@ -553,9 +632,14 @@ class BLIPFeatureFusion(nn.Module):
         return ids, att.sum(1).to(torch.int32).contiguous()
 
     @torch.no_grad()
-    def encode_multimodal_input(self, txt_dict_batched, image_batched, txt_mask=None, img_mask=None, use_momentum=False):
+    def encode_multimodal_input(self, txt_dict_batched, image_batched, txt_mask=None, img_mask=None, use_momentum=False,
+                                _drop_seed=None):
         """blip_ff.py:82-116: txt_mask / img_mask are accepted and ignored, exactly like the reference.
-        blip_sf.py:158-172 (MODE "sf"): text_proj(text [CLS]) * txt_mask + vision_proj(image class token) * img_mask."""
+        blip_sf.py:158-172 (MODE "sf"): text_proj(text [CLS]) * txt_mask + vision_proj(image class token) * img_mask.
+        In train mode the encoders run with dropout / DropPath like the reference's modules (fresh masks per call;
+        the training step passes its own seed so that the gradient-cache re-forward sees the same masks)."""
+        if _drop_seed is None and self._dropout_active():
+            _drop_seed = self._next_drop_seed()
         ids = txt_dict_batched["input_ids"] if isinstance(txt_dict_batched, dict) else txt_dict_batched.input_ids
         att = txt_dict_batched["attention_mask"] if isinstance(txt_dict_batched, dict) else txt_dict_batched.attention_mask
         dev = self.device_
@@ -584,7 +668,8 @@ class BLIPFeatureFusion(nn.Module):
                     mt_c = torch.cat([mt_c, mt_c.new_zeros(pad)]); mv_c = torch.cat([mv_c, mv_c.new_zeros(pad)])
             out[s:e] = enc.run(i_c.contiguous(), l_c.contiguous(), im_c.contiguous(),
                                mt=None if mt_c is None else mt_c.contiguous(),
-                               mv=None if mv_c is None else mv_c.contiguous(), use_graph=self.use_cuda_graphs)[:e - s]
+                               mv=None if mv_c is None else mv_c.contiguous(), use_graph=self.use_cuda_graphs,
+                               drop_seed=_drop_seed, item0=s)[:e - s]
         return out
 
     def forward(self, batch, alpha=None, encode_mbeir_batch=False):
@@ -656,9 +741,12 @@ class BLIPFeatureFusion(nn.Module):
         bs, n_items, S = q_idx.numel(), ids.shape[0], ids.shape[1]
         txt = {"input_ids": ids, "attention_mask": (torch.arange(S, device=dev)[None, :] < lens[:, None]).long()}
         mt, mv = self._masks(batch.get("txt_mask_batched"), batch.get("image_mask_batched"), n_items)
-        emb = self.encode_multimodal_input(txt, img, mt, mv)              # phase A, online (no activations kept)
+        # train mode: one mask seed for the online encoder (phase A and the phase-C re-forward share it), one for the
+        # momentum encoder (its modules are in train mode too in the reference)
+        seed, seed_m = (self._next_drop_seed(), self._next_drop_seed()) if self._dropout_active() else (None, None)
+        emb = self.encode_multimodal_input(txt, img, mt, mv, _drop_seed=seed)   # phase A, online (no activations kept)
         self._momentum_update()                                           # blip_ff.py:182
-        emb_m = self.encode_multimodal_input(txt, img, mt, mv, use_momentum=True)
+        emb_m = self.encode_multimodal_input(txt, img, mt, mv, use_momentum=True, _drop_seed=seed_m)
         f32 = dict(device=dev, dtype=torch.float32)
         qn, pn, qm, pm = (torch.empty(bs, E, **f32) for _ in range(4))
         qnorm, pnorm, tmpn = torch.empty(bs, **f32), torch.empty(bs, **f32), torch.empty(bs, **f32)
@@ -699,7 +787,7 @@ class BLIPFeatureFusion(nn.Module):
             self._dequeue_and_enqueue(qm, nc_m.view(bs, -1, E)[:, 0, :].contiguous(), nc_ids[:, 0].contiguous())
         else:
             self._dequeue_and_enqueue(qm, pm, pc_ids)                     # blip_ff.py:247
-        self._train_state = dict(ids=ids, lens=lens, img=img, d_emb=d_emb, d_temp=acc_l[3].clone(), mt=mt, mv=mv)
+        self._train_state = dict(ids=ids, lens=lens, img=img, d_emb=d_emb, d_temp=acc_l[3].clone(), mt=mt, mv=mv, seed=seed)
         return loss.clone(), acc.clone()
 
     @torch.no_grad()
@@ -724,5 +812,5 @@ class BLIPFeatureFusion(nn.Module):
             enc.run(st["ids"][s:e].contiguous(), st["lens"][s:e].contiguous(), st["img"][s:e].contiguous(),
                     mt=None if st["mt"] is None else st["mt"][s:e].contiguous(),
                     mv=None if st["mv"] is None else st["mv"][s:e].contiguous(), d_emb=st["d_emb"][s:e].contiguous(),
-                    use_graph=self.use_cuda_graphs)
+                    use_graph=self.use_cuda_graphs, drop_seed=st["seed"], item0=s)
         self._train_state = None

@@ -59,6 +59,8 @@ class Tower:
         bf = dict(device=dev, dtype=torch.bfloat16)
         f32 = dict(device=dev, dtype=torch.float32)
         self.x = torch.empty(T, D, **f32)          # residual stream
+        self.dp = None                             # DropPath (set_drop_path); dp_on: active for the current run
+        self.dp_on = False
         if train:
             self.acts = [_LayerActs(T, D, mb, heads, S, dev) for _ in range(layers)]
             self.x_out = torch.empty(T, D, **f32)      # tower output when the stream runs through acts
@@ -78,6 +80,24 @@ class Tower:
             self.att = torch.empty(T, D, **bf)
             self.big = torch.empty(T, 4 * D, **bf)
 
+    def set_drop_path(self, rate, ctx, site_base=4096):
+        """timm DropPath on both residual branches (vit.py:136,151-152): drop probability linspace(0, rate, depth)[layer]
+        (vit.py:217), one draw per sample and branch, kept branches scaled by 1 / (1 - p).  ctx: the encoder's
+        ops.drop_ctx buffer.  Active only while `dp_on` is set (training forward / re-forward / backward)."""
+        if rate <= 0:
+            self.dp = None
+            return
+        p_layer = torch.linspace(0, rate, self.nl)
+        p_sites = p_layer.repeat_interleave(2).contiguous()              # site 2l = attention branch, 2l + 1 = MLP branch
+        self.dp = dict(ctx=ctx, site_base=site_base, p=p_sites.tolist(), p_dev=p_sites.to(self.dev),
+                       scales=torch.ones(2 * self.nl, self.mb, device=self.dev, dtype=torch.float32))
+
+    def _branch_scale(self, site):
+        """Per-item scale vector of residual branch `site`, or None where the branch is never dropped."""
+        if not self.dp_on or self.dp["p"][site] == 0.0:
+            return None
+        return self.dp["scales"][site]
+
     def _n(self, i, leaf):
         """leaf is written in upstream-CLIP terms; translated for timm-style (BLIP) towers."""
         nm = self.nm
@@ -96,8 +116,11 @@ class Tower:
     def forward(self, save):
         P, B, S, H = self.P, self.mb, self.S, self.H
         w16, w = self.P.w16, self.P.w
+        if self.dp_on:
+            ops.droppath_scales(self.dp["ctx"], self.dp["site_base"], self.dp["p_dev"], B, out=self.dp["scales"])
         for i in range(self.nl):
             n = lambda leaf: self._n(i, leaf)
+            sa, sm = (self._branch_scale(2 * i), self._branch_scale(2 * i + 1)) if self.dp_on else (None, None)
             if save:
                 a = self.acts[i]
                 x_in = self.x if i == 0 else a.x_in
@@ -115,10 +138,12 @@ class Tower:
             ops.layernorm_fwd(x_in, w(n("ln_1.weight")), w(n("ln_1.bias")), self.eps, out=h1, stats=st1)
             ops.gemm(h1, w16(n("attn.in_proj_weight")), bias=w(n("attn.in_proj_bias")), out=qkv)
             ops.attn_fwd(qkv, B, S, H, self.causal, out=att, lse=lse, need_lse=save)
-            ops.gemm(att, w16(n("attn.out_proj.weight")), bias=w(n("attn.out_proj.bias")), residual=x_in, out=x_mid)
+            ops.gemm(att, w16(n("attn.out_proj.weight")), bias=w(n("attn.out_proj.bias")), residual=x_in, out=x_mid,
+                     row_scale=sa, row_scale_rows=S)
             ops.layernorm_fwd(x_mid, w(n("ln_2.weight")), w(n("ln_2.bias")), self.eps, out=h2, stats=st2)
             ops.gemm(h2, w16(n("mlp.c_fc.weight")), bias=w(n("mlp.c_fc.bias")), act=self.act, aux_out=pre, out=act)
-            ops.gemm(act, w16(n("mlp.c_proj.weight")), bias=w(n("mlp.c_proj.bias")), residual=x_mid, out=x_out)
+            ops.gemm(act, w16(n("mlp.c_proj.weight")), bias=w(n("mlp.c_proj.bias")), residual=x_mid, out=x_out,
+                     row_scale=sm, row_scale_rows=S)
         return self.x_out if save else self.x
 
     def top_bias_grad(self):
@@ -132,13 +157,20 @@ class Tower:
     # d_pre / d_qkv matrices need a separate column-sum pass.
     def backward(self, top_bias_done=False):
         P, dx, dxb, B, S, H = self.P, self.dx, self.dxb, self.mb, self.S, self.H
+        dp = self.dp_on
+        assert not (dp and top_bias_done), "under DropPath the bias gradients are summed after the per-item scaling"
         for i in reversed(range(self.nl)):
             a = self.acts[i]
             g = lambda leaf: P.g(self._n(i, leaf))
             w16 = lambda leaf: P.w16(self._n(i, leaf))
             # ---- MLP branch: x_out = x_mid + c_proj(quickgelu(c_fc(ln_2(x_mid))))
+            if dp:      # branch gradient = per-item scale o residual-stream gradient; dx itself passes unscaled
+                sm = self._branch_scale(2 * i + 1)
+                if sm is not None:
+                    ops.row_scale(dxb, sm, S)
+                ops.colsum_accum(dxb, g("mlp.c_proj.bias"))
             ops.wgrad(dxb, a.act, g("mlp.c_proj.weight"))
-            if i == self.nl - 1 and not top_bias_done:
+            if i == self.nl - 1 and not top_bias_done and not dp:
                 ops.colsum_accum(dxb, g("mlp.c_proj.bias"))
             ops.gemm(dxb, w16("mlp.c_proj.weight"), b_mn=True, act=self.act, act_grad_src=a.pre,
                      out=self.d_big)
@@ -146,8 +178,13 @@ class Tower:
             ops.colsum_accum(self.d_big, g("mlp.c_fc.bias"))
             ops.gemm(self.d_big, w16("mlp.c_fc.weight"), b_mn=True, out=self.d_h)
             ops.layernorm_bwd(self.d_h, a.x_mid, a.m2, a.r2, P.w(self._n(i, "ln_2.weight")), dx,
-                              g("ln_2.weight"), g("ln_2.bias"), dx_bf16=dxb, dcolsum=g("attn.out_proj.bias"))
+                              g("ln_2.weight"), g("ln_2.bias"), dx_bf16=dxb, dcolsum=(None if dp else g("attn.out_proj.bias")))
             # ---- attention branch: x_mid = x_in + out_proj(attn(in_proj(ln_1(x_in))))
+            if dp:
+                sa = self._branch_scale(2 * i)
+                if sa is not None:
+                    ops.row_scale(dxb, sa, S)
+                ops.colsum_accum(dxb, g("attn.out_proj.bias"))
             ops.wgrad(dxb, a.att, g("attn.out_proj.weight"))
             ops.gemm(dxb, w16("attn.out_proj.weight"), b_mn=True, out=self.d_h)
             ops.attn_bwd(a.qkv, a.att, self.d_h, a.lse, B, S, H, self.causal, dqkv=self.dqkv, delta=self.delta)
@@ -156,7 +193,7 @@ class Tower:
             ops.gemm(self.dqkv, w16("attn.in_proj_weight"), b_mn=True, out=self.d_h)
             ops.layernorm_bwd(self.d_h, a.x_in, a.m1, a.r1, P.w(self._n(i, "ln_1.weight")), dx,
                               g("ln_1.weight"), g("ln_1.bias"), dx_bf16=dxb,
-                              dcolsum=(P.g(self._n(i - 1, "mlp.c_proj.bias")) if i > 0 else None))
+                              dcolsum=(P.g(self._n(i - 1, "mlp.c_proj.bias")) if i > 0 and not dp else None))
 
 
 class CLIPEncoder:

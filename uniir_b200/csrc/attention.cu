@@ -16,6 +16,7 @@
 // round trip through HBM).
 #include <cuda_bf16.h>
 
+#include "dropout.cuh"
 #include "host_util.cuh"
 
 namespace uniir {
@@ -107,7 +108,18 @@ struct AttnParams {
   __nv_bfloat16* dqkv;       // [B*S, 3*D]
   int B, S, H, D, causal;
   float scale;               // 1/sqrt(64)
+  // attention-probability dropout (DROP instantiations only; med.py:217, T5Attention): element (b, h, q, key) of the
+  // batch-wide [items, H, Sq, Skv] probability tensor, counter-based mask of dropout.cuh
+  const uint32_t* drop_ctx;
+  uint32_t drop_site, drop_thresh;
+  float drop_scale;          // 1 / (1 - p)
 };
+
+// first element index of batch row b, head h in the batch-wide probability tensor (mod 2^32)
+__device__ __forceinline__ uint32_t drop_row_base(const AttnParams& p, int b, int h) {
+  return ((__ldg(p.drop_ctx + 1) + static_cast<uint32_t>(b)) * static_cast<uint32_t>(p.H) + static_cast<uint32_t>(h)) *
+         static_cast<uint32_t>(p.Sq);
+}
 
 // =================================================================================
 // Head-resident kernels: one CTA per (batch, head).  The whole K and V (forward, dQ) or
@@ -141,7 +153,9 @@ __device__ __forceinline__ void load_rows16_warp(uint32_t dst, const __nv_bfloat
 
 // BIAS = false is the tower kernel; BIAS = true adds p.bias[h, q, key] (in score units: divided by the scale
 // that rides in the exp2 FFMA) -- a separate instantiation, so the tower path compiles exactly as before.
-template <bool BIAS>
+// DROP = true (separate instantiations again): the un-normalised weights are masked and scaled by 1/(1-p) AFTER the
+// row sum, so O = dropout(softmax(S)) V as in the reference; the log-sum-exp is that of the undropped softmax.
+template <bool BIAS, bool DROP = false>
 __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams p, int spad) {
   extern __shared__ __align__(128) uint8_t sm[];
   const uint32_t sK = s_u32(sm), sV = sK + spad * 128, sQ0 = sV + spad * 128;
@@ -242,6 +256,18 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
       }
       l0 = l0 * c0 + rs0;
       l1 = l1 * c1 + rs1;
+      if constexpr (DROP) {
+        const uint32_t dkey = drop_key(p.drop_ctx, p.drop_site), dbase = drop_row_base(p, b, h);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t key = k0 + j * 8 + (lane & 3) * 2 + (e & 1);
+            const uint32_t qr = (e < 2) ? r0 : r1;
+            s[j][e] = drop_keep(dkey, (dbase + qr) * static_cast<uint32_t>(p.Skv) + key, p.drop_thresh) ? s[j][e] * p.drop_scale : 0.f;
+          }
+        }
+      }
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         if (2 * t < nt) {
@@ -298,7 +324,8 @@ __global__ void attn_delta_kernel(const AttnParams p) {
 // backward dQ: K, V resident; per warp 16 query rows (Q and dO tiles private).
 // BIAS (separate instantiation, the tower path compiles as before): scores get p.bias[h, q, key] / scale before the
 // exponential, and dS = P o (dP - delta) -- the gradient of the bias -- is accumulated over the batch into p.dbias.
-template <bool BIAS>
+// DROP: dP = mask / (1-p) o (dO V^T); delta = rowsum(dO o O) already holds the dropped output.
+template <bool BIAS, bool DROP = false>
 __global__ void __launch_bounds__(kAttnThreads, 2) attn_bwd_dq_kernel(const AttnParams p, int spad) {
   extern __shared__ __align__(128) uint8_t sm[];
   const uint32_t sK = s_u32(sm), sV = sK + spad * 128, sW = sV + spad * 128;
@@ -389,6 +416,18 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_bwd_dq_kernel(const Attn
           }
         }
       }
+      if constexpr (DROP) {
+        const uint32_t dkey = drop_key(p.drop_ctx, p.drop_site), dbase = drop_row_base(p, b, h);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t key = k0 + j * 8 + (lane & 3) * 2 + (e & 1);
+            const uint32_t qr = (e < 2) ? r0 : r1;
+            dpv[j][e] = drop_keep(dkey, (dbase + qr) * static_cast<uint32_t>(p.Skv) + key, p.drop_thresh) ? dpv[j][e] * p.drop_scale : 0.f;
+          }
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         s[j][0] *= dpv[j][0] - dl0; s[j][1] *= dpv[j][1] - dl0;
@@ -435,7 +474,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_bwd_dq_kernel(const Attn
 
 // backward dK/dV: Q, dO, LSE, delta resident; per warp 16 keys (K and V tiles private).
 // BIAS: as in the dQ kernel (scores only; the bias gradient is accumulated there).
-template <bool BIAS>
+// DROP: dV takes the dropped weights, dS = P o (mask / (1-p) o dP - delta).
+template <bool BIAS, bool DROP = false>
 __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dkv_kernel(const AttnParams p, int spad) {
   extern __shared__ __align__(128) uint8_t sm[];
   const uint32_t sQ = s_u32(sm), sDO = sQ + spad * 128, sW = sDO + spad * 128;
@@ -537,8 +577,23 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dkv_kernel(const AttnPa
             if (j >= nt || key >= kvl || q >= p.Sq || (p.causal && key > q)) pe[e] = 0.f;
           }
         }
-        de[0] = pe[0] * (dpt[j][0] - dl.x); de[1] = pe[1] * (dpt[j][1] - dl.y);
-        de[2] = pe[2] * (dpt[j][2] - dl.x); de[3] = pe[3] * (dpt[j][3] - dl.y);
+        if constexpr (DROP) {
+          const uint32_t dkey = drop_key(p.drop_ctx, p.drop_site), dbase = drop_row_base(p, b, h);
+          float ms[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t q = q0 + j * 8 + (lane & 3) * 2 + (e & 1);
+            const uint32_t key = (e < 2) ? key0 : key1;
+            ms[e] = drop_keep(dkey, (dbase + q) * static_cast<uint32_t>(p.Skv) + key, p.drop_thresh) ? p.drop_scale : 0.f;
+          }
+          de[0] = pe[0] * (dpt[j][0] * ms[0] - dl.x); de[1] = pe[1] * (dpt[j][1] * ms[1] - dl.y);
+          de[2] = pe[2] * (dpt[j][2] * ms[2] - dl.x); de[3] = pe[3] * (dpt[j][3] * ms[3] - dl.y);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) pe[e] *= ms[e];
+        } else {
+          de[0] = pe[0] * (dpt[j][0] - dl.x); de[1] = pe[1] * (dpt[j][1] - dl.y);
+          de[2] = pe[2] * (dpt[j][2] - dl.x); de[3] = pe[3] * (dpt[j][3] - dl.y);
+        }
         const int t = j >> 1, hi = (j & 1) * 2;
         pt[t][hi] = pack_bf16(pe[0], pe[1]);
         pt[t][hi + 1] = pack_bf16(pe[2], pe[3]);
@@ -594,6 +649,12 @@ static int attn_set_smem() {
     UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    UNIIR_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     done = true;
   }
   return UNIIR_OK;
@@ -607,7 +668,7 @@ int attn_fwd_tc_try(const __nv_bfloat16* q, long long ldq, const __nv_bfloat16* 
 
 static int attn_fwd_launch(AttnParams& p, void* stream) {
   // tcgen05 forward (attention_tc.cu) when enabled and the key range fits; > 0 means "not applicable"
-  if (!p.bias) {     // the tcgen05 kernel takes no score bias
+  if (!p.bias && !p.drop_ctx) {     // the tcgen05 kernel takes no score bias and no dropout
     const int tc = attn_fwd_tc_try(p.q, p.ldq, p.k, p.v, p.ldkv, p.B, p.Sq, p.Skv, p.H, p.causal, p.kv_len, p.out,
                                    p.ldo, p.lse, p.scale, stream);
     if (tc <= 0) return tc;
@@ -615,8 +676,13 @@ static int attn_fwd_launch(AttnParams& p, void* stream) {
   UNIIR_CHECK_ARG(p.Skv <= 768, "uniir_attn_fwd: Skv=%d exceeds the head-resident kernel's limit of 768", p.Skv);
   if (int rc = attn_set_smem()) return rc;
   const int spad = (p.Skv + 15) / 16 * 16;
-  if (p.bias) attn_fwd_kernel<true><<<dim3(p.H, p.B), kAttnThreads, attn_smem(spad, false), ST(stream)>>>(p, spad);
-  else attn_fwd_kernel<false><<<dim3(p.H, p.B), kAttnThreads, attn_smem(spad, false), ST(stream)>>>(p, spad);
+  const dim3 grid(p.H, p.B);
+  const int smem = attn_smem(spad, false);
+  if (p.drop_ctx) {
+    if (p.bias) attn_fwd_kernel<true, true><<<grid, kAttnThreads, smem, ST(stream)>>>(p, spad);
+    else attn_fwd_kernel<false, true><<<grid, kAttnThreads, smem, ST(stream)>>>(p, spad);
+  } else if (p.bias) attn_fwd_kernel<true><<<grid, kAttnThreads, smem, ST(stream)>>>(p, spad);
+  else attn_fwd_kernel<false><<<grid, kAttnThreads, smem, ST(stream)>>>(p, spad);
   count_launch();
   UNIIR_CUDA_OK(cudaGetLastError());
   return UNIIR_OK;
@@ -687,7 +753,7 @@ extern "C" int64_t uniir_attn_bwd_workspace_floats(int32_t B, int32_t Sq, int32_
 
 static int attn_bwd_launch(AttnParams& p, void* stream) {
   // tcgen05 backward (attention_bwd_tc.cu) when enabled and the shape fits; > 0 means "not applicable"
-  if (!p.bias) {     // the tcgen05 kernel takes no score bias
+  if (!p.bias && !p.drop_ctx) {     // the tcgen05 kernel takes no score bias and no dropout
     const int tc = attn_bwd_tc_try(p.q, p.ldq, p.k, p.v, p.ldkv, p.out, p.ldo, p.dout, p.lddo, p.lse, p.B, p.Sq, p.Skv,
                                    p.H, p.causal, p.kv_len, p.delta, p.dq, p.lddq, p.dk, p.dv, p.lddkv, p.scale, stream);
     if (tc <= 0) return tc;
@@ -697,7 +763,15 @@ static int attn_bwd_launch(AttnParams& p, void* stream) {
   const int spad_kv = (p.Skv + 15) / 16 * 16, spad_q = (p.Sq + 15) / 16 * 16;
   const long long warps = 1LL * p.B * p.Sq * p.H;
   attn_delta_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, ST(stream)>>>(p);
-  if (p.bias) {
+  if (p.drop_ctx) {
+    if (p.bias) {
+      attn_bwd_dq_kernel<true, true><<<dim3(p.H, p.B), kAttnThreads, attn_smem(spad_kv, true), ST(stream)>>>(p, spad_kv);
+      attn_bwd_dkv_kernel<true, true><<<dim3(p.H, p.B), kAttnThreads, attn_smem(spad_q, true), ST(stream)>>>(p, spad_q);
+    } else {
+      attn_bwd_dq_kernel<false, true><<<dim3(p.H, p.B), kAttnThreads, attn_smem(spad_kv, true), ST(stream)>>>(p, spad_kv);
+      attn_bwd_dkv_kernel<false, true><<<dim3(p.H, p.B), kAttnThreads, attn_smem(spad_q, true), ST(stream)>>>(p, spad_q);
+    }
+  } else if (p.bias) {
     attn_bwd_dq_kernel<true><<<dim3(p.H, p.B), kAttnThreads, attn_smem(spad_kv, true), ST(stream)>>>(p, spad_kv);
     attn_bwd_dkv_kernel<true><<<dim3(p.H, p.B), kAttnThreads, attn_smem(spad_q, true), ST(stream)>>>(p, spad_q);
   } else {
@@ -784,5 +858,63 @@ extern "C" int uniir_attn_bwd_bias(const void* q, int64_t ldq, const void* k, co
   p.dq = static_cast<__nv_bfloat16*>(dq); p.dk = static_cast<__nv_bfloat16*>(dk); p.dv = static_cast<__nv_bfloat16*>(dv);
   p.lddq = lddq; p.lddkv = lddkv;
   p.B = B; p.S = Sq; p.Sq = Sq; p.Skv = Skv; p.H = H; p.D = H * kHD; p.causal = 0; p.scale = scale;
+  return attn_bwd_launch(p, stream);
+}
+
+// ---- attention with dropout on the probabilities (training of the BLIP BERT stack and the CLIP_FF T5 stack).
+// General addressing (as the _ex / _bias entry points), optional key-padding mask, optional score bias, caller's scale.
+static void set_drop(AttnParams& p, const uint32_t* ctx, uint32_t site, float pd) {
+  p.drop_ctx = ctx; p.drop_site = site; p.drop_thresh = drop_thresh(pd); p.drop_scale = 1.f / (1.f - pd);
+}
+
+extern "C" int uniir_attn_fwd_drop(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, int32_t B,
+                                   int32_t Sq, int32_t Skv, int32_t H, int32_t causal, const int32_t* kv_len, float scale,
+                                   const float* bias, void* out, int64_t ldo, float* lse, const uint32_t* drop_ctx,
+                                   uint32_t site, float p_drop, void* stream) {
+  UNIIR_CHECK_ARG(q && k && v && out && drop_ctx && B > 0 && Sq > 0 && Skv > 0 && H > 0 && scale > 0.f && p_drop >= 0.f &&
+                  p_drop < 1.f, "uniir_attn_fwd_drop: bad args");
+  UNIIR_CHECK_ARG(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 2 == 0, "uniir_attn_fwd_drop: strides must keep 16 B row alignment");
+  UNIIR_CHECK_ARG(!causal || Sq == Skv, "uniir_attn_fwd_drop: causal needs Sq == Skv");
+  AttnParams p{};
+  p.q = static_cast<const __nv_bfloat16*>(q);
+  p.k = static_cast<const __nv_bfloat16*>(k);
+  p.v = static_cast<const __nv_bfloat16*>(v);
+  p.ldq = ldq; p.ldkv = ldkv; p.ldo = ldo;
+  p.Sq = Sq; p.Skv = Skv; p.kv_len = kv_len; p.bias = bias;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.lse = lse;
+  p.B = B; p.S = Sq; p.H = H; p.D = H * kHD; p.causal = causal; p.scale = scale;
+  set_drop(p, drop_ctx, site, p_drop);
+  return attn_fwd_launch(p, stream);
+}
+
+extern "C" int uniir_attn_bwd_drop(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const void* out,
+                                   int64_t ldo, const void* dout, int64_t lddo, const float* lse, int32_t B, int32_t Sq,
+                                   int32_t Skv, int32_t H, int32_t causal, const int32_t* kv_len, float scale,
+                                   const float* bias, float* dbias, float* delta_ws, void* dq, int64_t lddq, void* dk,
+                                   void* dv, int64_t lddkv, const uint32_t* drop_ctx, uint32_t site, float p_drop,
+                                   void* stream) {
+  UNIIR_CHECK_ARG(q && k && v && out && dout && lse && delta_ws && dq && dk && dv && drop_ctx && B > 0 && Sq > 0 && Skv > 0 &&
+                  H > 0 && scale > 0.f && p_drop >= 0.f && p_drop < 1.f && (!bias == !dbias), "uniir_attn_bwd_drop: bad args");
+  UNIIR_CHECK_ARG(ldq % 8 == 0 && ldkv % 8 == 0 && lddo % 8 == 0 && ldo % 2 == 0 && lddq % 2 == 0 && lddkv % 2 == 0,
+                  "uniir_attn_bwd_drop: strides must keep row alignment");
+  UNIIR_CHECK_ARG(!causal || Sq == Skv, "uniir_attn_bwd_drop: causal needs Sq == Skv");
+  AttnParams p{};
+  p.q = static_cast<const __nv_bfloat16*>(q);
+  p.k = static_cast<const __nv_bfloat16*>(k);
+  p.v = static_cast<const __nv_bfloat16*>(v);
+  p.ldq = ldq; p.ldkv = ldkv;
+  p.out = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(out));
+  p.ldo = ldo;
+  p.dout = static_cast<const __nv_bfloat16*>(dout);
+  p.lddo = lddo;
+  p.lse = const_cast<float*>(lse);
+  p.delta = delta_ws;
+  p.kv_len = kv_len;
+  p.bias = bias; p.dbias = dbias;
+  p.dq = static_cast<__nv_bfloat16*>(dq); p.dk = static_cast<__nv_bfloat16*>(dk); p.dv = static_cast<__nv_bfloat16*>(dv);
+  p.lddq = lddq; p.lddkv = lddkv;
+  p.B = B; p.S = Sq; p.Sq = Sq; p.Skv = Skv; p.H = H; p.D = H * kHD; p.causal = causal; p.scale = scale;
+  set_drop(p, drop_ctx, site, p_drop);
   return attn_bwd_launch(p, stream);
 }

@@ -16,6 +16,8 @@ extern "C" int uniir_gemm_epi(const uniir_gemm_desc* d, void* stream_) {
                   "uniir_gemm_epi: N, K must be multiples of 8 (N=%d K=%d)", d->N, d->K);
   UNIIR_CHECK_ARG(d->ldo % 4 == 0, "uniir_gemm_epi: ldo must be a multiple of 4");
   const bool atomic = d->split_k > 1;
+  UNIIR_CHECK_ARG(!d->row_scale || (d->row_scale_rows > 0 && d->split_k <= 1),
+                  "uniir_gemm_epi: row_scale needs row_scale_rows > 0 and no split_k");
   UNIIR_CHECK_ARG(!(atomic || d->accumulate) || d->out_dtype == UNIIR_F32,
                   "uniir_gemm_epi: accumulate/split_k need an fp32 output");
   UNIIR_CHECK_ARG(!atomic || (!d->bias && !d->residual && !d->aux_out && !d->act_grad_src &&
@@ -73,6 +75,7 @@ extern "C" int uniir_gemm_epi(const uniir_gemm_desc* d, void* stream_) {
   p.alpha = d->alpha;
   p.accumulate = d->accumulate;
   p.atomic = atomic ? 1 : 0;
+  p.row_scale = d->row_scale; p.rs_rows = d->row_scale ? d->row_scale_rows : 1;
 
   TileSched s;
   s.m_blocks = m_blocks;
@@ -87,8 +90,13 @@ extern "C" int uniir_gemm_epi(const uniir_gemm_desc* d, void* stream_) {
   const bool has_res = d->residual != nullptr, has_aux = d->aux_out != nullptr, has_ags = d->act_grad_src != nullptr;
   const bool has_act = d->act != UNIIR_ACT_NONE;
   const bool out32 = d->out_dtype == UNIIR_F32;
+  const bool has_rs = d->row_scale != nullptr;
   int epi = EPI_DYN;
-  if (!d->a_mn && !has_res && !has_aux && !has_ags && !has_act && !d->accumulate && !atomic)
+  if (has_rs) {
+    if (!d->a_mn && !d->b_mn && has_res && d->res_dtype == UNIIR_F32 && out32 && !has_aux && !has_ags && !has_act &&
+        !d->accumulate && !atomic)
+      epi = EPI_RES32_RS;
+  } else if (!d->a_mn && !has_res && !has_aux && !has_ags && !has_act && !d->accumulate && !atomic)
     epi = out32 ? EPI_STORE32 : EPI_STORE16;
   else if (!d->a_mn && !d->b_mn && !has_res && !has_ags && has_act && !out32 && !d->accumulate && !atomic)
     epi = has_aux ? EPI_ACT_AUX : EPI_ACT;
@@ -114,6 +122,7 @@ extern "C" int uniir_gemm_epi(const uniir_gemm_desc* d, void* stream_) {
       case EPI_ACT_AUX: UNIIR_GO2(false, false, EPI_ACT_AUX);
       case EPI_AGS: UNIIR_GO2(false, true, EPI_AGS);
       case EPI_RES32: UNIIR_GO2(false, false, EPI_RES32);
+      case EPI_RES32_RS: UNIIR_GO2(false, false, EPI_RES32_RS);
       case EPI_ACC32: UNIIR_GO2(true, true, EPI_ACC32);
       default: break;   // no pair instantiation: fall through to the single-CTA kernels
     }
@@ -133,6 +142,7 @@ extern "C" int uniir_gemm_epi(const uniir_gemm_desc* d, void* stream_) {
     case EPI_ACT_AUX: UNIIR_BY_BN(false, false, EPI_ACT_AUX);
     case EPI_AGS: UNIIR_BY_BN(false, true, EPI_AGS);
     case EPI_RES32: UNIIR_BY_BN(false, false, EPI_RES32);
+    case EPI_RES32_RS: UNIIR_BY_BN(false, false, EPI_RES32_RS);
     case EPI_ACC32: UNIIR_BY_BN(true, true, EPI_ACC32);
     case EPI_ATOMIC: UNIIR_BY_BN(true, true, EPI_ATOMIC);
     default: break;

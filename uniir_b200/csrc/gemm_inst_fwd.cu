@@ -12,4 +12,6 @@ UNIIR_INSTANTIATE_GEMM(128, false, false, EPI_ACT_AUX)
 UNIIR_INSTANTIATE_GEMM(256, false, false, EPI_ACT_AUX)
 UNIIR_INSTANTIATE_GEMM(128, false, false, EPI_RES32)
 UNIIR_INSTANTIATE_GEMM(256, false, false, EPI_RES32)
+UNIIR_INSTANTIATE_GEMM(128, false, false, EPI_RES32_RS)
+UNIIR_INSTANTIATE_GEMM(256, false, false, EPI_RES32_RS)
 }  // namespace uniir

@@ -22,6 +22,8 @@ struct GemmEpiParams {
   float alpha;
   int accumulate;
   int atomic;
+  const float* row_scale;   // optional fp32 [ceil(M / rs_rows)]: (value + bias) * row_scale[row / rs_rows] before the
+  int rs_rows;              // residual is added -- DropPath of a residual branch (vit.py:151-152), one scale per item
 };
 
 struct TileSched {
@@ -119,6 +121,7 @@ enum : int {
   EPI_RES32,     // +bias, + fp32 residual -> fp32               out_proj / c_proj forward
   EPI_ACC32,     // out += value (fp32)                          wgrad
   EPI_ATOMIC,    // atomicAdd(out, value) (fp32, split-K)        wgrad, narrow outputs
+  EPI_RES32_RS,  // (+bias) * row_scale[row / rs_rows] + fp32 residual -> fp32   out_proj / c_proj forward under DropPath
 };
 
 template <int BN, int EPI>
@@ -127,9 +130,10 @@ struct GemmEpilogue {
   __device__ __forceinline__ bool do_aux() const { return DYN ? p.aux_out != nullptr : EPI == EPI_ACT_AUX; }
   __device__ __forceinline__ bool do_act() const { return DYN ? (p.act != UNIIR_ACT_NONE && !p.ags) : (EPI == EPI_ACT || EPI == EPI_ACT_AUX); }
   __device__ __forceinline__ bool do_ags() const { return DYN ? p.ags != nullptr : EPI == EPI_AGS; }
-  __device__ __forceinline__ bool res32() const { return DYN ? (p.residual && p.res_dtype == UNIIR_F32) : EPI == EPI_RES32; }
+  __device__ __forceinline__ bool res32() const { return DYN ? (p.residual && p.res_dtype == UNIIR_F32) : (EPI == EPI_RES32 || EPI == EPI_RES32_RS); }
+  __device__ __forceinline__ bool row_scaled() const { return DYN ? p.row_scale != nullptr : EPI == EPI_RES32_RS; }
   __device__ __forceinline__ bool res16() const { return DYN ? (p.residual && p.res_dtype != UNIIR_F32) : false; }
-  __device__ __forceinline__ bool out32() const { return DYN ? p.out_dtype == UNIIR_F32 : (EPI == EPI_STORE32 || EPI == EPI_RES32 || EPI == EPI_ACC32 || EPI == EPI_ATOMIC); }
+  __device__ __forceinline__ bool out32() const { return DYN ? p.out_dtype == UNIIR_F32 : (EPI == EPI_STORE32 || EPI == EPI_RES32 || EPI == EPI_RES32_RS || EPI == EPI_ACC32 || EPI == EPI_ATOMIC); }
   __device__ __forceinline__ bool atomic() const { return DYN ? p.atomic != 0 : EPI == EPI_ATOMIC; }
   __device__ __forceinline__ bool acc() const { return DYN ? (p.accumulate && !p.atomic) : EPI == EPI_ACC32; }
 
@@ -204,6 +208,11 @@ struct GemmEpilogue {
         unpack8(in.b, p.in_dtype, s);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] *= act_bwd(s[j], p.act);
+    }
+    if (row_scaled()) {
+      const float rs = __ldg(p.row_scale + static_cast<int>(grow) / p.rs_rows);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= rs;
     }
     if (res32()) add8(v, in);
     if (res16()) {

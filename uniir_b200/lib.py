@@ -34,6 +34,7 @@ class GemmDesc(C.Structure):
         ("alpha", C.c_float),
         ("accumulate", C.c_int32),
         ("split_k", C.c_int32),
+        ("row_scale", C.c_void_p), ("row_scale_rows", C.c_int32),
     ]
 
 
@@ -95,6 +96,14 @@ _SIGS = {
     "uniir_blip_softce": (C.c_int, [VP, VP, VP, VP, I32, I32, C.c_float, C.c_float, VP, VP, VP, VP, VP]),
     "uniir_hardneg_loss": (C.c_int, [VP, VP, VP, VP, I32, I32, I32, I32, VP, VP, VP, VP, VP, VP]),
     "uniir_infonce_normalize_bwd": (C.c_int, [VP, VP, VP, VP, VP, VP, VP, VP, I32, I32, VP, VP]),
+    "uniir_dropout": (C.c_int, [VP, I32, VP, VP, I32, I64, VP, C.c_uint32, I64, C.c_float, VP]),
+    "uniir_dropout_mask": (C.c_int, [VP, C.c_uint32, I64, I64, C.c_float, VP, VP]),
+    "uniir_droppath_scales": (C.c_int, [VP, C.c_uint32, I32, I32, VP, VP, VP]),
+    "uniir_row_scale": (C.c_int, [VP, I64, I32, I64, VP, I32, VP]),
+    "uniir_attn_fwd_drop": (C.c_int, [VP, I64, VP, VP, I64, I32, I32, I32, I32, I32, VP, C.c_float, VP, VP, I64, VP, VP,
+                                      C.c_uint32, C.c_float, VP]),
+    "uniir_attn_bwd_drop": (C.c_int, [VP, I64, VP, VP, I64, VP, I64, VP, I64, VP, I32, I32, I32, I32, I32, VP, C.c_float,
+                                      VP, VP, VP, VP, I64, VP, VP, I64, VP, C.c_uint32, C.c_float, VP]),
 }
 
 _lib = None

@@ -51,8 +51,11 @@ def set_gemm_profiler(sink, events=False):
 
 
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=None, act=L.ACT_NONE,
-         residual=None, aux_out=None, act_grad_src=None, alpha=1.0, accumulate=False, split_k=1):
+         residual=None, aux_out=None, act_grad_src=None, alpha=1.0, accumulate=False, split_k=1, row_scale=None,
+         row_scale_rows=1):
     """out[M,N] (+)= epilogue(alpha * A . B^T); see include/uniir_b200.h.
+    row_scale (fp32 [ceil(M / row_scale_rows)]): the value is multiplied by row_scale[row // row_scale_rows] before the
+    residual is added (DropPath of a residual branch).
 
     a: [M,K] (a_mn False) or [K,M] (a_mn True);  b: [N,K] or [K,N] likewise."""
     _require_cuda(a, b)
@@ -86,6 +89,9 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=None, a
     d.alpha = alpha
     d.accumulate = int(accumulate)
     d.split_k = split_k
+    if row_scale is not None:
+        assert row_scale.dtype == torch.float32 and row_scale.is_contiguous() and row_scale.numel() * row_scale_rows >= M
+        d.row_scale, d.row_scale_rows = row_scale.data_ptr(), int(row_scale_rows)
     if _GEMM_PROF is not None:
         _GEMM_PROF.append(dict(M=M, N=N, K=K, a_mn=bool(a_mn), b_mn=bool(b_mn), dtype=a.dtype,
                                out_dtype=out.dtype, bias=bias is not None, act=act,
@@ -396,20 +402,27 @@ def attn_fwd(qkv, B, S, H, causal, out=None, lse=None, need_lse=True):
     return out, lse
 
 
-def attn_fwd_ex(q, k, v, B, Sq, Skv, H, *, causal=False, kv_len=None, out=None, lse=None):
+def attn_fwd_ex(q, k, v, B, Sq, Skv, H, *, causal=False, kv_len=None, out=None, lse=None, drop=None):
     """q [B*Sq, >=H*64] / k, v [B*Skv, >=H*64] bf16 row-strided views (column slices of packed projections are
-    fine), optional int32 kv_len[B] key-padding mask."""
+    fine), optional int32 kv_len[B] key-padding mask.  drop = (ctx, site, p): dropout on the probabilities."""
     assert q.dtype == torch.bfloat16 and q.stride(1) == 1 and k.stride(1) == 1 and v.stride(1) == 1
     assert k.stride(0) == v.stride(0)
     if out is None:
         out = torch.empty(B * Sq, H * 64, device=q.device, dtype=torch.bfloat16)
+    if drop is not None:
+        ctx, site, p = drop
+        L.check(L.load().uniir_attn_fwd_drop(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), B, Sq, Skv,
+                                             H, int(causal), _ptr(kv_len), 0.125, None, out.data_ptr(), out.stride(0),
+                                             _ptr(lse), ctx.data_ptr(), int(site), float(p), _stream()),
+                "uniir_attn_fwd_drop")
+        return out
     L.check(L.load().uniir_attn_fwd_ex(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), B, Sq, Skv, H,
                                        int(causal), _ptr(kv_len), out.data_ptr(), out.stride(0), _ptr(lse), _stream()),
             "uniir_attn_fwd_ex")
     return out
 
 
-def attn_fwd_bias(q, k, v, B, Sq, Skv, H, bias, scale=1.0, out=None, lse=None):
+def attn_fwd_bias(q, k, v, B, Sq, Skv, H, bias, scale=1.0, out=None, lse=None, drop=None):
     """softmax(scale * q k^T + bias) v with bias fp32 [H, Sq, Skv] shared by all batch rows (T5 relative-position
     bias; T5 does not scale the scores).  q / k / v: bf16 row-strided views as in attn_fwd_ex."""
     assert q.dtype == torch.bfloat16 and q.stride(1) == 1 and k.stride(1) == 1 and v.stride(1) == 1
@@ -417,18 +430,34 @@ def attn_fwd_bias(q, k, v, B, Sq, Skv, H, bias, scale=1.0, out=None, lse=None):
     assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.shape == (H, Sq, Skv)
     if out is None:
         out = torch.empty(B * Sq, H * 64, device=q.device, dtype=torch.bfloat16)
+    if drop is not None:
+        ctx, site, p = drop
+        L.check(L.load().uniir_attn_fwd_drop(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), B, Sq, Skv,
+                                             H, 0, None, float(scale), bias.data_ptr(), out.data_ptr(), out.stride(0),
+                                             _ptr(lse), ctx.data_ptr(), int(site), float(p), _stream()),
+                "uniir_attn_fwd_drop")
+        return out
     L.check(L.load().uniir_attn_fwd_bias(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), B, Sq, Skv, H,
                                          float(scale), bias.data_ptr(), out.data_ptr(), out.stride(0), _ptr(lse), _stream()),
             "uniir_attn_fwd_bias")
     return out
 
 
-def attn_bwd_bias(q, k, v, out, dout, lse, B, Sq, Skv, H, bias, dbias, dq, dk, dv, scale=1.0, delta=None):
+def attn_bwd_bias(q, k, v, out, dout, lse, B, Sq, Skv, H, bias, dbias, dq, dk, dv, scale=1.0, delta=None, drop=None):
     """Backward of attn_fwd_bias; dbias fp32 [H, Sq, Skv] += gradient of the bias (zero it first)."""
     if delta is None:
         delta = torch.empty(B * H * Sq, device=q.device, dtype=torch.float32)
     assert dk.stride(0) == dv.stride(0) and k.stride(0) == v.stride(0)
     assert bias.shape == dbias.shape == (H, Sq, Skv) and dbias.dtype == torch.float32 and dbias.is_contiguous()
+    if drop is not None:
+        ctx, site, p = drop
+        L.check(L.load().uniir_attn_bwd_drop(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0),
+                                             out.data_ptr(), out.stride(0), dout.data_ptr(), dout.stride(0), lse.data_ptr(),
+                                             B, Sq, Skv, H, 0, None, float(scale), bias.data_ptr(), dbias.data_ptr(),
+                                             delta.data_ptr(), dq.data_ptr(), dq.stride(0), dk.data_ptr(), dv.data_ptr(),
+                                             dk.stride(0), ctx.data_ptr(), int(site), float(p), _stream()),
+                "uniir_attn_bwd_drop")
+        return
     L.check(L.load().uniir_attn_bwd_bias(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), out.data_ptr(),
                                          out.stride(0), dout.data_ptr(), dout.stride(0), lse.data_ptr(), B, Sq, Skv, H,
                                          float(scale), bias.data_ptr(), dbias.data_ptr(), delta.data_ptr(), dq.data_ptr(),
@@ -545,11 +574,19 @@ def hardneg_loss(emb, q_idx, p_idx, n_idx, in_batch_neg_num, logit_scale, d_logi
     return sums[0] / bs, sums[1] / bs, d_emb
 
 
-def attn_bwd_ex(q, k, v, out, dout, lse, B, Sq, Skv, H, dq, dk, dv, *, causal=False, kv_len=None, delta=None):
+def attn_bwd_ex(q, k, v, out, dout, lse, B, Sq, Skv, H, dq, dk, dv, *, causal=False, kv_len=None, delta=None, drop=None):
     """Backward of attn_fwd_ex; dq/dk/dv are preallocated bf16 row-strided views (dk, dv share a stride)."""
     if delta is None:
         delta = torch.empty(attn_bwd_ws_floats(B, Sq, Skv, H), device=q.device, dtype=torch.float32)
     assert dk.stride(0) == dv.stride(0) and k.stride(0) == v.stride(0)
+    if drop is not None:
+        ctx, site, p = drop
+        L.check(L.load().uniir_attn_bwd_drop(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0),
+                                             out.data_ptr(), out.stride(0), dout.data_ptr(), dout.stride(0), lse.data_ptr(),
+                                             B, Sq, Skv, H, int(causal), _ptr(kv_len), 0.125, None, None, delta.data_ptr(),
+                                             dq.data_ptr(), dq.stride(0), dk.data_ptr(), dv.data_ptr(), dk.stride(0),
+                                             ctx.data_ptr(), int(site), float(p), _stream()), "uniir_attn_bwd_drop")
+        return
     L.check(L.load().uniir_attn_bwd_ex(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), out.data_ptr(),
                                        out.stride(0), dout.data_ptr(), dout.stride(0), lse.data_ptr(), B, Sq, Skv, H,
                                        int(causal), _ptr(kv_len), delta.data_ptr(), dq.data_ptr(), dq.stride(0),
@@ -581,3 +618,47 @@ def blip_softce(S, Sm, pc_id, id_all, alpha, gscale, temp, loss_sum, acc_sum, d_
     L.check(L.load().uniir_blip_softce(S.data_ptr(), Sm.data_ptr(), pc_id.data_ptr(), id_all.data_ptr(), bs, n, alpha,
                                        gscale, temp.data_ptr(), loss_sum.data_ptr(), _ptr(acc_sum), d_temp.data_ptr(),
                                        _stream()), "uniir_blip_softce")
+
+
+# ---- dropout / stochastic depth (include/uniir_b200.h; counter-based masks, nothing saved) -------------------------
+def drop_ctx(device):
+    """uint32[2] device buffer {seed of the step, first item of the micro-batch}; int32 storage (torch has no uint32
+    arithmetic), read as uint32 by the kernels."""
+    return torch.zeros(2, device=device, dtype=torch.int32)
+
+
+def dropout(x, ctx, site, per_item, p, *, residual=None, out=None):
+    """out = dropout(x) (+ residual): keep with probability 1 - p, scale 1 / (1 - p); x / out fp32 or bf16 contiguous,
+    residual fp32; out defaults to x (in place)."""
+    out = x if out is None else out
+    assert x.is_contiguous() and out.is_contiguous() and x.numel() == out.numel()
+    assert residual is None or (residual.dtype == torch.float32 and residual.is_contiguous() and residual.numel() == x.numel())
+    L.check(L.load().uniir_dropout(x.data_ptr(), _DT[x.dtype], _ptr(residual), out.data_ptr(), _DT[out.dtype], x.numel(),
+                                   ctx.data_ptr(), int(site), int(per_item), float(p), _stream()), "uniir_dropout")
+    return out
+
+
+def dropout_mask(ctx, site, per_item, n, p):
+    keep = torch.empty(n, device=ctx.device, dtype=torch.uint8)
+    L.check(L.load().uniir_dropout_mask(ctx.data_ptr(), int(site), int(per_item), n, float(p), keep.data_ptr(), _stream()),
+            "uniir_dropout_mask")
+    return keep
+
+
+def droppath_scales(ctx, site_base, p_sites, mb, out=None):
+    """fp32 [n_sites, mb]: 1 / (1 - p_sites[s]) where item b keeps residual branch s, else 0."""
+    n = p_sites.numel()
+    if out is None:
+        out = torch.empty(n, mb, device=ctx.device, dtype=torch.float32)
+    assert p_sites.dtype == torch.float32 and p_sites.is_contiguous() and out.is_contiguous()
+    L.check(L.load().uniir_droppath_scales(ctx.data_ptr(), int(site_base), n, mb, p_sites.data_ptr(), out.data_ptr(),
+                                           _stream()), "uniir_droppath_scales")
+    return out
+
+
+def row_scale(x, scales, rows_per_scale):
+    """x[r, :] *= scales[r // rows_per_scale]; x bf16 [rows, cols] row-strided, in place."""
+    assert x.dtype == torch.bfloat16 and x.stride(1) == 1 and scales.dtype == torch.float32 and scales.is_contiguous()
+    L.check(L.load().uniir_row_scale(x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), scales.data_ptr(),
+                                     int(rows_per_scale), _stream()), "uniir_row_scale")
+    return x
