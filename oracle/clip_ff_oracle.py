@@ -40,6 +40,20 @@ class _T5Norm(nn.Module):
         return self.weight * (x * torch.rsqrt(var + self.eps))
 
 
+# Dropout sites of transformers' encoder T5Stack in train mode (T5Config.dropout_rate = 0.1; the reference keeps the
+# default, clip_ff.py:82-98): T5Stack.forward `dropout(inputs_embeds)` and `dropout(final_layer_norm(h))`; T5Attention
+# `dropout(softmax(scores))`; T5LayerSelfAttention `h + dropout(attn)`; T5DenseActDense `wo(dropout(relu(wi(x))))`;
+# T5LayerFF `h + dropout(ff)`.  The restatement is the eval-mode arithmetic (identity at every site) unless a test
+# installs DROPOUT, a callable (kind, layer, x) -> x with kind in "input", "probs", "attn_out", "ff_inner", "ff_out",
+# "final": the masks then come from the caller (tests/test_oracle_clip_ff.py pins the SITES against transformers'
+# T5Stack in train mode by handing both the same masks).
+DROPOUT = None
+
+
+def _drop(kind, layer, x):
+    return x if DROPOUT is None else DROPOUT(kind, layer, x)
+
+
 def t5_relative_position_bucket(rel, num_buckets=32, max_distance=128):
     """Bidirectional bucketing of `memory_position - query_position` (modeling_t5 `_relative_position_bucket`)."""
     num_buckets //= 2
@@ -65,12 +79,12 @@ class _T5SelfAttention(nn.Module):
         if has_bias:
             self.relative_attention_bias = nn.Embedding(num_buckets, heads)
 
-    def forward(self, x, position_bias):
+    def forward(self, x, position_bias, layer=0):
         B, S, _ = x.shape
         sp = lambda t: t.view(B, S, self.heads, self.d_kv).transpose(1, 2)
         q, k, v = sp(self.q(x)), sp(self.k(x)), sp(self.v(x))
         scores = q @ k.transpose(-1, -2) + position_bias          # NB: no 1/sqrt(d_kv) (folded into the T5 init)
-        w = F.softmax(scores.float(), dim=-1).type_as(scores)
+        w = _drop("probs", layer, F.softmax(scores.float(), dim=-1).type_as(scores))
         return self.o((w @ v).transpose(1, 2).reshape(B, S, self.heads * self.d_kv))
 
 
@@ -103,7 +117,7 @@ class _T5Block(nn.Module):
 
 
 class T5StackOracle(nn.Module):
-    """Encoder `T5Stack` on `inputs_embeds` without mask, dropout off (eval) -- HF parameter names."""
+    """Encoder `T5Stack` on `inputs_embeds` without mask -- HF parameter names; dropout: see DROPOUT above."""
 
     def __init__(self, d_model=768, num_layers=2, heads=12, d_kv=64, d_ff=2048, num_buckets=32, max_distance=128):
         super().__init__()
@@ -119,11 +133,12 @@ class T5StackOracle(nn.Module):
 
     def forward(self, x):
         bias = self.position_bias(x.shape[1])
-        for blk in self.block:
+        x = _drop("input", 0, x)
+        for i, blk in enumerate(self.block):
             att, ff = blk.layer
-            x = x + att.SelfAttention(att.layer_norm(x), bias)
-            x = x + ff.DenseReluDense.wo(F.relu(ff.DenseReluDense.wi(ff.layer_norm(x))))
-        return self.final_layer_norm(x)
+            x = x + _drop("attn_out", i, att.SelfAttention(att.layer_norm(x), bias, i))
+            x = x + _drop("ff_out", i, ff.DenseReluDense.wo(_drop("ff_inner", i, F.relu(ff.DenseReluDense.wi(ff.layer_norm(x))))))
+        return _drop("final", 0, self.final_layer_norm(x))
 
 
 class CLIPFeatureFusionOracle(nn.Module):

@@ -51,7 +51,7 @@ def test_clip_ff_encode_matches_oracle_and_api_contract():
     with torch.no_grad():      # T5 weights at a scale where the fusion stack matters
         for n, p in orc.t5_layers.named_parameters():
             p.normal_(0.0, 0.08) if "layer_norm" not in n else p.normal_(1.0, 0.1)
-    m = CLIPFeatureFusion("tiny-test", device=dev, micro_batch=4)
+    m = CLIPFeatureFusion("tiny-test", device=dev, micro_batch=4).eval()      # eval: no T5 dropout, like the oracle
     missing, unexpected = m.load_state_dict(orc.state_dict(), strict=True)
     d = orc.clip_model.dims
     g = torch.Generator().manual_seed(5)
@@ -152,6 +152,7 @@ def test_clip_ff_training_step_matches_oracle():
             p.normal_(0.0, 0.08) if "layer_norm" not in n else p.normal_(1.0, 0.1)
     m = CLIPFeatureFusion("tiny-test", device=dev, micro_batch=8)
     m.train_micro_batch = 8
+    m.set_dropout(0.0)           # the deterministic arithmetic; train mode with the T5 dropout: tests/test_dropout_gpu.py
     m.load_state_dict(orc.state_dict(), strict=True)
     d = orc.clip_model.dims
     g = torch.Generator().manual_seed(22)

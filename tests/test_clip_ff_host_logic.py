@@ -126,3 +126,81 @@ def test_fused_adamw_parameter_groups_equal_the_reference_optimizer(monkeypatch)
         for n, p in ref.items():
             assert torch.allclose(P.w(n), p.detach(), atol=1e-7, rtol=1e-5), n
             assert P.g(n).abs().max().item() == 0                       # the fused step zeroes the gradients
+
+
+def t5_mask_hook(seed, p=0.1):
+    """oracle.clip_ff_oracle.DROPOUT hook that reproduces the product's counter-based masks (CLIPFFEncoder sites)."""
+    sites = {"probs": 1, "attn_out": 2, "ff_inner": 3, "ff_out": 4}
+
+    def hook(kind, layer, x):
+        site = 0 if kind == "input" else (1 + 4 * hook.layers if kind == "final" else sites[kind] + 4 * layer)
+        keep = cpu_kernels.keep_mask(seed, site, torch.arange(x.numel()), p).view(x.shape)
+        return x * keep.float() * cpu_kernels.drop_scale(p)
+    hook.layers = 2
+    return hook
+
+
+def test_clip_ff_encoder_with_dropout_matches_oracle_given_the_same_masks(monkeypatch):
+    """Train mode of the T5 fusion stack (dropout_rate 0.1 at transformers' sites; the oracle's hooks are pinned against
+    transformers' T5Stack in tests/test_oracle_clip_ff.py): with the product's counter-based masks fed to the oracle, the
+    forward and every parameter gradient agree; the no-activation forward (gradient-cache phase A, in-place residual
+    stream) encodes the same thing, also when the batch is tiled differently."""
+    import oracle.clip_ff_oracle as co
+    cpu_kernels.install(monkeypatch)
+    from uniir_b200.clip_ff import CLIPFFEncoder, clip_ff_param_specs, t5_heads
+    from uniir_b200.params import CLIP_CONFIGS, FlatParamModule
+    name, seed = "tiny-test", 4711
+    torch.manual_seed(13)
+    orc = CLIPFeatureFusionOracle(name).eval()
+    with torch.no_grad():
+        for n, p in orc.t5_layers.named_parameters():
+            p.normal_(0.0, 0.08) if "layer_norm" not in n else p.normal_(1.0, 0.1)
+    d = CLIP_CONFIGS[name]
+    root = torch.nn.Module()
+    P = FlatParamModule(clip_ff_param_specs(d, t5_heads(name)), "cpu", root=root)
+    root.load_state_dict(orc.state_dict(), strict=True)
+    P.refresh_shadow(force=True)
+    P.ensure_grad()
+    mb = 4
+    enc = CLIPFFEncoder(P, d, t5_heads(name), mb, "cpu", train=True)
+    enc.set_dropout(0.1)
+    enc.refresh_weights()
+    g = torch.Generator().manual_seed(14)
+    ids = torch.zeros(mb, d.context, dtype=torch.int32)
+    for i in range(mb):
+        n = int(torch.randint(1, d.context - 2, (1,), generator=g))
+        ids[i, 0] = d.vocab - 2; ids[i, 1:1 + n] = torch.randint(1, d.vocab - 2, (n,), generator=g).int(); ids[i, 1 + n] = d.vocab - 1
+    img = torch.randn(mb, 3, d.image_size, d.image_size, generator=g)
+    d_emb = torch.randn(mb, d.embed_dim, generator=g)
+    plain = orc.encode_multimodal_input(ids.long(), img).detach()
+    monkeypatch.setattr(co, "DROPOUT", t5_mask_hook(seed))
+    ref = orc.encode_multimodal_input(ids.long(), img)
+    ref.backward(d_emb)
+    monkeypatch.setattr(co, "DROPOUT", None)
+    assert (ref.detach() - plain).abs().max().item() > 1e-3
+    out = enc.forward(ids, img, save=True, drop_seed=seed, item0=0).clone()
+    assert F.cosine_similarity(out, ref.detach(), dim=-1).min().item() > 1 - 1e-3
+    enc.backward(d_emb)
+    worst = (1.0, "")
+    for n_, p_o in orc.named_parameters():
+        if n_ == "clip_model.logit_scale" or p_o.grad is None:
+            continue
+        a, gm = p_o.grad.flatten().double(), P.g(n_).flatten().double()
+        cos = (torch.dot(a, gm) / (a.norm() * gm.norm() + 1e-30)).item()
+        if n_.endswith("relative_attention_bias.weight"):
+            # 32 x heads bucket sums over every (query, key) pair of the batch: the most cancellation-prone gradient
+            # (0.9995 without dropout, the worst of all parameters there too); the masks add variance to each term
+            assert cos > 0.997, cos
+            continue
+        worst = min(worst, (cos, n_))
+    assert worst[0] > 0.999, worst
+    # phase A (no activations, in-place residual stream) with the same seed; then two micro-batches of two
+    again = enc.forward(ids, img, save=False, drop_seed=seed, item0=0).clone()
+    assert torch.allclose(again, out, atol=1e-5, rtol=1e-5)
+    half = CLIPFFEncoder(P, d, t5_heads(name), 2, "cpu")
+    half.set_dropout(0.1)
+    half.refresh_weights()
+    parts = [half.forward(ids[s:s + 2], img[s:s + 2], drop_seed=seed, item0=s).clone() for s in (0, 2)]
+    assert torch.allclose(torch.cat(parts), out, atol=2e-2, rtol=2e-2)
+    # no seed: the eval-mode encoder
+    assert F.cosine_similarity(enc.forward(ids, img), plain, dim=-1).min().item() > 1 - 1e-3

@@ -239,3 +239,57 @@ def test_blip_ff_training_step_in_train_mode_matches_oracle_with_the_same_masks(
     m.train()
     c = m.encode_multimodal_input({"input_ids": ids, "attention_mask": att}, img).cpu()
     assert (c - a).abs().max().item() > 1e-3                            # train mode: fresh masks per call, like nn.Dropout
+
+
+def test_clip_ff_training_step_in_train_mode_matches_oracle_with_the_same_masks():
+    """CLIP_FF in train mode: the T5 stack's dropout (rate 0.1 at transformers' six kinds of sites) with the product's
+    masks fed to the oracle; two steps (new seed each), 16 items re-forwarded in two micro-batches of 8."""
+    import oracle.clip_ff_oracle as co
+    from oracle.clip_ff_oracle import CLIPFeatureFusionOracle
+    from test_clip_ff_host_logic import t5_mask_hook
+    from uniir_b200.clip_ff import CLIPFeatureFusion
+    from uniir_b200.engine import FlatAdamW, train_step
+    torch.manual_seed(21)
+    orc = CLIPFeatureFusionOracle("tiny-test")
+    with torch.no_grad():
+        for n, p in orc.t5_layers.named_parameters():
+            p.normal_(0.0, 0.08) if "layer_norm" not in n else p.normal_(1.0, 0.1)
+    m = CLIPFeatureFusion("tiny-test", device=dev, micro_batch=8, seed=9)
+    assert m.training and m.t5_dropout_rate == 0.1
+    m.train_micro_batch = 8
+    m.load_state_dict(orc.state_dict(), strict=True)
+    d = orc.clip_model.dims
+    g = torch.Generator().manual_seed(22)
+    bs = 8
+    seeds = torch.Generator().manual_seed(9 * 1000003)
+    opt = FlatAdamW(m._flat, lr=1e-4)
+    for step in range(2):
+        ids = torch.zeros(2 * bs, d.context, dtype=torch.long)
+        for i in range(2 * bs):
+            n = int(torch.randint(1, d.context - 2, (1,), generator=g))
+            ids[i, 0] = d.vocab - 2; ids[i, 1:1 + n] = torch.randint(1, d.vocab - 2, (n,), generator=g); ids[i, 1 + n] = d.vocab - 1
+        img = torch.randn(2 * bs, 3, d.image_size, d.image_size, generator=g)
+        one = torch.ones(2 * bs, dtype=torch.long)
+        b = dict(txt_batched=ids, image_batched=img, txt_mask_batched=one, image_mask_batched=one,
+                 index_mapping={"query": [[2 * i] for i in range(bs)], "pos_cand": [[2 * i + 1] for i in range(bs)]})
+        with torch.no_grad():
+            plain = orc(b)["loss"].item()
+        orc.zero_grad()
+        co.DROPOUT = t5_mask_hook(int(torch.randint(0, 2 ** 31 - 1, (1,), generator=seeds)))
+        try:
+            ref = orc(b)
+            ref["loss"].backward()
+        finally:
+            co.DROPOUT = None
+        assert abs(ref["loss"].item() - plain) > 1e-4
+        loss, acc = train_step(m, {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in b.items()}, opt, do_step=False)
+        torch.cuda.synchronize()
+        assert abs(loss.item() - ref["loss"].item()) < 2e-2 * max(1.0, abs(ref["loss"].item())), (step, loss.item(), ref["loss"].item(), plain)
+        worst = (1.0, "")
+        for n_, p_o in orc.named_parameters():
+            a, c = p_o.grad.flatten().double(), m._flat.g(n_).cpu().flatten().double()
+            if a.numel() > 1:
+                worst = min(worst, ((torch.dot(a, c) / (a.norm() * c.norm() + 1e-30)).item(), n_))
+        assert worst[0] > 0.99, (step, worst)
+        for buf in m._flat.grad.values():
+            buf.zero_()

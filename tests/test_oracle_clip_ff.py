@@ -101,3 +101,48 @@ def test_product_parameter_layout_equals_the_oracle_state_dict(name):
     pos = torch.arange(334)
     ref = T5Attention._relative_position_bucket(pos[None, :] - pos[:, None], bidirectional=True, num_buckets=32, max_distance=128)
     assert torch.equal(product_bucket(334), ref)
+
+
+def test_t5_dropout_sites_match_huggingface_in_train_mode(monkeypatch):
+    """Train mode: transformers' T5Stack (dropout_rate 0.1, the default the reference keeps) and the oracle get the same
+    keep decisions in call order -- torch.nn.functional.dropout is what both nn.Dropout and T5Attention call --; outputs
+    and gradients agree only if every dropout of transformers' stack has its hook at the same place in the oracle."""
+    import oracle.clip_ff_oracle as co
+    d_model, heads, S = 128, 2, 41
+    hf, cfg = _hf_stack(d_model, heads)
+    assert cfg.dropout_rate == 0.1
+    hf.train()
+    torch.manual_seed(0)
+    with torch.no_grad():
+        for n, p in hf.named_parameters():
+            p.normal_(0.0, 0.05) if "layer_norm" not in n else p.normal_(1.0, 0.1)
+    orc = T5StackOracle(d_model=d_model, heads=heads).eval()
+    orc.load_state_dict({k: v for k, v in hf.state_dict().items() if not k.startswith("embed_tokens")}, strict=True)
+    x = torch.randn(3, S, d_model) * 0.7
+
+    class Seq:
+        def __init__(self):
+            self.i, self.log = 0, []
+
+        def keep(self, shape):
+            g = torch.Generator().manual_seed(500 + self.i)
+            self.i += 1
+            self.log.append(tuple(shape))
+            return (torch.rand(shape, generator=g) >= 0.1).float()
+    a, b = Seq(), Seq()
+    monkeypatch.setattr(torch.nn.functional, "dropout",
+                        lambda inp, p=0.5, training=True, inplace=False: inp if (not training or p == 0) else inp * a.keep(inp.shape) / (1 - p))
+    xr = x.clone().requires_grad_(True)
+    ref = hf(inputs_embeds=xr, attention_mask=None, use_cache=False, return_dict=True).last_hidden_state
+    ref.square().mean().backward()
+    monkeypatch.undo()
+    monkeypatch.setattr(co, "DROPOUT", lambda kind, layer, t: t * b.keep(t.shape) / (1 - 0.1))
+    xo = x.clone().requires_grad_(True)
+    out = orc(xo)
+    out.square().mean().backward()
+    assert a.log == b.log and a.i == 2 + 4 * 2                     # input, 2 x (probs, attn out, ff inner, ff out), final
+    assert torch.allclose(out, ref, atol=2e-5, rtol=1e-4), (out - ref).abs().max()
+    assert torch.allclose(xo.grad, xr.grad, atol=1e-6, rtol=1e-3)
+    for n in ("block.0.layer.0.SelfAttention.relative_attention_bias.weight", "block.1.layer.1.DenseReluDense.wi.weight",
+              "block.0.layer.0.SelfAttention.o.weight", "final_layer_norm.weight"):
+        assert torch.allclose(orc.get_parameter(n).grad, hf.get_parameter(n).grad, atol=1e-6, rtol=1e-3), n

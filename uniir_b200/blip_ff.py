@@ -9,10 +9,14 @@ with a plain ``load_state_dict``), ``encode_multimodal_input``, ``forward(batch,
 autograd via ``autograd_bridge``): EMA, queue, soft-label cross-entropy, gradient caching, and the hard-negative variant
 of the loss (blip_ff.py:126-131,160-171,208-218,233-246).
 
-DELIBERATE DEVIATION: no dropout.  The reference trains this model in ``model.train()`` with BERT
-``hidden_dropout_prob`` / ``attention_probs_dropout_prob`` = 0.1 (med_config.json) and DropPath 0.1 in the large ViT;
-the hand-written forward / backward here applies neither, so training regularises differently (parity is stated and
-tested in eval mode).
+Train mode (``model.train()``, the reference's engine.py:16): BERT ``hidden_dropout_prob`` / ``attention_probs_dropout_prob``
+(0.1 in med_config.json; med.py:97,217,244,325) and timm DropPath 0.1 in the large ViT (vit.py:151-152, blip.py:253), in the
+online AND the momentum encoders, with counter-based masks (include/uniir_b200.h): a pure function of (step seed, site,
+element index within the batch), so nothing is stored, the gradient-cache re-forward and the backward regenerate them
+under any micro-batch tiling, and CUDA graphs replay with a new seed.  The oracle's dropout sites are pinned against the
+reference's modules in train mode; product == oracle given the same masks (tests/test_dropout_gpu.py).  ``model.eval()``
+(or ``set_dropout(0, 0, 0)``) gives the deterministic encoder.  The mask BITS differ from torch's Philox stream, as they
+would between two torch seeds.
 
 Arithmetic (vendored reference code, restated in oracle/blip_oracle.py and pinned against the shimmed
 reference modules): ViT-L/16 with biased patch-embed, pre-LN blocks (eps 1e-6), exact GELU, final norm, all

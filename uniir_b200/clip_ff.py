@@ -16,8 +16,11 @@ Arithmetic (restated in oracle/clip_ff_oracle.py, whose T5 stack is pinned again
   fusion  cat([text, image]) -> 2-layer T5 encoder (RMS norm, q/k/v/o without bias, unscaled scores + relative-
           position bias, ReLU FFN 768 -> 2048 -> 768) -> final RMS norm -> mean over the 334 tokens (:161-192);
           ``txt_mask`` / ``img_mask`` are accepted and ignored, exactly like the reference (:173-176).
-DELIBERATE DEVIATION: no dropout -- the reference's T5Stack trains with ``dropout_rate`` 0.1 (T5Config default); the
-hand-written T5 forward / backward here applies none (parity is stated and tested in eval mode).
+Train mode: the T5 stack's dropout (T5Config default ``dropout_rate`` 0.1, which clip_ff.py:82-98 keeps) at
+transformers' sites -- stack input, attention probabilities, both sub-layer outputs, relu(wi x), final norm -- with
+counter-based masks (include/uniir_b200.h) that the gradient-cache re-forward and the backward regenerate; the oracle's
+sites are pinned against transformers' T5Stack in train mode (tests/test_oracle_clip_ff.py).  ``model.eval()`` or
+``set_dropout(0)`` give the deterministic encoder the parity tests use.
 Kernels: the CLIP towers of clip_towers.py (tcgen05 GEMMs, tcgen05 / mma.sync attention, LayerNorm), plus
 ``uniir_rmsnorm_fwd``, ``uniir_attn_fwd_bias`` (S = 334 > the tcgen05 forward's window: mma.sync kernel with the bias
 added in score units), the ReLU GEMM epilogue and ``uniir_token_mean``.
@@ -126,6 +129,7 @@ class CLIPFFEncoder:
         self.emb = torch.empty(mb, D, **f32)
         self.bucket = t5_relative_position_bucket(self.S).to(dev)
         self.bias = torch.empty(heads, self.S, self.S, **f32)
+        self.dctx, self.p_drop, self._drop = None, 0.0, False      # T5 dropout (set_dropout / forward(drop_seed=...))
         if train:
             Tv, Tt = mb * d.v_tokens, mb * d.context
             self.acts = [_T5Acts(T, D, inner, mb, heads, self.S, dev) for _ in range(layers)]
@@ -148,6 +152,14 @@ class CLIPFFEncoder:
             self.dx0 = torch.empty(mb, d.v_tokens, d.v_width, **f32)
             self.ids = None
 
+    # ---- dropout of the T5 stack in train mode (transformers T5Config.dropout_rate = 0.1, clip_ff.py:82-98 leaves the
+    # default): site 0 = the stack input (T5Stack.forward: dropout(inputs_embeds)); 1 + 4 i + {0: attention probabilities,
+    # 1: attention output, 2: relu(wi x), 3: wo output} of block i (T5Attention / T5LayerSelfAttention / T5DenseActDense /
+    # T5LayerFF); 1 + 4 layers = the output of the final layer norm.  Counter-based masks: include/uniir_b200.h. ----
+    def set_dropout(self, p):
+        self.p_drop = float(p)
+        self.dctx = ops.drop_ctx(self.dev) if p > 0 else None
+
     def refresh_weights(self):
         """bf16 copy of the (K-padded) patch-embedding weight and the [H, S, S] relative-position bias table
         (a gather of the [32, H] embedding: once per weight update, not per batch)."""
@@ -161,9 +173,15 @@ class CLIPFFEncoder:
         inner, D = shape
         return (bufs or self.P.flat16)[decay][off:off + 3 * inner * D].view(3 * inner, D)
 
-    def forward(self, ids, img, save=False):
-        """ids int32 [mb, 77], img fp32 [mb, 3, H, W] -> fused embedding fp32 [mb, embed_dim] (buffer reused)."""
+    def forward(self, ids, img, save=False, drop_seed=None, item0=0):
+        """ids int32 [mb, 77], img fp32 [mb, 3, H, W] -> fused embedding fp32 [mb, embed_dim] (buffer reused).
+        drop_seed (int, needs set_dropout): train-mode dropout masks of that seed; item0 = index of the micro-batch's
+        first item in the batch."""
         P, d, mb, S = self.P, self.d, self.mb, self.S
+        dr = self._drop = drop_seed is not None and self.dctx is not None
+        if dr:
+            self.dctx.copy_(torch.tensor([int(drop_seed) & 0x7FFFFFFF, int(item0)], dtype=torch.int32), non_blocking=True)
+        ctx, pd = self.dctx, self.p_drop
         w, w16 = P.w, P.w16
         cm = "clip_model."
         assert not save or self.train
@@ -192,6 +210,8 @@ class CLIPFFEncoder:
         # ---- T5 encoder stack (clip_ff.py:178-183)
         inner, H, D = self.inner, self.heads, d.embed_dim
         x_in = self.x.view(mb * S, D)
+        if dr:
+            ops.dropout(x_in, ctx, 0, S * D, pd)
         for i in range(self.layers):
             a, f = f"t5_layers.block.{i}.layer.0", f"t5_layers.block.{i}.layer.1"
             act = self.acts[i] if save else None
@@ -201,13 +221,26 @@ class CLIPFFEncoder:
             ops.rmsnorm_fwd(x_in, w(f"{a}.layer_norm.weight"), T5_EPS, out=h_a)
             ops.gemm(h_a, self._fused_qkv(i), out=qkv)
             ops.attn_fwd_bias(qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:], mb, S, S, H, self.bias,
-                              scale=1.0, out=att, lse=(act.lse if save else None))
-            ops.gemm(att, w16(f"{a}.SelfAttention.o.weight"), residual=x_in, out=x_mid)
+                              scale=1.0, out=att, lse=(act.lse if save else None), drop=((ctx, 1 + 4 * i, pd) if dr else None))
+            if dr:      # hidden = hidden + dropout(o(attn)); when x_mid aliases x_in the projection goes through self.y
+                tmp = self.y.view(mb * S, D) if x_mid is x_in else x_mid
+                ops.gemm(att, w16(f"{a}.SelfAttention.o.weight"), out=tmp)
+                ops.dropout(tmp, ctx, 2 + 4 * i, S * D, pd, residual=x_in, out=x_mid)
+            else:
+                ops.gemm(att, w16(f"{a}.SelfAttention.o.weight"), residual=x_in, out=x_mid)
             ops.rmsnorm_fwd(x_mid, w(f"{f}.layer_norm.weight"), T5_EPS, out=h_f)
             ops.gemm(h_f, w16(f"{f}.DenseReluDense.wi.weight"), act=L.ACT_RELU, out=ff)
-            ops.gemm(ff, w16(f"{f}.DenseReluDense.wo.weight"), residual=x_mid, out=x_out)
+            if dr:
+                ops.dropout(ff, ctx, 3 + 4 * i, S * T5_FF, pd)          # the saved ff is the dropped one (operand of wo)
+                tmp = self.y.view(mb * S, D) if x_out is x_mid else x_out
+                ops.gemm(ff, w16(f"{f}.DenseReluDense.wo.weight"), out=tmp)
+                ops.dropout(tmp, ctx, 4 + 4 * i, S * D, pd, residual=x_mid, out=x_out)
+            else:
+                ops.gemm(ff, w16(f"{f}.DenseReluDense.wo.weight"), residual=x_mid, out=x_out)
             x_in = x_out
         ops.rmsnorm_fwd(x_in, w("t5_layers.final_layer_norm.weight"), T5_EPS, out=self.y)
+        if dr:
+            ops.dropout(self.y.view(mb * S, D), ctx, 1 + 4 * self.layers, S * D, pd)
         return ops.token_mean(self.y, out=self.emb)           # mean pooling (clip_ff.py:185-192)
 
     def backward(self, d_emb):
@@ -219,8 +252,11 @@ class CLIPFFEncoder:
         inner, H, D = self.inner, self.heads, d.embed_dim
         T = mb * S
         dX = self.dX.view(T, D)
+        dr, ctx, pd = self._drop, self.dctx, self.p_drop
         # ---- mean pooling and the final RMS norm
         ops.token_mean_bwd(d_emb, S, self.d_h)
+        if dr:
+            ops.dropout(self.d_h, ctx, 1 + 4 * self.layers, S * D, pd)
         ops.rmsnorm_bwd(self.d_h, self.xs[2 * self.layers].view(T, D), w("t5_layers.final_layer_norm.weight"), T5_EPS, dX,
                         g("t5_layers.final_layer_norm.weight"), accumulate=False)
         self.dbias.zero_()
@@ -228,21 +264,29 @@ class CLIPFFEncoder:
             a, f = f"t5_layers.block.{i}.layer.0", f"t5_layers.block.{i}.layer.1"
             act = self.acts[i]
             x_a, x_f = self.xs[2 * i].view(T, D), self.xs[2 * i + 1].view(T, D)
-            # ---- feed-forward: x_out = x_f + wo(relu(wi(rmsnorm(x_f))))
-            ops.cast_bf16(dX, out=self.dXb)
+            # ---- feed-forward: x_out = x_f + wo(relu(wi(rmsnorm(x_f))))   [train mode: + dropout(wo(dropout(relu(.))))]
+            if dr:
+                ops.dropout(dX, ctx, 4 + 4 * i, S * D, pd, out=self.dXb)      # branch gradient; dX itself is the residual's
+            else:
+                ops.cast_bf16(dX, out=self.dXb)
             ops.wgrad(self.dXb, act.ff, g(f"{f}.DenseReluDense.wo.weight"))
             ops.gemm(self.dXb, w16(f"{f}.DenseReluDense.wo.weight"), b_mn=True, act=L.ACT_RELU, act_grad_src=act.ff, out=self.d_ff)
+            if dr:      # act.ff > 0 already zeroes the dropped units; this applies the 1 / (1 - p) of the kept ones
+                ops.dropout(self.d_ff, ctx, 3 + 4 * i, S * T5_FF, pd)
             ops.wgrad(self.d_ff, act.h_f, g(f"{f}.DenseReluDense.wi.weight"))
             ops.gemm(self.d_ff, w16(f"{f}.DenseReluDense.wi.weight"), b_mn=True, out=self.d_h)
             ops.rmsnorm_bwd(self.d_h, x_f, w(f"{f}.layer_norm.weight"), T5_EPS, dX, g(f"{f}.layer_norm.weight"))
             # ---- attention: x_f = x_a + o(attn(q|k|v(rmsnorm(x_a))))
-            ops.cast_bf16(dX, out=self.dXb)
+            if dr:
+                ops.dropout(dX, ctx, 2 + 4 * i, S * D, pd, out=self.dXb)
+            else:
+                ops.cast_bf16(dX, out=self.dXb)
             ops.wgrad(self.dXb, act.att, g(f"{a}.SelfAttention.o.weight"))
             ops.gemm(self.dXb, w16(f"{a}.SelfAttention.o.weight"), b_mn=True, out=self.d_att)
             q, k, v = act.qkv[:, :inner], act.qkv[:, inner:2 * inner], act.qkv[:, 2 * inner:]
             ops.attn_bwd_bias(q, k, v, act.att, self.d_att, act.lse, mb, S, S, H, self.bias, self.dbias,
                               self.dqkv[:, :inner], self.dqkv[:, inner:2 * inner], self.dqkv[:, 2 * inner:], scale=1.0,
-                              delta=self.delta)
+                              delta=self.delta, drop=((ctx, 1 + 4 * i, pd) if dr else None))
             ops.wgrad(self.dqkv, act.h_a, self._fused_qkv(i, P.grad))
             ops.gemm(self.dqkv, self._fused_qkv(i), b_mn=True, out=self.d_h)
             ops.rmsnorm_bwd(self.d_h, x_a, w(f"{a}.layer_norm.weight"), T5_EPS, dX, g(f"{a}.layer_norm.weight"))
@@ -251,6 +295,8 @@ class CLIPFFEncoder:
         g("t5_layers.block.0.layer.0.SelfAttention.relative_attention_bias.weight").index_add_(
             0, self.bucket.flatten(), self.dbias.permute(1, 2, 0).reshape(-1, H))
         # ---- split the gradient of cat([text, image])
+        if dr:
+            ops.dropout(dX, ctx, 0, S * D, pd)
         self.d_t.view(mb, d.context, D).copy_(self.dX[:, :d.context])
         self.d_vb.view(mb, d.v_tokens, D).copy_(self.dX[:, d.context:])
         # ---- text trunk
@@ -303,6 +349,30 @@ class CLIPFeatureFusion(nn.Module):
         self._enc = {}
         self._nce = None
         self._train_state = None
+        # transformers' T5Config() default, which clip_ff.py:82-98 keeps: dropout_rate 0.1 on the stack input, the
+        # attention probabilities, both sub-layer outputs, relu(wi x) and the final norm -- active in train mode
+        self.t5_dropout_rate = 0.1
+        self._drop_gen, self._drop_seed0 = None, seed
+
+    def set_dropout(self, rate):
+        """Override the T5 stack's train-mode dropout rate (0 switches it off; `model.eval()` does too)."""
+        self.t5_dropout_rate = float(rate)
+
+    def _dropout_active(self):
+        return self.training and self.t5_dropout_rate > 0
+
+    def _next_drop_seed(self):
+        import torch.distributed as dist
+        if self._drop_gen is None:
+            rank = dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+            self._drop_gen = torch.Generator(device="cpu").manual_seed(self._drop_seed0 * 1000003 + rank)
+        return int(torch.randint(0, 2 ** 31 - 1, (1,), generator=self._drop_gen))
+
+    def _with_dropout(self, enc):
+        if getattr(enc, "_drop_rate", None) != self.t5_dropout_rate:
+            enc.set_dropout(self.t5_dropout_rate)
+            enc._drop_rate = self.t5_dropout_rate
+        return enc
 
     def build_optimizer(self, learning_rate=1e-5, t5_learning_rate=5e-4, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.2):
         """The reference's three AdamW groups (clip_featurefusion/train.py:49-63, 200-206) on the fused optimizer: CLIP
@@ -333,12 +403,14 @@ class CLIPFeatureFusion(nn.Module):
         key = ("embed", mb)
         if key not in self._enc:
             self._enc = {key: CLIPFFEncoder(self._flat, self.dims, self.heads, mb, self.device_)}
-        return self._enc[key]
+        return self._with_dropout(self._enc[key])
 
     @torch.no_grad()
     def encode_multimodal_input(self, txt_tensor, img_tensor, txt_mask=None, img_mask=None):
-        """[B,77] int, [B,3,H,W] fp32 -> fp32 [B, embed_dim]; the masks are ignored like in the reference."""
+        """[B,77] int, [B,3,H,W] fp32 -> fp32 [B, embed_dim]; the masks are ignored like in the reference.  In train mode
+        the T5 stack runs with dropout (fresh masks per call), like the reference's module."""
         dev = self.device_
+        seed = self._next_drop_seed() if self._dropout_active() else None
         ids = txt_tensor.to(dev, torch.int32).contiguous()
         img = img_tensor.to(dev, torch.float32).contiguous()
         n = ids.shape[0]
@@ -353,7 +425,7 @@ class CLIPFeatureFusion(nn.Module):
             if e - s < mb:      # ragged tail: zero-padded items, dropped below
                 i_c = torch.cat([i_c, i_c.new_zeros(mb - (e - s), ids.shape[1])])
                 im_c = torch.cat([im_c, im_c.new_zeros(mb - (e - s), *img.shape[1:])])
-            out[s:e] = enc.forward(i_c.contiguous(), im_c.contiguous())[:e - s]
+            out[s:e] = enc.forward(i_c.contiguous(), im_c.contiguous(), drop_seed=seed, item0=s)[:e - s]
         return out
 
     # ---- training (clip_ff.py:197-270): the in-batch / hard-negative contrastive loss of CLIP_SF on the fused
@@ -390,7 +462,7 @@ class CLIPFeatureFusion(nn.Module):
         key = ("train", mb)
         if key not in self._enc:
             self._enc = {key: CLIPFFEncoder(self._flat, self.dims, self.heads, mb, self.device_, train=True)}
-        return self._enc[key]
+        return self._with_dropout(self._enc[key])
 
     @torch.no_grad()
     def _loss_forward(self, batch):
@@ -407,9 +479,10 @@ class CLIPFeatureFusion(nn.Module):
         P.refresh_shadow()
         enc.refresh_weights()
         emb = torch.empty(n_items, E, device=dev, dtype=torch.float32)
+        seed = self._next_drop_seed() if self._dropout_active() else None      # phase A and the phase-C re-forward share it
         for s in range(0, n_items, enc.mb):                     # phase A
-            emb[s:s + enc.mb] = enc.forward(ids[s:s + enc.mb], img[s:s + enc.mb], save=False)
-        st = dict(q_idx=q_idx, p_idx=p_idx, bs=bs, n_items=n_items, rank=rank, world=world, enc=enc, ids=ids, img=img)
+            emb[s:s + enc.mb] = enc.forward(ids[s:s + enc.mb], img[s:s + enc.mb], save=False, drop_seed=seed, item0=s)
+        st = dict(q_idx=q_idx, p_idx=p_idx, bs=bs, n_items=n_items, rank=rank, world=world, enc=enc, ids=ids, img=img, seed=seed)
         P.ensure_grad()
         ls = P.w("clip_model.logit_scale")
         if "neg_cand_list" in im:       # hard-negative branch (clip_ff.py:234-258): no gather, fused forward + backward
@@ -446,7 +519,7 @@ class CLIPFeatureFusion(nn.Module):
             d_emb = torch.zeros(st["n_items"], E, device=self.device_, dtype=torch.float32)
             nce.normalize_bwd(st["q_idx"], st["p_idx"], d_pn, d_emb, off)
         for s in range(0, st["n_items"], enc.mb):               # phase C
-            enc.forward(st["ids"][s:s + enc.mb], st["img"][s:s + enc.mb], save=True)
+            enc.forward(st["ids"][s:s + enc.mb], st["img"][s:s + enc.mb], save=True, drop_seed=st["seed"], item0=s)
             enc.backward(d_emb[s:s + enc.mb].contiguous())
         self._train_state = None
 
