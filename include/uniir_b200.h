@@ -73,8 +73,9 @@ typedef struct uniir_gemm_desc {
   int32_t accumulate;               /* out += value (out_dtype must be F32) */
   int32_t split_k;                  /* >1: split contraction, atomic fp32 accumulate */
   const float* row_scale;           /* optional fp32 [ceil(M / row_scale_rows)]: (alpha*AB + bias) is multiplied by   */
-  int32_t row_scale_rows;           /* row_scale[row / row_scale_rows] after the activation and before the residual   */
-                                    /* is added: per-item DropPath of a residual branch (vit.py:151-152, timm)        */
+  int32_t row_scale_rows;           /* row_scale[row / row_scale_rows] before the residual is added: per-item DropPath */
+                                    /* of a residual branch (vit.py:151-152, timm).  Only with the fp32-residual       */
+                                    /* epilogue: A, B K-major, fp32 residual, fp32 out, no act / aux / accumulate.     */
 } uniir_gemm_desc;
 int uniir_gemm_epi(const uniir_gemm_desc* d, void* stream);
 

@@ -75,7 +75,7 @@ extern "C" int uniir_gemm_epi(const uniir_gemm_desc* d, void* stream_) {
   p.alpha = d->alpha;
   p.accumulate = d->accumulate;
   p.atomic = atomic ? 1 : 0;
-  p.row_scale = d->row_scale; p.rs_rows = d->row_scale ? d->row_scale_rows : 1;
+  if (d->row_scale) { p.ags = d->row_scale; p.ld_ags = d->row_scale_rows; }   // EPI_RES32_RS borrows these (gemm_kernel.cuh)
 
   TileSched s;
   s.m_blocks = m_blocks;
@@ -93,9 +93,10 @@ extern "C" int uniir_gemm_epi(const uniir_gemm_desc* d, void* stream_) {
   const bool has_rs = d->row_scale != nullptr;
   int epi = EPI_DYN;
   if (has_rs) {
-    if (!d->a_mn && !d->b_mn && has_res && d->res_dtype == UNIIR_F32 && out32 && !has_aux && !has_ags && !has_act &&
-        !d->accumulate && !atomic)
-      epi = EPI_RES32_RS;
+    UNIIR_CHECK_ARG(!d->a_mn && !d->b_mn && has_res && d->res_dtype == UNIIR_F32 && out32 && !has_aux && !has_ags && !has_act &&
+                    !d->accumulate && !atomic,
+                    "uniir_gemm_epi: row_scale is implemented for the fp32 residual epilogue only (A, B K-major, fp32 out)");
+    epi = EPI_RES32_RS;
   } else if (!d->a_mn && !has_res && !has_aux && !has_ags && !has_act && !d->accumulate && !atomic)
     epi = out32 ? EPI_STORE32 : EPI_STORE16;
   else if (!d->a_mn && !d->b_mn && !has_res && !has_ags && has_act && !out32 && !d->accumulate && !atomic)
@@ -108,7 +109,7 @@ extern "C" int uniir_gemm_epi(const uniir_gemm_desc* d, void* stream_) {
   else if (d->a_mn && d->b_mn && out32 && !has_res && !has_aux && !has_ags && !has_act && !d->bias &&
            (atomic || d->accumulate))
     epi = atomic ? EPI_ATOMIC : EPI_ACC32;
-  if (getenv("UNIIR_GEMM_DYN")) epi = EPI_DYN;
+  if (getenv("UNIIR_GEMM_DYN") && !has_rs) epi = EPI_DYN;
 
   if (pair) {
     TileSched s2 = s;
