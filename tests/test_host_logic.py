@@ -167,3 +167,71 @@ def test_clip_image_preprocess_matches_torchvision_arithmetic():
         a, b = mine(img), ref(img)
         assert a.shape == b.shape == (3, 224, 224)
         assert torch.allclose(a, b, atol=1e-6), (w, h, (a - b).abs().max())
+
+
+def _blip_test_image(seed):
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    from make_golden_blip_transform import test_image
+    return test_image(seed)
+
+
+def test_blip_image_transforms_match_golden_vectors_of_the_reference():
+    """blip_image_preprocess (train: RandomResizedCrop + flip + RandomAugment(2, 5); eval: square bicubic resize)
+    against tensors the reference's own get_blip_transform produced for the same seeds
+    (scripts/make_golden_blip_transform.py).  Same PIL / cv2 / torch builds in this image: bit-exact."""
+    import os
+    import warnings
+    import numpy as np
+    from conftest import GOLDEN
+    from uniir_b200.preprocess import blip_image_preprocess
+    pytest.importorskip("cv2")
+    g = np.load(os.path.join(GOLDEN, "blip_transform.npz"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for seed in range(12):
+            img = _blip_test_image(seed)
+            for train in (True, False):
+                torch.manual_seed(seed); np.random.seed(seed)
+                out = blip_image_preprocess(32, is_train=train, min_scale=0.5)(img)
+                assert out.shape == (3, 32, 32) and out.dtype == torch.float32
+                assert np.array_equal(out.numpy(), g[f"{'train' if train else 'eval'}_{seed}"]), (seed, train)
+    a = {k for k in g.files if k.startswith("train")}
+    assert any(not np.array_equal(g[k], g[k.replace("train", "eval")]) for k in a)
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference/src/models/uniir_blip/backbone/transform"),
+                    reason="reference tree not present: the golden vectors cover it")
+def test_blip_train_transform_and_every_augment_op_match_the_reference_code():
+    """The reference's transform run here: 150 seeds of the whole train transform, and RandomAugment at other
+    magnitudes (levels 2 and 9 exercise Brightness / Sharpness away from their identity at level 5)."""
+    import os
+    import sys
+    import warnings
+    import numpy as np
+    pytest.importorskip("cv2")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    from make_golden_blip_transform import load_reference_transform
+    from uniir_b200.preprocess import BLIP_AUG_OPS, blip_image_preprocess, blip_random_augment
+    bt, ra = load_reference_transform()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for seed in range(150):
+            img = _blip_test_image(seed)
+            torch.manual_seed(seed); np.random.seed(seed)
+            ref = bt.get_blip_transform(64, 0.5, True)(img)
+            torch.manual_seed(seed); np.random.seed(seed)
+            assert torch.equal(blip_image_preprocess(64, is_train=True, min_scale=0.5)(img), ref), seed
+        seen = set()
+        for level in (2, 9):
+            aug = ra.RandomAugment(2, level, isPIL=True, augs=list(BLIP_AUG_OPS))
+            for seed in range(120):
+                img = _blip_test_image(seed)
+                np.random.seed(seed)
+                seen.update(np.random.choice(list(BLIP_AUG_OPS), 2))
+                np.random.seed(seed)
+                ref = aug(img)
+                np.random.seed(seed)
+                assert np.array_equal(blip_random_augment(img, 2, level), ref), (level, seed)
+        assert seen == set(BLIP_AUG_OPS)

@@ -575,8 +575,9 @@ class BLIPFeatureFusion(nn.Module):
 
     # ---- reference surface -------------------------------------------------------------
     def get_img_preprocess_fn(self):
+        """blip_ff.py:65-68: the train augmentation while the module is in train mode, the eval transform otherwise."""
         from .preprocess import blip_image_preprocess
-        return blip_image_preprocess(self.image_size)
+        return blip_image_preprocess(self.image_size, is_train=self.training, min_scale=0.5)
 
     def get_tokenizer(self):
         raise FileNotFoundError("the bert-base-uncased vocabulary (BertTokenizer, blip.py:221-226) is not available offline; "

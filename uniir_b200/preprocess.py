@@ -190,16 +190,168 @@ def synthetic_clip_tokens(n, generator=None, context_length=77, vocab=49408):
     return ids
 
 
-def blip_image_preprocess(size=224):
-    """BLIP eval transform (backbone/transform/blip_transform.py:42-48): bicubic resize to (size,size),
-    ToTensor, Normalize with the CLIP mean/std constants (blip_transform.py:9)."""
+# ---- BLIP train-time augmentation (backbone/transform/blip_transform.py:11-40): RandomResizedCrop(scale=(0.5, 1),
+# bicubic) -> RandomHorizontalFlip -> RandomAugment(N=2, M=5, ten ops) -> ToTensor -> Normalize.  The random streams
+# are consumed in the reference's order -- torch's global RNG for crop and flip (torchvision), numpy's global RNG for
+# the augment ops (backbone/transform/randaugment.py) -- so the same seeds give the same pixels.
+
+BLIP_AUG_OPS = ("Identity", "AutoContrast", "Brightness", "Sharpness", "Equalize", "ShearX", "ShearY", "TranslateX",
+                "TranslateY", "Rotate")                                            # blip_transform.py:24-35
+_AUG_FILL = (128, 128, 128)                                                        # randaugment.py:267 replace_value
+_AUG_MAX_LEVEL = 10
+
+
+def _lut_per_channel(img, table_of):
+    """Apply a 256-entry lookup table, computed per channel by `table_of(channel)` (None = leave the channel)."""
+    out = img.copy()
+    for c in range(img.shape[2]):
+        t = table_of(img[:, :, c])
+        if t is not None:
+            out[:, :, c] = t[img[:, :, c]]
+    return out
+
+
+def _autocontrast_table(ch):
+    """randaugment.py:10-40 with cutoff 0: stretch [min, max] to [0, 255].  The reference computes the offset as
+    `-low * scale` with `low` a numpy uint8 scalar, whose negation wraps modulo 256; reproduced here, because a drop-in
+    has to give the reference's pixels: a channel whose minimum is not 0 saturates."""
+    lo, hi = int(ch.min()), int(ch.max())
+    if hi <= lo:
+        return None
+    scale = 255 / (hi - lo)
+    offset = ((-lo) & 0xFF) * scale
+    return np.clip(np.clip(np.arange(256) * scale + offset, 0, 255), 0, 255).astype(np.uint8)
+
+
+def _equalize_table(ch):
+    """PIL.ImageOps.equalize's table as randaugment.py:43-63 builds it (integer arithmetic: the counts are exact)."""
+    hist = np.bincount(ch.reshape(-1), minlength=256).astype(np.int64)
+    nz = hist[hist != 0]
+    step = int(nz[:-1].sum()) // 255
+    if step == 0:
+        return None
+    shifted = np.concatenate([[step // 2], hist[:-1]])
+    return np.clip(np.cumsum(shifted) // step, 0, 255).astype(np.uint8)
+
+
+def _warp(img, matrix):
+    import cv2       # the reference's augment ops are cv2 calls (randaugment.py:1); same library, same pixels
+    h, w = img.shape[:2]
+    return cv2.warpAffine(img, np.float32(matrix), (w, h), borderValue=_AUG_FILL, flags=cv2.INTER_LINEAR).astype(np.uint8)
+
+
+def _sharpness(img, factor):
+    """randaugment.py:127-144: blend with a 3x3 smoothing (centre weight 5, /13), interior pixels only."""
+    import cv2
+    if factor == 1.0:
+        return img
+    k = np.ones((3, 3), dtype=np.float32)
+    k[1, 1] = 5
+    k /= 13
+    blurred = cv2.filter2D(img, -1, k)
+    if factor == 0.0:
+        return blurred
+    out = img.astype(np.float32)
+    inner = blurred.astype(np.float32)[1:-1, 1:-1, :]
+    out[1:-1, 1:-1, :] = inner + factor * (out[1:-1, 1:-1, :] - inner)
+    return out.astype(np.uint8)
+
+
+def _signed(magnitude, negative_if):
+    """One numpy draw decides the sign (randaugment.py:186-196, 250-256)."""
+    return -magnitude if negative_if(np.random.random()) else magnitude
+
+
+def blip_random_augment(img, n_ops=2, level=5, ops=BLIP_AUG_OPS):
+    """RandomAugment(N, M, isPIL=True, augs) of randaugment.py:289-317 on an HWC uint8 array: N ops drawn with
+    replacement, each applied with probability 0.5 at magnitude level / 10 of its range."""
+    img = np.array(img)
+    frac = level / _AUG_MAX_LEVEL
+    for name in np.random.choice(list(ops), n_ops):
+        if np.random.random() > 0.5:
+            continue
+        if name == "Identity":
+            pass
+        elif name == "AutoContrast":
+            img = _lut_per_channel(img, _autocontrast_table)
+        elif name == "Equalize":
+            img = _lut_per_channel(img, _equalize_table)
+        elif name == "Brightness":                                  # enhance factor 0.1 .. 1.9 (1.0 at level 5)
+            table = (np.arange(256, dtype=np.float32) * (frac * 1.8 + 0.1)).clip(0, 255).astype(np.uint8)
+            img = table[img]
+        elif name == "Sharpness":
+            img = _sharpness(img, frac * 1.8 + 0.1)
+        elif name == "ShearX":
+            f = _signed(frac * 0.3, lambda u: u > 0.5)
+            img = _warp(img, [[1, f, 0], [0, 1, 0]])
+        elif name == "ShearY":
+            f = _signed(frac * 0.3, lambda u: u > 0.5)
+            img = _warp(img, [[1, 0, 0], [f, 1, 0]])
+        elif name == "TranslateX":
+            o = _signed(frac * 10.0, lambda u: u > 0.5)
+            img = _warp(img, [[1, 0, -o], [0, 1, 0]])
+        elif name == "TranslateY":
+            o = _signed(frac * 10.0, lambda u: u > 0.5)
+            img = _warp(img, [[1, 0, 0], [0, 1, -o]])
+        elif name == "Rotate":
+            import cv2
+            deg = _signed(frac * 30, lambda u: u < 0.5)
+            h, w = img.shape[:2]
+            img = cv2.warpAffine(img, cv2.getRotationMatrix2D((w / 2, h / 2), deg, 1), (w, h), borderValue=_AUG_FILL)
+        else:
+            raise ValueError(f"unknown augmentation op {name!r}")
+    return img
+
+
+def _random_resized_crop_box(width, height, scale, ratio=(3.0 / 4.0, 4.0 / 3.0)):
+    """torchvision.transforms.RandomResizedCrop.get_params on torch's global RNG: ten attempts at a box of
+    scale x area and log-uniform aspect ratio, then the central fallback.  Returns (top, left, h, w)."""
+    import math
+    area = height * width
+    log_ratio = torch.log(torch.tensor(ratio))
+    for _ in range(10):
+        target = area * torch.empty(1).uniform_(scale[0], scale[1]).item()
+        aspect = torch.exp(torch.empty(1).uniform_(log_ratio[0], log_ratio[1])).item()
+        w = int(round(math.sqrt(target * aspect)))
+        h = int(round(math.sqrt(target / aspect)))
+        if 0 < w <= width and 0 < h <= height:
+            top = torch.randint(0, height - h + 1, size=(1,)).item()
+            left = torch.randint(0, width - w + 1, size=(1,)).item()
+            return top, left, h, w
+    in_ratio = float(width) / float(height)
+    if in_ratio < min(ratio):
+        w, h = width, int(round(width / min(ratio)))
+    elif in_ratio > max(ratio):
+        h, w = height, int(round(height * max(ratio)))
+    else:
+        w, h = width, height
+    return (height - h) // 2, (width - w) // 2, h, w
+
+
+def blip_image_preprocess(size=224, is_train=False, min_scale=0.5):
+    """get_blip_transform(image_size, min_scale, is_train) of backbone/transform/blip_transform.py.
+    Eval (:42-48): bicubic resize to (size, size), ToTensor, Normalize with the CLIP mean / std constants (:9).
+    Train (:11-40): RandomResizedCrop(size, scale=(min_scale, 1), bicubic), RandomHorizontalFlip, RandomAugment(2, 5,
+    the ten ops of BLIP_AUG_OPS), ToTensor, Normalize -- random draws in the reference's order and from the same global
+    generators (torch: crop, flip; numpy: augment), so equal seeds give equal tensors (tests/test_host_logic.py)."""
     mean = torch.tensor(CLIP_MEAN).view(3, 1, 1)
     std = torch.tensor(CLIP_STD).view(3, 1, 1)
 
-    def fn(img):
-        from PIL import Image
-        img = img.convert("RGB").resize((size, size), Image.BICUBIC)
-        t = torch.from_numpy(np.asarray(img, dtype=np.uint8).copy()).permute(2, 0, 1).float() / 255.0
+    def to_tensor(arr):
+        t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.uint8)).permute(2, 0, 1).float() / 255.0
         return (t - mean) / std
 
-    return fn
+    def eval_fn(img):
+        from PIL import Image
+        return to_tensor(np.asarray(img.convert("RGB").resize((size, size), Image.BICUBIC)))
+
+    def train_fn(img):
+        from PIL import Image
+        w, h = img.size
+        top, left, ch, cw = _random_resized_crop_box(w, h, (min_scale, 1.0))
+        img = img.crop((left, top, left + cw, top + ch)).resize((size, size), Image.BICUBIC)
+        if torch.rand(1) < 0.5:
+            img = img.transpose(Image.FLIP_LEFT_RIGHT)
+        return to_tensor(blip_random_augment(img))
+
+    return train_fn if is_train else eval_fn
