@@ -235,3 +235,27 @@ def test_blip_train_transform_and_every_augment_op_match_the_reference_code():
                 np.random.seed(seed)
                 assert np.array_equal(blip_random_augment(img, 2, level), ref), (level, seed)
         assert seen == set(BLIP_AUG_OPS)
+
+
+def test_blip_tokenizer_from_a_local_vocabulary(tmp_path, monkeypatch):
+    """blip.py:221-226 / blip_ff.py:70-80 with the vocabulary read from UNIIR_BERT_VOCAB (no hub download offline):
+    [DEC] and [ENC] are appended after the vocabulary (30522 -> 30524 for bert-base-uncased, the model's embedding size),
+    uncased WordPiece, [CLS] .. [SEP], max_length padding with a prefix attention mask."""
+    from uniir_b200.preprocess import blip_tokenizer
+    monkeypatch.delenv("UNIIR_BERT_VOCAB", raising=False)
+    with pytest.raises(FileNotFoundError):
+        blip_tokenizer(16)
+    words = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]", "a", "photo", "of", "dog", "##s", "red", "car", ",", "."]
+    (tmp_path / "vocab.txt").write_text("\n".join(words) + "\n")
+    monkeypatch.setenv("UNIIR_BERT_VOCAB", str(tmp_path))                  # a directory holding vocab.txt
+    wrap, tok = blip_tokenizer(12, model_vocab=len(words) + 2)
+    assert len(tok) == len(words) + 2 and tok.bos_token == "[DEC]" and tok.enc_token_id == len(words) + 1
+    out = wrap(["A photo of DOGS, a red car.", "zebra"])
+    ids, att = out["input_ids"], out["attention_mask"]
+    assert ids.shape == (2, 12) and att.shape == (2, 12)
+    v = {w: i for i, w in enumerate(words)}
+    want = [v[w] for w in ("[CLS]", "a", "photo", "of", "dog", "##s", ",", "a", "red", "car", ".", "[SEP]")]
+    assert ids[0].tolist() == want and att[0].tolist() == [1] * 12
+    assert ids[1].tolist() == [v["[CLS]"], v["[UNK]"], v["[SEP]"]] + [0] * 9 and att[1].tolist() == [1, 1, 1] + [0] * 9
+    with pytest.raises(ValueError):
+        blip_tokenizer(12, model_vocab=len(words))        # the two special tokens would not fit the embedding table

@@ -580,8 +580,14 @@ class BLIPFeatureFusion(nn.Module):
         return blip_image_preprocess(self.image_size, is_train=self.training, min_scale=0.5)
 
     def get_tokenizer(self):
-        raise FileNotFoundError("the bert-base-uncased vocabulary (BertTokenizer, blip.py:221-226) is not available offline; "
-                                "pass pre-tokenised {'input_ids','attention_mask'} batches")
+        """blip_ff.py:70-80: BertTokenizer("bert-base-uncased") + the "[DEC]" / "[ENC]" special tokens (blip.py:221-226),
+        wrapped with padding="max_length", truncation, max_length=config.tokenizer_max_length, return_tensors="pt".
+        The vocabulary is not in the reference tree and there is no network: UNIIR_BERT_VOCAB must point at
+        bert-base-uncased's vocab.txt (or a directory holding it, e.g. a HuggingFace snapshot)."""
+        from .preprocess import blip_tokenizer
+        wrapper, self.tokenizer = blip_tokenizer(self.config.tokenizer_max_length if self.config is not None else 100,
+                                                 model_vocab=self.dims.vocab)
+        return wrapper
 
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)

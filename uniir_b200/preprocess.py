@@ -355,3 +355,35 @@ def blip_image_preprocess(size=224, is_train=False, min_scale=0.5):
         return to_tensor(blip_random_augment(img))
 
     return train_fn if is_train else eval_fn
+
+
+def blip_tokenizer(max_length=100, model_vocab=None, vocab_path=None):
+    """The reference's BLIP tokenizer (blip.py:221-226 + blip_ff.py:70-80): BertTokenizer("bert-base-uncased") with the
+    "[DEC]" (bos) and "[ENC]" special tokens appended, called with padding="max_length", truncation=True,
+    max_length=config.tokenizer_max_length, return_tensors="pt".  Returns (wrapper, tokenizer).
+    The vocabulary is not in the reference tree and there is no network: `vocab_path` / UNIIR_BERT_VOCAB must point at
+    bert-base-uncased's vocab.txt (or a directory holding it, e.g. a HuggingFace snapshot)."""
+    path = vocab_path or os.environ.get("UNIIR_BERT_VOCAB", "")
+    if os.path.isdir(path):
+        path = os.path.join(path, "vocab.txt")
+    if not os.path.isfile(path):
+        raise FileNotFoundError("the bert-base-uncased vocabulary (BertTokenizer, blip.py:221-226) is not available offline: "
+                                "set UNIIR_BERT_VOCAB to its vocab.txt, or pass pre-tokenised "
+                                "{'input_ids','attention_mask'} batches")
+    import inspect
+    from transformers import BertTokenizer
+    if "vocab" in inspect.signature(BertTokenizer.__init__).parameters:     # transformers 5: token -> id mapping
+        with open(path, encoding="utf-8") as f:
+            vocab = {line.rstrip("\n"): i for i, line in enumerate(f)}
+        tok = BertTokenizer(vocab=vocab, do_lower_case=True)               # bert-base-uncased's tokenizer_config.json
+    else:                                                                   # transformers 4 (the reference pins 4.15)
+        tok = BertTokenizer(vocab_file=path, do_lower_case=True)
+    tok.add_special_tokens({"bos_token": "[DEC]"})
+    tok.add_special_tokens({"additional_special_tokens": ["[ENC]"]})
+    tok.enc_token_id = tok.convert_tokens_to_ids("[ENC]")      # == additional_special_tokens_ids[0] (attribute gone in transformers 5)
+    if model_vocab is not None and len(tok) > model_vocab:
+        raise ValueError(f"{path}: {len(tok)} tokens (with [DEC], [ENC]) exceed the model's vocabulary of {model_vocab}")
+
+    def tokenizer_wrapper(txt):
+        return tok(txt, padding="max_length", truncation=True, max_length=max_length, return_tensors="pt")
+    return tokenizer_wrapper, tok
