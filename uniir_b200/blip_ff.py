@@ -221,6 +221,8 @@ class BLIPEncoder:
         self.p_h, self.p_a = float(p_hidden), float(p_attn)
         self.dctx = ops.drop_ctx(self.dev)
         self.vis.set_drop_path(float(drop_path_rate), self.dctx)
+        if getattr(self, "_graphs", None):      # captured graphs carry the old probabilities as kernel arguments
+            self._graphs = {k: v for k, v in self._graphs.items() if not k.endswith("+drop")}
 
     def _site(self, layer, k):
         return 1 + 5 * layer + k
