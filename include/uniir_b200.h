@@ -293,7 +293,7 @@ int uniir_blip_softce(float* S, const float* Sm, const int64_t* pc_id, const int
  * (clip_ff.py:82-98, T5Config dropout_rate 0.1).  torch draws these masks from its stateful Philox stream; here a
  * mask is a pure function of (ctx[0] = seed of the step, site, element index within the WHOLE batch):
  *     keep = mix32(idx ^ mix32(seed + site * 0x9E3779B1)) >= floor(p * 2^32)
- * with mix32 the 32-bit finaliser x^=x>>16; x*=0x7feb352d; x^=x>>15; x*=0x846ca68b; x^=x>>16 and
+ * with mix32 the 32-bit finaliser x^=x>>17; x*=0xed5ad4bb; x^=x>>11; x*=0xac4c1b51; x^=x>>15; x*=0x31848bab; x^=x>>14 and
  * idx = ctx[1] * per_item + i (mod 2^32), ctx[1] = index of this micro-batch's first item in the batch.  Nothing is
  * saved: the gradient-cache re-forward and the backward regenerate the same bits under any micro-batch tiling, and
  * a captured CUDA graph replays with a new seed because ctx (uint32[2]) is device memory.

@@ -37,9 +37,10 @@ _M32 = 0xFFFFFFFF
 
 def mix32(x):
     x = x & _M32
-    x = x ^ (x >> 16); x = (x * 0x7feb352d) & _M32
-    x = x ^ (x >> 15); x = (x * 0x846ca68b) & _M32
-    return x ^ (x >> 16)
+    x = x ^ (x >> 17); x = (x * 0xed5ad4bb) & _M32
+    x = x ^ (x >> 11); x = (x * 0xac4c1b51) & _M32
+    x = x ^ (x >> 15); x = (x * 0x31848bab) & _M32
+    return x ^ (x >> 14)
 
 
 def drop_thresh(p):

@@ -259,3 +259,37 @@ def test_blip_tokenizer_from_a_local_vocabulary(tmp_path, monkeypatch):
     assert ids[1].tolist() == [v["[CLS]"], v["[UNK]"], v["[SEP]"]] + [0] * 9 and att[1].tolist() == [1, 1, 1] + [0] * 9
     with pytest.raises(ValueError):
         blip_tokenizer(12, model_vocab=len(words))        # the two special tokens would not fit the embedding table
+
+
+def test_counter_based_dropout_masks_behave_like_independent_bernoulli_draws():
+    """Statistics of the mask function of include/uniir_b200.h (restated in tests/cpu_kernels.py, bit-exact with the
+    kernel per tests/test_dropout_gpu.py): drop rate, no correlation between sites, consecutive seeds, neighbouring
+    elements or the rows / columns of a [tokens, width] activation -- each within 4.5 sigma of an ideal generator."""
+    import cpu_kernels as ck
+    n, p = 1 << 20, 0.1
+    idx = torch.arange(n, dtype=torch.int64)
+    sig = (p * (1 - p) / n) ** 0.5
+    masks = {}
+    for seed in (0, 1, 2, 123456789, 2 ** 31 - 2):
+        for site in (0, 1, 2, 61, 4096, 4143):
+            k = ck.keep_mask(seed, site, idx, p).float()
+            assert abs((1 - k.mean().item()) - p) < 4.5 * sig, (seed, site)
+            masks[(seed, site)] = k - (1 - p)
+    keys = list(masks)
+    var = p * (1 - p)
+    worst = 0.0
+    for i in range(len(keys)):
+        for j in range(i + 1, len(keys), 7):                       # a spread of (seed, site) pairs
+            worst = max(worst, abs((masks[keys[i]] * masks[keys[j]]).mean().item()) / var)
+    assert worst < 4.5 / n ** 0.5 * 1.3, worst                       # correlation coefficient of independent streams
+    m = masks[(1, 2)]
+    for lag in (1, 2, 3, 64, 256, 768, 1024, 3072, 4096, 768 * 77):      # neighbours, rows of width 768 / 1024 / 3072 / 4096, items
+        assert abs((m[lag:] * m[:-lag]).mean().item()) / var < 4.5 / n ** 0.5, lag
+    grid = (m + (1 - p))[:1024 * 768].view(1024, 768)                # 1024 tokens x 768 features
+    row_rate, col_rate = 1 - grid.mean(1), 1 - grid.mean(0)
+    assert (row_rate - p).abs().max().item() < 5 * (var / 768) ** 0.5
+    assert (col_rate - p).abs().max().item() < 5 * (var / 1024) ** 0.5
+    # batch position, not micro-batch position: element i of a micro-batch starting at item0 == element item0 * per_item + i
+    a = ck.keep_mask(7, 3, torch.arange(1000) + 5 * 1000, p)
+    b = ck.keep_mask(7, 3, torch.arange(6000), p)[5000:]
+    assert torch.equal(a, b)
