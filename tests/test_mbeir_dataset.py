@@ -272,3 +272,78 @@ def test_index_file_formats_roundtrip(tmp_path):
         np.savez(f, embeddings=emb, ids=ids)
     e, i = mr.read_index_rows(r, 0, 4)
     assert np.array_equal(e, emb[:4]) and np.array_equal(i, ids[:4])
+
+
+@pytest.mark.skipif(not has_ref, reason="/root/reference not present")
+def test_run_hard_negative_mining_matches_reference_function(tmp_path, tree, monkeypatch):
+    """The reference's own run_hard_negative_mining (mbeir_retriever.py:606-708, `faiss` / `omegaconf` stubbed) and
+    ours, fed the same search results: the mined training file must be byte-identical -- including the repetition rule
+    when fewer than num_hard_negs candidates survive the positive / negative filter."""
+    import json
+    import shutil
+    from types import SimpleNamespace as NS
+    from uniir_b200 import mbeir_retriever as mr
+    for n in ("faiss", "omegaconf"):
+        if n not in sys.modules:
+            sys.modules[n] = types.ModuleType(n)
+    if not hasattr(sys.modules["omegaconf"], "OmegaConf"):
+        sys.modules["omegaconf"].OmegaConf = object
+    for pth in (REF_SRC, os.path.join(REF_SRC, "common")):
+        if pth not in sys.path:
+            sys.path.insert(0, pth)
+    import mbeir_retriever as ref
+    root, data = tree
+    name, pool = "webqa_task2", "webqa_task2"
+    queries, cands = data[name]
+    rng = np.random.default_rng(11)
+    k, num_hard_negs = 6, 4
+    dids = [md.hash_did(c["did"]) for c in cands]
+    I = np.stack([rng.permutation(dids)[:k] for _ in queries]).astype(np.int64)
+    for qi, q in enumerate(queries):
+        pos = [md.hash_did(d) for d in q["pos_cand_list"]]
+        if qi % 4 == 0:                         # only two candidates survive the filter: the repetition rule
+            I[qi, :] = (pos * k)[:k]
+            others = [d for d in dids if d not in pos]
+            I[qi, 1], I[qi, 4] = others[qi % len(others)], others[(qi + 7) % len(others)]
+        elif qi % 4 == 1:                       # nothing survives: the reference warns and appends nothing
+            I[qi, :] = (pos * k)[:k]
+    D = np.sort(rng.random(I.shape).astype(np.float32))[:, ::-1].copy()
+    suffix = "CLIP_SF/Large/Instruct/InBatch/"
+    outs = {}
+    for tag, mod in (("mine", mr), ("ref", ref)):
+        mbeir, uniir = tmp_path / tag / "mbeir", tmp_path / tag / "uniir"
+        (mbeir / "train").mkdir(parents=True)
+        (mbeir / "cand_pool").mkdir(parents=True)
+        shutil.copy(os.path.join(root, "query", "train", f"mbeir_{name}_train.jsonl"), mbeir / "train" / f"mbeir_{name}_train.jsonl")
+        shutil.copy(os.path.join(root, "cand_pool", "local", f"mbeir_{pool}_cand_pool.jsonl"), mbeir / "cand_pool" / f"mbeir_{pool}_cand_pool.jsonl")
+        e = uniir / "embed" / suffix / "train"
+        e.mkdir(parents=True)
+        np.save(e / f"mbeir_{name}_train_ids.npy", np.array([md.hash_qid(q["qid"]) for q in queries], dtype=np.int64))
+        np.save(e / f"mbeir_{name}_train_embed.npy", np.zeros((len(queries), 4), np.float16))
+        cfg = NS(uniir_dir=str(uniir), mbeir_data_dir=str(mbeir), experiment=NS(path_suffix=suffix),
+                 retrieval_config=NS(embed_dir_name="embed", index_dir_name="index", hard_negs_dir_name="hard_negs", k=k,
+                                     num_hard_negs=num_hard_negs,
+                                     train_datasets_config=NS(enable_retrieve=True, datasets_name=[name.upper()],
+                                                              correspond_cand_pools_name=[pool.upper()])))
+
+        def fake_search(query_embed_path, cand_index_path, batch_size=10, num_cand_to_retrieve=10):
+            assert batch_size == len(queries) and num_cand_to_retrieve == k
+            assert cand_index_path.endswith(f"index/{suffix}cand_pool/mbeir_{pool}_cand_pool.index")
+            return D, I
+        monkeypatch.setattr(mod, "search_index", fake_search)
+        mod.run_hard_negative_mining(cfg)
+        outs[tag] = open(mbeir / "train" / "hard_negs" / f"mbeir_{name}_hard_negs_train.jsonl").read()
+    assert outs["mine"] == outs["ref"]
+    rows = [json.loads(l) for l in outs["mine"].splitlines()]
+    before = [json.loads(l) for l in open(os.path.join(root, "query", "train", f"mbeir_{name}_train.jsonl"))]
+    assert len(rows) == len(queries) == len(before)
+    for qi, (new, old) in enumerate(zip(rows, before)):
+        mined = new["neg_cand_list"][len(old["neg_cand_list"]):]
+        assert new["neg_cand_list"][:len(old["neg_cand_list"])] == old["neg_cand_list"]
+        assert not set(mined) & (set(old["pos_cand_list"]) | set(old["neg_cand_list"]))
+        if qi % 4 == 1:
+            assert mined == []                                   # nothing survived the filter
+        else:
+            assert len(mined) == num_hard_negs                   # repeated up to the length when only 1-2 survived
+            if qi % 4 == 0:
+                assert len(set(mined)) <= 2
