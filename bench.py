@@ -666,21 +666,38 @@ def cpu_blip_reference(steps, warmup, pairs=2, sf=False):
         b["txt_mask_batched"] = torch.ones(2 * pairs, dtype=torch.long)
         b["image_mask_batched"] = torch.ones(2 * pairs, dtype=torch.long)
 
+    # train mode like the reference's step (uniir_blip/engine.py:16): hidden / attention dropout 0.1 and DropPath 0.1 at the
+    # oracle's (reference-pinned) sites, masks from torch's RNG as in the reference
+    import oracle.blip_oracle as bo
+    dpr = torch.linspace(0, 0.1, model.dims.v_layers).tolist()
+
+    def train_mode_masks(tag, kind, layer, x):
+        if kind.startswith("path"):
+            if dpr[layer] == 0.0:
+                return x
+            keep = (torch.rand(x.shape[0], *([1] * (x.ndim - 1))) >= dpr[layer]).to(x.dtype)
+            return x * keep / (1 - dpr[layer])
+        return torch.nn.functional.dropout(x, 0.1, training=True)
+
     def step():
         out = model.compute_contrastive_loss(b, alpha=0.4)
         out["loss"].backward()
         opt.step()
         opt.zero_grad(set_to_none=True)
 
-    for _ in range(warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = (time.perf_counter() - t0) / steps
+    bo.DROPOUT = train_mode_masks
+    try:
+        for _ in range(warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        dt = (time.perf_counter() - t0) / steps
+    finally:
+        bo.DROPOUT = None
     return {"value": pairs / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
-            "sample": f"oracle {'BLIP_SF' if sf else 'BLIP_FF'} large fp32, {pairs} pairs/step (of the {BLIP_GLOBAL_BATCH}-pair batch), online+momentum "
-                      f"forward, loss, backward, AdamW, {steps} timed steps"}, dt
+            "sample": f"oracle {'BLIP_SF' if sf else 'BLIP_FF'} large fp32 in train mode (dropout 0.1 / 0.1, DropPath 0.1), {pairs} pairs/step "
+                      f"(of the {BLIP_GLOBAL_BATCH}-pair batch), online+momentum forward, loss, backward, AdamW, {steps} timed steps"}, dt
 
 
 def main():
